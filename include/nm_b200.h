@@ -1,0 +1,140 @@
+/* nm_b200 — C ABI of the B200-native Neural Marionette keypoint-detection hot path.
+ *
+ * The reference (jinseokbae/neural_marionette) is pure Python over torch.nn: it has no FFI / plugin
+ * interface.  The drop-in boundary is therefore its Python class surface; this header is the
+ * thin C ABI those classes call.  Each entry point names the reference code it replaces (file:line under the
+ * reference tree).  Conventions:
+ *   - every pointer is a DEVICE pointer unless the name says `host`; no allocation inside the library;
+ *     scratch memory is caller-provided (`*_workspace_bytes` gives the size);
+ *   - `stream` is a cudaStream_t passed as void*; the call only enqueues work on it (re-entrant per stream);
+ *   - return value 0 = ok, non-zero = error, message via nm_last_error() (thread-local);
+ *   - activations between kernels are fp16 channels-last (n, D, H, W, C) ("act" below); tensors that cross
+ *     the Python API (occupancy grids, heat-maps, keypoints, gaussians, reconstructions) are fp32 in the
+ *     reference's NCDHW layout.
+ */
+#ifndef NM_B200_H
+#define NM_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* nm_last_error(void);
+int nm_version(void);
+/* sm_100a check: returns 0 when the current device can run the kernels */
+int nm_device_supported(void);
+
+/* ---- voxelization ------------------------------------------------------------------------------------
+ * utils/dataset_utils.py:21-31 `voxelize(pos_coords, output_shape, is_binarized=True)`.
+ * points: (n_frames, n_points, 3) float64 (points_are_f64=1, what episodic_normalization returns) or float32.
+ * grid_out: (n_frames, G, G, G) fp32, fully overwritten (0/1).  err_flag (optional int) is OR-ed with 1 when a
+ * point falls outside [-1, 1) (numpy would wrap / raise there). */
+int nm_voxelize(const void* points, int points_are_f64, int n_frames, int n_points, int grid_size,
+                float* grid_out, int* err_flag, void* stream);
+/* utils/dataset_utils.py:9-19 + :21-31 fused: raw fp32 clips (n_clips, T, n_points, 3) -> clip-global bbox
+ * normalisation (fp32 op order of the reference, float64 translation) -> occupancy (n_clips*T, G, G, G).
+ * bounds_out (optional): (n_clips, 6) fp32 = bmin xyz, bmax xyz. */
+size_t nm_normalize_voxelize_workspace_bytes(int n_clips);
+int nm_normalize_voxelize(const float* raw_points, int n_clips, int T, int n_points, int grid_size, float scale,
+                          double x_trans, double z_trans, float* grid_out, float* bounds_out, void* workspace,
+                          int* err_flag, void* stream);
+
+/* ---- convolutions ------------------------------------------------------------------------------------
+ * nn.Conv3d weight (Cout, Cin, k, k, k) fp32 -> tensor-core operand layout [k^3][Cout][Cin] fp16. */
+int nm_pack_conv_weights(const float* weight, void* packed, int Cout, int Cin, int k, void* stream);
+/* modules/vox_modules.py:12,26,30,39,53; model/kypt_detector.py:429,435,444,450 — nn.Conv3d with
+ * (k in {1,3}, stride 1, pad (k-1)/2) or (k 2, stride 2).  tcgen05 implicit GEMM; x, out: act. */
+int nm_conv3d_tc(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
+                 int Cin, int Cout, int k, int stride, void* stream);
+/* same contract on CUDA cores from the raw fp32 weight; on-device cross-check of nm_conv3d_tc */
+int nm_conv3d_direct(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H, int W,
+                     int Cin, int Cout, int k, int stride, int pad, void* stream);
+/* modules/vox_modules.py:68 nn.ConvTranspose3d(k 2, stride 2); weight (Cin, Cout, 2, 2, 2) fp32 */
+int nm_conv_transpose3d_k2s2(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H,
+                             int W, int Cin, int Cout, void* stream);
+/* First layer: add_coord_channels (utils/kypt_detector_utils.py:4-26) + Conv3d(1+3, Cout, k5, pad 2)
+ * (model/kypt_detector.py:266).  occ: (n, G, G, G) fp32; weight (Cout, 4, 5, 5, 5) fp32; out: act (n,G,G,G,Cout).
+ * `tables` is built once per weight set by nm_first_conv_prepare. linspace: torch.linspace(-1,1,G) fp32. */
+size_t nm_first_conv_tables_bytes(int Cout);
+int nm_first_conv_prepare(const float* weight, int Cout, void* tables, void* stream);
+int nm_first_conv_k5(const float* occ, const void* tables, const float* bias, const float* linspace, int n, int G,
+                     int Cout, void* out, void* stream);
+
+/* ---- GroupNorm / pointwise ---------------------------------------------------------------------------
+ * nn.GroupNorm(C//16, C) statistics (modules/vox_modules.py:14,...) folded to per-(sample, channel)
+ * scale/shift: y = x*scale + shift.  x: act (n, S, C). */
+size_t nm_gn_workspace_bytes(int n, int S, int C);
+int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int groups, const float* gamma, const float* beta,
+                             float eps, float* scale, float* shift, void* workspace, void* stream);
+/* out = act1(x1*a1+b1) + (x2*a2+b2 | x2 | nothing); act1: 0 none, 1 LeakyReLU(0.01).
+ * Basic/Pool/Upsample blocks, Res3DBlock sums (vox_modules.py:44-47), HG skip adds (:111-118). */
+int nm_affine_act(const void* x1, const float* a1, const float* b1, int act1, const void* x2, const float* a2,
+                  const float* b2, void* out, int n, int S, int C, void* stream);
+/* nn.Upsample(scale 2, trilinear, align_corners=False) (kypt_detector.py:427,441) of act1(x*a+b) (a,b optional) */
+int nm_upsample2x(const void* x, const float* a, const float* b, int act, void* out, int n, int D, int H, int W, int C,
+                  void* stream);
+int nm_ndhwc_to_ncdhw_f32(const void* x, float* out, int n, int S, int C, long long in_sample_stride, void* stream);
+int nm_ncdhw_f32_to_ndhwc(const float* x, void* out, int n, int S, int C, void* stream);
+/* seq.mean(dim=1) (kypt_detector.py:312): (n_clips, T, S) fp32 -> (n_clips, S) */
+int nm_mean_over_frames(const float* seq, float* out, int n_clips, int T, long long S, void* stream);
+/* decoder tail: GN-apply + LeakyReLU + Conv3d(32,1,k1) + sigmoid(sharp*(tanh(x)+first_frame-trans))
+ * (kypt_detector.py:453-457,:410) and, when `target` is given, the per-frame mean BCE (:91-92). */
+size_t nm_final_recon_workspace_bytes(int n);
+int nm_final_recon(const void* x, const float* a, const float* b, const float* w, float bias, const float* first_frame,
+                   int frames_per_clip, float sharpness, float translation, float* recon, const float* target,
+                   float* bce_mean, void* workspace, int n, int S, int C, void* stream);
+/* get_volume_fitting_loss('chamfer') (utils/kypt_detector_utils.py:141-157): per-frame value, (n) fp32 */
+size_t nm_chamfer_workspace_bytes(int n);
+int nm_chamfer_vol_fit(const float* seq, const float* keypoints, const float* linspace, int n, int K, int G,
+                       float* out, void* workspace, void* stream);
+
+/* ---- heat-map heads / soft-argmax / Gaussian render --------------------------------------------------
+ * mode 0: heat = LeakyReLU(conv1x1(feature))                        (kypt_detector.py:315: ST head)
+ * mode 1: heat = Softplus(pw0*LeakyReLU(conv1x1(feature)) + pw1*prev[clip] + pb)   (:336-343)
+ *         keypoints = extract_keypoints_from_heatmap(heat)           (utils/kypt_detector_utils.py:28-55)
+ *         gaussians = extract_gaussian_map_from_keypoints(...)       (:57-90), optional
+ * feature: act (n, g^3, C); w1 (K, C); prev (n/frames_per_clip, K, g^3); heat/gaussians (n, K, g^3); keypoints (n,K,4).
+ * heat_mean (optional, (n,K)): per-keypoint heat-map mean = input of get_keypoint_sparsity_loss (:92-103).
+ * gauss_width = 2*(sigma/g)^2 computed by the caller in double. */
+int nm_heatmap_head(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K, int mode,
+                    const float* prev, int frames_per_clip, float pw0, float pw1, float pb, const float* linspace,
+                    float gauss_width, float* heat, float* keypoints, float* gaussians, float* heat_mean,
+                    void* stream);
+int nm_gaussian_render(const float* keypoints, int n, int K, int g, const float* linspace, float gauss_width,
+                       float* gaussians, void* stream);
+/* adjust_combined_representation (kypt_detector.py:381,404-408): 1x1 conv over cat[gauss_t, first_feature,
+ * gauss_0, coords] + LeakyReLU, with the clip-constant part hoisted.  first_feature: act (n_clips, g^3, 128);
+ * keypoints (n, K, 4) or gaussians (n, K, g^3) with n = n_clips*frames_per_clip; base_ws: n_clips*g^3*128 fp32;
+ * out: act (n, g^3, 128). */
+int nm_decoder_adjust(const void* first_feature, const float* keypoints, const float* gaussians, const float* weight,
+                      const float* bias, int n_clips, int frames_per_clip, int g, int K, const float* linspace,
+                      float gauss_width, float* base_ws, void* out, void* stream);
+
+/* ---- HSVRNN latent dynamics --------------------------------------------------------------------------
+ * Weights are passed TRANSPOSED ([in][out], fp32) so that output columns are contiguous. */
+typedef struct nm_hsvrnn_weights {
+  const float *post0_wt, *post0_b, *post2_wt, *post2_b;       /* extract_post_dist  (hsvrnn_bvh.py:29-34) */
+  const float *prior0_wt, *prior0_b, *prior2_wt, *prior2_b;   /* extract_prior_dist (:35-40) */
+  const float *root0_wt, *root0_b, *root2_wt, *root2_b;       /* root_intensity_decoder (:41-47) */
+  const float *joint0_wt, *joint0_b, *joint2_wt, *joint2_b;   /* joint_matrix_decoder (:49-54) */
+  const float *gru_ih_wt, *gru_hh_wt, *gru_ih_b, *gru_hh_b;   /* kypt_rnn_cell (:57-58), gate order r,z,n */
+} nm_hsvrnn_weights;
+/* One time step (hsvrnn_bvh.py:89-135 posterior / :208-225 prior).  `w` is a HOST pointer to the struct.
+ * h_in/h_out (B,512); kp (B,4K) detected keypoints (posterior); eps (S,B,128) standard-normal draws;
+ * offset (B,K,3); order/parents (K) int32 = priority.indices / parents; kp_out (B,4K) decoded keypoints fed to
+ * the GRU; optional outputs: z_out (B,128), R_out (B,K,9), post_out / prior_out (B,256) = mean | std. */
+int nm_hsvrnn_step(const nm_hsvrnn_weights* w, const float* h_in, const float* kp, const float* eps, const float* offset,
+                   const int* order, const int* parents, int B, int K, int S, int posterior, float* h_out,
+                   float* kp_out, float* z_out, float* R_out, float* post_out, float* prior_out, void* stream);
+/* extract_kypt_from_latent_and_state (hsvrnn_bvh.py:255-286): dec_in (B, 640) -> flat (B, 4K), R (B, K, 9) */
+int nm_hsvrnn_decode_pose(const nm_hsvrnn_weights* w, const float* dec_in, const float* offset, const int* order,
+                          const int* parents, int B, int K, float* flat_out, float* R_out, void* stream);
+/* get_offset (hsvrnn_bvh.py:236-253): keypoints (B,T,K,4) -> (B,K,3) */
+int nm_hsvrnn_bone_offsets(const float* keypoints, const int* parents, const float* offset_param, int B, int T, int K,
+                           float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NM_B200_H */

@@ -1,0 +1,123 @@
+"""ctypes binding of the nm_b200 C ABI (include/nm_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails the
+caller gets an exception.  PyTorch only supplies device memory (``data_ptr``)
+and the current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libnm_b200.so")
+
+_vp, _i, _f, _d, _sz, _ll = C.c_void_p, C.c_int, C.c_float, C.c_double, C.c_size_t, C.c_longlong
+
+
+class HsvrnnWeights(C.Structure):
+    _fields_ = [(n, _vp) for n in (
+        "post0_wt", "post0_b", "post2_wt", "post2_b",
+        "prior0_wt", "prior0_b", "prior2_wt", "prior2_b",
+        "root0_wt", "root0_b", "root2_wt", "root2_b",
+        "joint0_wt", "joint0_b", "joint2_wt", "joint2_b",
+        "gru_ih_wt", "gru_hh_wt", "gru_ih_b", "gru_hh_b")]
+
+
+# name -> (restype, argtypes); every symbol declared in include/nm_b200.h
+PROTOTYPES = {
+    "nm_last_error": (C.c_char_p, []),
+    "nm_version": (_i, []),
+    "nm_device_supported": (_i, []),
+    "nm_voxelize": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "nm_normalize_voxelize_workspace_bytes": (_sz, [_i]),
+    "nm_normalize_voxelize": (_i, [_vp, _i, _i, _i, _i, _f, _d, _d, _vp, _vp, _vp, _vp, _vp]),
+    "nm_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "nm_conv3d_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "nm_conv3d_direct": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "nm_conv_transpose3d_k2s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "nm_first_conv_tables_bytes": (_sz, [_i]),
+    "nm_first_conv_prepare": (_i, [_vp, _i, _vp, _vp]),
+    "nm_first_conv_k5": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nm_gn_workspace_bytes": (_sz, [_i, _i, _i]),
+    "nm_groupnorm_scale_shift": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "nm_affine_act": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_upsample2x": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nm_ndhwc_to_ncdhw_f32": (_i, [_vp, _vp, _i, _i, _i, _ll, _vp]),
+    "nm_ncdhw_f32_to_ndhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "nm_mean_over_frames": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
+    "nm_final_recon_workspace_bytes": (_sz, [_i]),
+    "nm_final_recon": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_chamfer_workspace_bytes": (_sz, [_i]),
+    "nm_chamfer_vol_fit": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "nm_heatmap_head": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _f, _vp, _vp, _vp, _vp,
+                             _vp]),
+    "nm_gaussian_render": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp]),
+    "nm_decoder_adjust": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _f, _vp, _vp, _vp]),
+    "nm_hsvrnn_step": (_i, [C.POINTER(HsvrnnWeights), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                            _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nm_hsvrnn_decode_pose": (_i, [C.POINTER(HsvrnnWeights), _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "nm_hsvrnn_bone_offsets": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+}
+
+_lib = None
+CALLS = 0   # C-ABI calls that enqueue kernels (bench.py reports the delta over its timed region)
+
+
+class NmError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into csrc/libnm_b200.so (nvcc cross-compiles without a GPU)."""
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    out = subprocess.run(["bash", script], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise NmError("building libnm_b200.so failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout.strip())
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NmError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  The tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "nm_b200 kernels take dense tensors"
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point and raise on failure."""
+    global CALLS
+    CALLS += 1
+    handle = lib()
+    rc = getattr(handle, name)(*args)
+    if rc != 0:
+        raise NmError(f"{name} failed ({rc}): {handle.nm_last_error().decode()}")
+
+
+def query(name: str, *args):
+    return getattr(lib(), name)(*args)

@@ -1,0 +1,405 @@
+// Implicit-GEMM 3-D convolution on the 5th-gen tensor cores (tcgen05 + TMEM), operands fed by TMA.
+//
+// Reference ops replaced: every nn.Conv3d with k in {1, 3} stride 1 and k = 2 stride 2 in
+// modules/vox_modules.py:12,26,30,39,53 and model/kypt_detector.py:429,435,444,450.
+//
+// GEMM view:  D[M = output voxels, N = Cout] = sum_{tap, ci} A[M, (tap, ci)] * W[(tap, ci), N]
+//   A  : activations, fp16 channels-last (n, D, H, W, Cin).  For tap (kd, kh, kw) the A tile of a box of
+//        128 output voxels is the same box shifted by (kd-p, kh-p, kw-p): one 5-D TMA load per (tap, 64-ch
+//        chunk); out-of-bounds coordinates are zero-filled by the TMA unit = the conv's zero padding.
+//        k2/s2 ("Pool3DBlock") uses one strided tensor map per tap (base shifted by the tap, strides x2).
+//   W  : pre-packed fp16 [tap][Cout][Cin] (K-major B operand), 3-D TMA box (BK, N_tile, 1).
+//   D  : fp32 accumulator in TMEM (double-buffered: 2 x N_tile columns), epilogue adds the bias and
+//        stores fp16 channels-last.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
+// Persistent: grid = #SMs, static round-robin over output tiles.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kMaxTaps = 27;
+constexpr uint64_t kWatchdogCycles = 8000000000ull;  // ~4 s: turn a protocol bug into a trap, not a hang
+
+struct ConvTcParams {
+  CUtensorMap tmap_a[8];
+  CUtensorMap tmap_b;
+  int taps, kchunks, block_k, n_tile, cout;
+  int tw, th, td, tn;            // output-voxel box of one tile (tw*th*td*tn == 128)
+  int nw, nh, nd, nn;            // tiles per dimension
+  int OW, OH, OD, N;             // output extent
+  int stages;
+  int8_t dx[kMaxTaps], dy[kMaxTaps], dz[kMaxTaps], map[kMaxTaps];
+  const float* bias;
+  act_t* out;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if ((uint64_t)(clock64() - t0) > kWatchdogCycles) {
+      printf("nm_conv3d_tc: mbarrier watchdog (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major),
+//   [32,46) stride byte offset >> 4 (= 8 rows * row bytes), [46,48) version = 1, [61,64) layout type.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(192, 1)
+conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment for the swizzled tiles
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int a_bytes = kTileM * p.block_k * 2;
+  const int b_bytes = p.n_tile * p.block_k * 2;
+  const int stage_bytes = a_bytes + b_bytes;
+  uint8_t* tiles = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* tfull = bars + 2 * p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.nw * p.nh * p.nd * p.nn;
+  const int k_iters = p.taps * p.kchunks;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.n_tile) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 8; i++)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[i]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
+    for (int s = 0; s < p.stages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int iw = t % p.nw; t /= p.nw;
+        const int ih = t % p.nh; t /= p.nh;
+        const int id = t % p.nd; t /= p.nd;
+        const int in_ = t;
+        const int w0 = iw * p.tw, h0 = ih * p.th, d0 = id * p.td, n0 = in_ * p.tn;
+        for (int tap = 0; tap < p.taps; tap++) {
+          const CUtensorMap* ma = &p.tmap_a[p.map[tap]];
+          for (int kc = 0; kc < p.kchunks; kc++) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = tiles + (size_t)stage * stage_bytes;
+            mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
+            tma_load_5d(sa, ma, &full[stage], kc * p.block_k, w0 + p.dx[tap], h0 + p.dy[tap], d0 + p.dz[tap], n0);
+            tma_load_3d(sa + a_bytes, &p.tmap_b, &full[stage], kc * p.block_k, 0, tap);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format F16 (0),
+    // K-major A and B, N >> 3 at [17,23), M >> 4 at [24,29)
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t row_bytes = p.block_k * 2;                       // 128 (SW128) or 64 (SW64)
+    const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+    const uint32_t sbo = 8 * row_bytes;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.n_tile);
+      for (int it = 0; it < k_iters; it++) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          for (int k = 0; k < p.block_k / 16; k++) {
+            const uint64_t da = make_smem_desc(sa + k * 32, sbo, layout);
+            const uint64_t db = make_smem_desc(sb + k * 32, sbo, layout);
+            umma_f16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                // frees the smem slot once these MMAs retire
+          if (it == k_iters - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;
+    const int rx = row % p.tw, ry = (row / p.tw) % p.th, rz = (row / (p.tw * p.th)) % p.td,
+              rn = row / (p.tw * p.th * p.td);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int t = tile;
+      const int iw = t % p.nw; t /= p.nw;
+      const int ih = t % p.nh; t /= p.nh;
+      const int id = t % p.nd; t /= p.nd;
+      const int in_ = t;
+      const int ow = iw * p.tw + rx, oh = ih * p.th + ry, od = id * p.td + rz, on = in_ * p.tn + rn;
+      const bool live = ow < p.OW && oh < p.OH && od < p.OD && on < p.N;
+      act_t* dst = p.out + ((((long long)on * p.OD + od) * p.OH + oh) * p.OW + ow) * (long long)p.cout;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(taddr + c0, r);
+        tmem_ld_wait();
+        if (live) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(r[j]) + ((c0 + j < p.cout) ? __ldg(p.bias + c0 + j) : 0.f);
+          if (c0 + 8 <= p.cout) *reinterpret_cast<half8*>(dst + c0) = nm_pack8(f);
+          if (c0 + 16 <= p.cout) *reinterpret_cast<half8*>(dst + c0 + 8) = nm_pack8(f + 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ weight pre-pack
+// nn.Conv3d weight (Cout, Cin, k, k, k) fp32 -> [tap][Cout][Cin] fp16
+__global__ void pack_weights_kernel(const float* __restrict__ w, act_t* __restrict__ out, int Cout, int Cin, int taps) {
+  const long long total = (long long)taps * Cout * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    const int co = (int)((i / Cin) % Cout);
+    const int tap = (int)(i / ((long long)Cin * Cout));
+    out[i] = __float2half_rn(w[((long long)co * Cin + ci) * taps + tap]);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+}  // namespace
+
+extern "C" int nm_pack_conv_weights(const float* weight, void* packed, int Cout, int Cin, int k, void* stream) {
+  NM_CHECK_ARG(weight && packed, "nm_pack_conv_weights: null pointer");
+  const int taps = k * k * k;
+  const long long total = (long long)taps * Cout * Cin;
+  pack_weights_kernel<<<(int)min((total + 255) / 256, 4096LL), 256, 0, (cudaStream_t)stream>>>(weight, (act_t*)packed,
+                                                                                              Cout, Cin, taps);
+  NM_CHECK_LAUNCH("pack_conv_weights");
+  return NM_OK;
+}
+
+// x: (n, D, H, W, Cin) fp16; packed_w: [k^3][Cout][Cin] fp16; out: (n, OD, OH, OW, Cout) fp16.
+// Supported: (k=1|3, stride 1, pad (k-1)/2) and (k=2, stride 2, pad 0); Cin, Cout multiples of 8; Cout <= 256.
+extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H,
+                            int W, int Cin, int Cout, int k, int stride, void* stream) {
+  NM_CHECK_ARG(x && packed_w && bias && out, "nm_conv3d_tc: null pointer");
+  NM_CHECK_ARG((stride == 1 && (k == 1 || k == 3)) || (stride == 2 && k == 2), "nm_conv3d_tc: k=%d stride=%d unsupported",
+               k, stride);
+  NM_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cout <= 256 && Cin >= 16, "nm_conv3d_tc: Cin=%d Cout=%d unsupported", Cin,
+               Cout);
+  NM_CHECK_ARG(stride == 1 || (D % 2 == 0 && H % 2 == 0 && W % 2 == 0), "nm_conv3d_tc: odd extent with stride 2");
+  if (n == 0) return NM_OK;
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    nm_set_error("nm_conv3d_tc: cuTensorMapEncodeTiled entry point not available");
+    return NM_ERR_DRIVER;
+  }
+  ConvTcParams p;
+  memset(&p, 0, sizeof(p));
+  const int pad = stride == 1 ? (k - 1) / 2 : 0;
+  p.taps = k * k * k;
+  p.OD = D / stride; p.OH = H / stride; p.OW = W / stride; p.N = n;
+  p.block_k = Cin >= 64 ? 64 : (Cin >= 32 ? 32 : 16);
+  p.kchunks = (Cin + p.block_k - 1) / p.block_k;
+  p.n_tile = ((Cout + 15) / 16) * 16;
+  p.cout = Cout;
+  p.tw = p.OW < 8 ? p.OW : 8;
+  p.th = p.OH < 4 ? p.OH : 4;
+  p.td = p.OD < 4 ? p.OD : 4;
+  NM_CHECK_ARG(kTileM % (p.tw * p.th * p.td) == 0, "nm_conv3d_tc: output extent (%d,%d,%d) cannot be tiled", p.OD, p.OH, p.OW);
+  p.tn = kTileM / (p.tw * p.th * p.td);
+  NM_CHECK_ARG(p.tn <= 256, "nm_conv3d_tc: tile batch extent too large");
+  p.nw = nm_cdiv(p.OW, p.tw); p.nh = nm_cdiv(p.OH, p.th); p.nd = nm_cdiv(p.OD, p.td); p.nn = nm_cdiv(n, p.tn);
+  p.bias = bias;
+  p.out = (act_t*)out;
+  {
+    int t = 0;
+    for (int a = 0; a < k; a++)
+      for (int b = 0; b < k; b++)
+        for (int c = 0; c < k; c++, t++) {
+          if (stride == 1) { p.dz[t] = (int8_t)(a - pad); p.dy[t] = (int8_t)(b - pad); p.dx[t] = (int8_t)(c - pad); p.map[t] = 0; }
+          else { p.dz[t] = p.dy[t] = p.dx[t] = 0; p.map[t] = (int8_t)t; }
+        }
+  }
+  const CUtensorMapSwizzle swz = p.block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : (p.block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  // activation maps
+  const int n_maps = stride == 1 ? 1 : 8;
+  for (int m = 0; m < 8; m++) {
+    const int mm = m < n_maps ? m : 0;
+    const int a = (mm >> 2) & 1, b = (mm >> 1) & 1, c = mm & 1;
+    const char* base = (const char*)x + (stride == 2 ? ((((size_t)a * H + b) * W + c) * Cin * 2) : 0);
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.OD, (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)stride * Cin * 2, (cuuint64_t)stride * W * Cin * 2,
+                             (cuuint64_t)stride * H * W * Cin * 2, (cuuint64_t)D * H * W * Cin * 2};
+    cuuint32_t box[5] = {(cuuint32_t)p.block_k, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.td, (cuuint32_t)p.tn};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&p.tmap_a[m], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)base, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      nm_set_error("nm_conv3d_tc: cuTensorMapEncodeTiled(A, map %d) failed with %d", m, (int)r);
+      return NM_ERR_DRIVER;
+    }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)p.taps};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+    cuuint32_t box[3] = {(cuuint32_t)p.block_k, (cuuint32_t)p.n_tile, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&p.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)packed_w, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      nm_set_error("nm_conv3d_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+      return NM_ERR_DRIVER;
+    }
+  }
+  const int stage_bytes = kTileM * p.block_k * 2 + p.n_tile * p.block_k * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 4) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = p.nw * p.nh * p.nd * p.nn;
+  const int grid = total_tiles < nm_num_sms() ? total_tiles : nm_num_sms();
+  conv3d_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(p);
+  NM_CHECK_LAUNCH("conv3d_tc");
+  return NM_OK;
+}

@@ -1,0 +1,144 @@
+"""3-D conv building blocks of the detector (drop-in for the reference's
+modules/vox_modules.py: same class names, constructor arguments and parameter
+names/shapes, so reference checkpoints load with strict=True).
+
+Each class is a parameter container (torch.nn layers own the weights) whose
+arithmetic runs through the nm_b200 kernels on fp16 channels-last activations:
+``run(x_act)`` is what the detector calls; ``forward(x)`` keeps the reference's
+NCDHW fp32 tensor contract for callers that use a block on its own.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def _norm(channels: int) -> nn.GroupNorm:
+    return nn.GroupNorm(channels // 16, channels)
+
+
+class _ActModule(nn.Module):
+    """forward() = NCDHW fp32 in/out around run() (inference only: no autograd graph)."""
+
+    def forward(self, x):
+        with torch.no_grad():
+            return ops.act_to_ncdhw(self.run(ops.ncdhw_to_act(x)))
+
+
+def conv_gn_lrelu(x, conv, gn):
+    raw = ops.conv3d(x, conv)
+    a, b = ops.gn_scale_shift(raw, gn)
+    return ops.affine_act(raw, a, b, True)
+
+
+class Basic3DBlock(_ActModule):
+    """conv(k, pad (k-1)//2) -> GroupNorm(C//16) -> LeakyReLU  (reference vox_modules.py:8-19)."""
+
+    def __init__(self, in_planes, out_planes, kernel_size):
+        super().__init__()
+        self.block = nn.Sequential(
+            nn.Conv3d(in_planes, out_planes, kernel_size=kernel_size, stride=1, padding=(kernel_size - 1) // 2),
+            _norm(out_planes), nn.LeakyReLU())
+
+    def run(self, x):
+        return conv_gn_lrelu(x, self.block[0], self.block[1])
+
+    def run_coordconv(self, occ):
+        """occ (n, G, G, G) fp32 occupancy; the 3 coordinate channels are synthesised in-kernel."""
+        raw = ops.first_conv(occ, self.block[0])
+        a, b = ops.gn_scale_shift(raw, self.block[1])
+        return ops.affine_act(raw, a, b, True)
+
+
+class Res3DBlock(_ActModule):
+    """[conv3,GN,LReLU,conv3,GN](x) + skip(x); skip = identity or conv1+GN.  The reference's trailing
+    ``F.leaky_relu(., True)`` has slope 1.0, i.e. no activation (reference vox_modules.py:22-47)."""
+
+    def __init__(self, in_planes, out_planes):
+        super().__init__()
+        self.res_branch = nn.Sequential(
+            nn.Conv3d(in_planes, out_planes, kernel_size=3, stride=1, padding=1), _norm(out_planes), nn.LeakyReLU(),
+            nn.Conv3d(out_planes, out_planes, kernel_size=3, stride=1, padding=1), _norm(out_planes))
+        if in_planes == out_planes:
+            self.skip_con = nn.Sequential()
+        else:
+            self.skip_con = nn.Sequential(
+                nn.Conv3d(in_planes, out_planes, kernel_size=1, stride=1, padding=0), _norm(out_planes))
+
+    def run(self, x):
+        h = conv_gn_lrelu(x, self.res_branch[0], self.res_branch[1])
+        raw = ops.conv3d(h, self.res_branch[3])
+        a, b = ops.gn_scale_shift(raw, self.res_branch[4])
+        if len(self.skip_con) == 0:
+            return ops.affine_act(raw, a, b, False, x2=x)
+        sraw = ops.conv3d(x, self.skip_con[0])
+        sa, sb = ops.gn_scale_shift(sraw, self.skip_con[1])
+        return ops.affine_act(raw, a, b, False, x2=sraw, a2=sa, b2=sb)
+
+
+class Pool3DBlock(_ActModule):
+    """Learned 2x down-sample: conv(k2, s2) -> GN -> LReLU (reference vox_modules.py:49-61)."""
+
+    def __init__(self, pool_size, input_plane):
+        super().__init__()
+        self.stride_conv = nn.Sequential(
+            nn.Conv3d(input_plane, input_plane, kernel_size=pool_size, stride=pool_size, padding=0),
+            _norm(input_plane), nn.LeakyReLU())
+
+    def run(self, x):
+        return conv_gn_lrelu(x, self.stride_conv[0], self.stride_conv[1])
+
+
+class Upsample3DBlock(_ActModule):
+    """ConvTranspose3d(k2, s2) -> GN -> LReLU (reference vox_modules.py:63-75)."""
+
+    def __init__(self, in_planes, out_planes, kernel_size, stride, output_padding=0):
+        super().__init__()
+        assert stride == 2
+        self.block = nn.Sequential(
+            nn.ConvTranspose3d(in_planes, out_planes, kernel_size=kernel_size, stride=stride, padding=0,
+                               output_padding=output_padding),
+            _norm(out_planes), nn.LeakyReLU())
+
+    def run(self, x, skip=None):
+        raw = ops.conv_transpose3d(x, self.block[0])
+        a, b = ops.gn_scale_shift(raw, self.block[1])
+        return ops.affine_act(raw, a, b, True, x2=skip)
+
+
+class HG(_ActModule):
+    """3-level hour-glass, channels in->32->48->72->72->48->32->out, additive skips
+    (reference vox_modules.py:78-120)."""
+
+    def __init__(self, input_channels, output_channels, N=88):
+        super().__init__()
+        outer_padding = [(N // 4) % 2, (N // 2) % 2, N % 2]
+        self.encoder_pool1 = Pool3DBlock(2, input_channels)
+        self.encoder_res1 = Res3DBlock(input_channels, 32)
+        self.encoder_pool2 = Pool3DBlock(2, 32)
+        self.encoder_res2 = Res3DBlock(32, 48)
+        self.encoder_pool3 = Pool3DBlock(2, 48)
+        self.encoder_res3 = Res3DBlock(48, 72)
+        self.decoder_res3 = Res3DBlock(72, 72)
+        self.decoder_upsample3 = Upsample3DBlock(72, 48, 2, 2, outer_padding[0])
+        self.decoder_res2 = Res3DBlock(48, 48)
+        self.decoder_upsample2 = Upsample3DBlock(48, 32, 2, 2, outer_padding[1])
+        self.decoder_res1 = Res3DBlock(32, 32)
+        self.decoder_upsample1 = Upsample3DBlock(32, output_channels, 2, 2, outer_padding[2])
+        self.skip_res1 = Res3DBlock(input_channels, output_channels)
+        self.skip_res2 = Res3DBlock(32, 32)
+        self.skip_res3 = Res3DBlock(48, 48)
+
+    def run(self, x):
+        s1 = self.skip_res1.run(x)
+        x = self.encoder_res1.run(self.encoder_pool1.run(x))
+        s2 = self.skip_res2.run(x)
+        x = self.encoder_res2.run(self.encoder_pool2.run(x))
+        s3 = self.skip_res3.run(x)
+        x = self.encoder_res3.run(self.encoder_pool3.run(x))
+        x = self.decoder_res3.run(x)
+        x = self.decoder_res2.run(self.decoder_upsample3.run(x, skip=s3))
+        x = self.decoder_res1.run(self.decoder_upsample2.run(x, skip=s2))
+        return self.decoder_upsample1.run(x, skip=s1)

@@ -1,0 +1,387 @@
+"""Tensor-level wrappers over the C ABI: allocate outputs with torch, launch on
+the current stream.  Activations ("act") are torch.float16 channels-last tensors
+of shape (n, D, H, W, C).  No CPU paths: every function requires CUDA tensors."""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+ACT_DTYPE = torch.float16
+_scratch = {}
+# bench.py sets this to a dict to bracket every tensor-core conv launch with CUDA events on the launching
+# stream: {(n, grid, Cin, Cout, k, stride, flops): [(start, end), ...]}
+PROFILE = None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.NmError("nm_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def workspace(nbytes: int, device, slot: str = "default") -> torch.Tensor:
+    """Grow-only byte scratch per (device, slot).  Kernels on one stream run in order, so a
+    scratch buffer may be reused by the next launch."""
+    key = (str(device), slot)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+_linspace = {}
+
+
+def linspace(n: int, device) -> torch.Tensor:
+    """torch.linspace(-1, 1, n) exactly as the reference builds it (kypt_detector_utils.py:21,37,73)."""
+    key = (n, str(device))
+    if key not in _linspace:
+        _linspace[key] = torch.linspace(-1.0, 1.0, n, device=device)
+    return _linspace[key]
+
+
+def gauss_width(sigma: float, g: int) -> float:
+    return 2.0 * (sigma / g) ** 2.0
+
+
+# ------------------------------------------------------------------ weight caches
+def _cached(module, tag: str, params, build):
+    """Cache derived (packed) weights on the module; rebuilt when a source parameter changes
+    in place (load_state_dict / optimizer step bump ``_version``) or moves (``.cuda()``)."""
+    key = tuple((p._version, p.data_ptr(), str(p.device)) for p in params)
+    slot = module.__dict__.setdefault("_nm_cache", {})
+    hit = slot.get(tag)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            slot[tag] = (key, build())
+    return slot[tag][1]
+
+
+def packed_conv_weight(conv: torch.nn.Conv3d) -> torch.Tensor:
+    def build():
+        w = conv.weight.detach().float().contiguous()
+        co, ci, k = w.shape[0], w.shape[1], w.shape[2]
+        out = torch.empty(k ** 3, co, ci, dtype=ACT_DTYPE, device=w.device)
+        L.call("nm_pack_conv_weights", L.ptr(w), L.ptr(out), co, ci, k, L.stream())
+        return out
+    return _cached(conv, "packed", [conv.weight], build)
+
+
+def f32(module, name: str) -> torch.Tensor:
+    p = getattr(module, name)
+    return _cached(module, "f32_" + name, [p], lambda: p.detach().float().contiguous())
+
+
+# ------------------------------------------------------------------ voxelize
+def voxelize_points(points: torch.Tensor, grid_size: int, check: bool = True) -> torch.Tensor:
+    """points (F, N, 3) float64/float32 CUDA -> (F, G, G, G) fp32 occupancy (dataset_utils.py:21-31)."""
+    _need_cuda(points)
+    assert points.dim() == 3 and points.shape[-1] == 3 and points.dtype in (torch.float64, torch.float32)
+    points = points.contiguous()
+    F, N = points.shape[:2]
+    out = torch.empty(F, grid_size, grid_size, grid_size, dtype=torch.float32, device=points.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=points.device) if check else None
+    L.call("nm_voxelize", L.ptr(points), int(points.dtype == torch.float64), F, N, grid_size, L.ptr(out),
+           L.ptr(flag), L.stream())
+    if check and int(flag.item()) != 0:
+        raise ValueError("voxelize: point outside [-1, 1) (numpy would wrap or raise here)")
+    return out
+
+
+def normalize_voxelize(raw: torch.Tensor, grid_size: int, scale: float = 1.0, x_trans: float = 0.0,
+                       z_trans: float = 0.0, check: bool = True) -> torch.Tensor:
+    """raw (B, T, N, 3) fp32 CUDA -> (B, T, 1, G, G, G) fp32: episodic_normalization + voxelize fused."""
+    _need_cuda(raw)
+    assert raw.dim() == 4 and raw.shape[-1] == 3 and raw.dtype == torch.float32
+    raw = raw.contiguous()
+    B, T, N = raw.shape[:3]
+    out = torch.empty(B, T, 1, grid_size, grid_size, grid_size, dtype=torch.float32, device=raw.device)
+    ws = workspace(L.query("nm_normalize_voxelize_workspace_bytes", B), raw.device, "vox")
+    flag = torch.zeros(1, dtype=torch.int32, device=raw.device) if check else None
+    L.call("nm_normalize_voxelize", L.ptr(raw), B, T, N, grid_size, float(scale), float(x_trans), float(z_trans),
+           L.ptr(out), None, L.ptr(ws), L.ptr(flag), L.stream())
+    if check and int(flag.item()) != 0:
+        raise ValueError("voxelize: point outside [-1, 1)")
+    return out
+
+
+# ------------------------------------------------------------------ convolutions
+def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
+    """act (n, D, H, W, Cin) -> raw conv output act (n, OD, OH, OW, Cout); bias included."""
+    _need_cuda(x)
+    n, D, H, W, Cin = x.shape
+    k, s, Cout = conv.kernel_size[0], conv.stride[0], conv.out_channels
+    assert Cin == conv.in_channels and x.dtype == ACT_DTYPE and x.is_contiguous()
+    out = torch.empty(n, D // s, H // s, W // s, Cout, dtype=ACT_DTYPE, device=x.device)
+    tc_ok = Cin % 8 == 0 and Cin >= 16 and Cout % 8 == 0 and Cout <= 256 and \
+        ((s == 1 and k in (1, 3) and conv.padding[0] == (k - 1) // 2) or (s == 2 and k == 2 and conv.padding[0] == 0))
+    if tc_ok:
+        pw, pb = packed_conv_weight(conv), f32(conv, "bias")
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        L.call("nm_conv3d_tc", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s, L.stream())
+        if PROFILE is not None:
+            e1.record()
+            flops = 2.0 * n * (D // s) * (H // s) * (W // s) * Cout * Cin * k ** 3
+            PROFILE.setdefault((n, D, Cin, Cout, k, s, flops), []).append((e0, e1))
+    else:
+        pad = conv.padding[0]
+        od = (D + 2 * pad - k) // s + 1
+        out = torch.empty(n, od, (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1, Cout, dtype=ACT_DTYPE,
+                          device=x.device)
+        L.call("nm_conv3d_direct", L.ptr(x), L.ptr(f32(conv, "weight")), L.ptr(f32(conv, "bias")), L.ptr(out),
+               n, D, H, W, Cin, Cout, k, s, pad, L.stream())
+    return out
+
+
+def conv3d_direct(x: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
+    """CUDA-core cross-check of conv3d (tests only)."""
+    n, D, H, W, Cin = x.shape
+    k, s, pad, Cout = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.out_channels
+    out = torch.empty(n, (D + 2 * pad - k) // s + 1, (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1, Cout,
+                      dtype=ACT_DTYPE, device=x.device)
+    L.call("nm_conv3d_direct", L.ptr(x), L.ptr(f32(conv, "weight")), L.ptr(f32(conv, "bias")), L.ptr(out),
+           n, D, H, W, Cin, Cout, k, s, pad, L.stream())
+    return out
+
+
+def conv_transpose3d(x: torch.Tensor, conv: torch.nn.ConvTranspose3d) -> torch.Tensor:
+    n, D, H, W, Cin = x.shape
+    Cout = conv.out_channels
+    assert conv.kernel_size[0] == 2 and conv.stride[0] == 2 and tuple(conv.output_padding) == (0, 0, 0), \
+        "only ConvTranspose3d(k2, s2, output_padding 0) is implemented (grid sizes divisible by 32)"
+    out = torch.empty(n, 2 * D, 2 * H, 2 * W, Cout, dtype=ACT_DTYPE, device=x.device)
+    L.call("nm_conv_transpose3d_k2s2", L.ptr(x), L.ptr(f32(conv, "weight")), L.ptr(f32(conv, "bias")), L.ptr(out),
+           n, D, H, W, Cin, Cout, L.stream())
+    return out
+
+
+def first_conv(occ: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
+    """occ (n, G, G, G) fp32 -> act (n, G, G, G, Cout): CoordConv k5 layer with analytic coordinate channels."""
+    _need_cuda(occ)
+    n, G = occ.shape[0], occ.shape[1]
+    Cout = conv.out_channels
+    assert conv.in_channels == 4 and conv.kernel_size[0] == 5 and occ.dtype == torch.float32 and occ.is_contiguous()
+
+    def build():
+        t = torch.empty(L.query("nm_first_conv_tables_bytes", Cout), dtype=torch.uint8, device=occ.device)
+        L.call("nm_first_conv_prepare", L.ptr(conv.weight.detach().float().contiguous()), Cout, L.ptr(t), L.stream())
+        return t
+    tables = _cached(conv, "first_tables", [conv.weight], build)
+    out = torch.empty(n, G, G, G, Cout, dtype=ACT_DTYPE, device=occ.device)
+    L.call("nm_first_conv_k5", L.ptr(occ), L.ptr(tables), L.ptr(f32(conv, "bias")), L.ptr(linspace(G, occ.device)),
+           n, G, Cout, L.ptr(out), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------ GroupNorm / pointwise
+def gn_scale_shift(raw: torch.Tensor, gn: torch.nn.GroupNorm) -> Tuple[torch.Tensor, torch.Tensor]:
+    n, C = raw.shape[0], raw.shape[-1]
+    S = raw.numel() // (n * C)
+    a = torch.empty(n, C, dtype=torch.float32, device=raw.device)
+    b = torch.empty_like(a)
+    ws = workspace(L.query("nm_gn_workspace_bytes", n, S, C), raw.device, "gn")
+    L.call("nm_groupnorm_scale_shift", L.ptr(raw), n, S, C, gn.num_groups, L.ptr(f32(gn, "weight")),
+           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.ptr(ws), L.stream())
+    return a, b
+
+
+def affine_act(x1, a1, b1, act: bool, x2=None, a2=None, b2=None) -> torch.Tensor:
+    n, C = x1.shape[0], x1.shape[-1]
+    S = x1.numel() // (n * C)
+    out = torch.empty_like(x1)
+    L.call("nm_affine_act", L.ptr(x1), L.ptr(a1), L.ptr(b1), int(act), L.ptr(x2), L.ptr(a2), L.ptr(b2), L.ptr(out),
+           n, S, C, L.stream())
+    return out
+
+
+def upsample2x(x, a=None, b=None, act: bool = False) -> torch.Tensor:
+    n, D, H, W, C = x.shape
+    out = torch.empty(n, 2 * D, 2 * H, 2 * W, C, dtype=ACT_DTYPE, device=x.device)
+    L.call("nm_upsample2x", L.ptr(x), L.ptr(a), L.ptr(b), int(act), L.ptr(out), n, D, H, W, C, L.stream())
+    return out
+
+
+def act_to_ncdhw(x: torch.Tensor) -> torch.Tensor:
+    n, D, H, W, C = x.shape
+    out = torch.empty(n, C, D, H, W, dtype=torch.float32, device=x.device)
+    L.call("nm_ndhwc_to_ncdhw_f32", L.ptr(x), L.ptr(out), n, D * H * W, C, D * H * W * C, L.stream())
+    return out
+
+
+def ncdhw_to_act(x: torch.Tensor) -> torch.Tensor:
+    _need_cuda(x)
+    x = x.float().contiguous()
+    n, C, D, H, W = x.shape
+    out = torch.empty(n, D, H, W, C, dtype=ACT_DTYPE, device=x.device)
+    L.call("nm_ncdhw_f32_to_ndhwc", L.ptr(x), L.ptr(out), n, D * H * W, C, L.stream())
+    return out
+
+
+def mean_over_frames(seq: torch.Tensor) -> torch.Tensor:
+    """(B, T, 1, G, G, G) fp32 -> (B, G, G, G)."""
+    B, T = seq.shape[:2]
+    G = seq.shape[-1]
+    out = torch.empty(B, G, G, G, dtype=torch.float32, device=seq.device)
+    L.call("nm_mean_over_frames", L.ptr(seq), L.ptr(out), B, T, G ** 3, L.stream())
+    return out
+
+
+def final_recon(raw, a, b, conv: torch.nn.Conv3d, first_frame, frames_per_clip, sharpness, translation,
+                target=None, out=None, bce_out=None):
+    """-> recon (n, G, G, G) fp32 [, per-frame BCE mean (n)]; `out` / `bce_out`: preallocated dense views."""
+    n, D, H, W, C = raw.shape
+    S = D * H * W
+    recon = out if out is not None else torch.empty(n, D, H, W, dtype=torch.float32, device=raw.device)
+    w = f32(conv, "weight").reshape(-1)
+    bias = _cached(conv, "bias_host", [conv.bias], lambda: float(conv.bias.detach().float().item()))
+    bce = None
+    if target is not None:
+        bce = bce_out if bce_out is not None else torch.empty(n, dtype=torch.float32, device=raw.device)
+    ws = workspace(L.query("nm_final_recon_workspace_bytes", n), raw.device, "recon") if target is not None else None
+    L.call("nm_final_recon", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), bias, L.ptr(first_frame), frames_per_clip,
+           float(sharpness), float(translation), L.ptr(recon), L.ptr(target), L.ptr(bce), L.ptr(ws), n, S, C,
+           L.stream())
+    return recon, bce
+
+
+def chamfer_vol_fit(seq_frames: torch.Tensor, keypoints: torch.Tensor) -> torch.Tensor:
+    """seq_frames (n, G, G, G) fp32, keypoints (n, K, 4) -> (n) fp32."""
+    n, G = seq_frames.shape[0], seq_frames.shape[-1]
+    K = keypoints.shape[1]
+    out = torch.empty(n, dtype=torch.float32, device=seq_frames.device)
+    ws = workspace(L.query("nm_chamfer_workspace_bytes", n), seq_frames.device, "chamfer")
+    L.call("nm_chamfer_vol_fit", L.ptr(seq_frames), L.ptr(keypoints), L.ptr(linspace(G, seq_frames.device)), n, K, G,
+           L.ptr(out), L.ptr(ws), L.stream())
+    return out
+
+
+# ------------------------------------------------------------------ heads
+def heatmap_head(feature, conv1: torch.nn.Conv3d, K: int, mode: int, prev=None, frames_per_clip: int = 1,
+                 prop: Optional[torch.nn.Conv3d] = None, sigma: float = 1.0, want_gaussians: bool = True,
+                 out=None):
+    """feature act (n, g, g, g, C).  mode 0 -> heat (n, K, g, g, g).
+    mode 1 -> (heat, keypoints (n, K, 4), gaussians (n, K, g, g, g) | None, heat_mean (n, K)).
+    `out` = preallocated dense (heat, keypoints, gaussians | None, heat_mean) views to write into."""
+    n, g, C = feature.shape[0], feature.shape[1], feature.shape[-1]
+    dev = feature.device
+    heat = out[0] if out is not None else torch.empty(n, K, g, g, g, dtype=torch.float32, device=dev)
+    w1 = f32(conv1, "weight").reshape(K, C)
+    b1 = f32(conv1, "bias")
+    if mode == 0:
+        L.call("nm_heatmap_head", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, 0, None, 1, 0.0, 0.0, 0.0,
+               L.ptr(linspace(g, dev)), 1.0, L.ptr(heat), None, None, None, L.stream())
+        return heat
+    pw = _cached(prop, "host", [prop.weight, prop.bias],
+                 lambda: [float(v) for v in prop.weight.detach().float().reshape(-1).tolist()] +
+                         [float(prop.bias.detach().float().item())])
+    if out is not None:
+        kp, gs, hm_mean = out[1], out[2], out[3]
+    else:
+        kp = torch.empty(n, K, 4, dtype=torch.float32, device=dev)
+        gs = torch.empty(n, K, g, g, g, dtype=torch.float32, device=dev) if want_gaussians else None
+        hm_mean = torch.empty(n, K, dtype=torch.float32, device=dev)
+    L.call("nm_heatmap_head", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, 1, L.ptr(prev), frames_per_clip,
+           pw[0], pw[1], pw[2], L.ptr(linspace(g, dev)), gauss_width(sigma, g), L.ptr(heat), L.ptr(kp), L.ptr(gs),
+           L.ptr(hm_mean), L.stream())
+    return heat, kp, gs, hm_mean
+
+
+def gaussian_render(keypoints: torch.Tensor, sigma: float, g: int) -> torch.Tensor:
+    """keypoints (n, K, 4) -> (n, K, g, g, g) fp32 (kypt_detector_utils.py:57-90, all keypoints at once)."""
+    _need_cuda(keypoints)
+    keypoints = keypoints.float().contiguous()
+    n, K = keypoints.shape[:2]
+    out = torch.empty(n, K, g, g, g, dtype=torch.float32, device=keypoints.device)
+    L.call("nm_gaussian_render", L.ptr(keypoints), n, K, g, L.ptr(linspace(g, keypoints.device)),
+           gauss_width(sigma, g), L.ptr(out), L.stream())
+    return out
+
+
+def decoder_adjust(ff_act, conv: torch.nn.Conv3d, frames_per_clip: int, g: int, K: int, sigma: float,
+                   keypoints=None, gaussians=None) -> torch.Tensor:
+    """ff_act (B, g, g, g, 128) act; keypoints (B*T, K, 4) or gaussians (B*T, K, g, g, g) -> act (B*T, g, g, g, 128)."""
+    B = ff_act.shape[0]
+    n = B * frames_per_clip
+    dev = ff_act.device
+    out = torch.empty(n, g, g, g, conv.out_channels, dtype=ACT_DTYPE, device=dev)
+    base = workspace(B * g ** 3 * conv.out_channels * 4, dev, "adjust")
+    w = f32(conv, "weight").reshape(conv.out_channels, -1)
+    L.call("nm_decoder_adjust", L.ptr(ff_act), L.ptr(keypoints), L.ptr(gaussians), L.ptr(w), L.ptr(f32(conv, "bias")),
+           B, frames_per_clip, g, K, L.ptr(linspace(g, dev)), gauss_width(sigma, g), L.ptr(base), L.ptr(out),
+           L.stream())
+    return out
+
+
+# ------------------------------------------------------------------ dynamics
+def hsvrnn_weight_struct(mod) -> "L.HsvrnnWeights":
+    """Transposed fp32 copies ([in][out]) of the HSVRNN matrices + the ctypes struct pointing at them."""
+    names = [("post0", mod.extract_post_dist[0]), ("post2", mod.extract_post_dist[2]),
+             ("prior0", mod.extract_prior_dist[0]), ("prior2", mod.extract_prior_dist[2]),
+             ("root0", mod.root_intensity_decoder[0]), ("root2", mod.root_intensity_decoder[2]),
+             ("joint0", mod.joint_matrix_decoder[0]), ("joint2", mod.joint_matrix_decoder[2])]
+    cell = mod.kypt_rnn_cell
+    params = [p for _, lin in names for p in (lin.weight, lin.bias)] + \
+             [cell.weight_ih, cell.weight_hh, cell.bias_ih, cell.bias_hh]
+
+    def build():
+        keep = []
+        st = L.HsvrnnWeights()
+        for tag, lin in names:
+            wt = lin.weight.detach().float().t().contiguous()
+            b = lin.bias.detach().float().contiguous()
+            keep += [wt, b]
+            setattr(st, tag + "_wt", wt.data_ptr())
+            setattr(st, tag + "_b", b.data_ptr())
+        for tag, p in (("gru_ih_wt", cell.weight_ih), ("gru_hh_wt", cell.weight_hh)):
+            wt = p.detach().float().t().contiguous()
+            keep.append(wt)
+            setattr(st, tag, wt.data_ptr())
+        for tag, p in (("gru_ih_b", cell.bias_ih), ("gru_hh_b", cell.bias_hh)):
+            b = p.detach().float().contiguous()
+            keep.append(b)
+            setattr(st, tag, b.data_ptr())
+        return st, keep
+    return _cached(mod, "hsvrnn", params, build)[0]
+
+
+def hsvrnn_step(wstruct, h, kp_flat, eps, offset, order, parents, K: int, posterior: bool,
+                want_z=False, want_R=False, want_post=False, want_prior=False):
+    """One fused time step.  eps: (S, B, Z) for posterior steps, (B, Z) for prior steps."""
+    B = h.shape[0]
+    dev = h.device
+    S = eps.shape[0] if posterior else 1
+    h_out = torch.empty_like(h)
+    kp_out = torch.empty(B, 4 * K, dtype=torch.float32, device=dev)
+    z_out = torch.empty(B, eps.shape[-1], dtype=torch.float32, device=dev) if want_z else None
+    R_out = torch.empty(B, K, 3, 3, dtype=torch.float32, device=dev) if want_R else None
+    post = torch.empty(B, 2 * eps.shape[-1], dtype=torch.float32, device=dev) if want_post else None
+    prior = torch.empty(B, 2 * eps.shape[-1], dtype=torch.float32, device=dev) if want_prior else None
+    L.call("nm_hsvrnn_step", ctypes.byref(wstruct), L.ptr(h), L.ptr(kp_flat), L.ptr(eps), L.ptr(offset), L.ptr(order),
+           L.ptr(parents), B, K, S, int(posterior), L.ptr(h_out), L.ptr(kp_out), L.ptr(z_out), L.ptr(R_out),
+           L.ptr(post), L.ptr(prior), L.stream())
+    return h_out, kp_out, z_out, R_out, post, prior
+
+
+def hsvrnn_decode_pose(wstruct, dec_in, offset, order, parents, K: int):
+    B = dec_in.shape[0]
+    flat = torch.empty(B, 4 * K, dtype=torch.float32, device=dec_in.device)
+    R = torch.empty(B, K, 3, 3, dtype=torch.float32, device=dec_in.device)
+    L.call("nm_hsvrnn_decode_pose", ctypes.byref(wstruct), L.ptr(dec_in), L.ptr(offset), L.ptr(order), L.ptr(parents),
+           B, K, L.ptr(flat), L.ptr(R), L.stream())
+    return flat, R
+
+
+def hsvrnn_bone_offsets(keypoints, parents, offset_param) -> torch.Tensor:
+    B, T, K = keypoints.shape[:3]
+    out = torch.empty(B, K, 3, dtype=torch.float32, device=keypoints.device)
+    L.call("nm_hsvrnn_bone_offsets", L.ptr(keypoints), L.ptr(parents), L.ptr(offset_param), B, T, K, L.ptr(out),
+           L.stream())
+    return out

@@ -1,0 +1,351 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ops.* are 1:1 wrappers of include/nm_b200.h).
+The checker is the CPU oracle (oracle/nm_oracle.py, pinned to the reference by tests/golden/).
+
+Tolerances (BASELINE.json north_star): occupancy grids bit-exact; keypoints <= 1e-3 of the grid extent
+(extent = 2 -> 2e-3 absolute); heat-maps <= 1e-2 relative to the tensor's peak.  Per-kernel tests are much
+tighter: fp16 activations carry 2^-11 relative rounding, accumulation is fp32.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from neural_marionette_b200 import ops as _ops
+    return _ops
+
+
+def to_act(x):  # NCDHW fp32 cpu -> channels-last fp16 cuda
+    return x.permute(0, 2, 3, 4, 1).contiguous().half().cuda()
+
+
+def from_act(y):  # channels-last fp16 cuda -> NCDHW fp32 cpu
+    return y.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def rel_err(got, ref):
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-6))
+
+
+# ------------------------------------------------------------------------------------------------ voxelize
+def test_voxelize_bit_exact_golden(golden_dir):
+    import neural_marionette_b200 as nm
+    cases = json.load(open(os.path.join(golden_dir, "voxelize_hashes.json")))
+    done = set()
+    for c in cases:
+        key = (c["seed"], c["N"], c["G"])
+        if key in done:
+            continue
+        done.add(key)
+        T = 1 + max(x["t"] for x in cases if x["seed"] == c["seed"])
+        raw = O.synthetic_clip(c["seed"], T, c["N"])
+        pts = O.episodic_normalization(raw)                              # float64, as the reference produces
+        grid = nm.voxelize_clip(pts, c["G"]).cpu().numpy()               # (T, 1, G, G, G)
+        fused = nm.voxelize_raw_clips(raw[None], c["G"])[0].cpu().numpy()
+        for x in (x for x in cases if x["seed"] == c["seed"]):
+            g = grid[x["t"]]
+            assert g.dtype == np.float32 and int(g.sum()) == x["occupied"]
+            assert hashlib.sha256(np.ascontiguousarray(g).tobytes()).hexdigest() == x["sha256"]
+            assert np.array_equal(fused[x["t"]], g), "fused normalise+voxelize differs"
+
+
+def test_voxelize_numpy_dropin_and_real_geometry(golden_dir):
+    import neural_marionette_b200 as nm
+    z = np.load(os.path.join(golden_dir, "voxelize_obj.npz"))
+    pts = O.episodic_normalization(z["obj_points_f32"][None], 0.8)[0]
+    g = nm.voxelize(pts, (64, 64, 64), is_binarized=True)
+    assert g.shape == (1, 64, 64, 64) and g.dtype == np.float32
+    assert np.array_equal(np.packbits(g.astype(np.uint8).ravel()), z["obj_grid_packed"])
+    fused = nm.voxelize_raw_clips(z["obj_points_f32"][None, None], 64, scale=0.8)[0, 0].cpu().numpy()
+    assert np.array_equal(fused, g)
+
+
+def test_voxelize_edge_cases():
+    import neural_marionette_b200 as nm
+    assert nm.voxelize(np.zeros((0, 3)), (8, 8, 8)).sum() == 0                      # empty cloud
+    p = np.array([[0.0, 0.0, 0.0]] * 70 + [[np.nextafter(1.0, 0.0)] * 3, [-1.0, -1.0, -1.0]])
+    g = nm.voxelize(p, (8, 8, 8))
+    assert np.array_equal(g, O.voxelize(p, (8, 8, 8)))                              # duplicates, both extremes
+    assert np.array_equal(nm.voxelize(p.astype(np.float32), (16,) * 3), O.voxelize(p.astype(np.float32), (16,) * 3))
+    with pytest.raises(ValueError):                                                 # numpy would raise IndexError
+        nm.voxelize(np.array([[1.5, 0.0, 0.0]]), (8, 8, 8))
+    rng = np.random.default_rng(0)                                                  # ragged sizes, heavy collisions
+    for n in (1, 31, 33, 255, 257, 100000):
+        q = rng.uniform(-1, 1, size=(n, 3)) * 0.2
+        assert np.array_equal(nm.voxelize(q, (128,) * 3), O.voxelize(q, (128,) * 3))
+
+
+def test_voxelize_translation_variants():
+    import neural_marionette_b200 as nm
+    raw = O.synthetic_clip(1004, 2, 5000)
+    for scale, xt, zt in [(0.8, 0.0, 0.0), (0.7, 0.1, 0.05)]:
+        ref = O.voxelize_clip(O.episodic_normalization(raw, scale, xt, zt), 64)
+        got = nm.voxelize_raw_clips(raw[None], 64, scale, xt, zt)[0].cpu().numpy()
+        assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+CONV_CASES = [
+    # (n, grid, Cin, Cout, k, stride)
+    (2, 8, 64, 64, 1, 1), (2, 8, 64, 64, 3, 1), (1, 16, 32, 64, 3, 1), (1, 16, 64, 32, 3, 1),
+    (1, 16, 128, 64, 3, 1), (1, 8, 128, 256, 3, 1), (1, 8, 256, 256, 1, 1), (3, 4, 48, 48, 3, 1),
+    (5, 2, 72, 72, 3, 1), (20, 2, 48, 72, 3, 1), (2, 16, 32, 32, 2, 2), (2, 8, 64, 64, 2, 2),
+    (3, 4, 48, 48, 2, 2), (1, 32, 32, 32, 3, 1), (2, 8, 32, 64, 1, 1), (3, 2, 48, 48, 2, 2),
+]
+
+
+@pytest.mark.parametrize("n,grid,cin,cout,k,stride", CONV_CASES)
+def test_conv3d_tc(ops, n, grid, cin, cout, k, stride):
+    g = torch.Generator().manual_seed(n * 1000 + grid * 10 + cin + cout + k)
+    conv = torch.nn.Conv3d(cin, cout, k, stride, (k - 1) // 2 if stride == 1 else 0)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (cin * k ** 3) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g))
+    x = torch.randn(n, cin, grid, grid, grid, generator=g)
+    xh = x.half().float()
+    wh = conv.weight.detach().half().float()
+    ref = F.conv3d(xh, wh, conv.bias.detach(), stride=stride, padding=conv.padding)
+    conv = conv.cuda()
+    got = from_act(ops.conv3d(to_act(x), conv))
+    chk = from_act(ops.conv3d_direct(to_act(x), conv))
+    torch.cuda.synchronize()
+    assert rel_err(chk, F.conv3d(xh, conv.weight.detach().cpu(), conv.bias.detach().cpu(), stride=stride,
+                                 padding=conv.padding)) < 3e-3, "direct (CUDA-core) conv wrong"
+    err = rel_err(got, ref)
+    if err >= 2e-3:  # leave evidence for offline diagnosis
+        os.makedirs("gpurun_out", exist_ok=True)
+        np.savez_compressed(f"gpurun_out/conv_fail_{n}_{grid}_{cin}_{cout}_{k}_{stride}.npz", got=got.numpy(),
+                            ref=ref.numpy(), x=xh.numpy(), w=wh.numpy())
+    assert err < 2e-3, f"tcgen05 conv rel err {err}"
+
+
+def test_first_conv_coordconv(ops):
+    for G, cout in [(16, 32), (32, 64)]:
+        g = torch.Generator().manual_seed(G + cout)
+        conv = torch.nn.Conv3d(4, cout, 5, 1, 2)
+        occ = (torch.rand(2, 1, G, G, G, generator=g) < 0.05).float()
+        occ[1] *= torch.rand(1, G, G, G, generator=g)          # non-binary values (the clip-mean input)
+        ref = conv(O.add_coord_channels(occ)).detach()
+        got = from_act(ops.first_conv(occ[:, 0].contiguous().cuda(), conv.cuda()))
+        assert rel_err(got, ref) < 2e-3
+
+
+def test_conv_transpose(ops):
+    g = torch.Generator().manual_seed(3)
+    conv = torch.nn.ConvTranspose3d(72, 48, 2, 2)
+    x = torch.randn(3, 72, 2, 2, 2, generator=g)
+    ref = conv(x.half().float()).detach()
+    got = from_act(ops.conv_transpose3d(to_act(x), conv.cuda()))
+    assert rel_err(got, ref) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ pointwise
+@pytest.mark.parametrize("C,grid", [(32, 16), (48, 4), (64, 8), (72, 2), (128, 8), (256, 4)])
+def test_groupnorm_affine(ops, C, grid):
+    g = torch.Generator().manual_seed(C)
+    gn = torch.nn.GroupNorm(C // 16, C)
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        gn.bias.copy_(0.3 * torch.randn(C, generator=g))
+    x = torch.randn(3, C, grid, grid, grid, generator=g) * 2 + 0.7
+    skip = torch.randn(3, C, grid, grid, grid, generator=g)
+    xh = x.half().float()
+    ref = F.leaky_relu(gn(xh), 0.01).detach()
+    gn = gn.cuda()
+    xa = to_act(x)
+    a, b = ops.gn_scale_shift(xa, gn)
+    got = from_act(ops.affine_act(xa, a, b, True))
+    assert (got - ref).abs().max() < 4e-3
+    ref2 = (gn.cpu()(xh) + skip.half().float()).detach()
+    got2 = from_act(ops.affine_act(xa, a, b, False, x2=to_act(skip)))
+    assert (got2 - ref2).abs().max() < 6e-3
+    got3 = from_act(ops.affine_act(xa, a, b, False, x2=xa, a2=a, b2=b))
+    assert (got3 - 2 * gn(xh).detach()).abs().max() < 8e-3
+
+
+def test_upsample_trilinear(ops):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 64, 6, 6, 6, generator=g)
+    ref = F.interpolate(x.half().float(), scale_factor=2.0, mode="trilinear", align_corners=False)
+    got = from_act(ops.upsample2x(to_act(x)))
+    assert (got - ref).abs().max() < 3e-3
+    a = (torch.rand(2, 64, generator=g) + 0.5).cuda()
+    b = torch.randn(2, 64, generator=g).cuda()
+    pre = F.leaky_relu(x.half().float() * a.cpu()[:, :, None, None, None] + b.cpu()[:, :, None, None, None], 0.01)
+    ref = F.interpolate(pre, scale_factor=2.0, mode="trilinear", align_corners=False)
+    got = from_act(ops.upsample2x(to_act(x), a, b, act=True))
+    assert (got - ref).abs().max() < 6e-3
+
+
+def test_layout_roundtrip_and_mean(ops):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(3, 128, 4, 4, 4, generator=g)
+    assert torch.equal(ops.act_to_ncdhw(ops.ncdhw_to_act(x.cuda())).cpu(), x.half().float())
+    seq = torch.rand(2, 5, 1, 8, 8, 8, generator=g)
+    got = ops.mean_over_frames(seq.cuda()).cpu()
+    assert (got - seq.mean(dim=1)[:, 0]).abs().max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ heads
+@pytest.mark.parametrize("g", [8, 16])
+def test_heatmap_head_softargmax_render(ops, g):
+    gen = torch.Generator().manual_seed(g)
+    K, C, B, T = 24, 128, 2, 3
+    conv1 = torch.nn.Conv3d(C, K, 1)
+    prop = torch.nn.Conv3d(2, 1, 1)
+    with torch.no_grad():
+        conv1.weight.mul_(6.0)
+        prop.weight.copy_(torch.tensor([1.5, 0.75]).view(1, 2, 1, 1, 1))
+        prop.bias.fill_(-1.0)
+    feat = torch.randn(B * T, C, g, g, g, generator=gen)
+    prev = torch.randn(B, K, g, g, g, generator=gen)
+    fh = feat.half().float()
+    hm = F.leaky_relu(conv1(fh), 0.01).reshape(B * T * K, 1, g, g, g)
+    pv = prev[:, None].expand(B, T, K, g, g, g).reshape(B * T * K, 1, g, g, g)
+    hm = F.softplus(prop(torch.cat([hm, pv], 1))).view(B * T, K, g, g, g).detach()
+    kp = O.keypoints_from_heatmap(hm)
+    gs = O.render_gaussians(kp, 1.5, g)
+    heat, kps, gss, hmean = ops.heatmap_head(to_act(feat), conv1.cuda(), K, 1, prev=prev.cuda(), frames_per_clip=T,
+                                             prop=prop.cuda(), sigma=1.5)
+    assert rel_err(heat.cpu(), hm) < 1e-4
+    assert (kps.cpu() - kp).abs().max() < 2e-5
+    assert (gss.cpu() - gs).abs().max() < 2e-4
+    assert (hmean.cpu() - hm.mean(dim=(2, 3, 4))).abs().max() < 1e-4 * float(hm.max())
+    # ST head (mode 0, C = 256)
+    conv2 = torch.nn.Conv3d(256, K, 1)
+    f2 = torch.randn(2, 256, g, g, g, generator=gen)
+    ref = F.leaky_relu(conv2(f2.half().float()), 0.01).detach()
+    got = ops.heatmap_head(to_act(f2), conv2.cuda(), K, 0)
+    assert rel_err(got.cpu(), ref) < 1e-4
+    # standalone render
+    assert (ops.gaussian_render(kp.cuda(), 1.5, g).cpu() - gs).abs().max() < 2e-4
+
+
+def test_decoder_adjust(ops):
+    gen = torch.Generator().manual_seed(4)
+    B, T, K, g = 2, 3, 24, 8
+    conv = torch.nn.Conv3d(128 + 2 * K + 3, 128, 1)
+    ff = torch.randn(B, 128, g, g, g, generator=gen)
+    kp = torch.cat([torch.rand(B, T, K, 3, generator=gen) - 0.5, torch.rand(B, T, K, 1, generator=gen)], -1)
+    gs = torch.stack([O.render_gaussians(kp[:, t], 1.5, g) for t in range(T)], 1)
+    ffh = ff.half().float()
+    ref = torch.stack([F.leaky_relu(conv(O.add_coord_channels(torch.cat([gs[:, t], ffh, gs[:, 0]], 1))), 0.01)
+                       for t in range(T)], 1).detach().reshape(B * T, 128, g, g, g)
+    conv = conv.cuda()
+    got = from_act(ops.decoder_adjust(to_act(ff), conv, T, g, K, 1.5, keypoints=kp.reshape(B * T, K, 4).cuda()))
+    assert rel_err(got, ref) < 2e-3
+    got = from_act(ops.decoder_adjust(to_act(ff), conv, T, g, K, 1.5,
+                                      gaussians=gs.reshape(B * T, K, g, g, g).contiguous().cuda()))
+    assert rel_err(got, ref) < 2e-3
+
+
+def test_final_recon_and_bce(ops):
+    gen = torch.Generator().manual_seed(6)
+    B, T, G, C = 2, 2, 16, 32
+    gn = torch.nn.GroupNorm(2, C)
+    conv = torch.nn.Conv3d(C, 1, 1)
+    with torch.no_grad():
+        conv.weight.mul_(4.0)
+    x = torch.randn(B * T, C, G, G, G, generator=gen)
+    first = (torch.rand(B, 1, G, G, G, generator=gen) < 0.1).float()
+    target = (torch.rand(B * T, 1, G, G, G, generator=gen) < 0.1).float()
+    xh = x.half().float()
+    pre = conv(F.leaky_relu(gn(xh), 0.01))
+    ff = first[:, None].expand(B, T, 1, G, G, G).reshape(B * T, 1, G, G, G)
+    ref = torch.sigmoid(10.0 * (torch.tanh(pre) + ff - 0.5)).detach()
+    ref_bce = F.binary_cross_entropy(ref, target, reduction="none").mean(dim=(1, 2, 3, 4))
+    gn, conv = gn.cuda(), conv.cuda()
+    xa = to_act(x)
+    a, b = ops.gn_scale_shift(xa, gn)
+    recon, bce = ops.final_recon(xa, a, b, conv, first[:, 0].contiguous().cuda(), T, 10.0, 0.5,
+                                 target=target[:, 0].contiguous().cuda())
+    assert (recon.cpu() - ref[:, 0]).abs().max() < 2e-2      # sigmoid slope 2.5 x fp16-rounded pre-activation
+    assert (recon.cpu() - ref[:, 0]).abs().mean() < 1e-3
+    assert (bce.cpu() - ref_bce).abs().max() < 2e-3 * float(ref_bce.max())
+
+
+def test_chamfer(ops):
+    gen = torch.Generator().manual_seed(8)
+    seq = (torch.rand(2, 3, 1, 16, 16, 16, generator=gen) < 0.05).float()
+    kp = torch.cat([torch.rand(2, 3, 24, 3, generator=gen) * 2 - 1, torch.rand(2, 3, 24, 1, generator=gen)], -1)
+    ref = O.chamfer_vol_fit(seq, kp)
+    got = ops.chamfer_vol_fit(seq.reshape(6, 16, 16, 16).cuda(), kp.reshape(6, 24, 4).cuda()).view(2, 3).cpu()
+    assert (got - ref).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ dynamics
+def _dyna_setup(seed):
+    import neural_marionette_b200 as nm
+    hp = O.default_hparams()
+    sd = O.synthetic_state_dict(hp, seed=seed)
+    net = nm.NeuralMarionette(hp)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    net.anneal(1)
+    return net, sd, hp
+
+
+def test_dynamics_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "dynamics.npz"))
+    net, sd, hp = _dyna_setup(int(z["seed"]))
+    dm = net.dyna_module
+    kp = torch.from_numpy(z["kp"]).cuda()
+    with torch.no_grad():
+        aff = net.kypt_detector.get_affinity()
+        enc = dm.encode(kp, aff, eps=torch.from_numpy(np.zeros((kp.shape[1], 10, kp.shape[0], 128), np.float32)).cuda())
+        assert dm.parents.cpu().tolist() == z["parents"].tolist()
+        assert dm.priority.indices.cpu().tolist() == z["order"].tolist()
+        assert enc["h_kypts"].shape == (3, 7, 512)
+        out = dm.generate(kp[:, :3], aff, Ttot=9, Tcond=3, eps_cond=torch.from_numpy(z["eps_cond"]).cuda(),
+                          eps_gen=torch.from_numpy(z["eps_gen"]).cuda())
+        assert (out["keypoints_cond"].cpu() - torch.from_numpy(z["keypoints_cond"])).abs().max() < 2e-4
+        assert (out["keypoints_gen"].cpu() - torch.from_numpy(z["keypoints_gen"])).abs().max() < 5e-4
+        off = dm.get_offset(kp)
+        assert off.shape == (3, 24, 3, 1)
+        assert (off.cpu() - torch.from_numpy(z["offset"])).abs().max() < 1e-6
+        flat, R = dm.extract_kypt_from_latent_and_state(torch.from_numpy(z["dec_in"]).cuda(), off)
+        assert (flat.cpu() - torch.from_numpy(z["dec_flat"])).abs().max() < 2e-5
+        assert (R.cpu() - torch.from_numpy(z["dec_R"])).abs().max() < 2e-5
+
+
+def test_dynamics_encode_vs_oracle():
+    net, sd, hp = _dyna_setup(33)
+    gen = torch.Generator().manual_seed(5)
+    B, T, K, Z = 5, 7, 24, 128
+    kp = torch.cat([torch.rand(B, T, K, 3, generator=gen) * 1.2 - 0.6, torch.rand(B, T, K, 1, generator=gen)], -1)
+    eps = torch.randn(T, 10, B, Z, generator=gen)
+    with torch.no_grad():
+        aff = net.kypt_detector.get_affinity()
+        got = net.dyna_module.encode(kp.cuda(), aff, eps=eps.cuda())
+        ref = O.dyna_encode(kp, O.skeleton_from_affinity(aff.cpu()), sd, hp, eps=eps)
+    for k in ["kypt_recon", "R", "z_kypts", "h_kypts"]:
+        assert (got[k].cpu() - ref[k]).abs().max() < 5e-4, k
+    assert abs(float(got["kl_kypt"]) - float(ref["kl_kypt"])) < 1e-3 * abs(float(ref["kl_kypt"]))
+    assert abs(float(got["kypt_recon_loss"]) - float(ref["kypt_recon_loss"])) < 1e-3 * float(ref["kypt_recon_loss"])
+
+
+def test_dynamics_large_batch_matches_small():
+    """The NB=4 kernel variant (B >= 4 x #SMs) must agree with the NB=1 variant."""
+    net, sd, hp = _dyna_setup(34)
+    gen = torch.Generator().manual_seed(6)
+    B, K, Z = 640, 24, 128
+    kp = torch.cat([torch.rand(B, 2, K, 3, generator=gen) - 0.5, torch.rand(B, 2, K, 1, generator=gen)], -1).cuda()
+    ec = torch.randn(2, 10, B, Z, generator=gen).cuda()
+    eg = torch.randn(2, B, Z, generator=gen).cuda()
+    with torch.no_grad():
+        aff = net.kypt_detector.get_affinity()
+        net.dyna_module.encode(kp[:2], aff)
+        big = net.dyna_module.generate(kp, aff, Ttot=4, Tcond=2, eps_cond=ec, eps_gen=eg)
+        small = net.dyna_module.generate(kp[:40], aff, Ttot=4, Tcond=2, eps_cond=ec[:, :, :40].contiguous(),
+                                         eps_gen=eg[:, :40].contiguous())
+    assert (big["keypoints_gen"][:40] - small["keypoints_gen"]).abs().max() < 1e-5
