@@ -37,6 +37,9 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
   float* s_m = s_b + KMAX;                 // [3][K][32] raw marginal sums along x, y, z
   float* s_kp = s_m + 3 * KMAX * 32;       // [K][4]
   float* s_e = s_kp + KMAX * 4;            // [K][3][32] separable gaussian factors
+  float* s_px = s_e + KMAX * 3 * 32;       // [8 warps][K]        per-iteration warp partials (x)
+  float* s_py = s_px + 8 * KMAX;           // [8 warps][K][4]     (y: one per run of `run` lanes)
+  float* s_pz = s_py + 8 * KMAX * 4;       // [8 warps][K][32]    (z)
   const int n = blockIdx.x;
   const int S = g * g * g;
   for (int i = threadIdx.x; i < K * C; i += 256) s_w[i] = w1[i];
@@ -47,8 +50,9 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
   const act_t* f = feature + (long long)n * S * C;
   const float* pv = prev ? prev + (long long)(n / frames_per_clip) * K * S : nullptr;
   float* hm_out = heat + (long long)n * K * S;
-  const int lane = threadIdx.x & 31;
-  const int run = g < 32 ? g : 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int run = g < 32 ? g : 32;          // lanes that share y
+  const int runs = 32 / run;                // y rows per warp
 
   // voxel s = (x*g + y)*g + z ; consecutive threads -> consecutive s (coalesced heat-map rows)
   for (int s0 = 0; s0 < S; s0 += 256) {
@@ -71,7 +75,6 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
         }
       }
     }
-    const int z = s % g, y = (s / g) % g, x = s / (g * g);
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
       if (k < K) {
@@ -79,20 +82,39 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
         if (mode == 1) h = softplus1(fmaf(pw0, h, fmaf(pw1, pv[(long long)k * S + s], pb)));
         hm_out[(long long)k * S + s] = h;
         if (mode == 1) {
-          // y: segmented sum over runs of `run` lanes
-          float hy = h;
+          // warp-level partial sums (shuffles only: deterministic)
+          float hy = h;                                    // y: segmented sum over runs of `run` lanes
           for (int o = 1; o < run; o <<= 1) hy += __shfl_xor_sync(0xffffffffu, hy, o);
-          // z: sum over lanes with equal lane % g
-          float hz = h;
+          float hz = h;                                    // z: sum over lanes with equal lane % g
           for (int o = run; o < 32; o <<= 1) hz += __shfl_xor_sync(0xffffffffu, hz, o);
-          // x: whole warp (reuse the run sums)
-          float hx = hy;
+          float hx = hy;                                   // x: whole warp
           for (int o = run; o < 32; o <<= 1) hx += __shfl_xor_sync(0xffffffffu, hx, o);
-          if (lane == 0) atomicAdd(s_m + (0 * KMAX + k) * 32 + x, hx);
-          if ((lane % run) == 0) atomicAdd(s_m + (1 * KMAX + k) * 32 + y, hy);
-          if (lane < run) atomicAdd(s_m + (2 * KMAX + k) * 32 + z, hz);
+          if (lane == 0) s_px[warp * KMAX + k] = hx;
+          if ((lane % run) == 0) s_py[(warp * KMAX + k) * 4 + lane / run] = hy;
+          if (lane < run) s_pz[(warp * KMAX + k) * 32 + lane] = hz;
         }
       }
+    }
+    if (mode == 1) {
+      // fold the 8 warps' partials into the marginals in a fixed order (no float atomics: results are
+      // bit-reproducible run to run, which the reference's callers rely on via cudnn.deterministic)
+      __syncthreads();
+      for (int i = threadIdx.x; i < K * (1 + 32); i += 256) {
+        const int k = i / 33, j = i % 33;
+        if (j == 32) {
+          for (int w = 0; w < 8; w++) {
+            const int sw = s0 + w * 32;                    // first voxel of warp w in this iteration
+            s_m[(0 * KMAX + k) * 32 + sw / (g * g)] += s_px[w * KMAX + k];
+            for (int r = 0; r < runs; r++)
+              s_m[(1 * KMAX + k) * 32 + ((sw + r * run) / g) % g] += s_py[(w * KMAX + k) * 4 + r];
+          }
+        } else if (j < run) {
+          float t = 0.f;
+          for (int w = 0; w < 8; w++) t += s_pz[(w * KMAX + k) * 32 + j];
+          s_m[(2 * KMAX + k) * 32 + j] += t;
+        }
+      }
+      __syncthreads();
     }
   }
   if (mode == 0) return;
@@ -284,7 +306,9 @@ adjust_frame_kernel(const float* __restrict__ base, const float* __restrict__ kp
   for (int j = 0; j < PER / 8; j++) dst[j] = nm_pack8(acc + j * 8);
 }
 
-size_t head_smem_bytes(int C) { return (size_t)(KMAX * C + KMAX + 3 * KMAX * 32 + KMAX * 4 + KMAX * 3 * 32) * 4; }
+size_t head_smem_bytes(int C) {
+  return (size_t)(KMAX * C + KMAX + 3 * KMAX * 32 + KMAX * 4 + KMAX * 3 * 32 + 8 * KMAX * (1 + 4 + 32)) * 4;
+}
 
 }  // namespace
 
@@ -301,12 +325,12 @@ extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float
   const size_t smem = head_smem_bytes(C);
   if (C == 128) {
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(head_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(head_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
     head_kernel<128><<<n, 256, smem, st>>>((const act_t*)feature, w1, b1, K, g, mode, prev, frames_per_clip, pw0,
                                            pw1, pb, linspace, width, heat, keypoints, gaussians, heat_mean);
   } else if (C == 256) {
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(head_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(head_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
     head_kernel<256><<<n, 256, smem, st>>>((const act_t*)feature, w1, b1, K, g, mode, prev, frames_per_clip, pw0,
                                            pw1, pb, linspace, width, heat, keypoints, gaussians, heat_mean);
   } else {

@@ -153,9 +153,9 @@ normalize_voxelize_kernel(const float* __restrict__ pts, int T, int n_pts, int G
 
 extern "C" int nm_voxelize(const void* points, int points_are_f64, int n_frames, int n_points, int grid_size,
                            float* grid_out, int* err_flag, void* stream) {
-  NM_CHECK_ARG(points && grid_out, "nm_voxelize: null pointer");
   NM_CHECK_ARG(n_frames >= 0 && n_points >= 0 && grid_size > 0 && grid_size <= 1024,
                "nm_voxelize: bad sizes F=%d N=%d G=%d", n_frames, n_points, grid_size);
+  NM_CHECK_ARG(grid_out && (points || n_points == 0 || n_frames == 0), "nm_voxelize: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t cells = (size_t)grid_size * grid_size * grid_size;
   if (n_frames == 0) return NM_OK;
