@@ -15,6 +15,8 @@
 // Persistent: grid = #SMs, static round-robin over output tiles.
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 namespace {
 
@@ -105,15 +107,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major),
-//   [32,46) stride byte offset >> 4 (= 8 rows * row bytes), [46,48) version = 1, [61,64) layout type.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(sbo_bytes >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
+//   [32,46) stride byte offset >> 4 (= stride between 8-row groups), [46,48) version = 1, [61,64) layout type.
+// The MMA-issuing thread is a single lane running scalar code: every instruction between two tcgen05.mma
+// costs issue latency (first version: ~30 dependent integer ops per MMA = ~165 cycles per MMA, 10x the
+// tensor-pipe time).  Descriptors are therefore split into a loop-invariant high word and a low word that
+// advances by plain 32-bit adds of (bytes >> 4).
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return (sbo_bytes >> 4) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc64(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+__device__ __forceinline__ void umma_f16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc)
+      : "memory");
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -195,7 +205,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
     const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t row_bytes = p.block_k * 2;                       // 128 (SW128) or 64 (SW64)
     const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
-    const uint32_t sbo = 8 * row_bytes;
+    const uint32_t hi = desc_hi(8 * row_bytes, layout);
+    const int ksteps = p.block_k / 16;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -209,12 +220,9 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          for (int k = 0; k < p.block_k / 16; k++) {
-            const uint64_t da = make_smem_desc(sa + k * 32, sbo, layout);
-            const uint64_t db = make_smem_desc(sb + k * 32, sbo, layout);
-            umma_f16(tmem_d, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
+          const uint32_t alo = desc_lo(sa), blo = desc_lo(sa + a_bytes);
+          umma_f16(tmem_d, desc64(hi, alo), desc64(hi, blo), idesc, it > 0 ? 1u : 0u);
+          for (int k = 1; k < ksteps; k++) umma_f16_acc(tmem_d, desc64(hi, alo + 2 * k), desc64(hi, blo + 2 * k), idesc);
           umma_commit(&empty[stage]);                // frees the smem slot once these MMAs retire
           if (it == k_iters - 1) umma_commit(&tfull[acc]);
         }
@@ -259,6 +267,192 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ slab-walking variant (k3, small Cout)
+// For Cout <= 64 the tap-streaming kernel above is bound by operand delivery: every tap re-fetches its
+// 128 x Cin A tile from L2 (27x re-read; ncu: 7 TB/s L2->SM, tensor pipe 8 %).  Here a CTA owns a column of
+// output tiles (16 h x 8 w voxels) and walks it along d: each input slice (18 x 10 halo rows) is fetched ONCE
+// by TMA into a 4-slot ring and reused by all 27 taps - a tap is just a different start address / the same
+// 8-row-group stride (10 rows) in the A descriptor (the 128B/64B swizzle is a function of the absolute
+// shared-memory address, so a row-shifted start stays consistent with what TMA wrote; verified on B200).
+// The weights of all taps stay resident in shared memory.
+struct ConvSlabParams {
+  CUtensorMap tmap_a;     // (C, W, H, D, N) box (BK, 10, 18, 1, 1)
+  CUtensorMap tmap_b;     // (Cin, Cout, 27) box (BK, n_tile, 1)
+  int kchunks, block_k, n_tile, cout;
+  int nw, nh;             // tiles per (w, h); columns = N * nh * nw
+  int D, H, W, N;
+  int slot_bytes;         // bytes of one ring slot (kchunks chunks)
+  int chunk_bytes;        // bytes of one (slice, k-chunk) = 180 rows, padded to 1 KiB
+  const float* bias;
+  act_t* out;
+};
+
+constexpr int kSlabRing = 4;
+constexpr int kHaloW = 10, kHaloH = 18;
+
+template <int BK>
+__global__ void __launch_bounds__(192, 1)
+conv3d_slab_kernel(const __grid_constant__ ConvSlabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int w_tile_bytes = p.n_tile * BK * 2;                         // one (tap, k-chunk) weight tile
+  const int w_bytes = 27 * p.kchunks * w_tile_bytes;
+  uint8_t* s_w = smem;
+  uint8_t* s_ring = smem + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)kSlabRing * p.slot_bytes);
+  uint64_t* full = bars;                 // [ring]
+  uint64_t* empty = bars + kSlabRing;    // [ring]
+  uint64_t* tfull = empty + kSlabRing;   // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint64_t* wfull = tempty + 2;          // [1] weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cols = p.N * p.nh * p.nw;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.n_tile) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
+    for (int s = 0; s < kSlabRing; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // resident weights: 27 * kchunks tiles, one barrier
+      mbar_expect_tx(wfull, (uint32_t)w_bytes);
+      for (int tap = 0; tap < 27; tap++)
+        for (int kc = 0; kc < p.kchunks; kc++)
+          tma_load_3d(s_w + (size_t)(tap * p.kchunks + kc) * w_tile_bytes, &p.tmap_b, wfull, kc * BK, 0, tap);
+      uint32_t fill = 0;                                  // running count of slice fills (ring position)
+      const uint32_t slice_tx = (uint32_t)(kHaloW * kHaloH * BK * 2 * p.kchunks);
+      for (int col = blockIdx.x; col < n_cols; col += gridDim.x) {
+        int t = col;
+        const int iw = t % p.nw; t /= p.nw;
+        const int ih = t % p.nh; t /= p.nh;
+        const int n = t;
+        for (int dz = -1; dz <= p.D; dz++, fill++) {
+          const int slot = fill % kSlabRing;
+          mbar_wait(&empty[slot], ((fill / kSlabRing) & 1) ^ 1);
+          mbar_expect_tx(&full[slot], slice_tx);
+          for (int kc = 0; kc < p.kchunks; kc++)
+            tma_load_5d(s_ring + (size_t)slot * p.slot_bytes + (size_t)kc * p.chunk_bytes, &p.tmap_a, &full[slot],
+                        kc * BK, iw * 8 - 1, ih * 16 - 1, dz, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t row_bytes = BK * 2;
+    constexpr uint32_t layout = row_bytes == 128 ? 2u : 4u;
+    // A: next 8-row group = next h row of the halo slice (10 rows further); B: dense 8-row groups
+    const uint32_t hi_a = desc_hi(kHaloW * row_bytes, layout), hi_b = desc_hi(8 * row_bytes, layout);
+    const uint32_t ring_lo = desc_lo(smem_u32(s_ring)), w_lo = desc_lo(smem_u32(s_w));
+    const uint32_t slot_step = (uint32_t)p.slot_bytes >> 4, chunk_step = (uint32_t)p.chunk_bytes >> 4;
+    const uint32_t w_step = (uint32_t)w_tile_bytes >> 4;
+    mbar_wait(wfull, 0);
+    uint32_t fill = 0;                                   // index of the next slice fill to wait for
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int col = blockIdx.x; col < n_cols; col += gridDim.x) {
+      // slices -1 and 0 of this column
+      for (int pre = 0; pre < 2; pre++, fill++) mbar_wait(&full[fill % kSlabRing], (fill / kSlabRing) & 1);
+      for (int d = 0; d < p.D; d++) {
+        mbar_wait(&full[fill % kSlabRing], (fill / kSlabRing) & 1);   // slice d + 1
+        fill++;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.n_tile);
+          const uint32_t first_fill = fill - 3;          // fill index of slice d - 1
+          uint32_t blo = w_lo;
+#pragma unroll 1
+          for (int kd = 0; kd < 3; kd++) {
+            const uint32_t slot_lo = ring_lo + ((first_fill + kd) % kSlabRing) * slot_step;
+#pragma unroll
+            for (int t9 = 0; t9 < 9; t9++) {
+              const uint32_t tap_lo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
+#pragma unroll 1
+              for (int kc = 0; kc < p.kchunks; kc++) {
+                const uint32_t alo = tap_lo + kc * chunk_step;
+                if (kd == 0 && t9 == 0 && kc == 0) umma_f16(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc, 0u);
+                else umma_f16_acc(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc);
+#pragma unroll
+                for (int k = 1; k < BK / 16; k++)
+                  umma_f16_acc(tmem_d, desc64(hi_a, alo + 2 * k), desc64(hi_b, blo + 2 * k), idesc);
+                blo += w_step;
+              }
+            }
+          }
+          umma_commit(&empty[first_fill % kSlabRing]);   // slice d - 1 is dead once these MMAs retire
+          umma_commit(&tfull[acc]);
+          if (d == p.D - 1) {                            // column done: slices D-1 and D are dead too
+            umma_commit(&empty[(first_fill + 1) % kSlabRing]);
+            umma_commit(&empty[(first_fill + 2) % kSlabRing]);
+          }
+        }
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int rx = row & 7, ry = row >> 3;               // row = h * 8 + w inside the 16 x 8 tile
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int col = blockIdx.x; col < n_cols; col += gridDim.x) {
+      int t = col;
+      const int iw = t % p.nw; t /= p.nw;
+      const int ih = t % p.nh; t /= p.nh;
+      const int n = t;
+      const int ow = iw * 8 + rx, oh = ih * 16 + ry;
+      for (int d = 0; d < p.D; d++) {
+        act_t* dst = p.out + ((((long long)n * p.D + d) * p.H + oh) * p.W + ow) * (long long)p.cout;
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n_tile);
+        for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(taddr + c0, r);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(r[j]) + ((c0 + j < p.cout) ? __ldg(p.bias + c0 + j) : 0.f);
+          if (c0 + 8 <= p.cout) *reinterpret_cast<half8*>(dst + c0) = nm_pack8(f);
+          if (c0 + 16 <= p.cout) *reinterpret_cast<half8*>(dst + c0 + 8) = nm_pack8(f + 8);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
     }
   }
   tc_fence_before();
@@ -324,6 +518,58 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
   if (!encode) {
     nm_set_error("nm_conv3d_tc: cuTensorMapEncodeTiled entry point not available");
     return NM_ERR_DRIVER;
+  }
+  // ---- slab-walking kernel: k3, weights resident in smem
+  {
+    static int slab_mode = -1;
+    if (slab_mode < 0) {
+      const char* e = getenv("NM_CONV_SLAB");   // A/B switch for profiling: 0 = always use the tap-streaming kernel
+      slab_mode = e ? atoi(e) : 1;
+    }
+    const int bk = Cin >= 64 ? 64 : 32;
+    const int kch = (Cin + bk - 1) / bk;
+    const int ntile = ((Cout + 15) / 16) * 16;
+    const size_t w_bytes = (size_t)27 * kch * ntile * bk * 2;
+    const int chunk_bytes = ((kHaloW * kHaloH * bk * 2 + 1023) / 1024) * 1024;
+    const size_t need = w_bytes + (size_t)kSlabRing * kch * chunk_bytes + 1024 + 16 * 8 + 16;
+    if (slab_mode && k == 3 && stride == 1 && Cin >= 32 && Cin % bk == 0 && W % 8 == 0 && H % 16 == 0 &&
+        need <= 227 * 1024) {
+      ConvSlabParams q;
+      memset(&q, 0, sizeof(q));
+      q.kchunks = kch; q.block_k = bk; q.n_tile = ntile; q.cout = Cout;
+      q.nw = W / 8; q.nh = H / 16; q.D = D; q.H = H; q.W = W; q.N = n;
+      q.chunk_bytes = chunk_bytes; q.slot_bytes = kch * chunk_bytes;
+      q.bias = bias; q.out = (act_t*)out;
+      const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+      cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
+      cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
+                               (cuuint64_t)D * H * W * Cin * 2};
+      cuuint32_t box[5] = {(cuuint32_t)bk, kHaloW, kHaloH, 1, 1};
+      cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      CUresult r = encode(&q.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)x, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab): cuTensorMapEncodeTiled(A) failed with %d", (int)r); return NM_ERR_DRIVER; }
+      cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 27};
+      cuuint64_t wstrides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+      cuuint32_t wbox[3] = {(cuuint32_t)bk, (cuuint32_t)ntile, 1};
+      cuuint32_t westr[3] = {1, 1, 1};
+      r = encode(&q.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)packed_w, wdims, wstrides, wbox, westr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab): cuTensorMapEncodeTiled(W) failed with %d", (int)r); return NM_ERR_DRIVER; }
+      static bool slab_attr = false;
+      if (!slab_attr) {
+        NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        slab_attr = true;
+      }
+      const int cols = n * q.nh * q.nw;
+      const int grid = cols < nm_num_sms() ? cols : nm_num_sms();
+      if (bk == 64) conv3d_slab_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+      else conv3d_slab_kernel<32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+      NM_CHECK_LAUNCH("conv3d_slab");
+      return NM_OK;
+    }
   }
   ConvTcParams p;
   memset(&p, 0, sizeof(p));
