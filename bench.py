@@ -232,7 +232,12 @@ def main():
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "launch_ms": t_ms / cnt, "share_of_step": t_ms / (ms * args.steps),
-                "all_tc_convs": {"achieved": tot_flop / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / (ms * args.steps)}}
+                "all_tc_convs": {"achieved": tot_flop / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / (ms * args.steps)},
+                "by_layer": [{"layer": f"n={k[0]} grid={k[1]} {k[2]}->{k[3]} k{k[4]}s{k[5]}", "launches": v[1],
+                              "ms_per_launch": round(v[0] / v[1], 4),
+                              "tflops": round(k[6] * v[1] / (v[0] / 1e3) / 1e12, 1),
+                              "share_of_step": round(v[0] / (ms * args.steps), 4)}
+                             for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:12]]}
 
     line = {
         "metric": "voxel frames/sec keypoint detection", "value": value, "unit": "frames/s", "n_gpus": world,

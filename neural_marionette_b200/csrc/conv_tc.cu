@@ -338,7 +338,14 @@ conv3d_slab_kernel(const __grid_constant__ ConvSlabParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // One CTA per SM and a single allocation: the allocator hands out column 0.  Treating the base as the
+  // literal 0 keeps every TMEM address a warp-uniform value (uniform registers), which removes an
+  // ELECT / R2UR.BROADCAST / branch sequence in front of every UTCHMMA in the issue loop.
+  if (*tmem_slot != 0u) {
+    printf("nm_conv3d_tc(slab): unexpected TMEM base %u\n", *tmem_slot);
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0u;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -463,6 +470,182 @@ conv3d_slab_kernel(const __grid_constant__ ConvSlabParams p) {
   }
 }
 
+// ------------------------------------------------------------------ slab kernel, 3 depth-taps per MMA (Cout = 32)
+// With N = Cout = 32 an MMA is 16 tensor-pipe cycles but costs ~70 cycles to issue from a single thread and
+// reads 4 KB of A for 1 KB of B: issue- and smem-bound.  Stack the weights of the three depth taps of a
+// (kh, kw) position into one B tile of N = 96 rows: one MMA then multiplies the window of input slice s with
+// W(kd=0), W(kd=1), W(kd=2) at once, i.e. it produces the contribution of slice s to the outputs s+1, s, s-1 in
+// three 32-column blocks of a TMEM group P(s).  A is read once instead of three times and the MMA count drops
+// 3x.  The epilogue forms out(j) = P(j-1)[0:32] + P(j)[32:64] + P(j+1)[64:96] (+ bias) from a ring of four
+// groups (4 x 96 TMEM columns).
+constexpr int kPGroups = 4;
+
+template <int BK>
+__global__ void __launch_bounds__(192, 1)
+conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kN = 32;
+  constexpr int w_tile_bytes = kN * BK * 2;                            // one tap
+  constexpr int w_bytes = 27 * w_tile_bytes;
+  uint8_t* s_w = smem;                                                 // [kh][kw][kd][32 rows][BK]
+  uint8_t* s_ring = smem + w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)kSlabRing * p.slot_bytes);
+  uint64_t* full = bars;                  // [ring]   slice landed
+  uint64_t* empty = full + kSlabRing;     // [ring]   slice consumed
+  uint64_t* pfull = empty + kSlabRing;    // [groups] P group complete
+  uint64_t* pempty = pfull + kPGroups;    // [groups] P group drained
+  uint64_t* wfull = pempty + kPGroups;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_cols = p.N * p.nh * p.nw;
+  constexpr uint32_t tmem_cols = 512;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
+    for (int s = 0; s < kSlabRing; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kPGroups; s++) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 4); }
+    mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (*tmem_slot != 0u) {       // single allocation per SM: base 0 keeps all TMEM addresses warp-uniform
+    printf("nm_conv3d_tc(slab3): unexpected TMEM base %u\n", *tmem_slot);
+    __trap();
+  }
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(wfull, (uint32_t)w_bytes);
+      for (int tap = 0; tap < 27; tap++) {
+        const int kd = tap / 9, khw = tap % 9;
+        tma_load_3d(s_w + (size_t)(khw * 3 + kd) * w_tile_bytes, &p.tmap_b, wfull, 0, 0, tap);
+      }
+      uint32_t fill = 0;
+      constexpr uint32_t slice_tx = (uint32_t)(kHaloW * kHaloH * BK * 2);
+      for (int col = blockIdx.x; col < n_cols; col += gridDim.x) {
+        int t = col;
+        const int iw = t % p.nw; t /= p.nw;
+        const int ih = t % p.nh; t /= p.nh;
+        const int n = t;
+        for (int dz = 0; dz < p.D; dz++, fill++) {
+          const int slot = fill % kSlabRing;
+          mbar_wait(&empty[slot], ((fill / kSlabRing) & 1) ^ 1);
+          mbar_expect_tx(&full[slot], slice_tx);
+          tma_load_5d(s_ring + (size_t)slot * p.slot_bytes, &p.tmap_a, &full[slot], 0, iw * 8 - 1, ih * 16 - 1, dz, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)((3 * kN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t row_bytes = BK * 2;
+    constexpr uint32_t layout = row_bytes == 128 ? 2u : 4u;
+    const uint32_t hi_a = desc_hi(kHaloW * row_bytes, layout), hi_b = desc_hi(8 * row_bytes, layout);
+    const uint32_t ring_lo = desc_lo(smem_u32(s_ring)), w_lo = desc_lo(smem_u32(s_w));
+    const uint32_t slot_step = (uint32_t)p.slot_bytes >> 4;
+    constexpr uint32_t w_step = (uint32_t)(3 * w_tile_bytes) >> 4;
+    mbar_wait(wfull, 0);
+    uint32_t q = 0;                                      // global slice counter (ring + P-group position)
+    for (int col = blockIdx.x; col < n_cols; col += gridDim.x) {
+      for (int sl = 0; sl < p.D; sl++, q++) {
+        mbar_wait(&full[q % kSlabRing], (q / kSlabRing) & 1);
+        mbar_wait(&pempty[q % kPGroups], ((q / kPGroups) & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t tmem_d = (q % kPGroups) * (3 * kN);
+          const uint32_t slot_lo = ring_lo + (q % kSlabRing) * slot_step;
+#pragma unroll
+          for (int t9 = 0; t9 < 9; t9++) {
+            const uint32_t alo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
+            const uint32_t blo = w_lo + t9 * w_step;
+            if (t9 == 0) umma_f16(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc, 0u);
+            else umma_f16_acc(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc);
+#pragma unroll
+            for (int k = 1; k < BK / 16; k++)
+              umma_f16_acc(tmem_d, desc64(hi_a, alo + 2 * k), desc64(hi_b, blo + 2 * k), idesc);
+          }
+          umma_commit(&empty[q % kSlabRing]);
+          umma_commit(&pfull[q % kPGroups]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int rx = row & 7, ry = row >> 3;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    float bias[kN];
+#pragma unroll
+    for (int j = 0; j < kN; j++) bias[j] = j < p.cout ? __ldg(p.bias + j) : 0.f;
+    uint32_t q0 = 0;                                     // global index of slice 0 of the current column
+    for (int col = blockIdx.x; col < n_cols; col += gridDim.x, q0 += p.D) {
+      int t = col;
+      const int iw = t % p.nw; t /= p.nw;
+      const int ih = t % p.nh; t /= p.nh;
+      const int n = t;
+      const int ow = iw * 8 + rx, oh = ih * 16 + ry;
+      int waited = 0;                                    // slices of this column whose group completion was observed
+      for (int j = 0; j < p.D; j++) {
+        const int need = j + 1 < p.D ? j + 1 : p.D - 1;
+        while (waited <= need) {
+          const uint32_t q = q0 + waited;
+          mbar_wait(&pfull[q % kPGroups], (q / kPGroups) & 1);
+          waited++;
+        }
+        tc_fence_after();
+        float f[kN];
+#pragma unroll
+        for (int c = 0; c < kN; c++) f[c] = bias[c];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          const int sl = j - 1 + b;                      // slice whose block b contributes to output j
+          if (sl >= 0 && sl < p.D) {
+            const uint32_t taddr = lane_addr + ((q0 + sl) % kPGroups) * (3 * kN) + b * kN;
+            uint32_t r0[16], r1[16];
+            tmem_ld16(taddr, r0);
+            tmem_ld16(taddr + 16, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; c++) {
+              f[c] += __uint_as_float(r0[c]);
+              f[16 + c] += __uint_as_float(r1[c]);
+            }
+          }
+        }
+        act_t* dst = p.out + ((((long long)n * p.D + j) * p.H + oh) * p.W + ow) * (long long)p.cout;
+#pragma unroll
+        for (int c0 = 0; c0 < kN; c0 += 8)
+          if (c0 + 8 <= p.cout) *reinterpret_cast<half8*>(dst + c0) = nm_pack8(f + c0);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (j >= 1) mbar_arrive(&pempty[(q0 + j - 1) % kPGroups]);     // P(j-1) feeds outputs j-2, j-1, j only
+          if (j == p.D - 1) mbar_arrive(&pempty[(q0 + j) % kPGroups]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(0u), "r"(tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------ weight pre-pack
 // nn.Conv3d weight (Cout, Cin, k, k, k) fp32 -> [tap][Cout][Cin] fp16
 __global__ void pack_weights_kernel(const float* __restrict__ w, act_t* __restrict__ out, int Cout, int Cin, int taps) {
@@ -524,7 +707,7 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
     static int slab_mode = -1;
     if (slab_mode < 0) {
       const char* e = getenv("NM_CONV_SLAB");   // A/B switch for profiling: 0 = always use the tap-streaming kernel
-      slab_mode = e ? atoi(e) : 1;
+      slab_mode = e ? atoi(e) : 2;   // 2: + the 3-depth-tap variant for Cout = 32
     }
     const int bk = Cin >= 64 ? 64 : 32;
     const int kch = (Cin + bk - 1) / bk;
@@ -565,7 +748,16 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
       }
       const int cols = n * q.nh * q.nw;
       const int grid = cols < nm_num_sms() ? cols : nm_num_sms();
-      if (bk == 64) conv3d_slab_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+      if (slab_mode >= 2 && ntile == 32 && kch == 1) {
+        static bool slab3_attr = false;
+        if (!slab3_attr) {
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          slab3_attr = true;
+        }
+        if (bk == 64) conv3d_slab3_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+        else conv3d_slab3_kernel<32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+      } else if (bk == 64) conv3d_slab_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       else conv3d_slab_kernel<32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       NM_CHECK_LAUNCH("conv3d_slab");
       return NM_OK;

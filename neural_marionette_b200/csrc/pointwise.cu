@@ -55,25 +55,37 @@ gn_stats_kernel(const act_t* __restrict__ x, int S, int C, int chunks, float* __
   }
 }
 
-__global__ void gn_finalize_kernel(const float* __restrict__ partial, int S, int C, int groups, int chunks,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift) {
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float* __restrict__ partial, int S, int C, int groups, int chunks,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   float* __restrict__ scale, float* __restrict__ shift) {
+  // one block per sample; warp w handles groups w, w+4, ...: lanes stride over (chunk, channel-in-group)
+  // pairs in a fixed order, fp64 accumulation, xor-shuffle tree -> deterministic
   const int n = blockIdx.x;
   const int cpg = C / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ double s_mean[32], s_rstd[32];
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  for (int g = warp; g < groups; g += 4) {
     double sum = 0.0, sq = 0.0;
-    for (int k = 0; k < chunks; k++)
-      for (int c = g * cpg; c < (g + 1) * cpg; c++) {
-        const float* p = partial + (((long long)n * chunks + k) * C + c) * 2;
-        sum += (double)p[0];
-        sq += (double)p[1];
-      }
-    const double cnt = (double)S * cpg;
-    const double mean = sum / cnt;
-    const double var = fmax(sq / cnt - mean * mean, 0.0);
-    s_mean[g] = mean;
-    s_rstd[g] = 1.0 / sqrt(var + (double)eps);
+    const int items = chunks * cpg;
+    for (int i = lane; i < items; i += 32) {
+      const int k = i / cpg, c = g * cpg + i % cpg;
+      const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)n * chunks + k) * C + c) * 2);
+      sum += (double)v.x;
+      sq += (double)v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+      const double cnt = (double)S * cpg;
+      const double mean = sum / cnt;
+      const double var = fmax(sq / cnt - mean * mean, 0.0);
+      s_mean[g] = mean;
+      s_rstd[g] = 1.0 / sqrt(var + (double)eps);
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
