@@ -138,58 +138,84 @@ affine_act_kernel(const act_t* __restrict__ x1, const float* __restrict__ a1, co
 // ------------------------------------------------------------------ trilinear x2 (align_corners=False)
 // Reference: nn.Upsample(scale_factor=2, mode='trilinear') at model/kypt_detector.py:427,441.
 // Optional fused prologue: v = lrelu(x*a + b) of the producing GroupNorm.
-__global__ void __launch_bounds__(256)
+// One thread per (input cell, 8 channels): it reads the 3x3x3 clamped neighbourhood once (27 16-byte loads)
+// and writes the 2x2x2 output block.  For scale 2 the source position of output 2i+a is i-0.25 (a=0) or
+// i+0.25 (a=1): weights (0.25, 0.75) on (i-1, i) resp. (0.75, 0.25) on (i, i+1), replicate-clamped at the
+// borders (identical to PyTorch's index clamping).  Separable: lerp along w, then h, then accumulate along d.
+template <bool AFFINE>
+__global__ void __launch_bounds__(128)
 upsample2x_kernel(const act_t* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b, int act,
                   act_t* __restrict__ out, int D, int H, int W, int C, long long total8) {
   const int c8n = C >> 3;
-  const int OD = 2 * D, OH = 2 * H, OW = 2 * W;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total8; i += (long long)gridDim.x * 256) {
-    const int c8 = (int)(i % c8n);
-    long long r = i / c8n;
-    const int ow = (int)(r % OW); r /= OW;
-    const int oh = (int)(r % OH); r /= OH;
-    const int od = (int)(r % OD);
-    const long long n = r / OD;
-    int i0[3], i1[3];
-    float l1[3];
-    const int o[3] = {od, oh, ow};
-    const int lim[3] = {D, H, W};
+  const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (i >= total8) return;
+  const int c8 = (int)(i % c8n);
+  long long r = i / c8n;
+  const int w = (int)(r % W); r /= W;
+  const int h = (int)(r % H); r /= H;
+  const int d = (int)(r % D);
+  const long long n = r / D;
+  float av[8], bv[8];
+  if (AFFINE) {
+    const float4* pa = reinterpret_cast<const float4*>(a + n * C + c8 * 8);
+    const float4* pb = reinterpret_cast<const float4*>(b + n * C + c8 * 8);
+    const float4 A0 = pa[0], A1 = pa[1], B0 = pb[0], B1 = pb[1];
+    av[0] = A0.x; av[1] = A0.y; av[2] = A0.z; av[3] = A0.w; av[4] = A1.x; av[5] = A1.y; av[6] = A1.z; av[7] = A1.w;
+    bv[0] = B0.x; bv[1] = B0.y; bv[2] = B0.z; bv[3] = B0.w; bv[4] = B1.x; bv[5] = B1.y; bv[6] = B1.z; bv[7] = B1.w;
+  }
+  const half8* base = reinterpret_cast<const half8*>(x) + n * (long long)D * H * W * c8n;
+  const int wi[3] = {max(w - 1, 0), w, min(w + 1, W - 1)};
+  const int hi[3] = {max(h - 1, 0), h, min(h + 1, H - 1)};
+  const int di[3] = {max(d - 1, 0), d, min(d + 1, D - 1)};
+  float acc[8][8];       // [output (a,b,c)][channel]
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
-      float src = 0.5f * ((float)o[k] + 0.5f) - 0.5f;
-      src = src < 0.f ? 0.f : src;
-      i0[k] = (int)src;
-      i1[k] = i0[k] + (i0[k] < lim[k] - 1 ? 1 : 0);
-      l1[k] = src - (float)i0[k];
-    }
-    float av[8], bv[8];
-    if (a) {
+  for (int o = 0; o < 8; o++)
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[o][k] = 0.f;
+#pragma unroll
+  for (int dd = 0; dd < 3; dd++) {
+    float row[3][2][8];  // after the w-lerp: [hh][c][channel]
+#pragma unroll
+    for (int hh = 0; hh < 3; hh++) {
+      float v[3][8];
+#pragma unroll
+      for (int ww = 0; ww < 3; ww++) {
+        nm_unpack8(base[((long long)(di[dd] * H + hi[hh]) * W + wi[ww]) * c8n + c8], v[ww]);
+        if (AFFINE) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const float t = fmaf(v[ww][k], av[k], bv[k]);
+            v[ww][k] = act ? nm_lrelu(t) : t;
+          }
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        av[k] = a[n * C + c8 * 8 + k];
-        bv[k] = b[n * C + c8 * 8 + k];
+        row[hh][0][k] = fmaf(0.25f, v[0][k], 0.75f * v[1][k]);
+        row[hh][1][k] = fmaf(0.25f, v[2][k], 0.75f * v[1][k]);
       }
     }
-    float acc[8];
+    // h-lerp -> plane[b][c], then accumulate along d with weights (a=0: .25,.75,0 ; a=1: 0,.75,.25)
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = 0.f;
-    const half8* base = reinterpret_cast<const half8*>(x) + n * (long long)D * H * W * c8n;
-#pragma unroll
-    for (int corner = 0; corner < 8; corner++) {
-      const int dz = (corner >> 2) & 1, dy = (corner >> 1) & 1, dx = corner & 1;
-      const int id = dz ? i1[0] : i0[0], ih = dy ? i1[1] : i0[1], iw = dx ? i1[2] : i0[2];
-      const float w = (dz ? l1[0] : 1.f - l1[0]) * (dy ? l1[1] : 1.f - l1[1]) * (dx ? l1[2] : 1.f - l1[2]);
-      float f[8];
-      nm_unpack8(base[((long long)(id * H + ih) * W + iw) * c8n + c8], f);
+    for (int c = 0; c < 2; c++)
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        float v = f[k];
-        if (a) v = fmaf(v, av[k], bv[k]);
-        if (act) v = nm_lrelu(v);
-        acc[k] = fmaf(w, v, acc[k]);
+        const float p0 = fmaf(0.25f, row[0][c][k], 0.75f * row[1][c][k]);   // b = 0
+        const float p1 = fmaf(0.25f, row[2][c][k], 0.75f * row[1][c][k]);   // b = 1
+        if (dd == 0) { acc[0 + c][k] += 0.25f * p0; acc[2 + c][k] += 0.25f * p1; }
+        if (dd == 1) {
+          acc[0 + c][k] = fmaf(0.75f, p0, acc[0 + c][k]); acc[2 + c][k] = fmaf(0.75f, p1, acc[2 + c][k]);
+          acc[4 + c][k] = fmaf(0.75f, p0, acc[4 + c][k]); acc[6 + c][k] = fmaf(0.75f, p1, acc[6 + c][k]);
+        }
+        if (dd == 2) { acc[4 + c][k] = fmaf(0.25f, p0, acc[4 + c][k]); acc[6 + c][k] = fmaf(0.25f, p1, acc[6 + c][k]); }
       }
-    }
-    reinterpret_cast<half8*>(out)[i] = nm_pack8(acc);
+  }
+  const int OH = 2 * H, OW = 2 * W;
+  half8* ob = reinterpret_cast<half8*>(out) + n * (long long)8 * D * H * W * c8n;
+#pragma unroll
+  for (int o = 0; o < 8; o++) {
+    const int oa = o >> 2, obb = (o >> 1) & 1, oc = o & 1;
+    ob[((long long)((2 * d + oa) * OH + 2 * h + obb) * OW + 2 * w + oc) * c8n + c8] = nm_pack8(acc[o]);
   }
 }
 
@@ -409,11 +435,15 @@ extern "C" int nm_upsample2x(const void* x, const float* a, const float* b, int 
                              int W, int C, void* stream) {
   NM_CHECK_ARG(x && out, "nm_upsample2x: null pointer");
   NM_CHECK_ARG(C % 8 == 0, "nm_upsample2x: C=%d not a multiple of 8", C);
-  const long long total8 = (long long)n * 8 * D * H * W * (C / 8);
+  const long long total8 = (long long)n * D * H * W * (C / 8);      // one thread per input cell x 8 channels
   if (total8 == 0) return NM_OK;
-  const int blocks = (int)min((long long)nm_num_sms() * 16, (total8 + 255) / 256);
-  upsample2x_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const act_t*)x, a, b, act, (act_t*)out, D, H, W, C,
-                                                              total8);
+  const int blocks = (int)((total8 + 127) / 128);
+  if (a)
+    upsample2x_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>((const act_t*)x, a, b, act, (act_t*)out, D, H,
+                                                                      W, C, total8);
+  else
+    upsample2x_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>((const act_t*)x, a, b, act, (act_t*)out, D, H,
+                                                                       W, C, total8);
   NM_CHECK_LAUNCH("upsample2x");
   return NM_OK;
 }
