@@ -293,6 +293,7 @@ struct ConvSlabParams {
   int D, H, W, N;
   int slot_bytes;         // bytes of one ring slot (kchunks chunks)
   int chunk_bytes;        // bytes of one (slice, k-chunk) = 180 rows, padded to 1 KiB
+  int ring;               // slab3: ring slots actually used (2..4)
   const float* bias;
   act_t* out;
 };
@@ -480,17 +481,19 @@ conv3d_slab_kernel(const __grid_constant__ ConvSlabParams p) {
 // groups (4 x 96 TMEM columns).
 constexpr int kPGroups = 4;
 
-template <int BK>
+// BK: channels per k-chunk (64 -> 128B swizzle, 32 -> 64B); PN: output channels per CTA "part" (32, or 16 when
+// Cin = 128 so that the 27 x kchunks resident weight tiles still fit); MMA N = 3 * PN.
+template <int BK, int PN>
 __global__ void __launch_bounds__(192, 1)
 conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int kN = 32;
-  constexpr int w_tile_bytes = kN * BK * 2;                            // one tap
-  constexpr int w_bytes = 27 * w_tile_bytes;
-  uint8_t* s_w = smem;                                                 // [kh][kw][kd][32 rows][BK]
+  constexpr int w_tile_bytes = PN * BK * 2;                            // one (tap, k-chunk)
+  const int w_bytes = 27 * p.kchunks * w_tile_bytes;
+  const int ring = p.ring;
+  uint8_t* s_w = smem;                                                 // [kh*3+kw][kc][kd][PN rows][BK]
   uint8_t* s_ring = smem + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)kSlabRing * p.slot_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)ring * p.slot_bytes);
   uint64_t* full = bars;                  // [ring]   slice landed
   uint64_t* empty = full + kSlabRing;     // [ring]   slice consumed
   uint64_t* pfull = empty + kSlabRing;    // [groups] P group complete
@@ -501,6 +504,11 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.N * p.nh * p.nw;
   constexpr uint32_t tmem_cols = 512;
+  // Cout > PN: the output channels are split into parts of PN; CTA b serves part b % parts with its own
+  // resident weights (A is re-read once per part, each pass runs at the N = 3*PN rate)
+  const int parts = p.n_tile / PN;
+  const int part = blockIdx.x % parts;
+  const int col0 = blockIdx.x / parts, col_step = gridDim.x / parts;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a) : "memory");
@@ -529,53 +537,62 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       mbar_expect_tx(wfull, (uint32_t)w_bytes);
       for (int tap = 0; tap < 27; tap++) {
         const int kd = tap / 9, khw = tap % 9;
-        tma_load_3d(s_w + (size_t)(khw * 3 + kd) * w_tile_bytes, &p.tmap_b, wfull, 0, 0, tap);
+        for (int kc = 0; kc < p.kchunks; kc++)
+          tma_load_3d(s_w + (size_t)((khw * p.kchunks + kc) * 3 + kd) * w_tile_bytes, &p.tmap_b, wfull, kc * BK,
+                      part * PN, tap);
       }
       uint32_t fill = 0;
-      constexpr uint32_t slice_tx = (uint32_t)(kHaloW * kHaloH * BK * 2);
-      for (int col = blockIdx.x; col < n_cols; col += gridDim.x) {
+      const uint32_t slice_tx = (uint32_t)(kHaloW * kHaloH * BK * 2 * p.kchunks);
+      for (int col = col0; col < n_cols; col += col_step) {
         int t = col;
         const int iw = t % p.nw; t /= p.nw;
         const int ih = t % p.nh; t /= p.nh;
         const int n = t;
         for (int dz = 0; dz < p.D; dz++, fill++) {
-          const int slot = fill % kSlabRing;
-          mbar_wait(&empty[slot], ((fill / kSlabRing) & 1) ^ 1);
+          const int slot = fill % ring;
+          mbar_wait(&empty[slot], ((fill / ring) & 1) ^ 1);
           mbar_expect_tx(&full[slot], slice_tx);
-          tma_load_5d(s_ring + (size_t)slot * p.slot_bytes, &p.tmap_a, &full[slot], 0, iw * 8 - 1, ih * 16 - 1, dz, n);
+          for (int kc = 0; kc < p.kchunks; kc++)
+            tma_load_5d(s_ring + (size_t)slot * p.slot_bytes + (size_t)kc * p.chunk_bytes, &p.tmap_a, &full[slot],
+                        kc * BK, iw * 8 - 1, ih * 16 - 1, dz, n);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)((3 * kN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)((3 * PN) >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     constexpr uint32_t row_bytes = BK * 2;
     constexpr uint32_t layout = row_bytes == 128 ? 2u : 4u;
     const uint32_t hi_a = desc_hi(kHaloW * row_bytes, layout), hi_b = desc_hi(8 * row_bytes, layout);
     const uint32_t ring_lo = desc_lo(smem_u32(s_ring)), w_lo = desc_lo(smem_u32(s_w));
-    const uint32_t slot_step = (uint32_t)p.slot_bytes >> 4;
-    constexpr uint32_t w_step = (uint32_t)(3 * w_tile_bytes) >> 4;
+    const uint32_t slot_step = (uint32_t)p.slot_bytes >> 4, chunk_step = (uint32_t)p.chunk_bytes >> 4;
+    constexpr uint32_t w_step = (uint32_t)(3 * w_tile_bytes) >> 4;       // one (khw, kc) B tile = 3 kd tiles
     mbar_wait(wfull, 0);
     uint32_t q = 0;                                      // global slice counter (ring + P-group position)
-    for (int col = blockIdx.x; col < n_cols; col += gridDim.x) {
+    for (int col = col0; col < n_cols; col += col_step) {
       for (int sl = 0; sl < p.D; sl++, q++) {
-        mbar_wait(&full[q % kSlabRing], (q / kSlabRing) & 1);
+        mbar_wait(&full[q % ring], (q / ring) & 1);
         mbar_wait(&pempty[q % kPGroups], ((q / kPGroups) & 1) ^ 1);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t tmem_d = (q % kPGroups) * (3 * kN);
-          const uint32_t slot_lo = ring_lo + (q % kSlabRing) * slot_step;
+          const uint32_t tmem_d = (q % kPGroups) * (3 * PN);
+          const uint32_t slot_lo = ring_lo + (q % ring) * slot_step;
+          uint32_t blo = w_lo;
 #pragma unroll
           for (int t9 = 0; t9 < 9; t9++) {
-            const uint32_t alo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
-            const uint32_t blo = w_lo + t9 * w_step;
-            if (t9 == 0) umma_f16(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc, 0u);
-            else umma_f16_acc(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc);
+            const uint32_t tap_lo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
+#pragma unroll 1
+            for (int kc = 0; kc < p.kchunks; kc++) {
+              const uint32_t alo = tap_lo + kc * chunk_step;
+              if (t9 == 0 && kc == 0) umma_f16(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc, 0u);
+              else umma_f16_acc(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc);
 #pragma unroll
-            for (int k = 1; k < BK / 16; k++)
-              umma_f16_acc(tmem_d, desc64(hi_a, alo + 2 * k), desc64(hi_b, blo + 2 * k), idesc);
+              for (int k = 1; k < BK / 16; k++)
+                umma_f16_acc(tmem_d, desc64(hi_a, alo + 2 * k), desc64(hi_b, blo + 2 * k), idesc);
+              blo += w_step;
+            }
           }
-          umma_commit(&empty[q % kSlabRing]);
+          umma_commit(&empty[q % ring]);
           umma_commit(&pfull[q % kPGroups]);
         }
         __syncwarp();
@@ -587,11 +604,11 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     const int row = quad * 32 + lane;
     const int rx = row & 7, ry = row >> 3;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    float bias[kN];
+    float bias[PN];
 #pragma unroll
-    for (int j = 0; j < kN; j++) bias[j] = j < p.cout ? __ldg(p.bias + j) : 0.f;
+    for (int j = 0; j < PN; j++) bias[j] = part * PN + j < p.cout ? __ldg(p.bias + part * PN + j) : 0.f;
     uint32_t q0 = 0;                                     // global index of slice 0 of the current column
-    for (int col = blockIdx.x; col < n_cols; col += gridDim.x, q0 += p.D) {
+    for (int col = col0; col < n_cols; col += col_step, q0 += p.D) {
       int t = col;
       const int iw = t % p.nw; t /= p.nw;
       const int ih = t % p.nh; t /= p.nh;
@@ -606,29 +623,28 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
           waited++;
         }
         tc_fence_after();
-        float f[kN];
+        float f[PN];
 #pragma unroll
-        for (int c = 0; c < kN; c++) f[c] = bias[c];
+        for (int c = 0; c < PN; c++) f[c] = bias[c];
 #pragma unroll
         for (int b = 0; b < 3; b++) {
           const int sl = j - 1 + b;                      // slice whose block b contributes to output j
           if (sl >= 0 && sl < p.D) {
-            const uint32_t taddr = lane_addr + ((q0 + sl) % kPGroups) * (3 * kN) + b * kN;
-            uint32_t r0[16], r1[16];
-            tmem_ld16(taddr, r0);
-            tmem_ld16(taddr + 16, r1);
-            tmem_ld_wait();
+            const uint32_t taddr = lane_addr + ((q0 + sl) % kPGroups) * (3 * PN) + b * PN;
 #pragma unroll
-            for (int c = 0; c < 16; c++) {
-              f[c] += __uint_as_float(r0[c]);
-              f[16 + c] += __uint_as_float(r1[c]);
+            for (int c0 = 0; c0 < PN; c0 += 16) {
+              uint32_t r0[16];
+              tmem_ld16(taddr + c0, r0);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 16; c++) f[c0 + c] += __uint_as_float(r0[c]);
             }
           }
         }
-        act_t* dst = p.out + ((((long long)n * p.D + j) * p.H + oh) * p.W + ow) * (long long)p.cout;
+        act_t* dst = p.out + ((((long long)n * p.D + j) * p.H + oh) * p.W + ow) * (long long)p.cout + part * PN;
 #pragma unroll
-        for (int c0 = 0; c0 < kN; c0 += 8)
-          if (c0 + 8 <= p.cout) *reinterpret_cast<half8*>(dst + c0) = nm_pack8(f + c0);
+        for (int c0 = 0; c0 < PN; c0 += 8)
+          if (part * PN + c0 + 8 <= p.cout) *reinterpret_cast<half8*>(dst + c0) = nm_pack8(f + c0);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -712,16 +728,21 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
     const int bk = Cin >= 64 ? 64 : 32;
     const int kch = (Cin + bk - 1) / bk;
     const int ntile = ((Cout + 15) / 16) * 16;
-    const size_t w_bytes = (size_t)27 * kch * ntile * bk * 2;
+    // 3-depth-tap variant: output channels in parts of PN = 32 (Cin <= 64) or 16 (Cin = 128)
+    const int pn = kch == 1 ? 32 : 16;
+    const bool use3 = slab_mode >= 2 && kch <= 2 && Cout % pn == 0 && Cout <= 128;
+    const size_t w_bytes = (size_t)27 * kch * (use3 ? pn : ntile) * bk * 2;
     const int chunk_bytes = ((kHaloW * kHaloH * bk * 2 + 1023) / 1024) * 1024;
-    const size_t need = w_bytes + (size_t)kSlabRing * kch * chunk_bytes + 1024 + 16 * 8 + 16;
+    int ring = kSlabRing;
+    if (use3) while (ring > 2 && w_bytes + (size_t)ring * kch * chunk_bytes + 1024 + 32 * 8 + 16 > 227 * 1024) ring--;
+    const size_t need = w_bytes + (size_t)ring * kch * chunk_bytes + 1024 + 32 * 8 + 16;
     if (slab_mode && k == 3 && stride == 1 && Cin >= 32 && Cin % bk == 0 && W % 8 == 0 && H % 16 == 0 &&
         need <= 227 * 1024) {
       ConvSlabParams q;
       memset(&q, 0, sizeof(q));
       q.kchunks = kch; q.block_k = bk; q.n_tile = ntile; q.cout = Cout;
       q.nw = W / 8; q.nh = H / 16; q.D = D; q.H = H; q.W = W; q.N = n;
-      q.chunk_bytes = chunk_bytes; q.slot_bytes = kch * chunk_bytes;
+      q.chunk_bytes = chunk_bytes; q.slot_bytes = kch * chunk_bytes; q.ring = ring;
       q.bias = bias; q.out = (act_t*)out;
       const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
@@ -735,7 +756,7 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
       if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab): cuTensorMapEncodeTiled(A) failed with %d", (int)r); return NM_ERR_DRIVER; }
       cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 27};
       cuuint64_t wstrides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
-      cuuint32_t wbox[3] = {(cuuint32_t)bk, (cuuint32_t)ntile, 1};
+      cuuint32_t wbox[3] = {(cuuint32_t)bk, (cuuint32_t)(use3 ? pn : ntile), 1};
       cuuint32_t westr[3] = {1, 1, 1};
       r = encode(&q.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)packed_w, wdims, wstrides, wbox, westr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -747,16 +768,20 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
         slab_attr = true;
       }
       const int cols = n * q.nh * q.nw;
-      const int grid = cols < nm_num_sms() ? cols : nm_num_sms();
-      if (slab_mode >= 2 && ntile == 32 && kch == 1) {
+      int grid = cols < nm_num_sms() ? cols : nm_num_sms();
+      if (use3) {
+        const int parts = ntile / pn;
+        grid = cols * parts < nm_num_sms() ? cols * parts : (nm_num_sms() / parts) * parts;
         static bool slab3_attr = false;
         if (!slab3_attr) {
-          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           slab3_attr = true;
         }
-        if (bk == 64) conv3d_slab3_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
-        else conv3d_slab3_kernel<32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+        if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+        else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+        else conv3d_slab3_kernel<32, 32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       } else if (bk == 64) conv3d_slab_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       else conv3d_slab_kernel<32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       NM_CHECK_LAUNCH("conv3d_slab");
