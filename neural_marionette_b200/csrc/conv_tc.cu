@@ -83,6 +83,31 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// One elected lane of a converged warp (PTX elect.sync).  Unlike `lane == 0`, ptxas knows that exactly one
+// thread executes the guarded region, so it does not wrap every tcgen05.mma in a per-active-thread
+// ELECT / BRA.U.ANY serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+      ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -102,6 +127,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, uint32_t* r) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(addr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(addr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -142,6 +172,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
   uint64_t* tfull = bars + 2 * p.stages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);      // [n_tile], zero beyond Cout
+  for (int i = threadIdx.x; i < p.n_tile; i += blockDim.x) s_bias[i] = i < p.cout ? p.bias[i] : 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.nw * p.nh * p.nd * p.nn;
@@ -218,7 +250,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
       for (int it = 0; it < k_iters; it++) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        __syncwarp();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(tiles + (size_t)stage * stage_bytes);
           const uint32_t alo = desc_lo(sa), blo = desc_lo(sa + a_bytes);
           umma_f16(tmem_d, desc64(hi, alo), desc64(hi, blo), idesc, it > 0 ? 1u : 0u);
@@ -251,16 +284,23 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n_tile);
-      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-        uint32_t r[16];
+      for (int c0 = 0; c0 < p.n_tile; c0 += 32) {
+        uint32_t r[32];
         tmem_ld16(taddr + c0, r);
+        if (c0 + 16 < p.n_tile) tmem_ld16(taddr + c0 + 16, r + 16);
         tmem_ld_wait();
         if (live) {
-          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; j++) f[j] = __uint_as_float(r[j]) + ((c0 + j < p.cout) ? __ldg(p.bias + c0 + j) : 0.f);
-          if (c0 + 8 <= p.cout) *reinterpret_cast<half8*>(dst + c0) = nm_pack8(f);
-          if (c0 + 16 <= p.cout) *reinterpret_cast<half8*>(dst + c0 + 8) = nm_pack8(f + 8);
+          for (int h = 0; h < 2; h++) {
+            const int cb = c0 + 16 * h;
+            if (cb < p.n_tile) {
+              float f[16];
+#pragma unroll
+              for (int j = 0; j < 16; j++) f[j] = __uint_as_float(r[16 * h + j]) + s_bias[cb + j];
+              if (cb + 8 <= p.cout) *reinterpret_cast<half8*>(dst + cb) = nm_pack8(f);
+              if (cb + 16 <= p.cout) *reinterpret_cast<half8*>(dst + cb + 8) = nm_pack8(f + 8);
+            }
+          }
         }
       }
       tc_fence_before();
@@ -288,12 +328,14 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
 struct ConvSlabParams {
   CUtensorMap tmap_a;     // (C, W, H, D, N) box (BK, 10, 18, 1, 1)
   CUtensorMap tmap_b;     // (Cin, Cout, 27) box (BK, n_tile, 1)
+  CUtensorMap tmap_o;     // slab3: output (Cout, W, H, D, N) box (PN, 8, 16, 1, 1) for the TMA-store epilogue
   int kchunks, block_k, n_tile, cout;
   int nw, nh;             // tiles per (w, h); columns = N * nh * nw
   int D, H, W, N;
   int slot_bytes;         // bytes of one ring slot (kchunks chunks)
   int chunk_bytes;        // bytes of one (slice, k-chunk) = 180 rows, padded to 1 KiB
   int ring;               // slab3: ring slots actually used (2..4)
+  int debug;              // NM_SLAB_DEBUG bit mask (profiling experiments only): 1 no stores, 2 no MMAs, 4 no A loads
   const float* bias;
   act_t* out;
 };
@@ -395,7 +437,8 @@ conv3d_slab_kernel(const __grid_constant__ ConvSlabParams p) {
         fill++;
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        __syncwarp();
+        if (elect_one()) {
           const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.n_tile);
           const uint32_t first_fill = fill - 3;          // fill index of slice d - 1
           uint32_t blo = w_lo;
@@ -479,12 +522,15 @@ conv3d_slab_kernel(const __grid_constant__ ConvSlabParams p) {
 // three 32-column blocks of a TMEM group P(s).  A is read once instead of three times and the MMA count drops
 // 3x.  The epilogue forms out(j) = P(j-1)[0:32] + P(j)[32:64] + P(j+1)[64:96] (+ bias) from a ring of four
 // groups (4 x 96 TMEM columns).
-constexpr int kPGroups = 4;
+constexpr int kPGroups = 5;    // 5 x 96 TMEM columns = 480 <= 512
 
 // BK: channels per k-chunk (64 -> 128B swizzle, 32 -> 64B); PN: output channels per CTA "part" (32, or 16 when
 // Cin = 128 so that the 27 x kchunks resident weight tiles still fit); MMA N = 3 * PN.
+constexpr int kSlab3EpiWarps = 8;
+constexpr int kSlab3Threads = 64 + 32 * kSlab3EpiWarps;
+
 template <int BK, int PN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kSlab3Threads, 1)
 conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -493,7 +539,9 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   const int ring = p.ring;
   uint8_t* s_w = smem;                                                 // [kh*3+kw][kc][kd][PN rows][BK]
   uint8_t* s_ring = smem + w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (size_t)ring * p.slot_bytes);
+  constexpr int stage_bytes = kTileM * PN * 2;                         // one output tile (128 rows x PN fp16)
+  uint8_t* s_out = s_ring + (size_t)ring * p.slot_bytes;               // [2][stage_bytes], 1 KiB aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 2 * stage_bytes);
   uint64_t* full = bars;                  // [ring]   slice landed
   uint64_t* empty = full + kSlabRing;     // [ring]   slice consumed
   uint64_t* pfull = empty + kSlabRing;    // [groups] P group complete
@@ -513,8 +561,9 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_o) : "memory");
     for (int s = 0; s < kSlabRing; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < kPGroups; s++) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], 4); }
+    for (int s = 0; s < kPGroups; s++) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], kSlab3EpiWarps); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -551,6 +600,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         for (int dz = 0; dz < p.D; dz++, fill++) {
           const int slot = fill % ring;
           mbar_wait(&empty[slot], ((fill / ring) & 1) ^ 1);
+          if (p.debug & 4) { mbar_arrive(&full[slot]); continue; }
           mbar_expect_tx(&full[slot], slice_tx);
           for (int kc = 0; kc < p.kchunks; kc++)
             tma_load_5d(s_ring + (size_t)slot * p.slot_bytes + (size_t)kc * p.chunk_bytes, &p.tmap_a, &full[slot],
@@ -574,10 +624,12 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         mbar_wait(&full[q % ring], (q / ring) & 1);
         mbar_wait(&pempty[q % kPGroups], ((q / kPGroups) & 1) ^ 1);
         tc_fence_after();
-        if (lane == 0) {
+        __syncwarp();
+        if (elect_one()) {
           const uint32_t tmem_d = (q % kPGroups) * (3 * PN);
           const uint32_t slot_lo = ring_lo + (q % ring) * slot_step;
           uint32_t blo = w_lo;
+          if (!(p.debug & 2))
 #pragma unroll
           for (int t9 = 0; t9 < 9; t9++) {
             const uint32_t tap_lo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
@@ -599,60 +651,92 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
+    // The epilogue (TMEM -> registers, 3-block sum, fp16 pack, store) is what bounds the low-K layers
+    // (Cin = 32: 18 MMAs per slice): two warps share each TMEM lane quadrant and split the PN columns.
+    constexpr int CW = PN / 2;                           // columns per warp
     const int quad = warp & 3;
+    const int chalf = (warp - 2) >> 2;                   // 0: columns [0, CW), 1: [CW, PN)
     const int row = quad * 32 + lane;
     const int rx = row & 7, ry = row >> 3;
-    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    float bias[PN];
+    const uint32_t lane_addr = ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * CW);
+    float bias[CW];
 #pragma unroll
-    for (int j = 0; j < PN; j++) bias[j] = part * PN + j < p.cout ? __ldg(p.bias + part * PN + j) : 0.f;
+    for (int j = 0; j < CW; j++) {
+      const int ch = part * PN + chalf * CW + j;
+      bias[j] = ch < p.cout ? __ldg(p.bias + ch) : 0.f;
+    }
     uint32_t q0 = 0;                                     // global index of slice 0 of the current column
+    uint32_t n_out = 0;                                  // output tiles staged so far (staging buffer parity)
+    const bool is_issuer = warp == 2 && lane == 0;       // the thread that owns the TMA-store bulk groups
     for (int col = col0; col < n_cols; col += col_step, q0 += p.D) {
       int t = col;
       const int iw = t % p.nw; t /= p.nw;
       const int ih = t % p.nh; t /= p.nh;
       const int n = t;
-      const int ow = iw * 8 + rx, oh = ih * 16 + ry;
-      int waited = 0;                                    // slices of this column whose group completion was observed
-      for (int j = 0; j < p.D; j++) {
-        const int need = j + 1 < p.D ? j + 1 : p.D - 1;
-        while (waited <= need) {
-          const uint32_t q = q0 + waited;
-          mbar_wait(&pfull[q % kPGroups], (q / kPGroups) & 1);
-          waited++;
-        }
+      // Event s = "group P(s) complete".  It finishes out(s-1) (needs P(s)[2]) and starts out(s)
+      // (P(s-1)[0] + P(s)[1]); after its TMEM loads P(s-1) is dead and is handed back to the MMA warp
+      // BEFORE the arithmetic / stores, so the issue loop runs up to kPGroups-1 slices ahead of the stores.
+      float partial[CW];
+      for (int sl = 0; sl < p.D; sl++) {
+        const uint32_t q = q0 + sl;
+        mbar_wait(&pfull[q % kPGroups], (q / kPGroups) & 1);
         tc_fence_after();
-        float f[PN];
+        const uint32_t g_cur = lane_addr + (q % kPGroups) * (3 * PN);
+        const uint32_t g_prev = lane_addr + ((q + kPGroups - 1) % kPGroups) * (3 * PN);
+        uint32_t ra[CW], rb[CW], rc[CW];
+        if (sl >= 1) {
+          if constexpr (CW == 16) { tmem_ld16(g_cur + 2 * PN, ra); tmem_ld16(g_prev, rc); }
+          else { tmem_ld8(g_cur + 2 * PN, ra); tmem_ld8(g_prev, rc); }
+        } else {
 #pragma unroll
-        for (int c = 0; c < PN; c++) f[c] = bias[c];
-#pragma unroll
-        for (int b = 0; b < 3; b++) {
-          const int sl = j - 1 + b;                      // slice whose block b contributes to output j
-          if (sl >= 0 && sl < p.D) {
-            const uint32_t taddr = lane_addr + ((q0 + sl) % kPGroups) * (3 * PN) + b * PN;
-#pragma unroll
-            for (int c0 = 0; c0 < PN; c0 += 16) {
-              uint32_t r0[16];
-              tmem_ld16(taddr + c0, r0);
-              tmem_ld_wait();
-#pragma unroll
-              for (int c = 0; c < 16; c++) f[c0 + c] += __uint_as_float(r0[c]);
-            }
-          }
+          for (int c = 0; c < CW; c++) { ra[c] = 0u; rc[c] = 0u; }
         }
-        act_t* dst = p.out + ((((long long)n * p.D + j) * p.H + oh) * p.W + ow) * (long long)p.cout + part * PN;
-#pragma unroll
-        for (int c0 = 0; c0 < PN; c0 += 8)
-          if (part * PN + c0 + 8 <= p.cout) *reinterpret_cast<half8*>(dst + c0) = nm_pack8(f + c0);
+        if constexpr (CW == 16) tmem_ld16(g_cur + PN, rb);
+        else tmem_ld8(g_cur + PN, rb);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if (j >= 1) mbar_arrive(&pempty[(q0 + j - 1) % kPGroups]);     // P(j-1) feeds outputs j-2, j-1, j only
-          if (j == p.D - 1) mbar_arrive(&pempty[(q0 + j) % kPGroups]);
+          if (sl >= 1) mbar_arrive(&pempty[(q + kPGroups - 1) % kPGroups]);
+          if (sl == p.D - 1) mbar_arrive(&pempty[q % kPGroups]);
         }
+        // out(sl-1) is complete now; out(D-1) completes together with the last event
+        for (int fin = (sl >= 1 ? 0 : 1); fin < (sl == p.D - 1 ? 2 : 1); fin++) {
+          float f[CW];
+          if (fin == 0) {
+#pragma unroll
+            for (int c = 0; c < CW; c++) f[c] = partial[c] + __uint_as_float(ra[c]) + bias[c];
+          } else {
+#pragma unroll
+            for (int c = 0; c < CW; c++) f[c] = __uint_as_float(rb[c]) + __uint_as_float(rc[c]) + bias[c];
+          }
+          const int od = fin == 0 ? sl - 1 : sl;
+          // stage the tile in shared memory (swizzled like the store tensor map), then one TMA store: the
+          // direct per-thread 16-byte stores touched 16 cache lines per warp instruction and ran at ~1 TB/s
+          uint8_t* buf = s_out + (n_out & 1) * stage_bytes;
+          if (is_issuer) bulk_wait_read<1>();            // the store that last read this buffer has drained
+          named_bar_sync(1, 32 * kSlab3EpiWarps);
+          constexpr int row_b = PN * 2;                  // 64 B (SWIZZLE_64B) or 32 B (SWIZZLE_32B)
+#pragma unroll
+          for (int c0 = 0; c0 < CW; c0 += 8) {
+            const uint32_t off = (uint32_t)row * row_b + (uint32_t)(chalf * CW + c0) * 2;
+            const uint32_t sw = off ^ (((off >> 7) & (row_b == 64 ? 3u : 1u)) << 4);
+            *reinterpret_cast<half8*>(buf + sw) = nm_pack8(f + c0);
+          }
+          fence_async_smem();
+          named_bar_sync(1, 32 * kSlab3EpiWarps);
+          if (is_issuer && !(p.debug & 1)) {
+            tma_store_5d(&p.tmap_o, buf, part * PN, iw * 8, ih * 16, od, n);
+            bulk_commit();
+          }
+          n_out++;
+        }
+#pragma unroll
+        for (int c = 0; c < CW; c++) partial[c] = __uint_as_float(rb[c]) + __uint_as_float(rc[c]);
       }
     }
+    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -734,8 +818,9 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
     const size_t w_bytes = (size_t)27 * kch * (use3 ? pn : ntile) * bk * 2;
     const int chunk_bytes = ((kHaloW * kHaloH * bk * 2 + 1023) / 1024) * 1024;
     int ring = kSlabRing;
-    if (use3) while (ring > 2 && w_bytes + (size_t)ring * kch * chunk_bytes + 1024 + 32 * 8 + 16 > 227 * 1024) ring--;
-    const size_t need = w_bytes + (size_t)ring * kch * chunk_bytes + 1024 + 32 * 8 + 16;
+    const size_t extra = 1024 + 32 * 8 + 16 + (use3 ? (size_t)2 * kTileM * pn * 2 : 0);   // align, barriers, store staging
+    if (use3) while (ring > 2 && w_bytes + (size_t)ring * kch * chunk_bytes + extra > 227 * 1024) ring--;
+    const size_t need = w_bytes + (size_t)ring * kch * chunk_bytes + extra;
     if (slab_mode && k == 3 && stride == 1 && Cin >= 32 && Cin % bk == 0 && W % 8 == 0 && H % 16 == 0 &&
         need <= 227 * 1024) {
       ConvSlabParams q;
@@ -743,6 +828,7 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
       q.kchunks = kch; q.block_k = bk; q.n_tile = ntile; q.cout = Cout;
       q.nw = W / 8; q.nh = H / 16; q.D = D; q.H = H; q.W = W; q.N = n;
       q.chunk_bytes = chunk_bytes; q.slot_bytes = kch * chunk_bytes; q.ring = ring;
+      { const char* dbg = getenv("NM_SLAB_DEBUG"); q.debug = dbg ? atoi(dbg) : 0; }
       q.bias = bias; q.out = (act_t*)out;
       const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
@@ -761,6 +847,16 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
       r = encode(&q.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)packed_w, wdims, wstrides, wbox, westr,
                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab): cuTensorMapEncodeTiled(W) failed with %d", (int)r); return NM_ERR_DRIVER; }
+      if (use3) {
+        cuuint64_t odims[5] = {(cuuint64_t)Cout, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
+        cuuint64_t ostrides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)W * Cout * 2, (cuuint64_t)H * W * Cout * 2,
+                                  (cuuint64_t)D * H * W * Cout * 2};
+        cuuint32_t obox[5] = {(cuuint32_t)pn, 8, 16, 1, 1};
+        r = encode(&q.tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, out, odims, ostrides, obox, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, pn == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab3): cuTensorMapEncodeTiled(out) failed with %d", (int)r); return NM_ERR_DRIVER; }
+      }
       static bool slab_attr = false;
       if (!slab_attr) {
         NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -779,9 +875,9 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           slab3_attr = true;
         }
-        if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, 192, need, (cudaStream_t)stream>>>(q);
-        else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
-        else conv3d_slab3_kernel<32, 32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
+        if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, kSlab3Threads, need, (cudaStream_t)stream>>>(q);
+        else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, kSlab3Threads, need, (cudaStream_t)stream>>>(q);
+        else conv3d_slab3_kernel<32, 32><<<grid, kSlab3Threads, need, (cudaStream_t)stream>>>(q);
       } else if (bk == 64) conv3d_slab_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       else conv3d_slab_kernel<32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       NM_CHECK_LAUNCH("conv3d_slab");
@@ -854,7 +950,7 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 4) * 8 + 16;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 4) * 8 + 16 + 256 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
