@@ -49,7 +49,7 @@ first_conv_kernel(const float* __restrict__ occ, const float* __restrict__ wocc,
                   const float* __restrict__ bias, const float* __restrict__ lin, int G, act_t* __restrict__ out) {
   // tile: 4 (x) x 8 (y) x 8 (z) outputs, halo 8 x 12 x 12
   __shared__ float halo[8][12][12];
-  extern __shared__ float s_w[];  // [125][COUT]
+  extern __shared__ float s_w[];  // [125][COUT] weights, later reused as the [256][COUT] fp16 store staging (128*COUT floats)
   const int n = blockIdx.y;
   const int tz = G / 8, ty = G / 8;
   int b = blockIdx.x;
@@ -121,9 +121,23 @@ first_conv_kernel(const float* __restrict__ occ, const float* __restrict__ wocc,
           }
         }
   }
-  half8* dst = reinterpret_cast<half8*>(out + (((long long)n * G + x) * G * G + (long long)y * G + z) * COUT);
+  // Stage the block's 256 voxel rows in shared memory (reusing the weight buffer), then write them out with
+  // fully coalesced 16-byte stores: per-thread row stores touch a different cache line in every lane.
+  __syncthreads();
+  half8* stage = reinterpret_cast<half8*>(s_w);            // [256 voxels][COUT/8] 16-byte chunks, XOR-swizzled
+  constexpr int CH = COUT / 8;
 #pragma unroll
-  for (int c8 = 0; c8 < COUT / 8; c8++) dst[c8] = nm_pack8(acc + c8 * 8);
+  for (int c8 = 0; c8 < CH; c8++) stage[threadIdx.x * CH + (c8 ^ (threadIdx.x & (CH - 1)))] = nm_pack8(acc + c8 * 8);
+  __syncthreads();
+  // the tile is 32 (x, y) rows of 8 consecutive z voxels = 8 * COUT * 2 contiguous bytes each
+  constexpr int ROW_CHUNKS = 8 * CH;
+  for (int i = threadIdx.x; i < 256 * CH; i += 256) {
+    const int r = i / ROW_CHUNKS, pos = i % ROW_CHUNKS;     // r = lx * 8 + ly
+    const int v = r * 8 + pos / CH, c8 = pos % CH;          // voxel index inside the block, channel chunk
+    half8* dst = reinterpret_cast<half8*>(
+        out + (((long long)n * G + x0 + (r >> 3)) * G * G + (long long)(y0 + (r & 7)) * G + z0) * COUT);
+    dst[pos] = stage[v * CH + (c8 ^ (v & (CH - 1)))];
+  }
 }
 
 // ------------------------------------------------------------------ generic direct conv (cross-check)
@@ -212,9 +226,9 @@ extern "C" int nm_first_conv_k5(const float* occ, const void* tables, const floa
   dim3 grid((G / 4) * (G / 8) * (G / 8), n);
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout == 32) {
-    first_conv_kernel<32><<<grid, 256, 125 * 32 * sizeof(float), st>>>(occ, wocc, t, bias, linspace, G, (act_t*)out);
+    first_conv_kernel<32><<<grid, 256, 128 * 32 * sizeof(float), st>>>(occ, wocc, t, bias, linspace, G, (act_t*)out);
   } else if (Cout == 64) {
-    first_conv_kernel<64><<<grid, 256, 125 * 64 * sizeof(float), st>>>(occ, wocc, t, bias, linspace, G, (act_t*)out);
+    first_conv_kernel<64><<<grid, 256, 128 * 64 * sizeof(float), st>>>(occ, wocc, t, bias, linspace, G, (act_t*)out);
   } else {
     NM_CHECK_ARG(false, "nm_first_conv_k5: Cout=%d unsupported", Cout);
   }

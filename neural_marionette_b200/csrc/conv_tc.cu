@@ -27,6 +27,7 @@ constexpr uint64_t kWatchdogCycles = 8000000000ull;  // ~4 s: turn a protocol bu
 struct ConvTcParams {
   CUtensorMap tmap_a[8];
   CUtensorMap tmap_b;
+  CUtensorMap tmap_o;            // output (Cout, OW, OH, OD, N), box (32, tw, th, td, tn): TMA-store epilogue
   int taps, kchunks, block_k, n_tile, cout;
   int tw, th, td, tn;            // output-voxel box of one tile (tw*th*td*tn == 128)
   int nw, nh, nd, nn;            // tiles per dimension
@@ -166,7 +167,8 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
   const int b_bytes = p.n_tile * p.block_k * 2;
   const int stage_bytes = a_bytes + b_bytes;
   uint8_t* tiles = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* s_out = smem + (size_t)p.stages * stage_bytes;             // [2][128 rows x 32 ch fp16] store staging
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 2 * 8192);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tfull = bars + 2 * p.stages;
@@ -185,6 +187,7 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
     for (int i = 0; i < 8; i++)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a[i]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_o) : "memory");
     for (int s = 0; s < p.stages; s++) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -266,10 +269,13 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================
+    // TMEM -> registers (+bias) -> fp16 -> swizzled smem staging (32 channels x 128 rows) -> one TMA store per
+    // 32-channel chunk.  (Per-thread 16-byte global stores of a row each touch a different cache line per lane
+    // and ran at ~1 TB/s; the TMA store also clips partial tiles / channel remainders.)
     const int quad = warp & 3;                     // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
-    const int rx = row % p.tw, ry = (row / p.tw) % p.th, rz = (row / (p.tw * p.th)) % p.td,
-              rn = row / (p.tw * p.th * p.td);
+    const bool is_issuer = warp == 2 && lane == 0;
+    uint32_t n_out = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -278,9 +284,6 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
       const int ih = t % p.nh; t /= p.nh;
       const int id = t % p.nd; t /= p.nd;
       const int in_ = t;
-      const int ow = iw * p.tw + rx, oh = ih * p.th + ry, od = id * p.td + rz, on = in_ * p.tn + rn;
-      const bool live = ow < p.OW && oh < p.OH && od < p.OD && on < p.N;
-      act_t* dst = p.out + ((((long long)on * p.OD + od) * p.OH + oh) * p.OW + ow) * (long long)p.cout;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * p.n_tile);
@@ -289,25 +292,36 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
         tmem_ld16(taddr + c0, r);
         if (c0 + 16 < p.n_tile) tmem_ld16(taddr + c0 + 16, r + 16);
         tmem_ld_wait();
-        if (live) {
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int cb = c0 + 16 * h;
-            if (cb < p.n_tile) {
-              float f[16];
-#pragma unroll
-              for (int j = 0; j < 16; j++) f[j] = __uint_as_float(r[16 * h + j]) + s_bias[cb + j];
-              if (cb + 8 <= p.cout) *reinterpret_cast<half8*>(dst + cb) = nm_pack8(f);
-              if (cb + 16 <= p.cout) *reinterpret_cast<half8*>(dst + cb + 8) = nm_pack8(f + 8);
-            }
-          }
+        if (c0 + 32 >= p.n_tile) {                 // last chunk read: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[acc]);
         }
+        uint8_t* buf = s_out + (n_out & 1) * 8192;
+        if (is_issuer) bulk_wait_read<1>();
+        named_bar_sync(1, 128);
+#pragma unroll
+        for (int h = 0; h < 4; h++) {              // four 16-byte chunks of the row's 64-byte staging line
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const int c = c0 + h * 8 + j;
+            f[j] = c < p.n_tile ? __uint_as_float(r[h * 8 + j]) + s_bias[c] : 0.f;
+          }
+          const uint32_t off = (uint32_t)row * 64 + h * 16;
+          *reinterpret_cast<half8*>(buf + (off ^ (((off >> 7) & 3u) << 4))) = nm_pack8(f);
+        }
+        fence_async_smem();
+        named_bar_sync(1, 128);
+        if (is_issuer) {
+          tma_store_5d(&p.tmap_o, buf, c0, iw * p.tw, ih * p.th, id * p.td, in_ * p.tn);
+          bulk_commit();
+        }
+        n_out++;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -945,12 +959,26 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
       return NM_ERR_DRIVER;
     }
   }
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cout, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.OD, (cuuint64_t)n};
+    cuuint64_t strides[4] = {(cuuint64_t)Cout * 2, (cuuint64_t)p.OW * Cout * 2, (cuuint64_t)p.OH * p.OW * Cout * 2,
+                             (cuuint64_t)p.OD * p.OH * p.OW * Cout * 2};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.tw, (cuuint32_t)p.th, (cuuint32_t)p.td, (cuuint32_t)p.tn};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&p.tmap_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, out, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      nm_set_error("nm_conv3d_tc: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+      return NM_ERR_DRIVER;
+    }
+  }
   const int stage_bytes = kTileM * p.block_k * 2 + p.n_tile * p.block_k * 2;
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = (184 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 4) * 8 + 16 + 256 * 4;
+  const size_t smem = (size_t)stages * stage_bytes + 2 * 8192 + 1024 /*align*/ + (2 * stages + 4) * 8 + 16 + 256 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
