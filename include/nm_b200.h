@@ -46,7 +46,11 @@ int nm_pack_conv_weights(const float* weight, void* packed, int Cout, int Cin, i
 /* modules/vox_modules.py:12,26,30,39,53; model/kypt_detector.py:429,435,444,450 — nn.Conv3d with
  * (k in {1,3}, stride 1, pad (k-1)/2) or (k 2, stride 2).  tcgen05 implicit GEMM; x, out: act. */
 int nm_conv3d_tc(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
-                 int Cin, int Cout, int k, int stride, void* stream);
+                 int Cin, int Cout, int k, int stride, float* stats_partial, void* stream);
+/* GroupNorm statistics fused into the conv epilogue: when nm_conv3d_stats_chunks(...) > 0 the conv can write
+ * per-sample partial (sum, sum of squares) of its fp32 output to stats_partial [n][chunks][Cout][2]; feed them
+ * to nm_groupnorm_finalize instead of re-reading the tensor with nm_groupnorm_scale_shift. */
+int nm_conv3d_stats_chunks(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);
 /* same contract on CUDA cores from the raw fp32 weight; on-device cross-check of nm_conv3d_tc */
 int nm_conv3d_direct(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H, int W,
                      int Cin, int Cout, int k, int stride, int pad, void* stream);
@@ -67,6 +71,8 @@ int nm_first_conv_k5(const float* occ, const void* tables, const float* bias, co
 size_t nm_gn_workspace_bytes(int n, int S, int C);
 int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int groups, const float* gamma, const float* beta,
                              float eps, float* scale, float* shift, void* workspace, void* stream);
+int nm_groupnorm_finalize(const float* partial, int n, int S, int C, int groups, int chunks, const float* gamma,
+                          const float* beta, float eps, float* scale, float* shift, void* stream);
 /* out = act1(x1*a1+b1) + (x2*a2+b2 | x2 | nothing); act1: 0 none, 1 LeakyReLU(0.01).
  * Basic/Pool/Upsample blocks, Res3DBlock sums (vox_modules.py:44-47), HG skip adds (:111-118). */
 int nm_affine_act(const void* x1, const float* a1, const float* b1, int act1, const void* x2, const float* a2,

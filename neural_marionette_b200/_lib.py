@@ -36,7 +36,9 @@ PROTOTYPES = {
     "nm_normalize_voxelize_workspace_bytes": (_sz, [_i]),
     "nm_normalize_voxelize": (_i, [_vp, _i, _i, _i, _i, _f, _d, _d, _vp, _vp, _vp, _vp, _vp]),
     "nm_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _vp]),
-    "nm_conv3d_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "nm_conv3d_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "nm_conv3d_stats_chunks": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "nm_groupnorm_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "nm_conv3d_direct": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_conv_transpose3d_k2s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_first_conv_tables_bytes": (_sz, [_i]),

@@ -36,6 +36,7 @@ struct ConvTcParams {
   int8_t dx[kMaxTaps], dy[kMaxTaps], dz[kMaxTaps], map[kMaxTaps];
   const float* bias;
   act_t* out;
+  float* stats;                  // optional GroupNorm partials [n][tiles_per_sample*4][Cout][2] (tn == 1 only)
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -135,6 +136,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t addr, uint32_t* r) {
                : "r"(addr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Column sums over the 32 lanes of a warp for 32 per-lane values: recursive halving (31 shuffles instead of
+// 160 for a butterfly all-reduce).  On exit lane l holds the total of column l in v[0].
+__device__ __forceinline__ void warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++) {
+      const float send = upper ? v[i] : v[i + half];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, half);
+      v[i] = (upper ? v[i + half] : v[i]) + recv;
+    }
+  }
+}
 
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for swizzled K-major),
@@ -300,16 +316,29 @@ conv3d_tc_kernel(const __grid_constant__ ConvTcParams p) {
         uint8_t* buf = s_out + (n_out & 1) * 8192;
         if (is_issuer) bulk_wait_read<1>();
         named_bar_sync(1, 128);
+        float v32[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) v32[j] = c0 + j < p.n_tile ? __uint_as_float(r[j]) + s_bias[c0 + j] : 0.f;
 #pragma unroll
         for (int h = 0; h < 4; h++) {              // four 16-byte chunks of the row's 64-byte staging line
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const int c = c0 + h * 8 + j;
-            f[j] = c < p.n_tile ? __uint_as_float(r[h * 8 + j]) + s_bias[c] : 0.f;
-          }
           const uint32_t off = (uint32_t)row * 64 + h * 16;
-          *reinterpret_cast<half8*>(buf + (off ^ (((off >> 7) & 3u) << 4))) = nm_pack8(f);
+          *reinterpret_cast<half8*>(buf + (off ^ (((off >> 7) & 3u) << 4))) = nm_pack8(v32 + h * 8);
+        }
+        if (p.stats) {
+          // fused GroupNorm statistics: per-channel sum / sum of squares over this warp's 32 rows
+          float sq32[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) sq32[j] = v32[j] * v32[j];
+          warp_reduce_scatter32(v32, lane);
+          warp_reduce_scatter32(sq32, lane);
+          const int ch = c0 + lane;
+          if (ch < p.cout) {
+            const int tiles_per_sample = p.nw * p.nh * p.nd;
+            const long long chunk = (long long)(tile % tiles_per_sample) * 4 + quad;
+            float2* dst = reinterpret_cast<float2*>(p.stats) +
+                          ((long long)in_ * tiles_per_sample * 4 + chunk) * p.cout + ch;
+            *dst = make_float2(v32[0], sq32[0]);
+          }
         }
         fence_async_smem();
         named_bar_sync(1, 128);
@@ -350,6 +379,7 @@ struct ConvSlabParams {
   int chunk_bytes;        // bytes of one (slice, k-chunk) = 180 rows, padded to 1 KiB
   int ring;               // slab3: ring slots actually used (2..4)
   int debug;              // NM_SLAB_DEBUG bit mask (profiling experiments only): 1 no stores, 2 no MMAs, 4 no A loads
+  float* stats;           // slab3: optional GroupNorm partials [n][nh*nw*4][Cout][2] (sum, sum of squares)
   const float* bias;
   act_t* out;
 };
@@ -692,6 +722,9 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       // (P(s-1)[0] + P(s)[1]); after its TMEM loads P(s-1) is dead and is handed back to the MMA warp
       // BEFORE the arithmetic / stores, so the issue loop runs up to kPGroups-1 slices ahead of the stores.
       float partial[CW];
+      float ssum[CW], ssq[CW];                           // fused GroupNorm statistics of this thread's row
+#pragma unroll
+      for (int c = 0; c < CW; c++) { ssum[c] = 0.f; ssq[c] = 0.f; }
       for (int sl = 0; sl < p.D; sl++) {
         const uint32_t q = q0 + sl;
         mbar_wait(&pfull[q % kPGroups], (q / kPGroups) & 1);
@@ -725,6 +758,8 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
 #pragma unroll
             for (int c = 0; c < CW; c++) f[c] = __uint_as_float(rb[c]) + __uint_as_float(rc[c]) + bias[c];
           }
+#pragma unroll
+          for (int c = 0; c < CW; c++) { ssum[c] += f[c]; ssq[c] = fmaf(f[c], f[c], ssq[c]); }
           const int od = fin == 0 ? sl - 1 : sl;
           // stage the tile in shared memory (swizzled like the store tensor map), then one TMA store: the
           // direct per-thread 16-byte stores touched 16 cache lines per warp instruction and ran at ~1 TB/s
@@ -748,6 +783,26 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         }
 #pragma unroll
         for (int c = 0; c < CW; c++) partial[c] = __uint_as_float(rb[c]) + __uint_as_float(rc[c]);
+      }
+      if (p.stats) {
+        // column done: fold the 32 rows of this warp (fixed butterfly order -> deterministic) and emit one
+        // partial per (sample, tile column, TMEM quadrant): chunk = (ih * nw + iw) * 4 + quad
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            ssum[c] += __shfl_xor_sync(0xffffffffu, ssum[c], o);
+            ssq[c] += __shfl_xor_sync(0xffffffffu, ssq[c], o);
+          }
+        }
+        const int chunks = p.nh * p.nw * 4;
+        const long long chunk = (long long)(ih * p.nw + iw) * 4 + quad;
+#pragma unroll
+        for (int c = 0; c < CW; c++) {
+          const int ch = part * PN + chalf * CW + c;
+          if (lane == c && ch < p.cout)
+            reinterpret_cast<float2*>(p.stats)[((long long)n * chunks + chunk) * p.cout + ch] = make_float2(ssum[c], ssq[c]);
+        }
       }
     }
     if (is_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -802,8 +857,56 @@ extern "C" int nm_pack_conv_weights(const float* weight, void* packed, int Cout,
 
 // x: (n, D, H, W, Cin) fp16; packed_w: [k^3][Cout][Cin] fp16; out: (n, OD, OH, OW, Cout) fp16.
 // Supported: (k=1|3, stride 1, pad (k-1)/2) and (k=2, stride 2, pad 0); Cin, Cout multiples of 8; Cout <= 256.
+namespace {
+int slab_mode_env() {
+  static int slab_mode = -1;
+  if (slab_mode < 0) {
+    const char* e = getenv("NM_CONV_SLAB");   // A/B switch for profiling: 0 = tap-streaming kernel only, 1 = no slab3
+    slab_mode = e ? atoi(e) : 2;
+  }
+  return slab_mode;
+}
+// Which kernel serves this conv, and how many GroupNorm partial chunks per sample it can emit (0 = none).
+struct ConvPlan { bool slab, use3; int bk, kch, ntile, pn, ring, chunk_bytes; size_t need; int stats_chunks; };
+ConvPlan plan_conv(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
+  ConvPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  const int slab_mode = slab_mode_env();
+  pl.bk = Cin >= 64 ? 64 : 32;
+  pl.kch = (Cin + pl.bk - 1) / pl.bk;
+  pl.ntile = ((Cout + 15) / 16) * 16;
+  pl.pn = pl.kch == 1 ? 32 : 16;
+  pl.use3 = slab_mode >= 2 && pl.kch <= 2 && Cout % pl.pn == 0 && Cout <= 128;
+  const size_t w_bytes = (size_t)27 * pl.kch * (pl.use3 ? pl.pn : pl.ntile) * pl.bk * 2;
+  pl.chunk_bytes = ((kHaloW * kHaloH * pl.bk * 2 + 1023) / 1024) * 1024;
+  pl.ring = kSlabRing;
+  const size_t extra = 1024 + 32 * 8 + 16 + (pl.use3 ? (size_t)2 * kTileM * pl.pn * 2 : 0);
+  if (pl.use3)
+    while (pl.ring > 2 && w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra > 227 * 1024) pl.ring--;
+  pl.need = w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra;
+  pl.slab = slab_mode && k == 3 && stride == 1 && Cin >= 32 && Cin % pl.bk == 0 && W % 8 == 0 && H % 16 == 0 &&
+            pl.need <= 227 * 1024;
+  if (pl.slab) {
+    pl.stats_chunks = pl.use3 ? (H / 16) * (W / 8) * 4 : 0;
+  } else {
+    const int OD = D / stride, OH = H / stride, OW = W / stride;
+    const int tw = OW < 8 ? OW : 8, th = OH < 4 ? OH : 4, td = OD < 4 ? OD : 4;
+    const bool one_sample = tw * th * td == kTileM && OW % tw == 0 && OH % th == 0 && OD % td == 0;
+    pl.stats_chunks = one_sample ? (OW / tw) * (OH / th) * (OD / td) * 4 : 0;
+  }
+  (void)n;
+  return pl;
+}
+}  // namespace
+
+// Number of GroupNorm partial chunks per sample nm_conv3d_tc writes when `stats_partial` is given (0: this shape
+// cannot fuse the statistics; use nm_groupnorm_scale_shift on the output instead).
+extern "C" int nm_conv3d_stats_chunks(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
+  return plan_conv(n, D, H, W, Cin, Cout, k, stride).stats_chunks;
+}
+
 extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H,
-                            int W, int Cin, int Cout, int k, int stride, void* stream) {
+                            int W, int Cin, int Cout, int k, int stride, float* stats_partial, void* stream) {
   NM_CHECK_ARG(x && packed_w && bias && out, "nm_conv3d_tc: null pointer");
   NM_CHECK_ARG((stride == 1 && (k == 1 || k == 3)) || (stride == 2 && k == 2), "nm_conv3d_tc: k=%d stride=%d unsupported",
                k, stride);
@@ -816,34 +919,21 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
     nm_set_error("nm_conv3d_tc: cuTensorMapEncodeTiled entry point not available");
     return NM_ERR_DRIVER;
   }
-  // ---- slab-walking kernel: k3, weights resident in smem
+  // ---- slab-walking kernels: k3, weights resident in smem
+  const ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, k, stride);
+  NM_CHECK_ARG(!stats_partial || pl.stats_chunks > 0, "nm_conv3d_tc: this shape cannot fuse GroupNorm statistics");
   {
-    static int slab_mode = -1;
-    if (slab_mode < 0) {
-      const char* e = getenv("NM_CONV_SLAB");   // A/B switch for profiling: 0 = always use the tap-streaming kernel
-      slab_mode = e ? atoi(e) : 2;   // 2: + the 3-depth-tap variant for Cout = 32
-    }
-    const int bk = Cin >= 64 ? 64 : 32;
-    const int kch = (Cin + bk - 1) / bk;
-    const int ntile = ((Cout + 15) / 16) * 16;
-    // 3-depth-tap variant: output channels in parts of PN = 32 (Cin <= 64) or 16 (Cin = 128)
-    const int pn = kch == 1 ? 32 : 16;
-    const bool use3 = slab_mode >= 2 && kch <= 2 && Cout % pn == 0 && Cout <= 128;
-    const size_t w_bytes = (size_t)27 * kch * (use3 ? pn : ntile) * bk * 2;
-    const int chunk_bytes = ((kHaloW * kHaloH * bk * 2 + 1023) / 1024) * 1024;
-    int ring = kSlabRing;
-    const size_t extra = 1024 + 32 * 8 + 16 + (use3 ? (size_t)2 * kTileM * pn * 2 : 0);   // align, barriers, store staging
-    if (use3) while (ring > 2 && w_bytes + (size_t)ring * kch * chunk_bytes + extra > 227 * 1024) ring--;
-    const size_t need = w_bytes + (size_t)ring * kch * chunk_bytes + extra;
-    if (slab_mode && k == 3 && stride == 1 && Cin >= 32 && Cin % bk == 0 && W % 8 == 0 && H % 16 == 0 &&
-        need <= 227 * 1024) {
+    const int bk = pl.bk, kch = pl.kch, ntile = pl.ntile, pn = pl.pn, ring = pl.ring, chunk_bytes = pl.chunk_bytes;
+    const bool use3 = pl.use3;
+    const size_t need = pl.need;
+    if (pl.slab) {
       ConvSlabParams q;
       memset(&q, 0, sizeof(q));
       q.kchunks = kch; q.block_k = bk; q.n_tile = ntile; q.cout = Cout;
       q.nw = W / 8; q.nh = H / 16; q.D = D; q.H = H; q.W = W; q.N = n;
       q.chunk_bytes = chunk_bytes; q.slot_bytes = kch * chunk_bytes; q.ring = ring;
       { const char* dbg = getenv("NM_SLAB_DEBUG"); q.debug = dbg ? atoi(dbg) : 0; }
-      q.bias = bias; q.out = (act_t*)out;
+      q.bias = bias; q.out = (act_t*)out; q.stats = use3 ? stats_partial : nullptr;
       const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
       cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
@@ -916,6 +1006,7 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
   p.nw = nm_cdiv(p.OW, p.tw); p.nh = nm_cdiv(p.OH, p.th); p.nd = nm_cdiv(p.OD, p.td); p.nn = nm_cdiv(n, p.tn);
   p.bias = bias;
   p.out = (act_t*)out;
+  p.stats = stats_partial;
   {
     int t = 0;
     for (int a = 0; a < k; a++)

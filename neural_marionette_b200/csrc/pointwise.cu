@@ -418,6 +418,20 @@ extern "C" int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int 
   return NM_OK;
 }
 
+// Finalize GroupNorm scale/shift from partial sums produced elsewhere (the conv epilogues emit them):
+// partial [n][chunks][C][2] = (sum, sum of squares) over disjoint pieces of each sample.
+extern "C" int nm_groupnorm_finalize(const float* partial, int n, int S, int C, int groups, int chunks,
+                                     const float* gamma, const float* beta, float eps, float* scale, float* shift,
+                                     void* stream) {
+  NM_CHECK_ARG(partial && gamma && beta && scale && shift, "nm_groupnorm_finalize: null pointer");
+  NM_CHECK_ARG(groups > 0 && groups <= 32 && C % groups == 0 && chunks > 0, "nm_groupnorm_finalize: bad C=%d groups=%d chunks=%d",
+               C, groups, chunks);
+  if (n == 0) return NM_OK;
+  gn_finalize_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(partial, S, C, groups, chunks, gamma, beta, eps, scale, shift);
+  NM_CHECK_LAUNCH("gn_finalize");
+  return NM_OK;
+}
+
 extern "C" int nm_affine_act(const void* x1, const float* a1, const float* b1, int act1, const void* x2,
                              const float* a2, const float* b2, void* out, int n, int S, int C, void* stream) {
   NM_CHECK_ARG(x1 && a1 && b1 && out, "nm_affine_act: null pointer");

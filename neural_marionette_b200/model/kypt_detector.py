@@ -171,17 +171,13 @@ class KyptToVoxNet(nn.Module):
                 x = ops.decoder_adjust(first_feature_act[b0:b1], self.adjust_combined_representation[0], T, g, K,
                                        sigma, keypoints=kp, gaussians=gs)
                 x = ops.upsample2x(x)
-                raw = ops.conv3d(x, dec[1])
-                a, b = ops.gn_scale_shift(raw, dec[2])
+                raw, a, b = ops.conv3d(x, dec[1], dec[2])
                 x = ops.affine_act(raw, a, b, True)
-                raw = ops.conv3d(x, dec[4])
-                a, b = ops.gn_scale_shift(raw, dec[5])
+                raw, a, b = ops.conv3d(x, dec[4], dec[5])
                 x = ops.upsample2x(raw, a, b, act=True)
-                raw = ops.conv3d(x, dec[8])
-                a, b = ops.gn_scale_shift(raw, dec[9])
+                raw, a, b = ops.conv3d(x, dec[8], dec[9])
                 x = ops.affine_act(raw, a, b, True)
-                raw = ops.conv3d(x, dec[11])
-                a, b = ops.gn_scale_shift(raw, dec[12])
+                raw, a, b = ops.conv3d(x, dec[11], dec[12])
                 tgt = target[b0:b1].view(n, G, G, G) if target is not None else None
                 ops.final_recon(raw, a, b, dec[14], first_frame[b0:b1], T, sharpness, translation, target=tgt,
                                 out=recon[b0:b1].view(n, G, G, G),

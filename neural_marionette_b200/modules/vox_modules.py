@@ -28,8 +28,7 @@ class _ActModule(nn.Module):
 
 
 def conv_gn_lrelu(x, conv, gn):
-    raw = ops.conv3d(x, conv)
-    a, b = ops.gn_scale_shift(raw, gn)
+    raw, a, b = ops.conv3d(x, conv, gn)
     return ops.affine_act(raw, a, b, True)
 
 
@@ -69,12 +68,10 @@ class Res3DBlock(_ActModule):
 
     def run(self, x):
         h = conv_gn_lrelu(x, self.res_branch[0], self.res_branch[1])
-        raw = ops.conv3d(h, self.res_branch[3])
-        a, b = ops.gn_scale_shift(raw, self.res_branch[4])
+        raw, a, b = ops.conv3d(h, self.res_branch[3], self.res_branch[4])
         if len(self.skip_con) == 0:
             return ops.affine_act(raw, a, b, False, x2=x)
-        sraw = ops.conv3d(x, self.skip_con[0])
-        sa, sb = ops.gn_scale_shift(sraw, self.skip_con[1])
+        sraw, sa, sb = ops.conv3d(x, self.skip_con[0], self.skip_con[1])
         return ops.affine_act(raw, a, b, False, x2=sraw, a2=sa, b2=sb)
 
 

@@ -112,33 +112,48 @@ def normalize_voxelize(raw: torch.Tensor, grid_size: int, scale: float = 1.0, x_
 
 
 # ------------------------------------------------------------------ convolutions
-def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
-    """act (n, D, H, W, Cin) -> raw conv output act (n, OD, OH, OW, Cout); bias included."""
+def _tc_ok(conv, Cin):
+    k, s, Cout = conv.kernel_size[0], conv.stride[0], conv.out_channels
+    return Cin % 8 == 0 and Cin >= 16 and Cout % 8 == 0 and Cout <= 256 and \
+        ((s == 1 and k in (1, 3) and conv.padding[0] == (k - 1) // 2) or (s == 2 and k == 2 and conv.padding[0] == 0))
+
+
+def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None):
+    """act (n, D, H, W, Cin) -> raw conv output act (n, OD, OH, OW, Cout); bias included.
+    With `gn`: returns (raw, scale, shift) of the GroupNorm that follows; the statistics come out of the conv
+    epilogue when the kernel supports it (no extra pass over the output), else from a reduction kernel."""
     _need_cuda(x)
     n, D, H, W, Cin = x.shape
     k, s, Cout = conv.kernel_size[0], conv.stride[0], conv.out_channels
     assert Cin == conv.in_channels and x.dtype == ACT_DTYPE and x.is_contiguous()
+    if not _tc_ok(conv, Cin):
+        out = conv3d_direct(x, conv)
+        return (out,) + gn_scale_shift(out, gn) if gn is not None else out
     out = torch.empty(n, D // s, H // s, W // s, Cout, dtype=ACT_DTYPE, device=x.device)
-    tc_ok = Cin % 8 == 0 and Cin >= 16 and Cout % 8 == 0 and Cout <= 256 and \
-        ((s == 1 and k in (1, 3) and conv.padding[0] == (k - 1) // 2) or (s == 2 and k == 2 and conv.padding[0] == 0))
-    if tc_ok:
-        pw, pb = packed_conv_weight(conv), f32(conv, "bias")
-        if PROFILE is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-        L.call("nm_conv3d_tc", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s, L.stream())
-        if PROFILE is not None:
-            e1.record()
-            flops = 2.0 * n * (D // s) * (H // s) * (W // s) * Cout * Cin * k ** 3
-            PROFILE.setdefault((n, D, Cin, Cout, k, s, flops), []).append((e0, e1))
-    else:
-        pad = conv.padding[0]
-        od = (D + 2 * pad - k) // s + 1
-        out = torch.empty(n, od, (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1, Cout, dtype=ACT_DTYPE,
-                          device=x.device)
-        L.call("nm_conv3d_direct", L.ptr(x), L.ptr(f32(conv, "weight")), L.ptr(f32(conv, "bias")), L.ptr(out),
-               n, D, H, W, Cin, Cout, k, s, pad, L.stream())
-    return out
+    pw, pb = packed_conv_weight(conv), f32(conv, "bias")
+    chunks = L.query("nm_conv3d_stats_chunks", n, D, H, W, Cin, Cout, k, s) if gn is not None else 0
+    partial = None
+    if chunks > 0:
+        partial = workspace(n * chunks * Cout * 8, x.device, "gn").view(torch.float32)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.call("nm_conv3d_tc", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
+           L.ptr(partial), L.stream())
+    if PROFILE is not None:
+        e1.record()
+        flops = 2.0 * n * (D // s) * (H // s) * (W // s) * Cout * Cin * k ** 3
+        PROFILE.setdefault((n, D, Cin, Cout, k, s, flops), []).append((e0, e1))
+    if gn is None:
+        return out
+    if chunks == 0:
+        return (out,) + gn_scale_shift(out, gn)
+    a = torch.empty(n, Cout, dtype=torch.float32, device=x.device)
+    b = torch.empty_like(a)
+    S = out.numel() // (n * Cout)
+    L.call("nm_groupnorm_finalize", L.ptr(partial), n, S, Cout, gn.num_groups, chunks, L.ptr(f32(gn, "weight")),
+           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+    return out, a, b
 
 
 def conv3d_direct(x: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:

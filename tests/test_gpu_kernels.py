@@ -127,6 +127,16 @@ def test_conv3d_tc(ops, n, grid, cin, cout, k, stride):
         np.savez_compressed(f"gpurun_out/conv_fail_{n}_{grid}_{cin}_{cout}_{k}_{stride}.npz", got=got.numpy(),
                             ref=ref.numpy(), x=xh.numpy(), w=wh.numpy())
     assert err < 2e-3, f"tcgen05 conv rel err {err}"
+    # GroupNorm statistics fused into the conv epilogue == statistics of the stored output
+    if cout % 16 == 0:
+        gn = torch.nn.GroupNorm(cout // 16, cout).cuda()
+        with torch.no_grad():
+            gn.weight.copy_(1 + 0.3 * torch.randn(cout, generator=g))
+            gn.bias.copy_(0.3 * torch.randn(cout, generator=g))
+        raw, a, b = ops.conv3d(to_act(x), conv, gn)
+        a2, b2 = ops.gn_scale_shift(raw, gn)
+        assert torch.equal(raw, ops.conv3d(to_act(x), conv))
+        assert (a - a2).abs().max() <= 2e-3 * a2.abs().max() and (b - b2).abs().max() <= 2e-3 * (1 + b2.abs().max())
 
 
 def test_first_conv_coordconv(ops):
