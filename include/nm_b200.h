@@ -54,7 +54,8 @@ int nm_conv3d_stats_chunks(int n, int D, int H, int W, int Cin, int Cout, int k,
 /* same contract on CUDA cores from the raw fp32 weight; on-device cross-check of nm_conv3d_tc */
 int nm_conv3d_direct(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H, int W,
                      int Cin, int Cout, int k, int stride, int pad, void* stream);
-/* modules/vox_modules.py:68 nn.ConvTranspose3d(k 2, stride 2); weight (Cin, Cout, 2, 2, 2) fp32 */
+/* modules/vox_modules.py:68 nn.ConvTranspose3d(k 2, stride 2); weight: the (Cin, Cout, 2, 2, 2) fp32 parameter
+ * permuted to tap-major (8, Cin, Cout) */
 int nm_conv_transpose3d_k2s2(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H,
                              int W, int Cin, int Cout, void* stream);
 /* First layer: add_coord_channels (utils/kypt_detector_utils.py:4-26) + Conv3d(1+3, Cout, k5, pad 2)

@@ -174,7 +174,7 @@ conv_direct_kernel(const act_t* __restrict__ x, const float* __restrict__ w, con
 }
 
 // ------------------------------------------------------------------ ConvTranspose3d k2 s2
-// x: (n, D, H, W, Cin) fp16; w: (Cin, Cout, 2, 2, 2) fp32 (nn.ConvTranspose3d layout); out (n, 2D, 2H, 2W, Cout)
+// x: (n, D, H, W, Cin) fp16; w: tap-major (8, Cin, Cout) fp32; out (n, 2D, 2H, 2W, Cout)
 // one thread per (output voxel, 8 output channels)
 __global__ void __launch_bounds__(128)
 convT_k2s2_kernel(const act_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
@@ -193,10 +193,21 @@ convT_k2s2_kernel(const act_t* __restrict__ x, const float* __restrict__ w, cons
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) acc[k] = bias[c8 * 8 + k];
-  for (int ci = 0; ci < Cin; ci++) {
-    const float v = __half2float(px[ci]);
+  // w is tap-major [8][Cin][Cout] (host-side permute of the (Cin, Cout, 2, 2, 2) parameter): the 8 output
+  // channels of this thread are two float4 loads per input channel
+  const float4* pw = reinterpret_cast<const float4*>(w + ((long long)tap * Cin) * Cout + c8 * 8);
+  for (int ci8 = 0; ci8 < Cin; ci8 += 8) {
+    float xv[8];
+    nm_unpack8(*reinterpret_cast<const half8*>(px + ci8), xv);
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = fmaf(v, __ldg(w + ((long long)ci * Cout + c8 * 8 + k) * 8 + tap), acc[k]);
+    for (int j = 0; j < 8; j++) {
+      const float4 w0 = __ldg(pw + (long long)(ci8 + j) * (Cout / 4));
+      const float4 w1 = __ldg(pw + (long long)(ci8 + j) * (Cout / 4) + 1);
+      acc[0] = fmaf(xv[j], w0.x, acc[0]); acc[1] = fmaf(xv[j], w0.y, acc[1]);
+      acc[2] = fmaf(xv[j], w0.z, acc[2]); acc[3] = fmaf(xv[j], w0.w, acc[3]);
+      acc[4] = fmaf(xv[j], w1.x, acc[4]); acc[5] = fmaf(xv[j], w1.y, acc[5]);
+      acc[6] = fmaf(xv[j], w1.z, acc[6]); acc[7] = fmaf(xv[j], w1.w, acc[7]);
+    }
   }
   reinterpret_cast<half8*>(out)[i] = nm_pack8(acc);
 }
@@ -252,7 +263,7 @@ extern "C" int nm_conv3d_direct(const void* x, const float* weight, const float*
 extern "C" int nm_conv_transpose3d_k2s2(const void* x, const float* weight, const float* bias, void* out, int n,
                                         int D, int H, int W, int Cin, int Cout, void* stream) {
   NM_CHECK_ARG(x && weight && bias && out, "nm_conv_transpose3d_k2s2: null pointer");
-  NM_CHECK_ARG(Cout % 8 == 0, "nm_conv_transpose3d_k2s2: Cout=%d not a multiple of 8", Cout);
+  NM_CHECK_ARG(Cout % 8 == 0 && Cin % 8 == 0, "nm_conv_transpose3d_k2s2: Cin=%d Cout=%d not multiples of 8", Cin, Cout);
   const long long total8 = (long long)n * 8 * D * H * W * (Cout / 8);
   if (total8 == 0) return NM_OK;
   convT_k2s2_kernel<<<nm_cdiv(total8, 128), 128, 0, (cudaStream_t)stream>>>((const act_t*)x, weight, bias,

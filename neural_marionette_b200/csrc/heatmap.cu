@@ -21,20 +21,60 @@ __device__ __forceinline__ float softplus1(float x) {
   return x > 20.f ? x : log1pf(expf(x));
 }
 
-// feature: (n, g^3, C) fp16 channels-last (finished activation of the last Res3DBlock)
-// w1: (K, C) fp32, b1: (K); mode 0: out = lrelu(w1 f + b1) -> heat (ST head, fp32 (n,K,g^3))
-// mode 1: hm = softplus(pw0 * lrelu(w1 f + b1) + pw1 * prev[clip] + pb); + keypoints + gaussians
-// g in {8, 16, 32}: a warp's 32 consecutive voxels share x; y is constant over runs of min(g,32) lanes.
+// Phase 1 (parallel over voxels): heat-map values.  grid = (g^3 / 256, n); one voxel per thread.
+//   mode 0: heat = lrelu(w1 f + b1);  mode 1: heat = softplus(pw0 * lrelu(w1 f + b1) + pw1 * prev[clip] + pb)
 template <int C>
 __global__ void __launch_bounds__(256)
-head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, const float* __restrict__ b1,
-            int K, int g, int mode, const float* __restrict__ prev, int frames_per_clip, float pw0, float pw1,
-            float pb, const float* __restrict__ lin, float gauss_width, float* __restrict__ heat,
-            float* __restrict__ keypoints, float* __restrict__ gaussians, float* __restrict__ heat_mean) {
+head_heat_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, const float* __restrict__ b1,
+                 int K, int S, int mode, const float* __restrict__ prev, int frames_per_clip, float pw0, float pw1,
+                 float pb, float* __restrict__ heat) {
   extern __shared__ float smem[];
   float* s_w = smem;                       // [K][C]
   float* s_b = s_w + KMAX * C;             // [K]
-  float* s_m = s_b + KMAX;                 // [3][K][32] raw marginal sums along x, y, z
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < K * C; i += 256) s_w[i] = w1[i];
+  for (int i = threadIdx.x; i < K; i += 256) s_b[i] = b1[i];
+  __syncthreads();
+  const int s = blockIdx.x * 256 + threadIdx.x;
+  if (s >= S) return;
+  float acc[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) acc[k] = 0.f;
+  const half8* p = reinterpret_cast<const half8*>(feature + ((long long)n * S + s) * C);
+#pragma unroll 2
+  for (int c8 = 0; c8 < C / 8; c8++) {
+    float v[8];
+    nm_unpack8(p[c8], v);
+#pragma unroll
+    for (int k = 0; k < KMAX; k++) {
+      if (k < K) {
+        const float4 wa = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8);
+        const float4 wb = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8 + 4);
+        acc[k] = fmaf(v[0], wa.x, fmaf(v[1], wa.y, fmaf(v[2], wa.z, fmaf(v[3], wa.w, acc[k]))));
+        acc[k] = fmaf(v[4], wb.x, fmaf(v[5], wb.y, fmaf(v[6], wb.z, fmaf(v[7], wb.w, acc[k]))));
+      }
+    }
+  }
+  const float* pv = prev ? prev + (long long)(n / frames_per_clip) * K * S : nullptr;
+  float* hm_out = heat + (long long)n * K * S;
+#pragma unroll
+  for (int k = 0; k < KMAX; k++) {
+    if (k < K) {
+      float h = nm_lrelu(acc[k] + s_b[k]);
+      if (mode == 1) h = softplus1(fmaf(pw0, h, fmaf(pw1, pv[(long long)k * S + s], pb)));
+      hm_out[(long long)k * S + s] = h;
+    }
+  }
+}
+
+// Phase 2 (one CTA per frame): marginals of the heat-maps -> soft-argmax keypoints -> Gaussian re-render.
+// heat: (n, K, g^3) fp32 written by head_heat_kernel.  g in {8, 16, 32}: a warp's 32 consecutive voxels share x;
+// y is constant over runs of min(g, 32) lanes.  No float atomics: the result is bit-reproducible.
+__global__ void __launch_bounds__(256)
+head_reduce_kernel(int K, int g, const float* __restrict__ lin, float gauss_width, const float* __restrict__ heat,
+                   float* __restrict__ keypoints, float* __restrict__ gaussians, float* __restrict__ heat_mean) {
+  extern __shared__ float smem[];
+  float* s_m = smem;                       // [3][K][32] raw marginal sums along x, y, z
   float* s_kp = s_m + 3 * KMAX * 32;       // [K][4]
   float* s_e = s_kp + KMAX * 4;            // [K][3][32] separable gaussian factors
   float* s_px = s_e + KMAX * 3 * 32;       // [8 warps][K]        per-iteration warp partials (x)
@@ -42,14 +82,10 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
   float* s_pz = s_py + 8 * KMAX * 4;       // [8 warps][K][32]    (z)
   const int n = blockIdx.x;
   const int S = g * g * g;
-  for (int i = threadIdx.x; i < K * C; i += 256) s_w[i] = w1[i];
-  for (int i = threadIdx.x; i < K; i += 256) s_b[i] = b1[i];
   for (int i = threadIdx.x; i < 3 * KMAX * 32; i += 256) s_m[i] = 0.f;
   __syncthreads();
 
-  const act_t* f = feature + (long long)n * S * C;
-  const float* pv = prev ? prev + (long long)(n / frames_per_clip) * K * S : nullptr;
-  float* hm_out = heat + (long long)n * K * S;
+  const float* hm_out = heat + (long long)n * K * S;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int run = g < 32 ? g : 32;          // lanes that share y
   const int runs = 32 / run;                // y rows per warp
@@ -57,31 +93,11 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
   // voxel s = (x*g + y)*g + z ; consecutive threads -> consecutive s (coalesced heat-map rows)
   for (int s0 = 0; s0 < S; s0 += 256) {
     const int s = s0 + threadIdx.x;        // S is a multiple of 256 for g >= 8
-    float acc[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) acc[k] = 0.f;
-    const half8* p = reinterpret_cast<const half8*>(f + (long long)s * C);
-#pragma unroll 2
-    for (int c8 = 0; c8 < C / 8; c8++) {
-      float v[8];
-      nm_unpack8(p[c8], v);
-#pragma unroll
-      for (int k = 0; k < KMAX; k++) {
-        if (k < K) {
-          const float4 wa = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8);
-          const float4 wb = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8 + 4);
-          acc[k] = fmaf(v[0], wa.x, fmaf(v[1], wa.y, fmaf(v[2], wa.z, fmaf(v[3], wa.w, acc[k]))));
-          acc[k] = fmaf(v[4], wb.x, fmaf(v[5], wb.y, fmaf(v[6], wb.z, fmaf(v[7], wb.w, acc[k]))));
-        }
-      }
-    }
 #pragma unroll
     for (int k = 0; k < KMAX; k++) {
       if (k < K) {
-        float h = nm_lrelu(acc[k] + s_b[k]);
-        if (mode == 1) h = softplus1(fmaf(pw0, h, fmaf(pw1, pv[(long long)k * S + s], pb)));
-        hm_out[(long long)k * S + s] = h;
-        if (mode == 1) {
+        const float h = hm_out[(long long)k * S + s];     // written by head_heat_kernel
+        {
           // warp-level partial sums (shuffles only: deterministic)
           float hy = h;                                    // y: segmented sum over runs of `run` lanes
           for (int o = 1; o < run; o <<= 1) hy += __shfl_xor_sync(0xffffffffu, hy, o);
@@ -95,7 +111,7 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
         }
       }
     }
-    if (mode == 1) {
+    {
       // fold the 8 warps' partials into the marginals in a fixed order (no float atomics: results are
       // bit-reproducible run to run, which the reference's callers rely on via cudnn.deterministic)
       __syncthreads();
@@ -117,7 +133,6 @@ head_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, con
       __syncthreads();
     }
   }
-  if (mode == 0) return;
   __syncthreads();
 
   // ---- soft-argmax (utils/kypt_detector_utils.py:28-55)
@@ -306,10 +321,6 @@ adjust_frame_kernel(const float* __restrict__ base, const float* __restrict__ kp
   for (int j = 0; j < PER / 8; j++) dst[j] = nm_pack8(acc + j * 8);
 }
 
-size_t head_smem_bytes(int C) {
-  return (size_t)(KMAX * C + KMAX + 3 * KMAX * 32 + KMAX * 4 + KMAX * 3 * 32 + 8 * KMAX * (1 + 4 + 32)) * 4;
-}
-
 }  // namespace
 
 extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K,
@@ -320,23 +331,29 @@ extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float
   NM_CHECK_ARG(K <= KMAX && (g == 8 || g == 16 || g == 32), "nm_heatmap_head: K=%d g=%d unsupported", K, g);
   NM_CHECK_ARG(mode == 0 || (prev && keypoints), "nm_heatmap_head: mode 1 needs prev and keypoints");
   if (n == 0) return NM_OK;
-  const float width = gauss_width;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = head_smem_bytes(C);
+  const int S = g * g * g;
+  const size_t smem1 = (size_t)(KMAX * C + KMAX) * sizeof(float);
+  dim3 grid1(nm_cdiv(S, 256), n);
   if (C == 128) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(head_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
-    head_kernel<128><<<n, 256, smem, st>>>((const act_t*)feature, w1, b1, K, g, mode, prev, frames_per_clip, pw0,
-                                           pw1, pb, linspace, width, heat, keypoints, gaussians, heat_mean);
+    head_heat_kernel<128><<<grid1, 256, smem1, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
+                                                     pw0, pw1, pb, heat);
   } else if (C == 256) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(head_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
-    head_kernel<256><<<n, 256, smem, st>>>((const act_t*)feature, w1, b1, K, g, mode, prev, frames_per_clip, pw0,
-                                           pw1, pb, linspace, width, heat, keypoints, gaussians, heat_mean);
+    head_heat_kernel<256><<<grid1, 256, smem1, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
+                                                     pw0, pw1, pb, heat);
   } else {
     NM_CHECK_ARG(false, "nm_heatmap_head: C=%d unsupported", C);
   }
-  NM_CHECK_LAUNCH("heatmap_head");
+  NM_CHECK_LAUNCH("heatmap_head(heat)");
+  if (mode == 0) return NM_OK;
+  const size_t smem2 = (size_t)(3 * KMAX * 32 + KMAX * 4 + KMAX * 3 * 32 + 8 * KMAX * (1 + 4 + 32)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(head_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    attr = true;
+  }
+  head_reduce_kernel<<<n, 256, smem2, st>>>(K, g, linspace, gauss_width, heat, keypoints, gaussians, heat_mean);
+  NM_CHECK_LAUNCH("heatmap_head(reduce)");
   return NM_OK;
 }
 

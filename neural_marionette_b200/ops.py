@@ -173,7 +173,9 @@ def conv_transpose3d(x: torch.Tensor, conv: torch.nn.ConvTranspose3d) -> torch.T
     assert conv.kernel_size[0] == 2 and conv.stride[0] == 2 and tuple(conv.output_padding) == (0, 0, 0), \
         "only ConvTranspose3d(k2, s2, output_padding 0) is implemented (grid sizes divisible by 32)"
     out = torch.empty(n, 2 * D, 2 * H, 2 * W, Cout, dtype=ACT_DTYPE, device=x.device)
-    L.call("nm_conv_transpose3d_k2s2", L.ptr(x), L.ptr(f32(conv, "weight")), L.ptr(f32(conv, "bias")), L.ptr(out),
+    wt = _cached(conv, "tapmajor", [conv.weight],
+                 lambda: conv.weight.detach().float().permute(2, 3, 4, 0, 1).reshape(8, Cin, Cout).contiguous())
+    L.call("nm_conv_transpose3d_k2s2", L.ptr(x), L.ptr(wt), L.ptr(f32(conv, "bias")), L.ptr(out),
            n, D, H, W, Cin, Cout, L.stream())
     return out
 
