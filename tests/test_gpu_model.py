@@ -150,3 +150,24 @@ def test_training_mode_raises():
     vox = torch.zeros(1, 2, 1, 32, 32, 32, device="cuda")
     with pytest.raises(NotImplementedError):
         net.kypt_detector(vox)
+
+
+def test_stress_resolution_g128_vs_oracle():
+    """Config #5: 2x the grid per axis (128^3, heat-map grid 32^3) with 100k points per frame."""
+    import neural_marionette_b200 as nm
+    G, T, N = 128, 2, 100000
+    hp = O.default_hparams(grid_size=G)
+    net, sd = build(hp, 61)
+    raw = O.synthetic_clip(6100, T, N)[None]
+    vox = nm.voxelize_raw_clips(raw, G)
+    ref_vox = O.voxelize_clip(O.episodic_normalization(raw[0]), G)[None]
+    assert np.array_equal(vox.cpu().numpy(), ref_vox)                  # scatter contention: bit-exact
+    with torch.no_grad():
+        hm, kp, gs, ff = net.kypt_detector.vox_to_kypt(vox)
+        ref = O.vox_to_kypt(torch.from_numpy(ref_vox), sd, hp)
+    assert (kp.cpu() - ref[1]).abs().max() <= KP_TOL
+    assert float((hm.cpu() - ref[0]).abs().max() / ref[0].max()) <= HM_TOL
+    with torch.no_grad():
+        rec = net.kypt_detector.kypt_to_vox.decode(net.kypt_detector.vox_to_kypt.detect(vox)["first_feature_act"],
+                                                   vox[:, 0], keypoints=kp[:, :1], sigma=1.5)
+    assert rec.shape == (1, 1, 1, G, G, G) and bool(torch.isfinite(rec).all())
