@@ -39,7 +39,8 @@ def parse():
     ap.add_argument("--frames", type=int, default=20)
     ap.add_argument("--points", type=int, default=20000)
     ap.add_argument("--grid", type=int, default=64)
-    ap.add_argument("--cpu-baseline-frames", type=int, default=2)
+    ap.add_argument("--cpu-baseline-frames", type=int, default=20,
+                    help="frames of the ONE clip the CPU arm processes per step (default = a full clip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -127,20 +128,23 @@ def main():
                           f"on {B} synthetic AIST-shape clips x {T} frames x {N} pts per GPU, grid {G}^3, K=24",
               "clips_per_gpu": B, "frames_per_clip": T, "points_per_frame": N, "grid": G,
               "l2": "inputs (307 MB of points, >20 GB of activations per step) exceed the 126 MB L2",
+              "precision": "fp16 activations/weights at rest, fp32 accumulation (tcgen05 kind::f16), fp32 GroupNorm "
+                           "statistics / heads / losses",
               "parallelism": f"clip-sharded x{world}, no data-path collective"}
 
     if args.impl == "reference":
         if rank != 0:
             return
         frames = max(2, args.cpu_baseline_frames)
-        fps, t, cores = cpu_reference_run(args, max(1, min(args.steps, 3)), 1, frames)
+        fps, t, cores = cpu_reference_run(args, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)), frames)
         print(json.dumps({
             "impl": "reference", "metric": "voxel frames/sec keypoint detection", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"1 clip x {frames} frames per step (same per-frame work as the GPU arm)"},
+                             "sample": f"1 clip x {frames} frames per step (voxelize + detector forward; same per-frame work "
+                                       f"as the GPU arm)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -176,10 +180,7 @@ def main():
         kp = out["keypoints"].cpu()
         return kp, float(out["recon_loss"])
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    from neural_marionette_b200.parallel import barrier, max_over_ranks
 
     def timed(fn, steps):
         barrier()
@@ -189,10 +190,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()) / steps
+        return max_over_ranks(e0.elapsed_time(e1), dev) / steps      # device time, slowest rank
 
     with torch.no_grad():
         for _ in range(max(3, args.warmup)):
@@ -229,7 +227,10 @@ def main():
         ach = tflop * cnt / (t_ms / 1e3) / 1e12
         roof = {"bound": "tensor", "kernel": "conv3d_tc_kernel",
                 "layer": f"n={tn} grid={tD} Cin={tci} Cout={tco} k={tk} s={ts}", "achieved": ach,
-                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"], "traffic": None,
+                "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of the dec.8 launch (60 frames) from the ncu --set full
+                # capture in profiles/ (algorithmic: 60 x (33.5 MB in + 16.8 MB out) = 3.02 GB)
+                "traffic": 3.007e9 if (tn, tD, tci, tco, tk) == (60, 64, 64, 32, 3) else None,
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "launch_ms": t_ms / cnt, "share_of_step": t_ms / (ms * args.steps),
                 "all_tc_convs": {"achieved": tot_flop / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / (ms * args.steps)},
@@ -242,7 +243,7 @@ def main():
     line = {
         "metric": "voxel frames/sec keypoint detection", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp16 storage / fp32 accumulate (kind::f16)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp16",
         "data": "synthetic", "config": config, "clocks": clocks,
         "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(raw_host.numel() * 4),
                 "d2h_bytes_per_step": int(B * T * 24 * 4 * 4 + 4), "ms_per_step": ms_e2e},
@@ -255,8 +256,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, t, cores = cpu_reference_run(args, 2, 1, args.cpu_baseline_frames)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"1 clip x {args.cpu_baseline_frames} frames, 2 timed reps "
-                                          f"({t:.1f} s each), same per-frame work"}
+                                "sample": f"1 clip x {args.cpu_baseline_frames} frames (voxelize + detector forward), "
+                                          f"1 warm-up + 2 timed reps of {t:.1f} s; same per-frame work as the GPU arm"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -1,0 +1,59 @@
+"""world_size-2 gloo test of the clip-sharding host logic (the N>1 path of bench.py / multi-GPU inference)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from neural_marionette_b200 import parallel as P
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _fake_keypoints(clip_ids):
+    # deterministic "output" of clip i, so that any mis-ordering of the gather is visible
+    return torch.stack([torch.full((3, 24, 4), float(i)) + torch.arange(4.0) for i in clip_ids]) if len(clip_ids) \
+        else torch.zeros(0, 3, 24, 4)
+
+
+def _worker(rank, world, port, n_clips, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = P.shard_range(n_clips, rank, world)
+    local = _fake_keypoints(range(lo, hi))
+    full = P.gather_clip_outputs(local, n_clips)
+    slowest = P.max_over_ranks(10.0 + rank)
+    P.barrier()
+    ok = torch.equal(full, _fake_keypoints(range(n_clips))) and slowest == 10.0 + world - 1
+    out.put((rank, bool(ok), (lo, hi)))
+    dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_exactly_once():
+    for n in (0, 1, 7, 64, 513):
+        for w in (1, 2, 3, 8):
+            r = [P.shard_range(n, k, w) for k in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert max(h - l for l, h in r) - min(h - l for l, h in r) <= 1
+            assert P.shard_sizes(n, w) == [h - l for l, h in r]
+
+
+def test_gloo_world2_gather_and_timing():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 7, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True]
+    assert [r[2] for r in res] == [(0, 4), (4, 7)]
