@@ -225,7 +225,10 @@ def main():
         top = max(by_shape.items(), key=lambda kv: kv[1][0])
         (tn, tD, tci, tco, tk, ts, tflop), (t_ms, cnt) = top
         ach = tflop * cnt / (t_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "conv3d_tc_kernel",
+        slab3 = tk == 3 and ts == 1 and tD % 16 == 0 and tci in (32, 64, 128) and tco <= 128 and \
+            tco % (32 if tci <= 64 else 16) == 0
+        roof = {"bound": "tensor",
+                "kernel": ("conv3d_slab3_kernel" if slab3 else "conv3d_tc_kernel") + " (nm_conv3d_tc, tcgen05 implicit GEMM)",
                 "layer": f"n={tn} grid={tD} Cin={tci} Cout={tco} k={tk} s={ts}", "achieved": ach,
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of the dec.8 launch (60 frames) from the ncu --set full

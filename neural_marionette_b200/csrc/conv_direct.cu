@@ -49,6 +49,8 @@ first_conv_kernel(const float* __restrict__ occ, const float* __restrict__ wocc,
                   const float* __restrict__ bias, const float* __restrict__ lin, int G, act_t* __restrict__ out) {
   // tile: 4 (x) x 8 (y) x 8 (z) outputs, halo 8 x 12 x 12
   __shared__ float halo[8][12][12];
+  __shared__ uint32_t hbits[8][12];        // bit z of [hx][hy]: halo[hx][hy][z] != 0
+  __shared__ float4 s_lin[COUT];           // interior blocks: (K0 + bias, Sx, Sy, Sz) per channel
   extern __shared__ float s_w[];  // [125][COUT] weights, later reused as the [256][COUT] fp16 store staging (128*COUT floats)
   const int n = blockIdx.y;
   const int tz = G / 8, ty = G / 8;
@@ -69,19 +71,43 @@ first_conv_kernel(const float* __restrict__ occ, const float* __restrict__ wocc,
     any |= (v != 0.f);
   }
   const int block_any = __syncthreads_or(any);
-  if (block_any)
+  if (block_any) {
     for (int i = threadIdx.x; i < 125 * COUT / 4; i += 256)
       reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(wocc)[i];
+    if (threadIdx.x < 96) {
+      const int hx = threadIdx.x / 12, hy = threadIdx.x % 12;
+      uint32_t word = 0;
+#pragma unroll
+      for (int z = 0; z < 12; z++) word |= (halo[hx][hy][z] != 0.f ? 1u : 0u) << z;
+      hbits[hx][hy] = word;
+    }
+  }
+  // A block whose voxels are all >= 2 cells away from every face sees the full 5^3 window everywhere: the
+  // CoordConv term is then one affine function of (x, y, z) per channel (boundary class (2,2,2)).
+  const bool interior = x0 >= 2 && x0 + 4 <= G - 2 && y0 >= 2 && y0 + 8 <= G - 2 && z0 >= 2 && z0 + 8 <= G - 2;
+  if (interior && threadIdx.x >= 128 && threadIdx.x < 128 + COUT) {
+    const int c = threadIdx.x - 128;
+    const float step = 2.0f / (float)(G - 1);
+    const float2* t = reinterpret_cast<const float2*>(tables) + (long long)(62 * 3) * COUT;   // class (2,2,2) = 62
+    const float2 sx = __ldg(t + c), sy = __ldg(t + COUT + c), sz = __ldg(t + 2 * COUT + c);
+    s_lin[c] = make_float4(bias[c] + step * (sx.y + sy.y + sz.y), sx.x, sy.x, sz.x);
+  }
   __syncthreads();
 
   const int lz = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lx = threadIdx.x >> 6;
   const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
   float acc[COUT];
+  if (interior) {
+    const float lx_ = lin[x], ly_ = lin[y], lz_ = lin[z];
 #pragma unroll
-  for (int c = 0; c < COUT; c++) acc[c] = bias[c];
-
-  // CoordConv channels: per-class affine form
-  {
+    for (int c = 0; c < COUT; c++) {
+      const float4 k = s_lin[c];
+      acc[c] = fmaf(lx_, k.y, fmaf(ly_, k.z, fmaf(lz_, k.w, k.x)));
+    }
+  } else {
+    // CoordConv channels: per-class affine form
+#pragma unroll
+    for (int c = 0; c < COUT; c++) acc[c] = bias[c];
     const int p[3] = {x, y, z};
     int cls = 0;
 #pragma unroll
@@ -96,30 +122,36 @@ first_conv_kernel(const float* __restrict__ occ, const float* __restrict__ wocc,
       const float2* t = reinterpret_cast<const float2*>(tables) + ((long long)cls * 3 + a) * COUT;
 #pragma unroll
       for (int c = 0; c < COUT; c++) {
-        const float2 s = __ldg(t + c);
-        acc[c] = fmaf(base, s.x, fmaf(step, s.y, acc[c]));
+        const float2 sv = __ldg(t + c);
+        acc[c] = fmaf(base, sv.x, fmaf(step, sv.y, acc[c]));
       }
     }
   }
-  // occupancy channel: only non-zero taps
+  // occupancy channel: only non-zero taps.  One 5-bit row mask per (kx, ky) from the bit-halo replaces five
+  // per-tap loads + tests; a tap's FMA block still runs once per warp when any lane has a hit.
   if (block_any) {
     for (int kx = 0; kx < 5; kx++)
-      for (int ky = 0; ky < 5; ky++)
 #pragma unroll
-        for (int kz = 0; kz < 5; kz++) {
-          const float v = halo[lx + kx][ly + ky][lz + kz];
-          if (v != 0.f) {
-            const float4* wr = reinterpret_cast<const float4*>(s_w + ((kx * 5 + ky) * 5 + kz) * COUT);
+      for (int ky = 0; ky < 5; ky++) {
+        const uint32_t m = (hbits[lx + kx][ly + ky] >> lz) & 31u;
+        if (__any_sync(0xffffffffu, m != 0)) {
 #pragma unroll
-            for (int c4 = 0; c4 < COUT / 4; c4++) {
-              const float4 w4 = wr[c4];
-              acc[c4 * 4 + 0] = fmaf(v, w4.x, acc[c4 * 4 + 0]);
-              acc[c4 * 4 + 1] = fmaf(v, w4.y, acc[c4 * 4 + 1]);
-              acc[c4 * 4 + 2] = fmaf(v, w4.z, acc[c4 * 4 + 2]);
-              acc[c4 * 4 + 3] = fmaf(v, w4.w, acc[c4 * 4 + 3]);
+          for (int kz = 0; kz < 5; kz++) {
+            if ((m >> kz) & 1u) {
+              const float v = halo[lx + kx][ly + ky][lz + kz];
+              const float4* wr = reinterpret_cast<const float4*>(s_w + ((kx * 5 + ky) * 5 + kz) * COUT);
+#pragma unroll
+              for (int c4 = 0; c4 < COUT / 4; c4++) {
+                const float4 w4 = wr[c4];
+                acc[c4 * 4 + 0] = fmaf(v, w4.x, acc[c4 * 4 + 0]);
+                acc[c4 * 4 + 1] = fmaf(v, w4.y, acc[c4 * 4 + 1]);
+                acc[c4 * 4 + 2] = fmaf(v, w4.z, acc[c4 * 4 + 2]);
+                acc[c4 * 4 + 3] = fmaf(v, w4.w, acc[c4 * 4 + 3]);
+              }
             }
           }
         }
+      }
   }
   // Stage the block's 256 voxel rows in shared memory (reusing the weight buffer), then write them out with
   // fully coalesced 16-byte stores: per-thread row stores touch a different cache line in every lane.
