@@ -55,44 +55,47 @@ gn_stats_kernel(const act_t* __restrict__ x, int S, int C, int chunks, float* __
   }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float* __restrict__ partial, int S, int C, int groups, int chunks,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    float* __restrict__ scale, float* __restrict__ shift) {
-  // one block per sample; warp w handles groups w, w+4, ...: lanes stride over (chunk, channel-in-group)
-  // pairs in a fixed order, fp64 accumulation, xor-shuffle tree -> deterministic
-  const int n = blockIdx.x;
+  // one block per (sample, group): 256 threads stride over the (chunk, channel-in-group) partials in a fixed
+  // order, fp64 accumulation, shuffle tree + fixed-order fold of the 8 warps -> deterministic.  (The conv
+  // epilogues emit up to 1024 chunks per sample; a single warp per group was latency-bound at ~20 us.)
+  const int n = blockIdx.x, g = blockIdx.y;
   const int cpg = C / groups;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __shared__ double s_mean[32], s_rstd[32];
-  for (int g = warp; g < groups; g += 4) {
-    double sum = 0.0, sq = 0.0;
-    const int items = chunks * cpg;
-    for (int i = lane; i < items; i += 32) {
-      const int k = i / cpg, c = g * cpg + i % cpg;
-      const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)n * chunks + k) * C + c) * 2);
-      sum += (double)v.x;
-      sq += (double)v.y;
-    }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double sum = 0.0, sq = 0.0;
+  const int items = chunks * cpg;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const int k = i / cpg, c = g * cpg + i % cpg;
+    const float2 v = *reinterpret_cast<const float2*>(partial + (((long long)n * chunks + k) * C + c) * 2);
+    sum += (double)v.x;
+    sq += (double)v.y;
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    }
-    if (lane == 0) {
-      const double cnt = (double)S * cpg;
-      const double mean = sum / cnt;
-      const double var = fmax(sq / cnt - mean * mean, 0.0);
-      s_mean[g] = mean;
-      s_rstd[g] = 1.0 / sqrt(var + (double)eps);
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  }
+  __shared__ double s_part[8][2];
+  __shared__ double s_stat[2];
+  if (lane == 0) { s_part[warp][0] = sum; s_part[warp][1] = sq; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, q = 0.0;
+    for (int w = 0; w < 8; w++) { a += s_part[w][0]; q += s_part[w][1]; }
+    const double cnt = (double)S * cpg;
+    const double mean = a / cnt;
+    const double var = fmax(q / cnt - mean * mean, 0.0);
+    s_stat[0] = mean;
+    s_stat[1] = 1.0 / sqrt(var + (double)eps);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double a = (double)gamma[c] * s_rstd[g];
+  for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += 256) {
+    const double a = (double)gamma[c] * s_stat[1];
     scale[(long long)n * C + c] = (float)a;
-    shift[(long long)n * C + c] = (float)((double)beta[c] - s_mean[g] * a);
+    shift[(long long)n * C + c] = (float)((double)beta[c] - s_stat[0] * a);
   }
 }
 
@@ -348,6 +351,9 @@ final_recon_kernel(const act_t* __restrict__ x, const float* __restrict__ a, con
                    const float* __restrict__ w, float bias, const float* __restrict__ first_frame,
                    int frames_per_clip, float sharp, float trans, float* __restrict__ recon,
                    const float* __restrict__ target, float* __restrict__ bce_partial, int S) {
+  // C/8 lanes per voxel: each loads one 16-byte channel chunk (consecutive lanes -> consecutive addresses),
+  // partial dot product, shuffle-reduce inside the lane group
+  constexpr int LPV = C / 8;                       // lanes per voxel (4 for C = 32)
   const int n = blockIdx.y;
   __shared__ float sa[C], sb[C], sw[C];
   if (threadIdx.x < C) {
@@ -357,23 +363,26 @@ final_recon_kernel(const act_t* __restrict__ x, const float* __restrict__ a, con
   }
   __syncthreads();
   const int clip = n / frames_per_clip;
+  const int sub = threadIdx.x % LPV;
   float loss = 0.f;
-  for (int s = blockIdx.x * 256 + threadIdx.x; s < S; s += gridDim.x * 256) {
-    const half8* p = reinterpret_cast<const half8*>(x + ((long long)n * S + s) * C);
-    float acc = bias;
+  const half8* base = reinterpret_cast<const half8*>(x + (long long)n * S * C);
+  for (int s = blockIdx.x * (256 / LPV) + threadIdx.x / LPV; s < S; s += gridDim.x * (256 / LPV)) {
+    float f[8];
+    nm_unpack8(base[(long long)s * LPV + sub], f);
+    float acc = 0.f;
 #pragma unroll
-    for (int j = 0; j < C / 8; j++) {
-      float f[8];
-      nm_unpack8(p[j], f);
+    for (int k = 0; k < 8; k++) acc = fmaf(nm_lrelu(fmaf(f[k], sa[sub * 8 + k], sb[sub * 8 + k])), sw[sub * 8 + k], acc);
 #pragma unroll
-      for (int k = 0; k < 8; k++) acc = fmaf(nm_lrelu(fmaf(f[k], sa[j * 8 + k], sb[j * 8 + k])), sw[j * 8 + k], acc);
-    }
-    const float z = sharp * (tanhf(acc) + first_frame[(long long)clip * S + s] - trans);
-    const float r = 1.0f / (1.0f + expf(-z));
-    recon[(long long)n * S + s] = r;
-    if (target) {
-      const float t = target[(long long)n * S + s];
-      loss -= t * fmaxf(logf(r), -100.f) + (1.f - t) * fmaxf(logf(1.f - r), -100.f);
+    for (int o = LPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sub == 0) {
+      acc += bias;
+      const float z = sharp * (tanhf(acc) + first_frame[(long long)clip * S + s] - trans);
+      const float r = 1.0f / (1.0f + expf(-z));
+      recon[(long long)n * S + s] = r;
+      if (target) {
+        const float t = target[(long long)n * S + s];
+        loss -= t * fmaxf(logf(r), -100.f) + (1.f - t) * fmaxf(logf(1.f - r), -100.f);
+      }
     }
   }
   if (bce_partial) {
@@ -475,7 +484,7 @@ extern "C" int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int 
   const int chunks = nm_gn_stats_chunks(S);
   gn_stats_kernel<<<dim3(chunks, n), kStatThreads, 0, st>>>((const act_t*)x, S, C, chunks, (float*)workspace);
   NM_CHECK_LAUNCH("gn_stats");
-  gn_finalize_kernel<<<n, 128, 0, st>>>((const float*)workspace, S, C, groups, chunks, gamma, beta, eps, scale, shift);
+  gn_finalize_kernel<<<dim3(n, groups), 256, 0, st>>>((const float*)workspace, S, C, groups, chunks, gamma, beta, eps, scale, shift);
   NM_CHECK_LAUNCH("gn_finalize");
   return NM_OK;
 }
@@ -489,7 +498,7 @@ extern "C" int nm_groupnorm_finalize(const float* partial, int n, int S, int C, 
   NM_CHECK_ARG(groups > 0 && groups <= 32 && C % groups == 0 && chunks > 0, "nm_groupnorm_finalize: bad C=%d groups=%d chunks=%d",
                C, groups, chunks);
   if (n == 0) return NM_OK;
-  gn_finalize_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(partial, S, C, groups, chunks, gamma, beta, eps, scale, shift);
+  gn_finalize_kernel<<<dim3(n, groups), 256, 0, (cudaStream_t)stream>>>(partial, S, C, groups, chunks, gamma, beta, eps, scale, shift);
   NM_CHECK_LAUNCH("gn_finalize");
   return NM_OK;
 }
