@@ -51,6 +51,15 @@ int nm_conv3d_tc(const void* x, const void* packed_w, const float* bias, void* o
  * per-sample partial (sum, sum of squares) of its fp32 output to stats_partial [n][chunks][Cout][2]; feed them
  * to nm_groupnorm_finalize instead of re-reading the tensor with nm_groupnorm_scale_shift. */
 int nm_conv3d_stats_chunks(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);
+/* Same conv with the producing layer's GroupNorm (+LeakyReLU) fused into the operand path: the input is the RAW
+ * output of the previous conv and x <- act(x * in_scale[n][c] + in_shift[n][c]) is applied to each halo slice in
+ * shared memory before the MMAs read it (zero padding preserved), so the activated tensor is never written to HBM
+ * (replaces the nn.GroupNorm + nn.LeakyReLU between two convs, modules/vox_modules.py:26-32,
+ * model/kypt_detector.py:429-453).  Only where nm_conv3d_can_fuse_input(...) == 1. */
+int nm_conv3d_can_fuse_input(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);
+int nm_conv3d_tc_fused(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
+                       int Cin, int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
+                       float* stats_partial, void* stream);
 /* same contract on CUDA cores from the raw fp32 weight; on-device cross-check of nm_conv3d_tc */
 int nm_conv3d_direct(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H, int W,
                      int Cin, int Cout, int k, int stride, int pad, void* stream);

@@ -38,6 +38,8 @@ PROTOTYPES = {
     "nm_pack_conv_weights": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nm_conv3d_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "nm_conv3d_stats_chunks": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_can_fuse_input": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_tc_fused": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "nm_groupnorm_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
     "nm_conv3d_direct": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_conv_transpose3d_k2s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),

@@ -110,6 +110,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -380,6 +388,10 @@ struct ConvSlabParams {
   int ring;               // slab3: ring slots actually used (2..4)
   int debug;              // NM_SLAB_DEBUG bit mask (profiling experiments only): 1 no stores, 2 no MMAs, 4 no A loads
   float* stats;           // slab3: optional GroupNorm partials [n][nh*nw*4][Cout][2] (sum, sum of squares)
+  const float* in_scale;  // slab3: optional fused input transform x <- act(x * in_scale[n][c] + in_shift[n][c]),
+  const float* in_shift;  //        i.e. the GroupNorm (+LeakyReLU) of the producing layer applied on the halo
+  int in_act;             //        slice in shared memory (zero padding preserved); (n, Cin) fp32 each
+  int cin;
   const float* bias;
   act_t* out;
 };
@@ -572,9 +584,10 @@ constexpr int kPGroups = 5;    // 5 x 96 TMEM columns = 480 <= 512
 // Cin = 128 so that the 27 x kchunks resident weight tiles still fit); MMA N = 3 * PN.
 constexpr int kSlab3EpiWarps = 8;
 constexpr int kSlab3Threads = 64 + 32 * kSlab3EpiWarps;
+constexpr int kSlab3XformWarps = 4;   // extra warps (only launched when the input transform is fused)
 
 template <int BK, int PN>
-__global__ void __launch_bounds__(kSlab3Threads, 1)
+__global__ void __launch_bounds__(kSlab3Threads + 32 * kSlab3XformWarps, 1)
 conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -591,7 +604,10 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   uint64_t* pfull = empty + kSlabRing;    // [groups] P group complete
   uint64_t* pempty = pfull + kPGroups;    // [groups] P group drained
   uint64_t* wfull = pempty + kPGroups;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* ready = wfull + 1;            // [ring]   slice transformed (fused input GroupNorm / LeakyReLU)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kSlabRing);
+  float* s_ab = reinterpret_cast<float*>(tmem_slot + 4);   // [2][Cin] scale | shift of the current sample
+  const bool xform = p.in_scale != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.N * p.nh * p.nw;
@@ -608,6 +624,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_o) : "memory");
     for (int s = 0; s < kSlabRing; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < kPGroups; s++) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], kSlab3EpiWarps); }
+    for (int s = 0; s < kSlabRing; s++) mbar_init(&ready[s], kSlab3XformWarps);
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -623,6 +640,77 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     printf("nm_conv3d_tc(slab3): unexpected TMEM base %u\n", *tmem_slot);
     __trap();
   }
+
+  if (warp >= 2 + kSlab3EpiWarps) {
+    // ===================== input transform (warps 10..13, only with a fused prologue) =====================
+    // The GroupNorm affine (+LeakyReLU) of the producing layer is applied to each halo slice in place, once,
+    // before the 9 x kchunks x BK/16 MMAs read it: the activated tensor never exists in HBM.  Rows outside the
+    // tensor stay zero (conv padding applies to the activated tensor).  The 16-byte chunk c of row r sits at
+    // position c ^ ((r * row_bytes >> 7) & mask) (TMA 128B / 64B swizzle on a 1 KiB-aligned slot).
+    constexpr int row_bytes = BK * 2;
+    constexpr int cpr = row_bytes / 16;                  // chunks per row: 8 (SW128) or 4 (SW64)
+    const int tid = threadIdx.x - 32 * (2 + kSlab3EpiWarps);
+    // thread <-> (logical 16-byte channel chunk lc, rows r0, r0 + rstep, ...): a warp covers whole rows
+    const int lc = tid % cpr, r0 = tid / cpr;
+    constexpr int rstep = 32 * kSlab3XformWarps / cpr;
+    uint32_t fill = 0;
+    int cur_n = -1;
+    for (int col = col0; col < n_cols; col += col_step) {
+      int t = col;
+      const int iw = t % p.nw; t /= p.nw;
+      const int ih = t % p.nh; t /= p.nh;
+      const int n = t;
+      if (n != cur_n) {                                  // (re)load this sample's scale / shift
+        named_bar_sync(2, 32 * kSlab3XformWarps);
+        for (int i = tid; i < p.cin; i += 32 * kSlab3XformWarps) {
+          s_ab[i] = p.in_scale[(long long)n * p.cin + i];
+          s_ab[p.cin + i] = p.in_shift[(long long)n * p.cin + i];
+        }
+        named_bar_sync(2, 32 * kSlab3XformWarps);
+        cur_n = n;
+      }
+      for (int dz = 0; dz < p.D; dz++, fill++) {
+        const int slot = fill % ring;
+        mbar_wait(&full[slot], (fill / ring) & 1);
+        uint8_t* base = s_ring + (size_t)slot * p.slot_bytes;
+        for (int kc = 0; kc < p.kchunks; kc++) {
+          // this thread's 8 channels: logical chunk lc of k-chunk kc (scale / shift stay in registers)
+          float sc[8], sh[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            sc[k] = s_ab[kc * BK + lc * 8 + k];
+            sh[k] = s_ab[p.cin + kc * BK + lc * 8 + k];
+          }
+          const uint32_t cbase = smem_u32(base) + (uint32_t)kc * p.chunk_bytes;   // shared-space address
+          int hh = r0 / kHaloW, ww = r0 % kHaloW;          // rstep rows further = (rstep / 10, rstep % 10) steps
+          for (int r = r0; r < kHaloW * kHaloH; r += rstep) {
+            const int h = ih * 16 - 1 + hh, w = iw * 8 - 1 + ww;
+            if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) {
+              const int pc = lc ^ (row_bytes == 128 ? (r & 7) : ((r >> 1) & 3));
+              const uint32_t addr = cbase + r * row_bytes + pc * 16;
+              uint4 raw = lds128(addr);
+              half8 hv = *reinterpret_cast<half8*>(&raw);
+              float f[8];
+              nm_unpack8(hv, f);
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                const float v = fmaf(f[k], sc[k], sh[k]);
+                f[k] = p.in_act ? nm_lrelu(v) : v;
+              }
+              hv = nm_pack8(f);
+              sts128(addr, *reinterpret_cast<uint4*>(&hv));
+            }
+            ww += rstep % kHaloW;
+            hh += rstep / kHaloW;
+            if (ww >= kHaloW) { ww -= kHaloW; hh++; }
+          }
+        }
+        fence_async_smem();                              // generic-proxy writes -> visible to the UMMA reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[slot]);
+      }
+    }
+  } else
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -665,7 +753,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     uint32_t q = 0;                                      // global slice counter (ring + P-group position)
     for (int col = col0; col < n_cols; col += col_step) {
       for (int sl = 0; sl < p.D; sl++, q++) {
-        mbar_wait(&full[q % ring], (q / ring) & 1);
+        mbar_wait(xform ? &ready[q % ring] : &full[q % ring], (q / ring) & 1);
         mbar_wait(&pempty[q % kPGroups], ((q / kPGroups) & 1) ^ 1);
         tc_fence_after();
         __syncwarp();
@@ -880,7 +968,7 @@ ConvPlan plan_conv(int n, int D, int H, int W, int Cin, int Cout, int k, int str
   const size_t w_bytes = (size_t)27 * pl.kch * (pl.use3 ? pl.pn : pl.ntile) * pl.bk * 2;
   pl.chunk_bytes = ((kHaloW * kHaloH * pl.bk * 2 + 1023) / 1024) * 1024;
   pl.ring = kSlabRing;
-  const size_t extra = 1024 + 32 * 8 + 16 + (pl.use3 ? (size_t)2 * kTileM * pl.pn * 2 : 0);
+  const size_t extra = 1024 + 40 * 8 + 16 + 2 * 256 * 4 + (pl.use3 ? (size_t)2 * kTileM * pl.pn * 2 : 0);
   if (pl.use3)
     while (pl.ring > 2 && w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra > 227 * 1024) pl.ring--;
   pl.need = w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra;
@@ -905,8 +993,28 @@ extern "C" int nm_conv3d_stats_chunks(int n, int D, int H, int W, int Cin, int C
   return plan_conv(n, D, H, W, Cin, Cout, k, stride).stats_chunks;
 }
 
+// 1 when nm_conv3d_tc_fused can apply the producer's GroupNorm scale/shift (+LeakyReLU) to its input on the fly
+extern "C" int nm_conv3d_can_fuse_input(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
+  // Measured on B200: the in-smem transform pays off when a slice carries enough MMA work to hide it and is not
+  // repeated by many output-channel parts: Cin = 64 (one 128-byte k-chunk), Cout <= 64.  For Cin = 32 (dec.11)
+  // and Cin = 128 with 8 parts the separate HBM-bound affine pass is faster.
+  const ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, k, stride);
+  return pl.slab && pl.use3 && pl.kch == 1 && pl.bk == 64 && Cout <= 64 ? 1 : 0;
+}
+
+extern "C" int nm_conv3d_tc_fused(const void* x, const void* packed_w, const float* bias, void* out, int n, int D,
+                                  int H, int W, int Cin, int Cout, int k, int stride, const float* in_scale,
+                                  const float* in_shift, int in_act, float* stats_partial, void* stream);
+
 extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H,
                             int W, int Cin, int Cout, int k, int stride, float* stats_partial, void* stream) {
+  return nm_conv3d_tc_fused(x, packed_w, bias, out, n, D, H, W, Cin, Cout, k, stride, nullptr, nullptr, 0,
+                            stats_partial, stream);
+}
+
+extern "C" int nm_conv3d_tc_fused(const void* x, const void* packed_w, const float* bias, void* out, int n, int D,
+                                  int H, int W, int Cin, int Cout, int k, int stride, const float* in_scale,
+                                  const float* in_shift, int in_act, float* stats_partial, void* stream) {
   NM_CHECK_ARG(x && packed_w && bias && out, "nm_conv3d_tc: null pointer");
   NM_CHECK_ARG((stride == 1 && (k == 1 || k == 3)) || (stride == 2 && k == 2), "nm_conv3d_tc: k=%d stride=%d unsupported",
                k, stride);
@@ -922,6 +1030,9 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
   // ---- slab-walking kernels: k3, weights resident in smem
   const ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, k, stride);
   NM_CHECK_ARG(!stats_partial || pl.stats_chunks > 0, "nm_conv3d_tc: this shape cannot fuse GroupNorm statistics");
+  NM_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "nm_conv3d_tc: in_scale and in_shift go together");
+  NM_CHECK_ARG(!in_scale || (pl.slab && pl.use3 && Cin <= 256),
+               "nm_conv3d_tc: this shape cannot fuse the input transform (see nm_conv3d_can_fuse_input)");
   {
     const int bk = pl.bk, kch = pl.kch, ntile = pl.ntile, pn = pl.pn, ring = pl.ring, chunk_bytes = pl.chunk_bytes;
     const bool use3 = pl.use3;
@@ -934,6 +1045,7 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
       q.chunk_bytes = chunk_bytes; q.slot_bytes = kch * chunk_bytes; q.ring = ring;
       { const char* dbg = getenv("NM_SLAB_DEBUG"); q.debug = dbg ? atoi(dbg) : 0; }
       q.bias = bias; q.out = (act_t*)out; q.stats = use3 ? stats_partial : nullptr;
+      q.in_scale = in_scale; q.in_shift = in_shift; q.in_act = in_act; q.cin = Cin;
       const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
       cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
       cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
@@ -979,9 +1091,10 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           slab3_attr = true;
         }
-        if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, kSlab3Threads, need, (cudaStream_t)stream>>>(q);
-        else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, kSlab3Threads, need, (cudaStream_t)stream>>>(q);
-        else conv3d_slab3_kernel<32, 32><<<grid, kSlab3Threads, need, (cudaStream_t)stream>>>(q);
+        const int threads3 = kSlab3Threads + (in_scale ? 32 * kSlab3XformWarps : 0);
+        if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+        else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+        else conv3d_slab3_kernel<32, 32><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
       } else if (bk == 64) conv3d_slab_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       else conv3d_slab_kernel<32><<<grid, 192, need, (cudaStream_t)stream>>>(q);
       NM_CHECK_LAUNCH("conv3d_slab");

@@ -145,6 +145,14 @@ class KyptToVoxNet(nn.Module):
             nn.Conv3d(f // 4, f // 4, 3, 1, 1), nn.GroupNorm(f // 64, f // 4), nn.LeakyReLU(),
             nn.Conv3d(f // 4, 1, kernel_size=1))
 
+    @staticmethod
+    def _conv_after_gn(raw, a, b, conv, gn):
+        """conv(LeakyReLU(GroupNorm(raw))): the normalisation is fused into the conv's operand path when the
+        kernel supports it, otherwise applied by a separate pass."""
+        if ops.can_fuse_input(raw, conv):
+            return ops.conv3d(raw, conv, gn, in_affine=(a, b, True))
+        return ops.conv3d(ops.affine_act(raw, a, b, True), conv, gn)
+
     def decode(self, first_feature_act, first_frame, keypoints=None, gaussians=None, sigma=1.5, sharpness=10.0,
                translation=0.5, target=None):
         """first_feature_act (B, g, g, g, 128) act; first_frame (B, 1, G, G, G); keypoints (B, T, K, 4) or
@@ -172,14 +180,12 @@ class KyptToVoxNet(nn.Module):
                                        sigma, keypoints=kp, gaussians=gs)
                 x = ops.upsample2x(x)
                 raw, a, b = ops.conv3d(x, dec[1], dec[2])
-                x = ops.affine_act(raw, a, b, True)
-                raw, a, b = ops.conv3d(x, dec[4], dec[5])
+                raw, a, b = self._conv_after_gn(raw, a, b, dec[4], dec[5])
                 # GroupNorm affine + LeakyReLU on the low-resolution tensor (HBM-bound, 8x fewer elements than the
                 # output), then the half2 interpolation kernel: fewer instructions than the fused variant
                 x = ops.upsample2x(ops.affine_act(raw, a, b, True))
                 raw, a, b = ops.conv3d(x, dec[8], dec[9])
-                x = ops.affine_act(raw, a, b, True)
-                raw, a, b = ops.conv3d(x, dec[11], dec[12])
+                raw, a, b = self._conv_after_gn(raw, a, b, dec[11], dec[12])
                 tgt = target[b0:b1].view(n, G, G, G) if target is not None else None
                 ops.final_recon(raw, a, b, dec[14], first_frame[b0:b1], T, sharpness, translation, target=tgt,
                                 out=recon[b0:b1].view(n, G, G, G),

@@ -67,8 +67,12 @@ class Res3DBlock(_ActModule):
                 nn.Conv3d(in_planes, out_planes, kernel_size=1, stride=1, padding=0), _norm(out_planes))
 
     def run(self, x):
-        h = conv_gn_lrelu(x, self.res_branch[0], self.res_branch[1])
-        raw, a, b = ops.conv3d(h, self.res_branch[3], self.res_branch[4])
+        raw1, a1, b1 = ops.conv3d(x, self.res_branch[0], self.res_branch[1])
+        if ops.can_fuse_input(raw1, self.res_branch[3]):
+            # GroupNorm + LeakyReLU of the first conv applied inside the second conv's operand path
+            raw, a, b = ops.conv3d(raw1, self.res_branch[3], self.res_branch[4], in_affine=(a1, b1, True))
+        else:
+            raw, a, b = ops.conv3d(ops.affine_act(raw1, a1, b1, True), self.res_branch[3], self.res_branch[4])
         if len(self.skip_con) == 0:
             return ops.affine_act(raw, a, b, False, x2=x)
         sraw, sa, sb = ops.conv3d(x, self.skip_con[0], self.skip_con[1])

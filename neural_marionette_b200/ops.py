@@ -118,8 +118,17 @@ def _tc_ok(conv, Cin):
         ((s == 1 and k in (1, 3) and conv.padding[0] == (k - 1) // 2) or (s == 2 and k == 2 and conv.padding[0] == 0))
 
 
-def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None):
+def can_fuse_input(x: torch.Tensor, conv: torch.nn.Conv3d) -> bool:
+    """True when conv3d(x, conv, in_affine=...) can apply the producer's GroupNorm (+LeakyReLU) on the fly."""
+    n, D, H, W, Cin = x.shape
+    return _tc_ok(conv, Cin) and bool(L.query("nm_conv3d_can_fuse_input", n, D, H, W, Cin, conv.out_channels,
+                                              conv.kernel_size[0], conv.stride[0]))
+
+
+def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
     """act (n, D, H, W, Cin) -> raw conv output act (n, OD, OH, OW, Cout); bias included.
+    `in_affine` = (scale, shift, act): x is the RAW output of the previous conv and act(x*scale+shift) is applied
+    inside the kernel's operand path (only when can_fuse_input(x, conv)).
     With `gn`: returns (raw, scale, shift) of the GroupNorm that follows; the statistics come out of the conv
     epilogue when the kernel supports it (no extra pass over the output), else from a reduction kernel."""
     _need_cuda(x)
@@ -127,6 +136,7 @@ def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNo
     k, s, Cout = conv.kernel_size[0], conv.stride[0], conv.out_channels
     assert Cin == conv.in_channels and x.dtype == ACT_DTYPE and x.is_contiguous()
     if not _tc_ok(conv, Cin):
+        assert in_affine is None
         out = conv3d_direct(x, conv)
         return (out,) + gn_scale_shift(out, gn) if gn is not None else out
     out = torch.empty(n, D // s, H // s, W // s, Cout, dtype=ACT_DTYPE, device=x.device)
@@ -138,8 +148,12 @@ def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNo
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    L.call("nm_conv3d_tc", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
-           L.ptr(partial), L.stream())
+    if in_affine is None:
+        L.call("nm_conv3d_tc", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
+               L.ptr(partial), L.stream())
+    else:
+        L.call("nm_conv3d_tc_fused", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
+               L.ptr(in_affine[0]), L.ptr(in_affine[1]), int(in_affine[2]), L.ptr(partial), L.stream())
     if PROFILE is not None:
         e1.record()
         flops = 2.0 * n * (D // s) * (H // s) * (W // s) * Cout * Cin * k ** 3

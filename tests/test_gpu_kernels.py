@@ -139,6 +139,32 @@ def test_conv3d_tc(ops, n, grid, cin, cout, k, stride):
         assert (a - a2).abs().max() <= 2e-3 * a2.abs().max() and (b - b2).abs().max() <= 2e-3 * (1 + b2.abs().max())
 
 
+@pytest.mark.parametrize("n,grid,cin,cout", [(2, 16, 64, 64), (1, 32, 64, 32), (3, 16, 64, 64)])
+def test_conv3d_fused_input_groupnorm(ops, n, grid, cin, cout):
+    """conv(LeakyReLU(GroupNorm(raw))) with the normalisation applied inside the conv's operand path."""
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    conv = torch.nn.Conv3d(cin, cout, 3, 1, 1).cuda()
+    gn_out = torch.nn.GroupNorm(cout // 16, cout).cuda()
+    raw_in = to_act(torch.randn(n, cin, grid, grid, grid, generator=g) * 1.5 + 0.3)
+    a = (0.5 + torch.rand(n, cin, generator=g)).cuda()
+    b = torch.randn(n, cin, generator=g).cuda()
+    assert ops.can_fuse_input(raw_in, conv)
+    assert not ops.can_fuse_input(to_act(torch.zeros(1, 32, 16, 16, 16)), torch.nn.Conv3d(32, 32, 3, 1, 1).cuda())
+    ref_in = ops.affine_act(raw_in, a, b, True)                       # separate pass (rounds to fp16)
+    ref, ra, rb = ops.conv3d(ref_in, conv, gn_out)
+    got, ga, gb = ops.conv3d(raw_in, conv, gn_out, in_affine=(a, b, True))
+    torch.cuda.synchronize()
+    assert rel_err(got.float().cpu(), ref.float().cpu()) < 2e-3      # same arithmetic up to fp16 rounding order
+    assert (ga - ra).abs().max() <= 2e-3 * ra.abs().max() and (gb - rb).abs().max() <= 2e-3 * (1 + rb.abs().max())
+    # borders: the zero padding must stay zero AFTER the affine (shift != 0)
+    x = torch.zeros(1, cin, grid, grid, grid)
+    x[:, :, 0, 0, 0] = 1.0
+    a1, b1 = torch.ones(1, cin).cuda(), torch.full((1, cin), 0.7).cuda()
+    got = ops.conv3d(to_act(x), conv, in_affine=(a1, b1, False))
+    ref = ops.conv3d(ops.affine_act(to_act(x), a1, b1, False), conv)
+    assert rel_err(got.float().cpu(), ref.float().cpu()) < 2e-3
+
+
 def test_first_conv_coordconv(ops):
     for G, cout in [(16, 32), (32, 64)]:
         g = torch.Generator().manual_seed(G + cout)
