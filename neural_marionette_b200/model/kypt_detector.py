@@ -24,9 +24,10 @@ from ..utils.kypt_detector_utils import (get_graph_consistency_loss, get_graph_t
                                          get_temporal_separation_loss, get_volume_fitting_loss,
                                          sparsity_loss_from_means)
 
-# frames pushed through the conv stack per pass (bounds activation memory: the widest tensor is the
-# decoder's up-sampled 64ch @ G^3 input = 33.5 MB/frame at G = 64)
-FRAME_CHUNK = 64
+# Frames pushed through the conv stack per pass.  Bounds activation memory (the widest tensor is the decoder's
+# up-sampled 64 ch @ G^3 input = 33.5 MB/frame at G = 64 -> ~11 GB at 320 frames) while keeping every launch large:
+# measured on B200 (B = 64, T = 20): 20 frames/pass 369 ms/step, 60 -> 281, 120 -> 263, 320 -> 251, 1280 -> 250.
+FRAME_CHUNK = int(__import__("os").environ.get("NM_FRAME_CHUNK", "320"))
 
 
 def _no_training(module):
