@@ -61,27 +61,31 @@ first_conv_kernel(const float* __restrict__ occ, const float* __restrict__ wocc,
   const int x0 = bx * 4, y0 = by * 8, z0 = bz * 8;
   const float* src = occ + (long long)n * G * G * G;
   bool any = false;
-  for (int i = threadIdx.x; i < 8 * 12 * 12; i += 256) {
-    const int hz = i % 12, hy = (i / 12) % 12, hx = i / 144;
-    const int x = x0 + hx - 2, y = y0 + hy - 2, z = z0 + hz - 2;
-    float v = 0.f;
-    if ((unsigned)x < (unsigned)G && (unsigned)y < (unsigned)G && (unsigned)z < (unsigned)G)
-      v = src[((long long)x * G + y) * G + z];
-    halo[hx][hy][hz] = v;
-    any |= (v != 0.f);
+  // halo: 96 (x, y) rows of 12 z-values; one thread per row, six 8-byte loads (z0 - 2 is 8-byte aligned),
+  // the row's occupancy bit mask is built in the same pass
+  if (threadIdx.x < 96) {
+    const int hx = threadIdx.x / 12, hy = threadIdx.x % 12;
+    const int x = x0 + hx - 2, y = y0 + hy - 2;
+    const bool row_ok = (unsigned)x < (unsigned)G && (unsigned)y < (unsigned)G;
+    const float2* rp = reinterpret_cast<const float2*>(src + ((long long)x * G + y) * G + (z0 - 2));
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      const int z = z0 - 2 + 2 * j;                 // both elements of a pair are in or out together (G, z0 even)
+      float2 v = make_float2(0.f, 0.f);
+      if (row_ok && (unsigned)z < (unsigned)G) v = __ldg(rp + j);
+      halo[hx][hy][2 * j] = v.x;
+      halo[hx][hy][2 * j + 1] = v.y;
+      word |= (v.x != 0.f ? 1u : 0u) << (2 * j);
+      word |= (v.y != 0.f ? 1u : 0u) << (2 * j + 1);
+    }
+    hbits[hx][hy] = word;
+    any = word != 0;
   }
   const int block_any = __syncthreads_or(any);
-  if (block_any) {
+  if (block_any)
     for (int i = threadIdx.x; i < 125 * COUT / 4; i += 256)
       reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(wocc)[i];
-    if (threadIdx.x < 96) {
-      const int hx = threadIdx.x / 12, hy = threadIdx.x % 12;
-      uint32_t word = 0;
-#pragma unroll
-      for (int z = 0; z < 12; z++) word |= (halo[hx][hy][z] != 0.f ? 1u : 0u) << z;
-      hbits[hx][hy] = word;
-    }
-  }
   // A block whose voxels are all >= 2 cells away from every face sees the full 5^3 window everywhere: the
   // CoordConv term is then one affine function of (x, y, z) per channel (boundary class (2,2,2)).
   const bool interior = x0 >= 2 && x0 + 4 <= G - 2 && y0 >= 2 && y0 + 8 <= G - 2 && z0 >= 2 && z0 + 8 <= G - 2;
