@@ -280,12 +280,16 @@ adjust_frame_kernel(const float* __restrict__ base, const float* __restrict__ kp
                     const float* __restrict__ gs /* optional (n,K,S) */, const float* __restrict__ w, int ld,
                     int K, int g, int frames_per_clip, const float* __restrict__ lin, float gauss_width,
                     act_t* __restrict__ out) {
-  __shared__ float s_w[CO * KMAX];       // [CO][K]
+  // block: 64 voxels of one frame; thread <-> (voxel slot tid / 16, 8 output channels tid % 16), four rounds of 16
+  // voxels.  W^T [K][CO] and the Gaussian values of the 64 voxels are staged in shared memory; base reads and
+  // output stores are 16/32-byte vectors, contiguous across the 16 threads of a voxel.
+  __shared__ float s_wt[KMAX * CO];      // [K][CO]
   __shared__ float s_e[KMAX * 3 * 32];
   __shared__ float s_i[KMAX];
+  __shared__ float s_g[64 * KMAX];       // [voxel][K]
   const int n = blockIdx.y, clip = n / frames_per_clip;
   const int S = g * g * g;
-  for (int i = threadIdx.x; i < CO * K; i += 256) s_w[i] = w[(i / K) * ld + (i % K)];
+  for (int i = threadIdx.x; i < CO * K; i += 256) s_wt[(i % K) * CO + i / K] = w[(i / K) * ld + (i % K)];
   if (!gs) {
     for (int i = threadIdx.x; i < K * 3 * g; i += 256) {
       const int k = i / (3 * g), a = (i / g) % 3, j = i % g;
@@ -295,30 +299,41 @@ adjust_frame_kernel(const float* __restrict__ base, const float* __restrict__ kp
     for (int i = threadIdx.x; i < K; i += 256) s_i[i] = kp[((long long)n * K + i) * 4 + 3];
   }
   __syncthreads();
-  const int q = threadIdx.x & 3;
-  const int s = blockIdx.x * 64 + (threadIdx.x >> 2);
-  if (s >= S) return;
-  const int z = s % g, y = (s / g) % g, x = s / (g * g);
-  constexpr int PER = CO / 4;
-  float acc[PER];
-  const float4* bp = reinterpret_cast<const float4*>(base + ((long long)clip * S + s) * CO + q * PER);
-#pragma unroll
-  for (int j = 0; j < PER / 4; j++) {
-    const float4 v = bp[j];
-    acc[j * 4] = v.x; acc[j * 4 + 1] = v.y; acc[j * 4 + 2] = v.z; acc[j * 4 + 3] = v.w;
+  const int s0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 64 * K; i += 256) {
+    const int v = i / K, k = i % K, s = s0 + v;
+    float gv = 0.f;
+    if (s < S) {
+      if (gs) gv = gs[((long long)n * K + k) * S + s];
+      else {
+        const int z = s % g, y = (s / g) % g, x = s / (g * g);
+        gv = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + y]) * s_e[(k * 3 + 2) * 32 + z] * s_i[k];
+      }
+    }
+    s_g[v * KMAX + k] = gv;
   }
-  for (int k = 0; k < K; k++) {
-    float gv;
-    if (gs) gv = gs[((long long)n * K + k) * S + s];
-    else gv = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + y]) * s_e[(k * 3 + 2) * 32 + z] * s_i[k];
+  __syncthreads();
+  const int c8 = threadIdx.x & 15;
+#pragma unroll 1
+  for (int round = 0; round < 4; round++) {
+    const int v = round * 16 + (threadIdx.x >> 4), s = s0 + v;
+    if (s >= S) continue;
+    float acc[8];
+    const float4* bp = reinterpret_cast<const float4*>(base + ((long long)clip * S + s) * CO + c8 * 8);
+    const float4 b0 = bp[0], b1 = bp[1];
+    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    for (int k = 0; k < K; k++) {
+      const float gv = s_g[v * KMAX + k];
+      const float4 w0 = *reinterpret_cast<const float4*>(s_wt + k * CO + c8 * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_wt + k * CO + c8 * 8 + 4);
+      acc[0] = fmaf(gv, w0.x, acc[0]); acc[1] = fmaf(gv, w0.y, acc[1]); acc[2] = fmaf(gv, w0.z, acc[2]);
+      acc[3] = fmaf(gv, w0.w, acc[3]); acc[4] = fmaf(gv, w1.x, acc[4]); acc[5] = fmaf(gv, w1.y, acc[5]);
+      acc[6] = fmaf(gv, w1.z, acc[6]); acc[7] = fmaf(gv, w1.w, acc[7]);
+    }
 #pragma unroll
-    for (int j = 0; j < PER; j++) acc[j] = fmaf(gv, s_w[(q * PER + j) * K + k], acc[j]);
+    for (int j = 0; j < 8; j++) acc[j] = nm_lrelu(acc[j]);
+    *reinterpret_cast<half8*>(out + ((long long)n * S + s) * CO + c8 * 8) = nm_pack8(acc);
   }
-#pragma unroll
-  for (int j = 0; j < PER; j++) acc[j] = nm_lrelu(acc[j]);
-  half8* dst = reinterpret_cast<half8*>(out + ((long long)n * S + s) * CO + q * PER);
-#pragma unroll
-  for (int j = 0; j < PER / 8; j++) dst[j] = nm_pack8(acc + j * 8);
 }
 
 }  // namespace

@@ -366,23 +366,39 @@ final_recon_kernel(const act_t* __restrict__ x, const float* __restrict__ a, con
   const int sub = threadIdx.x % LPV;
   float loss = 0.f;
   const half8* base = reinterpret_cast<const half8*>(x + (long long)n * S * C);
-  for (int s = blockIdx.x * (256 / LPV) + threadIdx.x / LPV; s < S; s += gridDim.x * (256 / LPV)) {
-    float f[8];
-    nm_unpack8(base[(long long)s * LPV + sub], f);
-    float acc = 0.f;
+  // A group of LPV lanes handles LPV consecutive voxels per iteration: lane `sub` loads channel chunk `sub` of
+  // each of them, the partial dot products are transpose-reduced so that lane j ends up with the full sum of
+  // voxel j, and every lane then runs the tanh / sigmoid / log tail for ONE voxel (no divergent scalar tail).
+  const int groups_per_block = 256 / LPV;
+  for (int v0 = (blockIdx.x * groups_per_block + threadIdx.x / LPV) * LPV; v0 < S; v0 += gridDim.x * groups_per_block * LPV) {
+    float part[LPV];
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc = fmaf(nm_lrelu(fmaf(f[k], sa[sub * 8 + k], sb[sub * 8 + k])), sw[sub * 8 + k], acc);
+    for (int j = 0; j < LPV; j++) {
+      float f[8];
+      nm_unpack8(base[(long long)(v0 + j) * LPV + sub], f);
+      float acc = 0.f;
 #pragma unroll
-    for (int o = LPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (sub == 0) {
-      acc += bias;
-      const float z = sharp * (tanhf(acc) + first_frame[(long long)clip * S + s] - trans);
-      const float r = 1.0f / (1.0f + expf(-z));
-      recon[(long long)n * S + s] = r;
-      if (target) {
-        const float t = target[(long long)n * S + s];
-        loss -= t * fmaxf(logf(r), -100.f) + (1.f - t) * fmaxf(logf(1.f - r), -100.f);
+      for (int k = 0; k < 8; k++) acc = fmaf(nm_lrelu(fmaf(f[k], sa[sub * 8 + k], sb[sub * 8 + k])), sw[sub * 8 + k], acc);
+      part[j] = acc;
+    }
+    // recursive halving inside the LPV-lane group: after it, lane `sub` holds the total of voxel `sub`
+#pragma unroll
+    for (int half = LPV / 2; half >= 1; half >>= 1) {
+      const bool upper = (sub & half) != 0;
+#pragma unroll
+      for (int i = 0; i < half; i++) {
+        const float send = upper ? part[i] : part[i + half];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, half);
+        part[i] = (upper ? part[i + half] : part[i]) + recv;
       }
+    }
+    const int s = v0 + sub;
+    const float z = sharp * (tanhf(part[0] + bias) + first_frame[(long long)clip * S + s] - trans);
+    const float r = 1.0f / (1.0f + expf(-z));
+    recon[(long long)n * S + s] = r;
+    if (target) {
+      const float t = target[(long long)n * S + s];
+      loss -= t * fmaxf(logf(r), -100.f) + (1.f - t) * fmaxf(logf(1.f - r), -100.f);
     }
   }
   if (bce_partial) {
