@@ -12,167 +12,246 @@
 namespace {
 
 // ------------------------------------------------------------------ first layer
-// tables[cls][c][co][2]: cls = (cx*5+cy)*5+cz with per-axis class 0,1 (p=0,1), 2 (interior),
-// 3,4 (p=G-2,G-1); [0] = sum of valid-tap weights, [1] = sum of (k_c-2)*weight.
+// cls = (cx*5+cy)*5+cz with per-axis class 0,1 (p=0,1), 2 (interior), 3,4 (p=G-2,G-1).
+// cls_tab[cls][co] = (sum_a S1_a, S0_x, S0_y, S0_z) with S0_a = sum of the valid-tap weights of coordinate
+// channel a and S1_a = sum of (k_a - 2) * weight: the CoordConv term of a voxel of that class is
+// bias + step*.x + .y*lin[x] + .z*lin[y] + .w*lin[z], step = 2/(G-1).
+// wfrag[s][nb][lane]: the occupancy-channel weights as fp16 B fragments of mma.m16n8k16.  K index = s*16 + col,
+// col < 8: window row r = 2s (r = kx*5+ky), kz = col; col >= 8: r = 2s+1, kz = col-8; kz >= 5 and r = 25 are zero.
+constexpr int kFirstKSteps = 13;
+
 __global__ void first_conv_prep_kernel(const float* __restrict__ w /* (Cout,4,5,5,5) */, int Cout,
-                                       float* __restrict__ tables, float* __restrict__ wocc /* [125][Cout] */) {
+                                       float4* __restrict__ cls_tab, uint2* __restrict__ wfrag) {
   const int cls = blockIdx.x;
   const int cl[3] = {cls / 25, (cls / 5) % 5, cls % 5};
-  // valid tap range per class
   int lo[3], hi[3];
   for (int a = 0; a < 3; a++) {
     lo[a] = cl[a] == 0 ? 2 : (cl[a] == 1 ? 1 : 0);
     hi[a] = cl[a] == 4 ? 2 : (cl[a] == 3 ? 3 : 4);
   }
   for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
+    double s0[3], s1 = 0.0;
     for (int c = 0; c < 3; c++) {
-      double s0 = 0.0, s1 = 0.0;
+      s0[c] = 0.0;
       for (int kx = lo[0]; kx <= hi[0]; kx++)
         for (int ky = lo[1]; ky <= hi[1]; ky++)
           for (int kz = lo[2]; kz <= hi[2]; kz++) {
             const double v = (double)w[(((long long)co * 4 + 1 + c) * 5 + kx) * 25 + ky * 5 + kz];
             const int kc = c == 0 ? kx : (c == 1 ? ky : kz);
-            s0 += v;
+            s0[c] += v;
             s1 += v * (double)(kc - 2);
           }
-      tables[(((long long)cls * 3 + c) * Cout + co) * 2] = (float)s0;
-      tables[(((long long)cls * 3 + c) * Cout + co) * 2 + 1] = (float)s1;
     }
-    if (cls == 0)
-      for (int tap = 0; tap < 125; tap++) wocc[tap * Cout + co] = w[((long long)co * 4) * 125 + tap];
+    cls_tab[cls * Cout + co] = make_float4((float)s1, (float)s0[0], (float)s0[1], (float)s0[2]);
+  }
+  // B fragments: b0 = {B[2t][g], B[2t+1][g]}, b1 = {B[2t+8][g], B[2t+9][g]} with n = nb*8 + g
+  const int NB = Cout / 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kFirstKSteps * NB * 32; i += gridDim.x * blockDim.x) {
+    const int lane = i & 31, nb = (i >> 5) % NB, s = (i >> 5) / NB;
+    const int g = lane >> 2, t = lane & 3, co = nb * 8 + g;
+    auto wv = [&](int col) -> float {
+      const int r = 2 * s + (col >> 3), kz = col & 7;
+      if (r >= 25 || kz >= 5) return 0.f;
+      return w[((long long)co * 4) * 125 + r * 5 + kz];
+    };
+    __half2 b0 = __floats2half2_rn(wv(2 * t), wv(2 * t + 1));
+    __half2 b1 = __floats2half2_rn(wv(2 * t + 8), wv(2 * t + 9));
+    wfrag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
   }
 }
 
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4], const uint2 b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+
+__device__ __forceinline__ int axis_class(int p, int G) {
+  return p == 0 ? 0 : (p == 1 ? 1 : (p == G - 2 ? 3 : (p == G - 1 ? 4 : 2)));
+}
+
+// One 256-thread block owns a 4 (x) x 8 (y) column of the volume and walks it along z in 8-voxel tiles.  The
+// column's halo (8 x 12 rows of G + 8 cells, fp16, zero padded) is loaded once with coalesced 16-byte loads, together
+// with one occupancy bit mask per row.  Warp w owns x = w>>1 and four y rows; an M-tile of the warp-level MMA is
+// two y rows x 8 z voxels (fragment row g = z, rows 8..15 = the second y row).  The accumulators start as the
+// analytic CoordConv term (per-thread coefficient registers; voxels in the 2-cell shell of the volume look their
+// boundary class up); the occupancy channel is added by tensor-core MMAs over K = (window row, kz), skipping every
+// 16-wide K step whose two window rows are empty for the M-tile - the input is a sparse surface, so most M-tiles
+// skip all 13.  fp16 operands (occupancy 0/1 is exact), fp32 accumulation.  Channels are processed 32 at a time.
 template <int COUT>
-__global__ void __launch_bounds__(256)
-first_conv_kernel(const float* __restrict__ occ, const float* __restrict__ wocc, const float* __restrict__ tables,
+__global__ void __launch_bounds__(256, 2)
+first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_tab, const uint2* __restrict__ wfrag,
                   const float* __restrict__ bias, const float* __restrict__ lin, int G, act_t* __restrict__ out) {
-  // tile: 4 (x) x 8 (y) x 8 (z) outputs, halo 8 x 12 x 12
-  __shared__ float halo[8][12][12];
-  __shared__ uint32_t hbits[8][12];        // bit z of [hx][hy]: halo[hx][hy][z] != 0
-  __shared__ float4 s_lin[COUT];           // interior blocks: (K0 + bias, Sx, Sy, Sz) per channel
-  extern __shared__ float s_w[];  // [125][COUT] weights, later reused as the [256][COUT] fp16 store staging (128*COUT floats)
-  const int n = blockIdx.y;
-  const int tz = G / 8, ty = G / 8;
-  int b = blockIdx.x;
-  const int bz = b % tz; b /= tz;
-  const int by = b % ty; b /= ty;
-  const int bx = b;
-  const int x0 = bx * 4, y0 = by * 8, z0 = bz * 8;
+  extern __shared__ __align__(16) uint32_t dyn_smem[];
+  // halo_w[R][HW]: row R = hx*12 + hy, half index i = z + 2 (z = -2 .. G+5 and zero padding up to 2*HW)
+  // hb[R][HBW]: bit i of the row: halo value != 0
+  const int HW = G / 2 + 8, HBW = (G + 4 + 31) / 32 + 1;
+  uint32_t* halo_w = dyn_smem;
+  uint32_t* hb = dyn_smem + 96 * HW;
+  __shared__ float4 s_tab[5][COUT];               // classes (2, 2, cz)
+  __shared__ float s_bias[COUT];
+  __shared__ __align__(16) uint32_t stage[8][16 * 16];
+  const int n = blockIdx.z;
+  const int x0 = blockIdx.y * 4, y0 = blockIdx.x * 8;
   const float* src = occ + (long long)n * G * G * G;
-  bool any = false;
-  // halo: 96 (x, y) rows of 12 z-values; one thread per row, six 8-byte loads (z0 - 2 is 8-byte aligned),
-  // the row's occupancy bit mask is built in the same pass
-  if (threadIdx.x < 96) {
-    const int hx = threadIdx.x / 12, hy = threadIdx.x % 12;
-    const int x = x0 + hx - 2, y = y0 + hy - 2;
-    const bool row_ok = (unsigned)x < (unsigned)G && (unsigned)y < (unsigned)G;
-    const float2* rp = reinterpret_cast<const float2*>(src + ((long long)x * G + y) * G + (z0 - 2));
-    uint32_t word = 0;
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
-      const int z = z0 - 2 + 2 * j;                 // both elements of a pair are in or out together (G, z0 even)
-      float2 v = make_float2(0.f, 0.f);
-      if (row_ok && (unsigned)z < (unsigned)G) v = __ldg(rp + j);
-      halo[hx][hy][2 * j] = v.x;
-      halo[hx][hy][2 * j + 1] = v.y;
-      word |= (v.x != 0.f ? 1u : 0u) << (2 * j);
-      word |= (v.y != 0.f ? 1u : 0u) << (2 * j + 1);
-    }
-    hbits[hx][hy] = word;
-    any = word != 0;
+  const int Q = G / 4;                            // float4 per row
+  const int total = 96 * Q;
+  const bool p2 = (Q & (Q - 1)) == 0;
+  const int qsh = __ffs(Q) - 1;
+
+  for (int i = threadIdx.x; i < 96 * HBW; i += 256) hb[i] = 0;
+  for (int i = threadIdx.x; i < 96 * 8; i += 256) {           // border words of every row: 0 and G/2+1 .. G/2+7
+    const int R = i >> 3, j = i & 7;
+    halo_w[R * HW + (j == 0 ? 0 : G / 2 + j)] = 0;
   }
-  const int block_any = __syncthreads_or(any);
-  if (block_any)
-    for (int i = threadIdx.x; i < 125 * COUT / 4; i += 256)
-      reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(wocc)[i];
-  // A block whose voxels are all >= 2 cells away from every face sees the full 5^3 window everywhere: the
-  // CoordConv term is then one affine function of (x, y, z) per channel (boundary class (2,2,2)).
-  const bool interior = x0 >= 2 && x0 + 4 <= G - 2 && y0 >= 2 && y0 + 8 <= G - 2 && z0 >= 2 && z0 + 8 <= G - 2;
-  if (interior && threadIdx.x >= 128 && threadIdx.x < 128 + COUT) {
-    const int c = threadIdx.x - 128;
-    const float step = 2.0f / (float)(G - 1);
-    const float2* t = reinterpret_cast<const float2*>(tables) + (long long)(62 * 3) * COUT;   // class (2,2,2) = 62
-    const float2 sx = __ldg(t + c), sy = __ldg(t + COUT + c), sz = __ldg(t + 2 * COUT + c);
-    s_lin[c] = make_float4(bias[c] + step * (sx.y + sy.y + sz.y), sx.x, sy.x, sz.x);
+  if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
+  for (int i = threadIdx.x; i < 5 * COUT; i += 256) s_tab[i / COUT][i % COUT] = __ldg(cls_tab + (60 + i / COUT) * COUT + i % COUT);
+  for (int base = 0; base < total; base += 256 * 6) {
+    float4 v[6];
+    int Rr[6], qq[6];
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+      const int i = base + u * 256 + threadIdx.x;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      Rr[u] = -1;
+      if (i < total) {
+        const int R = p2 ? (i >> qsh) : (i / Q), q = i - R * Q;
+        Rr[u] = R; qq[u] = q;
+        const int hx = R / 12, hy = R - hx * 12;
+        const int x = x0 + hx - 2, y = y0 + hy - 2;
+        if ((unsigned)x < (unsigned)G && (unsigned)y < (unsigned)G)
+          v[u] = __ldg(reinterpret_cast<const float4*>(src + ((long long)x * G + y) * G) + q);
+      }
+    }
+    if (base == 0) __syncthreads();               // hb zeroed before the atomicOr's below
+#pragma unroll
+    for (int u = 0; u < 6; u++) {
+      if (Rr[u] < 0) continue;
+      __half2 h0 = __floats2half2_rn(v[u].x, v[u].y), h1 = __floats2half2_rn(v[u].z, v[u].w);
+      uint32_t* row = halo_w + Rr[u] * HW + 2 * qq[u] + 1;   // half index 4q + 2
+      row[0] = *reinterpret_cast<uint32_t*>(&h0);
+      row[1] = *reinterpret_cast<uint32_t*>(&h1);
+      const uint32_t nib = (v[u].x != 0.f ? 1u : 0u) | (v[u].y != 0.f ? 2u : 0u) | (v[u].z != 0.f ? 4u : 0u) |
+                           (v[u].w != 0.f ? 8u : 0u);
+      if (nib) {
+        const int bit = 4 * qq[u] + 2;
+        atomicOr(hb + Rr[u] * HBW + (bit >> 5), nib << (bit & 31));
+        if ((bit & 31) > 28) atomicOr(hb + Rr[u] * HBW + (bit >> 5) + 1, nib >> (32 - (bit & 31)));
+      }
+    }
   }
   __syncthreads();
 
-  const int lz = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lx = threadIdx.x >> 6;
-  const int x = x0 + lx, y = y0 + ly, z = z0 + lz;
-  float acc[COUT];
-  if (interior) {
-    const float lx_ = lin[x], ly_ = lin[y], lz_ = lin[z];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int lx = warp >> 1, yw = (warp & 1) * 4;
+  const int x = x0 + lx;
+  const float step = 2.0f / (float)(G - 1);
+  const float linx = __ldg(lin + x);
+  const int cx5 = axis_class(x, G) * 5;
+  float liny[4];
+  int cxy[4];
 #pragma unroll
-    for (int c = 0; c < COUT; c++) {
-      const float4 k = s_lin[c];
-      acc[c] = fmaf(lx_, k.y, fmaf(ly_, k.z, fmaf(lz_, k.w, k.x)));
-    }
-  } else {
-    // CoordConv channels: per-class affine form
-#pragma unroll
-    for (int c = 0; c < COUT; c++) acc[c] = bias[c];
-    const int p[3] = {x, y, z};
-    int cls = 0;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      const int c = p[a] == 0 ? 0 : (p[a] == 1 ? 1 : (p[a] == G - 2 ? 3 : (p[a] == G - 1 ? 4 : 2)));
-      cls = cls * 5 + c;
-    }
-    const float step = 2.0f / (float)(G - 1);
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      const float base = lin[p[a]];
-      const float2* t = reinterpret_cast<const float2*>(tables) + ((long long)cls * 3 + a) * COUT;
-#pragma unroll
-      for (int c = 0; c < COUT; c++) {
-        const float2 sv = __ldg(t + c);
-        acc[c] = fmaf(base, sv.x, fmaf(step, sv.y, acc[c]));
-      }
-    }
+  for (int v = 0; v < 4; v++) {
+    liny[v] = __ldg(lin + y0 + yw + v);
+    cxy[v] = (cx5 + axis_class(y0 + yw + v, G)) * 5;
   }
-  // occupancy channel: only non-zero taps.  One 5-bit row mask per (kx, ky) from the bit-halo replaces five
-  // per-tap loads + tests; a tap's FMA block still runs once per warp when any lane has a hit.
-  if (block_any) {
-    for (int kx = 0; kx < 5; kx++)
+  uint32_t* stg = stage[warp];
+  // window rows of this lane for the emptiness test (lanes 0..24), M-tile 0
+  const int lr = lane < 25 ? lane : 0;
+  const int Rlane = (lx + lr / 5) * 12 + yw + lr % 5;
+  const int swz = (g >> 1) & 3;
+
+#pragma unroll 1
+  for (int chb = 0; chb < COUT; chb += 32) {
+    float bxy[8], sy[8], sz[8];
 #pragma unroll
-      for (int ky = 0; ky < 5; ky++) {
-        const uint32_t m = (hbits[lx + kx][ly + ky] >> lz) & 31u;
-        if (__any_sync(0xffffffffu, m != 0)) {
+    for (int nb = 0; nb < 4; nb++)
 #pragma unroll
-          for (int kz = 0; kz < 5; kz++) {
-            if ((m >> kz) & 1u) {
-              const float v = halo[lx + kx][ly + ky][lz + kz];
-              const float4* wr = reinterpret_cast<const float4*>(s_w + ((kx * 5 + ky) * 5 + kz) * COUT);
+      for (int j = 0; j < 2; j++) {
+        const int ch = chb + nb * 8 + 2 * t + j;
+        const float4 k = s_tab[2][ch];
+        bxy[nb * 2 + j] = fmaf(k.y, linx, fmaf(step, k.x, s_bias[ch]));
+        sy[nb * 2 + j] = k.z;
+        sz[nb * 2 + j] = k.w;
+      }
+    act_t* outp = out + ((((long long)n * G + x) * G + (y0 + yw)) * G) * COUT + chb;
+#pragma unroll 1
+    for (int z0 = 0; z0 < G; z0 += 8) {
+      const int z = z0 + g;
+      const float linz = __ldg(lin + z);
+      const int cz = axis_class(z, G);
+#pragma unroll 1
+      for (int mt = 0; mt < 2; mt++) {
+        float c[4][4];
 #pragma unroll
-              for (int c4 = 0; c4 < COUT / 4; c4++) {
-                const float4 w4 = wr[c4];
-                acc[c4 * 4 + 0] = fmaf(v, w4.x, acc[c4 * 4 + 0]);
-                acc[c4 * 4 + 1] = fmaf(v, w4.y, acc[c4 * 4 + 1]);
-                acc[c4 * 4 + 2] = fmaf(v, w4.z, acc[c4 * 4 + 2]);
-                acc[c4 * 4 + 3] = fmaf(v, w4.w, acc[c4 * 4 + 3]);
-              }
+        for (int i = 0; i < 8; i++) {
+          const float tt = fmaf(sz[i], linz, bxy[i]);
+          c[i >> 1][i & 1] = fmaf(sy[i], mt ? liny[2] : liny[0], tt);
+          c[i >> 1][2 + (i & 1)] = fmaf(sy[i], mt ? liny[3] : liny[1], tt);
+        }
+        // voxels in the 2-cell shell of the volume see a clipped window: per-class coefficients
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int cxyv = mt ? cxy[2 + h] : cxy[h];
+          const int cls = cxyv + cz;
+          if (cls != 62) {
+            const float4* tab = (cxyv == 60 ? &s_tab[cz][0] : cls_tab + cls * COUT) + chb;   // generic pointer
+            const float ly = mt ? liny[2 + h] : liny[h];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const int ch = (i >> 1) * 8 + 2 * t + (i & 1);
+              const float4 k = tab[ch];
+              c[i >> 1][2 * h + (i & 1)] =
+                  fmaf(k.y, linx, fmaf(k.z, ly, fmaf(k.w, linz, fmaf(step, k.x, s_bias[chb + ch]))));
             }
           }
         }
-      }
-  }
-  // Stage the block's 256 voxel rows in shared memory (reusing the weight buffer), then write them out with
-  // fully coalesced 16-byte stores: per-thread row stores touch a different cache line in every lane.
-  __syncthreads();
-  half8* stage = reinterpret_cast<half8*>(s_w);            // [256 voxels][COUT/8] 16-byte chunks, XOR-swizzled
-  constexpr int CH = COUT / 8;
+        // occupancy channel
+        {
+          const uint32_t* hr = hb + (Rlane + 2 * mt) * HBW + (z0 >> 5);
+          const uint32_t w0 = hr[0] | hr[HBW], w1 = hr[1] | hr[HBW + 1];
+          const uint32_t win = __funnelshift_r(w0, w1, z0 & 31) & 0xfffu;
+          const uint32_t rowmask = __ballot_sync(0xffffffffu, lane < 25 && win != 0);
+          uint32_t km = (rowmask | (rowmask >> 1)) & 0x1555555u;    // bit 2s: K step s has a non-empty window row
+          while (km) {
+            const int s = (__ffs(km) - 1) >> 1;
+            km &= km - 1;
+            const int r0 = 2 * s, r1 = min(2 * s + 1, 24);         // r = 25 has zero weights: any finite operand
+            const int ya = yw + 2 * mt;
+            const int R0 = (lx + r0 / 5) * 12 + ya + r0 % 5, R1 = (lx + r1 / 5) * 12 + ya + r1 % 5;
+            const int wi = (z0 >> 1) + (g >> 1) + t;               // halves z0 + g + 2t, + 1 (odd g: straddles)
+            const int sh = (g & 1) * 16;
+            uint32_t a[4];
+            const uint32_t* p0 = halo_w + R0 * HW + wi;
+            const uint32_t* p1 = halo_w + R1 * HW + wi;
+            a[0] = __funnelshift_r(p0[0], p0[1], sh);
+            a[1] = __funnelshift_r(p0[HW], p0[HW + 1], sh);
+            a[2] = __funnelshift_r(p1[0], p1[1], sh);
+            a[3] = __funnelshift_r(p1[HW], p1[HW + 1], sh);
+            const uint2* wf = wfrag + (s * (COUT / 8) + (chb >> 3)) * 32 + lane;
 #pragma unroll
-  for (int c8 = 0; c8 < CH; c8++) stage[threadIdx.x * CH + (c8 ^ (threadIdx.x & (CH - 1)))] = nm_pack8(acc + c8 * 8);
-  __syncthreads();
-  // the tile is 32 (x, y) rows of 8 consecutive z voxels = 8 * COUT * 2 contiguous bytes each
-  constexpr int ROW_CHUNKS = 8 * CH;
-  for (int i = threadIdx.x; i < 256 * CH; i += 256) {
-    const int r = i / ROW_CHUNKS, pos = i % ROW_CHUNKS;     // r = lx * 8 + ly
-    const int v = r * 8 + pos / CH, c8 = pos % CH;          // voxel index inside the block, channel chunk
-    half8* dst = reinterpret_cast<half8*>(
-        out + (((long long)n * G + x0 + (r >> 3)) * G * G + (long long)(y0 + (r & 7)) * G + z0) * COUT);
-    dst[pos] = stage[v * CH + (c8 ^ (v & (CH - 1)))];
+            for (int nb = 0; nb < 4; nb++) mma_m16n8k16(c[nb], a, __ldg(wf + nb * 32));
+          }
+        }
+        // stage the 16 voxel rows (XOR-swizzled 16-byte chunks), then two 512-byte coalesced stores
+#pragma unroll
+        for (int nb = 0; nb < 4; nb++) {
+          __half2 h0 = __floats2half2_rn(c[nb][0], c[nb][1]);
+          __half2 h1 = __floats2half2_rn(c[nb][2], c[nb][3]);
+          stg[g * 16 + ((nb ^ swz) << 2) + t] = *reinterpret_cast<uint32_t*>(&h0);
+          stg[(g + 8) * 16 + ((nb ^ swz) << 2) + t] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int v = h * 8 + (lane >> 2), chk = lane & 3;
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + v * 16 + ((chk ^ ((v >> 1) & 3)) << 2));
+          act_t* dst = outp + ((long long)(2 * mt + h) * G + z0 + (lane >> 2)) * COUT + chk * 8;
+          *reinterpret_cast<uint4*>(dst) = val;
+        }
+        __syncwarp();
+      }
+    }
   }
 }
 
@@ -251,14 +330,14 @@ convT_k2s2_kernel(const act_t* __restrict__ x, const float* __restrict__ w, cons
 }  // namespace
 
 extern "C" size_t nm_first_conv_tables_bytes(int Cout) {
-  return ((size_t)125 * 3 * Cout * 2 + (size_t)125 * Cout) * sizeof(float);
+  return (size_t)125 * Cout * sizeof(float4) + (size_t)kFirstKSteps * (Cout / 8) * 32 * sizeof(uint2);
 }
 
 extern "C" int nm_first_conv_prepare(const float* weight, int Cout, void* tables, void* stream) {
   NM_CHECK_ARG(weight && tables, "nm_first_conv_prepare: null pointer");
   NM_CHECK_ARG(Cout == 32 || Cout == 64, "nm_first_conv_prepare: Cout=%d unsupported", Cout);
-  float* t = (float*)tables;
-  first_conv_prep_kernel<<<125, 64, 0, (cudaStream_t)stream>>>(weight, Cout, t, t + (size_t)125 * 3 * Cout * 2);
+  float4* t = (float4*)tables;
+  first_conv_prep_kernel<<<125, 64, 0, (cudaStream_t)stream>>>(weight, Cout, t, (uint2*)(t + (size_t)125 * Cout));
   NM_CHECK_LAUNCH("first_conv_prepare");
   return NM_OK;
 }
@@ -268,14 +347,16 @@ extern "C" int nm_first_conv_k5(const float* occ, const void* tables, const floa
   NM_CHECK_ARG(occ && tables && bias && linspace && out, "nm_first_conv_k5: null pointer");
   NM_CHECK_ARG(G % 8 == 0 && G >= 8, "nm_first_conv_k5: grid %d must be a multiple of 8", G);
   if (n == 0) return NM_OK;
-  const float* t = (const float*)tables;
-  const float* wocc = t + (size_t)125 * 3 * Cout * 2;
-  dim3 grid((G / 4) * (G / 8) * (G / 8), n);
+  const float4* t = (const float4*)tables;
+  const uint2* wf = (const uint2*)(t + (size_t)125 * Cout);
+  NM_CHECK_ARG(n <= 65535 && G <= 128, "nm_first_conv_k5: n=%d (max 65535) or grid %d (max 128) too large", n, G);
+  dim3 grid(G / 8, G / 4, n);
+  const size_t smem = (size_t)96 * (G / 2 + 8 + (G + 4 + 31) / 32 + 1) * sizeof(uint32_t);
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout == 32) {
-    first_conv_kernel<32><<<grid, 256, 128 * 32 * sizeof(float), st>>>(occ, wocc, t, bias, linspace, G, (act_t*)out);
+    first_conv_kernel<32><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out);
   } else if (Cout == 64) {
-    first_conv_kernel<64><<<grid, 256, 128 * 64 * sizeof(float), st>>>(occ, wocc, t, bias, linspace, G, (act_t*)out);
+    first_conv_kernel<64><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out);
   } else {
     NM_CHECK_ARG(false, "nm_first_conv_k5: Cout=%d unsupported", Cout);
   }
