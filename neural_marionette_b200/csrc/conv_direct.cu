@@ -74,10 +74,14 @@ __device__ __forceinline__ int axis_class(int p, int G) {
 // column's halo (8 x 12 rows of G + 8 cells, fp16, zero padded) is loaded once with coalesced 16-byte loads, together
 // with one occupancy bit mask per row.  Warp w owns x = w>>1 and four y rows; an M-tile of the warp-level MMA is
 // two y rows x 8 z voxels (fragment row g = z, rows 8..15 = the second y row).  The accumulators start as the
-// analytic CoordConv term (per-thread coefficient registers; voxels in the 2-cell shell of the volume look their
-// boundary class up); the occupancy channel is added by tensor-core MMAs over K = (window row, kz), skipping every
-// 16-wide K step whose two window rows are empty for the M-tile - the input is a sparse surface, so most M-tiles
-// skip all 13.  fp16 operands (occupancy 0/1 is exact), fp32 accumulation.  Channels are processed 32 at a time.
+// analytic CoordConv term from per-thread coefficient registers (reloaded for the first / last z tile, where a
+// thread's z sits in the 2-cell shell of the volume; x / y shell rows look their boundary class up); the occupancy
+// channel is added by tensor-core MMAs over K = (window row, kz), skipping every 16-wide K step whose two window
+// rows are empty for the M-tile - the input is a sparse surface, so most M-tiles skip all 13.  fp16 operands
+// (occupancy 0/1 is exact), fp32 accumulation.  Channels are processed 32 at a time.
+__constant__ int c_first_row_off[26] = {0, 1, 2, 3, 4, 12, 13, 14, 15, 16, 24, 25, 26, 27, 28, 36, 37, 38, 39, 40,
+                                        48, 49, 50, 51, 52, 52};   // (r/5)*12 + r%5; r = 25 (zero weights) -> 24
+
 template <int COUT>
 __global__ void __launch_bounds__(256, 2)
 first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_tab, const uint2* __restrict__ wfrag,
@@ -85,19 +89,21 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
   extern __shared__ __align__(16) uint32_t dyn_smem[];
   // halo_w[R][HW]: row R = hx*12 + hy, half index i = z + 2 (z = -2 .. G+5 and zero padding up to 2*HW)
   // hb[R][HBW]: bit i of the row: halo value != 0
-  const int HW = G / 2 + 8, HBW = (G + 4 + 31) / 32 + 1;
+  // win[zt][hx*13 + hyp]: 12-bit occupancy window of z tile zt, rows (hx, hyp) | (hx, hyp+1)  (hyp = 0..10)
+  const int HW = G / 2 + 8, HBW = (G + 4 + 31) / 32 + 1, NZT = G / 8;
   uint32_t* halo_w = dyn_smem;
   uint32_t* hb = dyn_smem + 96 * HW;
-  __shared__ float4 s_tab[5][COUT];               // classes (2, 2, cz)
+  uint32_t* win = hb + 96 * HBW;
+  __shared__ float4 s_tab[5][COUT];               // classes (2, 2, cz), .x = step * sum S1 + bias
   __shared__ float s_bias[COUT];
   __shared__ __align__(16) uint32_t stage[8][16 * 16];
   const int n = blockIdx.z;
   const int x0 = blockIdx.y * 4, y0 = blockIdx.x * 8;
   const float* src = occ + (long long)n * G * G * G;
+  const float step = 2.0f / (float)(G - 1);
   const int Q = G / 4;                            // float4 per row
   const int total = 96 * Q;
-  const bool p2 = (Q & (Q - 1)) == 0;
-  const int qsh = __ffs(Q) - 1;
+  const uint32_t qmagic = 0xffffffffu / (uint32_t)Q + 1u;   // i / Q = umulhi(i, qmagic) for the small i used here
 
   for (int i = threadIdx.x; i < 96 * HBW; i += 256) hb[i] = 0;
   for (int i = threadIdx.x; i < 96 * 8; i += 256) {           // border words of every row: 0 and G/2+1 .. G/2+7
@@ -105,47 +111,56 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
     halo_w[R * HW + (j == 0 ? 0 : G / 2 + j)] = 0;
   }
   if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
-  for (int i = threadIdx.x; i < 5 * COUT; i += 256) s_tab[i / COUT][i % COUT] = __ldg(cls_tab + (60 + i / COUT) * COUT + i % COUT);
+  for (int i = threadIdx.x; i < 5 * COUT; i += 256) {
+    float4 k = __ldg(cls_tab + 60 * COUT + i);
+    k.x = fmaf(step, k.x, bias[i % COUT]);
+    s_tab[i / COUT][i % COUT] = k;
+  }
+  __syncthreads();                                // hb zeroed before the atomicOr's below
+#pragma unroll 1
   for (int base = 0; base < total; base += 256 * 6) {
     float4 v[6];
-    int Rr[6], qq[6];
 #pragma unroll
     for (int u = 0; u < 6; u++) {
       const int i = base + u * 256 + threadIdx.x;
       v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      Rr[u] = -1;
       if (i < total) {
-        const int R = p2 ? (i >> qsh) : (i / Q), q = i - R * Q;
-        Rr[u] = R; qq[u] = q;
+        const int R = (int)__umulhi((uint32_t)i, qmagic), q = i - R * Q;
         const int hx = R / 12, hy = R - hx * 12;
         const int x = x0 + hx - 2, y = y0 + hy - 2;
         if ((unsigned)x < (unsigned)G && (unsigned)y < (unsigned)G)
           v[u] = __ldg(reinterpret_cast<const float4*>(src + ((long long)x * G + y) * G) + q);
       }
     }
-    if (base == 0) __syncthreads();               // hb zeroed before the atomicOr's below
 #pragma unroll
     for (int u = 0; u < 6; u++) {
-      if (Rr[u] < 0) continue;
+      const int i = base + u * 256 + threadIdx.x;
+      if (i >= total) continue;
+      const int R = (int)__umulhi((uint32_t)i, qmagic), q = i - R * Q;
       __half2 h0 = __floats2half2_rn(v[u].x, v[u].y), h1 = __floats2half2_rn(v[u].z, v[u].w);
-      uint32_t* row = halo_w + Rr[u] * HW + 2 * qq[u] + 1;   // half index 4q + 2
+      uint32_t* row = halo_w + R * HW + 2 * q + 1;             // half index 4q + 2
       row[0] = *reinterpret_cast<uint32_t*>(&h0);
       row[1] = *reinterpret_cast<uint32_t*>(&h1);
       const uint32_t nib = (v[u].x != 0.f ? 1u : 0u) | (v[u].y != 0.f ? 2u : 0u) | (v[u].z != 0.f ? 4u : 0u) |
                            (v[u].w != 0.f ? 8u : 0u);
       if (nib) {
-        const int bit = 4 * qq[u] + 2;
-        atomicOr(hb + Rr[u] * HBW + (bit >> 5), nib << (bit & 31));
-        if ((bit & 31) > 28) atomicOr(hb + Rr[u] * HBW + (bit >> 5) + 1, nib >> (32 - (bit & 31)));
+        const int bit = 4 * q + 2;
+        atomicOr(hb + R * HBW + (bit >> 5), nib << (bit & 31));
+        if ((bit & 31) > 28) atomicOr(hb + R * HBW + (bit >> 5) + 1, nib >> (32 - (bit & 31)));
       }
     }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NZT * 8 * 11; i += 256) {
+    const int zt = i / 88, rem = i - zt * 88, hx = rem / 11, hyp = rem - hx * 11;
+    const uint32_t* hr = hb + (hx * 12 + hyp) * HBW + (zt >> 2);
+    win[zt * 104 + hx * 13 + hyp] = __funnelshift_r(hr[0] | hr[HBW], hr[1] | hr[HBW + 1], (zt & 3) * 8) & 0xfffu;
   }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int lx = warp >> 1, yw = (warp & 1) * 4;
   const int x = x0 + lx;
-  const float step = 2.0f / (float)(G - 1);
   const float linx = __ldg(lin + x);
   const int cx5 = axis_class(x, G) * 5;
   float liny[4];
@@ -158,77 +173,75 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
   uint32_t* stg = stage[warp];
   // window rows of this lane for the emptiness test (lanes 0..24), M-tile 0
   const int lr = lane < 25 ? lane : 0;
-  const int Rlane = (lx + lr / 5) * 12 + yw + lr % 5;
+  const uint32_t* win_lane = win + (lx + lr / 5) * 13 + yw + lr % 5;
   const int swz = (g >> 1) & 3;
+  uint32_t* stg_w = stg + g * 16 + t;
+  const uint32_t* stg_r = stg + (lane >> 2) * 16 + (((lane & 3) ^ ((lane >> 3) & 3)) << 2);
+  const uint32_t* halo_lane = halo_w + (lx * 12 + yw) * HW + (g >> 1) + t;   // + row offset * HW + z0 / 2
+  const int sh = (g & 1) * 16;
 
 #pragma unroll 1
   for (int chb = 0; chb < COUT; chb += 32) {
     float bxy[8], sy[8], sz[8];
-#pragma unroll
-    for (int nb = 0; nb < 4; nb++)
-#pragma unroll
-      for (int j = 0; j < 2; j++) {
-        const int ch = chb + nb * 8 + 2 * t + j;
-        const float4 k = s_tab[2][ch];
-        bxy[nb * 2 + j] = fmaf(k.y, linx, fmaf(step, k.x, s_bias[ch]));
-        sy[nb * 2 + j] = k.z;
-        sz[nb * 2 + j] = k.w;
-      }
-    act_t* outp = out + ((((long long)n * G + x) * G + (y0 + yw)) * G) * COUT + chb;
+    act_t* outp = out + ((((long long)n * G + x) * G + (y0 + yw)) * G + (lane >> 2)) * COUT + chb + (lane & 3) * 8;
+    const uint2* wf_lane = wfrag + (chb >> 3) * 32 + lane;
 #pragma unroll 1
-    for (int z0 = 0; z0 < G; z0 += 8) {
+    for (int zt = 0; zt < NZT; zt++) {
+      const int z0 = zt * 8;
       const int z = z0 + g;
       const float linz = __ldg(lin + z);
       const int cz = axis_class(z, G);
-#pragma unroll 1
+      if (zt <= 1 || zt == NZT - 1) {
+        // (re)load the coefficient registers: this thread's z class changes only at the first / last z tile
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float4 k = s_tab[cz][chb + (i >> 1) * 8 + 2 * t + (i & 1)];
+          bxy[i] = fmaf(k.y, linx, k.x);
+          sy[i] = k.z;
+          sz[i] = k.w;
+        }
+      }
+      float tt[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) tt[i] = fmaf(sz[i], linz, bxy[i]);
+#pragma unroll
       for (int mt = 0; mt < 2; mt++) {
         float c[4][4];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          const float tt = fmaf(sz[i], linz, bxy[i]);
-          c[i >> 1][i & 1] = fmaf(sy[i], mt ? liny[2] : liny[0], tt);
-          c[i >> 1][2 + (i & 1)] = fmaf(sy[i], mt ? liny[3] : liny[1], tt);
+          c[i >> 1][i & 1] = fmaf(sy[i], liny[2 * mt], tt[i]);
+          c[i >> 1][2 + (i & 1)] = fmaf(sy[i], liny[2 * mt + 1], tt[i]);
         }
-        // voxels in the 2-cell shell of the volume see a clipped window: per-class coefficients
+        // rows in the x / y shell of the volume see a clipped window: per-class coefficients
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const int cxyv = mt ? cxy[2 + h] : cxy[h];
-          const int cls = cxyv + cz;
-          if (cls != 62) {
-            const float4* tab = (cxyv == 60 ? &s_tab[cz][0] : cls_tab + cls * COUT) + chb;   // generic pointer
-            const float ly = mt ? liny[2 + h] : liny[h];
+          const int cxyv = cxy[2 * mt + h];
+          if (cxyv != 60) {
+            const float4* tab = cls_tab + (cxyv + cz) * COUT + chb;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
               const int ch = (i >> 1) * 8 + 2 * t + (i & 1);
-              const float4 k = tab[ch];
+              const float4 k = __ldg(tab + ch);
               c[i >> 1][2 * h + (i & 1)] =
-                  fmaf(k.y, linx, fmaf(k.z, ly, fmaf(k.w, linz, fmaf(step, k.x, s_bias[chb + ch]))));
+                  fmaf(k.y, linx, fmaf(k.z, liny[2 * mt + h], fmaf(k.w, linz, fmaf(step, k.x, s_bias[chb + ch]))));
             }
           }
         }
         // occupancy channel
         {
-          const uint32_t* hr = hb + (Rlane + 2 * mt) * HBW + (z0 >> 5);
-          const uint32_t w0 = hr[0] | hr[HBW], w1 = hr[1] | hr[HBW + 1];
-          const uint32_t win = __funnelshift_r(w0, w1, z0 & 31) & 0xfffu;
-          const uint32_t rowmask = __ballot_sync(0xffffffffu, lane < 25 && win != 0);
+          const uint32_t rowmask = __ballot_sync(0xffffffffu, lane < 25 && win_lane[zt * 104 + 2 * mt] != 0);
           uint32_t km = (rowmask | (rowmask >> 1)) & 0x1555555u;    // bit 2s: K step s has a non-empty window row
           while (km) {
-            const int s = (__ffs(km) - 1) >> 1;
+            const int s2 = __ffs(km) - 1;                           // 2 * s
             km &= km - 1;
-            const int r0 = 2 * s, r1 = min(2 * s + 1, 24);         // r = 25 has zero weights: any finite operand
-            const int ya = yw + 2 * mt;
-            const int R0 = (lx + r0 / 5) * 12 + ya + r0 % 5, R1 = (lx + r1 / 5) * 12 + ya + r1 % 5;
-            const int wi = (z0 >> 1) + (g >> 1) + t;               // halves z0 + g + 2t, + 1 (odd g: straddles)
-            const int sh = (g & 1) * 16;
-            uint32_t a[4];
-            const uint32_t* p0 = halo_w + R0 * HW + wi;
-            const uint32_t* p1 = halo_w + R1 * HW + wi;
+            const uint32_t* p0 = halo_lane + (c_first_row_off[s2] + 2 * mt) * HW + (z0 >> 1);
+            const uint32_t* p1 = halo_lane + (c_first_row_off[s2 + 1] + 2 * mt) * HW + (z0 >> 1);
+            uint32_t a[4];                                          // halves z0 + g + 2t, + 1 (odd g straddles two words)
             a[0] = __funnelshift_r(p0[0], p0[1], sh);
             a[1] = __funnelshift_r(p0[HW], p0[HW + 1], sh);
             a[2] = __funnelshift_r(p1[0], p1[1], sh);
             a[3] = __funnelshift_r(p1[HW], p1[HW + 1], sh);
-            const uint2* wf = wfrag + (s * (COUT / 8) + (chb >> 3)) * 32 + lane;
+            const uint2* wf = wf_lane + (s2 >> 1) * (COUT / 8) * 32;
 #pragma unroll
             for (int nb = 0; nb < 4; nb++) mma_m16n8k16(c[nb], a, __ldg(wf + nb * 32));
           }
@@ -238,17 +251,15 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
         for (int nb = 0; nb < 4; nb++) {
           __half2 h0 = __floats2half2_rn(c[nb][0], c[nb][1]);
           __half2 h1 = __floats2half2_rn(c[nb][2], c[nb][3]);
-          stg[g * 16 + ((nb ^ swz) << 2) + t] = *reinterpret_cast<uint32_t*>(&h0);
-          stg[(g + 8) * 16 + ((nb ^ swz) << 2) + t] = *reinterpret_cast<uint32_t*>(&h1);
+          stg_w[(nb ^ swz) << 2] = *reinterpret_cast<uint32_t*>(&h0);
+          stg_w[128 + ((nb ^ swz) << 2)] = *reinterpret_cast<uint32_t*>(&h1);
         }
         __syncwarp();
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int v = h * 8 + (lane >> 2), chk = lane & 3;
-          const uint4 val = *reinterpret_cast<const uint4*>(stg + v * 16 + ((chk ^ ((v >> 1) & 3)) << 2));
-          act_t* dst = outp + ((long long)(2 * mt + h) * G + z0 + (lane >> 2)) * COUT + chk * 8;
-          *reinterpret_cast<uint4*>(dst) = val;
-        }
+        const uint4 v0 = *reinterpret_cast<const uint4*>(stg_r);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(stg_r + 128);
+        act_t* dst = outp + ((long long)(2 * mt) * G + z0) * COUT;
+        *reinterpret_cast<uint4*>(dst) = v0;
+        *reinterpret_cast<uint4*>(dst + (long long)G * COUT) = v1;
         __syncwarp();
       }
     }
@@ -351,7 +362,7 @@ extern "C" int nm_first_conv_k5(const float* occ, const void* tables, const floa
   const uint2* wf = (const uint2*)(t + (size_t)125 * Cout);
   NM_CHECK_ARG(n <= 65535 && G <= 128, "nm_first_conv_k5: n=%d (max 65535) or grid %d (max 128) too large", n, G);
   dim3 grid(G / 8, G / 4, n);
-  const size_t smem = (size_t)96 * (G / 2 + 8 + (G + 4 + 31) / 32 + 1) * sizeof(uint32_t);
+  const size_t smem = ((size_t)96 * (G / 2 + 8 + (G + 4 + 31) / 32 + 1) + (size_t)(G / 8) * 104) * sizeof(uint32_t);
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout == 32) {
     first_conv_kernel<32><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out);
