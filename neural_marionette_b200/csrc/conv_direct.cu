@@ -16,7 +16,8 @@ namespace {
 // cls_tab[cls][co] = (sum_a S1_a, S0_x, S0_y, S0_z) with S0_a = sum of the valid-tap weights of coordinate
 // channel a and S1_a = sum of (k_a - 2) * weight: the CoordConv term of a voxel of that class is
 // bias + step*.x + .y*lin[x] + .z*lin[y] + .w*lin[z], step = 2/(G-1).
-// wfrag[s][nb][lane]: the occupancy-channel weights as fp16 B fragments of mma.m16n8k16.  K index = s*16 + col,
+// wfrag[s][nb][lane]: the occupancy-channel weights as fp16 B fragments of mma.m16n8k16 (columns permuted, see
+// first_conv_prep_kernel).  K index = s*16 + col,
 // col < 8: window row r = 2s (r = kx*5+ky), kz = col; col >= 8: r = 2s+1, kz = col-8; kz >= 5 and r = 25 are zero.
 constexpr int kFirstKSteps = 13;
 
@@ -48,7 +49,9 @@ __global__ void first_conv_prep_kernel(const float* __restrict__ w /* (Cout,4,5,
   const int NB = Cout / 8;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kFirstKSteps * NB * 32; i += gridDim.x * blockDim.x) {
     const int lane = i & 31, nb = (i >> 5) % NB, s = (i >> 5) / NB;
-    const int g = lane >> 2, t = lane & 3, co = nb * 8 + g;
+    // fragment column g of n-block nb is output channel (nb/4)*32 + (g>>1)*8 + (nb%4)*2 + (g&1): thread t of a quad
+    // then owns the 8 consecutive channels t*8 .. t*8+7 of a voxel (one 16-byte store, no staging)
+    const int g = lane >> 2, t = lane & 3, co = (nb >> 2) * 32 + (g >> 1) * 8 + (nb & 3) * 2 + (g & 1);
     auto wv = [&](int col) -> float {
       const int r = 2 * s + (col >> 3), kz = col & 7;
       if (r >= 25 || kz >= 5) return 0.f;
@@ -74,11 +77,12 @@ __device__ __forceinline__ int axis_class(int p, int G) {
 // column's halo (8 x 12 rows of G + 8 cells, fp16, zero padded) is loaded once with coalesced 16-byte loads, together
 // with one occupancy bit mask per row.  Warp w owns x = w>>1 and four y rows; an M-tile of the warp-level MMA is
 // two y rows x 8 z voxels (fragment row g = z, rows 8..15 = the second y row).  The accumulators start as the
-// analytic CoordConv term from per-thread coefficient registers (reloaded for the first / last z tile, where a
-// thread's z sits in the 2-cell shell of the volume; x / y shell rows look their boundary class up); the occupancy
-// channel is added by tensor-core MMAs over K = (window row, kz), skipping every 16-wide K step whose two window
-// rows are empty for the M-tile - the input is a sparse surface, so most M-tiles skip all 13.  fp16 operands
-// (occupancy 0/1 is exact), fp32 accumulation.  Channels are processed 32 at a time.
+// analytic CoordConv term - one FMA per output from per-thread coefficient registers that already contain the x and
+// y parts; they are reloaded where the thread's boundary class changes (first, second and last z tile).  The
+// occupancy channel is added by tensor-core MMAs over K = (window row, kz), skipping every 16-wide K step whose two
+// window rows are empty for the M-tile - the input is a sparse surface, so most M-tiles skip all 13.  fp16 operands
+// (occupancy 0/1 is exact), fp32 accumulation.  Channels are processed 32 at a time; fragment columns are permuted
+// so that a thread owns 8 consecutive channels of a voxel and stores them directly.
 __constant__ int c_first_row_off[26] = {0, 1, 2, 3, 4, 12, 13, 14, 15, 16, 24, 25, 26, 27, 28, 36, 37, 38, 39, 40,
                                         48, 49, 50, 51, 52, 52};   // (r/5)*12 + r%5; r = 25 (zero weights) -> 24
 
@@ -90,13 +94,13 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
   // halo_w[R][HW]: row R = hx*12 + hy, half index i = z + 2 (z = -2 .. G+5 and zero padding up to 2*HW)
   // hb[R][HBW]: bit i of the row: halo value != 0
   // win[zt][hx*13 + hyp]: 12-bit occupancy window of z tile zt, rows (hx, hyp) | (hx, hyp+1)  (hyp = 0..10)
-  const int HW = G / 2 + 8, HBW = (G + 4 + 31) / 32 + 1, NZT = G / 8;
-  uint32_t* halo_w = dyn_smem;
-  uint32_t* hb = dyn_smem + 96 * HW;
+  // tab[(xl*NYL + yl)*5 + cz][COUT]: coefficient rows of the boundary classes this block touches (xl, yl = class
+  //   minus the class of the block's first x / y), .x = step * sum S1 + bias, channels (i, t)-transposed per 32
+  const int HW = G / 2 + 8, HBW = (G + 4 + 31) / 32 + 1, NZT = G / 8, NYL = G == 8 ? 5 : 3;
+  float4* tab = reinterpret_cast<float4*>(dyn_smem);
+  uint32_t* halo_w = dyn_smem + 3 * NYL * 5 * COUT * 4;
+  uint32_t* hb = halo_w + 96 * HW;
   uint32_t* win = hb + 96 * HBW;
-  __shared__ float4 s_tab[5][COUT];               // classes (2, 2, cz), .x = step * sum S1 + bias
-  __shared__ float s_bias[COUT];
-  __shared__ __align__(16) uint32_t stage[8][16 * 16];
   const int n = blockIdx.z;
   const int x0 = blockIdx.y * 4, y0 = blockIdx.x * 8;
   const float* src = occ + (long long)n * G * G * G;
@@ -110,11 +114,15 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
     const int R = i >> 3, j = i & 7;
     halo_w[R * HW + (j == 0 ? 0 : G / 2 + j)] = 0;
   }
-  if (threadIdx.x < COUT) s_bias[threadIdx.x] = bias[threadIdx.x];
-  for (int i = threadIdx.x; i < 5 * COUT; i += 256) {
-    float4 k = __ldg(cls_tab + 60 * COUT + i);
-    k.x = fmaf(step, k.x, bias[i % COUT]);
-    s_tab[i / COUT][i % COUT] = k;
+  {
+    const int xbase = axis_class(x0, G), ybase = axis_class(y0, G);
+    const int nx = axis_class(x0 + 3, G) - xbase + 1, ny = axis_class(y0 + 7, G) - ybase + 1;
+    for (int i = threadIdx.x; i < nx * ny * 5 * COUT; i += 256) {
+      const int ch = i % COUT, row = i / COUT, cz = row % 5, yl = (row / 5) % ny, xl = row / (5 * ny);
+      float4 k = __ldg(cls_tab + (((xbase + xl) * 5 + ybase + yl) * 5 + cz) * COUT + ch);
+      k.x = fmaf(step, k.x, __ldg(bias + ch));
+      tab[((xl * NYL + yl) * 5 + cz) * COUT + (ch & ~31) + (ch & 7) * 4 + ((ch >> 3) & 3)] = k;
+    }
   }
   __syncthreads();                                // hb zeroed before the atomicOr's below
 #pragma unroll 1
@@ -162,106 +170,83 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
   const int lx = warp >> 1, yw = (warp & 1) * 4;
   const int x = x0 + lx;
   const float linx = __ldg(lin + x);
-  const int cx5 = axis_class(x, G) * 5;
-  float liny[4];
-  int cxy[4];
-#pragma unroll
-  for (int v = 0; v < 4; v++) {
-    liny[v] = __ldg(lin + y0 + yw + v);
-    cxy[v] = (cx5 + axis_class(y0 + yw + v, G)) * 5;
-  }
-  uint32_t* stg = stage[warp];
+  const int xl = axis_class(x, G) - axis_class(x0, G);
   // window rows of this lane for the emptiness test (lanes 0..24), M-tile 0
   const int lr = lane < 25 ? lane : 0;
   const uint32_t* win_lane = win + (lx + lr / 5) * 13 + yw + lr % 5;
-  const int swz = (g >> 1) & 3;
-  uint32_t* stg_w = stg + g * 16 + t;
-  const uint32_t* stg_r = stg + (lane >> 2) * 16 + (((lane & 3) ^ ((lane >> 3) & 3)) << 2);
   const uint32_t* halo_lane = halo_w + (lx * 12 + yw) * HW + (g >> 1) + t;   // + row offset * HW + z0 / 2
   const int sh = (g & 1) * 16;
 
 #pragma unroll 1
-  for (int chb = 0; chb < COUT; chb += 32) {
-    float bxy[8], sy[8], sz[8];
-    act_t* outp = out + ((((long long)n * G + x) * G + (y0 + yw)) * G + (lane >> 2)) * COUT + chb + (lane & 3) * 8;
+  for (int pass = 0; pass < COUT / 16; pass++) {            // (32-channel group, M-tile)
+    const int chb = (pass >> 1) * 32, mt = pass & 1;
+    const int ya = yw + 2 * mt;
+    const float liny0 = __ldg(lin + y0 + ya), liny1 = __ldg(lin + y0 + ya + 1);
+    const int yl0 = axis_class(y0 + ya, G) - axis_class(y0, G), yl1 = axis_class(y0 + ya + 1, G) - axis_class(y0, G);
+    const float4* tab0 = tab + ((xl * NYL + yl0) * 5) * COUT + chb + t;
+    const float4* tab1 = tab + ((xl * NYL + yl1) * 5) * COUT + chb + t;
+    float kb[2][8], kz[2][8];                               // c = kb + kz * lin[z]
+    act_t* outp = out + ((((long long)n * G + x) * G + (y0 + ya)) * G + g) * COUT + chb + t * 8;
     const uint2* wf_lane = wfrag + (chb >> 3) * 32 + lane;
+    const uint32_t* win_p = win_lane + 2 * mt;
+    const uint32_t* halo_p = halo_lane + 2 * mt * HW;
+    float linz = __ldg(lin + g);
 #pragma unroll 1
     for (int zt = 0; zt < NZT; zt++) {
       const int z0 = zt * 8;
-      const int z = z0 + g;
-      const float linz = __ldg(lin + z);
-      const int cz = axis_class(z, G);
       if (zt <= 1 || zt == NZT - 1) {
-        // (re)load the coefficient registers: this thread's z class changes only at the first / last z tile
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          const float4 k = s_tab[cz][chb + (i >> 1) * 8 + 2 * t + (i & 1)];
-          bxy[i] = fmaf(k.y, linx, k.x);
-          sy[i] = k.z;
-          sz[i] = k.w;
-        }
-      }
-      float tt[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) tt[i] = fmaf(sz[i], linz, bxy[i]);
-#pragma unroll
-      for (int mt = 0; mt < 2; mt++) {
-        float c[4][4];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-          c[i >> 1][i & 1] = fmaf(sy[i], liny[2 * mt], tt[i]);
-          c[i >> 1][2 + (i & 1)] = fmaf(sy[i], liny[2 * mt + 1], tt[i]);
-        }
-        // rows in the x / y shell of the volume see a clipped window: per-class coefficients
+        // this thread's boundary class changes only at the first, second and last z tile
+        const int cz = axis_class(z0 + g, G);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          const int cxyv = cxy[2 * mt + h];
-          if (cxyv != 60) {
-            const float4* tab = cls_tab + (cxyv + cz) * COUT + chb;
+          const float4* tp = (h ? tab1 : tab0) + cz * COUT;
+          const float ly = h ? liny1 : liny0;
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-              const int ch = (i >> 1) * 8 + 2 * t + (i & 1);
-              const float4 k = __ldg(tab + ch);
-              c[i >> 1][2 * h + (i & 1)] =
-                  fmaf(k.y, linx, fmaf(k.z, liny[2 * mt + h], fmaf(k.w, linz, fmaf(step, k.x, s_bias[chb + ch]))));
-            }
+          for (int i = 0; i < 8; i++) {
+            const float4 k = tp[i * 4];
+            kb[h][i] = fmaf(k.y, linx, fmaf(k.z, ly, k.x));
+            kz[h][i] = k.w;
           }
         }
-        // occupancy channel
-        {
-          const uint32_t rowmask = __ballot_sync(0xffffffffu, lane < 25 && win_lane[zt * 104 + 2 * mt] != 0);
-          uint32_t km = (rowmask | (rowmask >> 1)) & 0x1555555u;    // bit 2s: K step s has a non-empty window row
-          while (km) {
-            const int s2 = __ffs(km) - 1;                           // 2 * s
-            km &= km - 1;
-            const uint32_t* p0 = halo_lane + (c_first_row_off[s2] + 2 * mt) * HW + (z0 >> 1);
-            const uint32_t* p1 = halo_lane + (c_first_row_off[s2 + 1] + 2 * mt) * HW + (z0 >> 1);
-            uint32_t a[4];                                          // halves z0 + g + 2t, + 1 (odd g straddles two words)
-            a[0] = __funnelshift_r(p0[0], p0[1], sh);
-            a[1] = __funnelshift_r(p0[HW], p0[HW + 1], sh);
-            a[2] = __funnelshift_r(p1[0], p1[1], sh);
-            a[3] = __funnelshift_r(p1[HW], p1[HW + 1], sh);
-            const uint2* wf = wf_lane + (s2 >> 1) * (COUT / 8) * 32;
-#pragma unroll
-            for (int nb = 0; nb < 4; nb++) mma_m16n8k16(c[nb], a, __ldg(wf + nb * 32));
-          }
-        }
-        // stage the 16 voxel rows (XOR-swizzled 16-byte chunks), then two 512-byte coalesced stores
-#pragma unroll
-        for (int nb = 0; nb < 4; nb++) {
-          __half2 h0 = __floats2half2_rn(c[nb][0], c[nb][1]);
-          __half2 h1 = __floats2half2_rn(c[nb][2], c[nb][3]);
-          stg_w[(nb ^ swz) << 2] = *reinterpret_cast<uint32_t*>(&h0);
-          stg_w[128 + ((nb ^ swz) << 2)] = *reinterpret_cast<uint32_t*>(&h1);
-        }
-        __syncwarp();
-        const uint4 v0 = *reinterpret_cast<const uint4*>(stg_r);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(stg_r + 128);
-        act_t* dst = outp + ((long long)(2 * mt) * G + z0) * COUT;
-        *reinterpret_cast<uint4*>(dst) = v0;
-        *reinterpret_cast<uint4*>(dst + (long long)G * COUT) = v1;
-        __syncwarp();
       }
+      float c[4][4];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        c[i >> 1][i & 1] = fmaf(kz[0][i], linz, kb[0][i]);
+        c[i >> 1][2 + (i & 1)] = fmaf(kz[1][i], linz, kb[1][i]);
+      }
+      linz = __ldg(lin + min(z0 + 8 + g, G - 1));           // next tile's
+      // occupancy channel
+      {
+        const uint32_t rowmask = __ballot_sync(0xffffffffu, lane < 25 && win_p[zt * 104] != 0);
+        uint32_t km = (rowmask | (rowmask >> 1)) & 0x1555555u;      // bit 2s: K step s has a non-empty window row
+        while (km) {
+          const int s2 = __ffs(km) - 1;                             // 2 * s
+          km &= km - 1;
+          const uint32_t* p0 = halo_p + c_first_row_off[s2] * HW + (z0 >> 1);
+          const uint32_t* p1 = halo_p + c_first_row_off[s2 + 1] * HW + (z0 >> 1);
+          uint32_t a[4];                                            // halves z0 + g + 2t, + 1 (odd g straddles two words)
+          a[0] = __funnelshift_r(p0[0], p0[1], sh);
+          a[1] = __funnelshift_r(p0[HW], p0[HW + 1], sh);
+          a[2] = __funnelshift_r(p1[0], p1[1], sh);
+          a[3] = __funnelshift_r(p1[HW], p1[HW + 1], sh);
+          const uint2* wf = wf_lane + (s2 >> 1) * (COUT / 8) * 32;
+#pragma unroll
+          for (int nb = 0; nb < 4; nb++) mma_m16n8k16(c[nb], a, __ldg(wf + nb * 32));
+        }
+      }
+      // thread (g, t) holds channels t*8 .. t*8+7 of voxel g in both y rows: two 512-byte coalesced warp stores
+      uint32_t pk[8];
+#pragma unroll
+      for (int nb = 0; nb < 4; nb++) {
+        __half2 h0 = __floats2half2_rn(c[nb][0], c[nb][1]);
+        __half2 h1 = __floats2half2_rn(c[nb][2], c[nb][3]);
+        pk[nb] = *reinterpret_cast<uint32_t*>(&h0);
+        pk[4 + nb] = *reinterpret_cast<uint32_t*>(&h1);
+      }
+      act_t* dst = outp + (long long)z0 * COUT;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      *reinterpret_cast<uint4*>(dst + (long long)G * COUT) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
   }
 }
@@ -362,7 +347,14 @@ extern "C" int nm_first_conv_k5(const float* occ, const void* tables, const floa
   const uint2* wf = (const uint2*)(t + (size_t)125 * Cout);
   NM_CHECK_ARG(n <= 65535 && G <= 128, "nm_first_conv_k5: n=%d (max 65535) or grid %d (max 128) too large", n, G);
   dim3 grid(G / 8, G / 4, n);
-  const size_t smem = ((size_t)96 * (G / 2 + 8 + (G + 4 + 31) / 32 + 1) + (size_t)(G / 8) * 104) * sizeof(uint32_t);
+  const size_t smem = ((size_t)96 * (G / 2 + 8 + (G + 4 + 31) / 32 + 1) + (size_t)(G / 8) * 104) * sizeof(uint32_t) +
+                      (size_t)3 * (G == 8 ? 5 : 3) * 5 * Cout * sizeof(float4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NM_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    NM_CHECK_CUDA(cudaFuncSetAttribute(first_conv_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout == 32) {
     first_conv_kernel<32><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out);
