@@ -67,6 +67,20 @@ int nm_conv3d_direct(const void* x, const float* weight, const float* bias, void
  * permuted to tap-major (8, Cin, Cout) */
 int nm_conv_transpose3d_k2s2(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H,
                              int W, int Cin, int Cout, void* stream);
+/* Pointwise-shaped convolutions with Cin = 32 on mma.sync, organised around the memory pipe: Conv3d(k2, s2) of
+ * Pool3DBlock (modules/vox_modules.py:49-61) and the 1x1 skip convolution of Res3DBlock (modules/vox_modules.py:35-38),
+ * Cout in {32, 64}.  Optional fused input transform act(x*in_scale+in_shift) with in_scale/in_shift (n, Cin) fp32 (the
+ * producer's GroupNorm folded to scale/shift; in_act != 0: LeakyReLU 0.01) and fused GroupNorm statistics of the
+ * output: stats_partial [n][chunks][Cout][2] for nm_groupnorm_finalize, chunks = nm_conv3d_pw_stats_chunks(...).
+ * packed_w comes from nm_pack_conv_pw_weights (weight: the nn.Conv3d (Cout, Cin, k, k, k) fp32 tensor). */
+int nm_conv3d_pw_supported(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);
+int nm_conv3d_pw_stats_chunks(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);
+size_t nm_conv3d_pw_packed_bytes(int Cin, int Cout, int k);
+int nm_pack_conv_pw_weights(const float* weight, int Cin, int Cout, int k, void* packed, void* stream);
+int nm_conv3d_pw(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W, int Cin,
+                 int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
+                 float* stats_partial, void* stream);
+
 /* First layer: add_coord_channels (utils/kypt_detector_utils.py:4-26) + Conv3d(1+3, Cout, k5, pad 2)
  * (model/kypt_detector.py:266).  occ: (n, G, G, G) fp32; weight (Cout, 4, 5, 5, 5) fp32; out: act (n,G,G,G,Cout).
  * `tables` is built once per weight set by nm_first_conv_prepare. linspace: torch.linspace(-1,1,G) fp32. */

@@ -1,0 +1,319 @@
+// Pointwise-shaped convolutions of the feature nets, Cin = 32: the learned 2x down-sample Conv3d(k2, s2)
+// (Pool3DBlock, reference modules/vox_modules.py:49-61) and the 1x1 skip convolution of Res3DBlock
+// (modules/vox_modules.py:35-38).  These layers move 10-20 bytes per FLOP-hundred: they are HBM-bound, so the kernel
+// is organised around the memory pipe, not the tensor pipe:
+//   * every input byte is loaded exactly once, by 16-byte coalesced global loads straight into the registers that
+//     become the mma.sync A fragments - the K order of the GEMM is permuted (here and in the packed weights) so that
+//     the 8 consecutive channels a lane loads are exactly the K slots that lane owns in two k-steps: no shared-memory
+//     staging, no shuffles;
+//   * the producer's GroupNorm scale/shift + LeakyReLU is applied to those registers (fp32 math), so the activated
+//     tensor never exists in HBM;
+//   * fragment columns are permuted so that a lane owns 8 consecutive output channels: 16-byte coalesced stores
+//     straight from the accumulators;
+//   * the per-channel sum / sum of squares the following GroupNorm needs are accumulated from the fp32 accumulators
+//     and written as one deterministic partial per block.
+// fp16 operands, fp32 accumulation (same numerics as the tcgen05 kernels).
+#include "common.cuh"
+#include "../../include/nm_b200.h"
+
+namespace {
+
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                             const uint32_t a3, const uint2 b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+}
+
+// Output channel of fragment column g of n-block nb (see the header comment)
+__host__ __device__ inline int pw_channel(int nb, int g) { return (nb >> 2) * 32 + (g >> 1) * 8 + (nb & 3) * 2 + (g & 1); }
+
+// wfrag[(tap*2 + s)][nb][lane] = B fragment of k-step s of tap `tap`: K slot (2t+j+8*hi) <-> ci = t*8 + s*4 + hi*2 + j
+__global__ void pack_pw_kernel(const float* __restrict__ w /* (Cout, 32, k, k, k) */, int Cout, int taps,
+                               uint2* __restrict__ wfrag) {
+  const int NB = Cout / 8;
+  const int total = taps * 2 * NB * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int lane = i & 31, nb = (i >> 5) % NB, ks = (i >> 5) / NB, tap = ks >> 1, s = ks & 1;
+    const int g = lane >> 2, t = lane & 3, co = pw_channel(nb, g);
+    auto wv = [&](int ci) -> float { return w[((long long)co * 32 + ci) * taps + tap]; };
+    const int c0 = t * 8 + s * 4;
+    __half2 b0 = __floats2half2_rn(wv(c0), wv(c0 + 1));
+    __half2 b1 = __floats2half2_rn(wv(c0 + 2), wv(c0 + 3));
+    wfrag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+  }
+}
+
+// 8 fp16 channels: y = lrelu?(x * a + b), fp32 math, back to fp16
+__device__ __forceinline__ uint4 xform8(const uint4 v, const float (&a)[8], const float (&b)[8], const bool act) {
+  const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[i]));
+    __half2 h = __floats2half2_rn(fmaf(f.x, a[2 * i], b[2 * i]), fmaf(f.y, a[2 * i + 1], b[2 * i + 1]));
+    if (act) h = __hmax2(h, __hmul2(h, __float2half2_rn(0.01f)));
+    o[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+struct PwParams {
+  const act_t* x;
+  const uint2* wfrag;
+  const float* bias;
+  act_t* out;
+  const float* in_scale;   // (n, 32) or null
+  const float* in_shift;
+  float* stats;            // [n][chunks][COUT][2] or null
+  int in_act;
+  int H, W;                // input dims (D implied)
+  int OH, OW;              // output dims
+  long long in_frame, out_frame;   // elements per frame
+  int tiles_per_block;     // M-tiles (16 output voxels) per block
+  uint32_t ow_magic, oh_magic;
+};
+
+// TAPS = 1: 1x1 conv; TAPS = 8: k2 s2.  MT M-tiles per warp iteration.
+template <int COUT, int TAPS, int MT>
+__global__ void __launch_bounds__(256, 2) conv_pw_kernel(const PwParams p) {
+  constexpr int NB = COUT / 8;
+  constexpr int KS = TAPS * 2;
+  extern __shared__ __align__(16) uint2 s_w[];           // [KS][NB][32]
+  __shared__ float s_red[8][COUT][2];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < KS * NB * 32; i += 256) s_w[i] = __ldg(p.wfrag + i);
+  const bool xf = p.in_scale != nullptr;
+  const bool act = p.in_act != 0;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    sa[i] = xf ? __ldg(p.in_scale + n * 32 + t * 8 + i) : 1.f;
+    sb[i] = xf ? __ldg(p.in_shift + n * 32 + t * 8 + i) : 0.f;
+  }
+  float bia[NB][2];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) {
+    bia[nb][0] = __ldg(p.bias + pw_channel(nb, 2 * t));
+    bia[nb][1] = __ldg(p.bias + pw_channel(nb, 2 * t + 1));
+  }
+  float ssum[NB][2], ssq[NB][2];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) ssum[nb][0] = ssum[nb][1] = ssq[nb][0] = ssq[nb][1] = 0.f;
+  __syncthreads();
+
+  const act_t* xin = p.x + (long long)n * p.in_frame + t * 8;
+  act_t* xout = p.out + (long long)n * p.out_frame + t * 8;
+  const int tile_base = chunk * p.tiles_per_block;
+  const int pairs = p.tiles_per_block / MT;
+
+  // input offset (elements) of output voxel o, tap 0
+  auto in_off = [&](int o) -> int {
+    if (TAPS == 1) return o * 32;
+    const int q = (int)__umulhi((uint32_t)o, p.ow_magic);       // o / OW
+    const int oz = o - q * p.OW;
+    const int ox = (int)__umulhi((uint32_t)q, p.oh_magic);      // q / OH
+    const int oy = q - ox * p.OH;
+    return (((2 * ox) * p.H + 2 * oy) * p.W + 2 * oz) * 32;
+  };
+  auto tap_off = [&](int tap) -> int {
+    if (TAPS == 1) return 0;
+    return ((((tap >> 2) & 1) * p.H + ((tap >> 1) & 1)) * p.W + (tap & 1)) * 32;
+  };
+
+  uint4 cur[MT][2], nxt[MT][2];
+  int off[MT][2];
+  if (warp < pairs) {
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        off[m][r] = in_off((tile_base + warp * MT + m) * 16 + r * 8 + g);
+        cur[m][r] = __ldg(reinterpret_cast<const uint4*>(xin + off[m][r]));
+      }
+  }
+#pragma unroll 1
+  for (int pr = warp; pr < pairs; pr += 8) {
+    const int tile0 = tile_base + pr * MT;
+    float c[MT][NB][4];
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) {
+        c[m][nb][0] = c[m][nb][2] = bia[nb][0];
+        c[m][nb][1] = c[m][nb][3] = bia[nb][1];
+      }
+    int noff[MT][2];
+    const bool more = pr + 8 < pairs;
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) noff[m][r] = more ? in_off((tile0 + 8 * MT + m) * 16 + r * 8 + g) : off[m][r];
+#pragma unroll
+    for (int tap = 0; tap < TAPS; tap++) {
+      // prefetch the next step's rows (next tap, or tap 0 of this warp's next M-tiles)
+#pragma unroll
+      for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+          if (tap + 1 < TAPS) nxt[m][r] = __ldg(reinterpret_cast<const uint4*>(xin + off[m][r] + tap_off(tap + 1)));
+          else if (more) nxt[m][r] = __ldg(reinterpret_cast<const uint4*>(xin + noff[m][r]));
+        }
+#pragma unroll
+      for (int m = 0; m < MT; m++) {
+        const uint4 r0 = xf ? xform8(cur[m][0], sa, sb, act) : cur[m][0];
+        const uint4 r1 = xf ? xform8(cur[m][1], sa, sb, act) : cur[m][1];
+#pragma unroll
+        for (int nb = 0; nb < NB; nb++) {
+          mma_m16n8k16(c[m][nb], r0.x, r1.x, r0.y, r1.y, s_w[((tap * 2) * NB + nb) * 32 + lane]);
+          mma_m16n8k16(c[m][nb], r0.z, r1.z, r0.w, r1.w, s_w[((tap * 2 + 1) * NB + nb) * 32 + lane]);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < MT; m++)
+#pragma unroll
+        for (int r = 0; r < 2; r++) cur[m][r] = nxt[m][r];
+    }
+#pragma unroll
+    for (int m = 0; m < MT; m++)
+#pragma unroll
+      for (int r = 0; r < 2; r++) off[m][r] = noff[m][r];
+    // epilogue: statistics from the fp32 accumulators, 16-byte stores of 8 consecutive channels
+#pragma unroll
+    for (int m = 0; m < MT; m++) {
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const float v0 = c[m][nb][j], v1 = c[m][nb][2 + j];
+          ssum[nb][j] += v0 + v1;
+          ssq[nb][j] = fmaf(v0, v0, fmaf(v1, v1, ssq[nb][j]));
+        }
+      act_t* o0 = xout + (long long)((tile0 + m) * 16 + g) * COUT;
+#pragma unroll
+      for (int q = 0; q < NB / 4; q++) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          __half2 h0 = __floats2half2_rn(c[m][4 * q + i][0], c[m][4 * q + i][1]);
+          __half2 h1 = __floats2half2_rn(c[m][4 * q + i][2], c[m][4 * q + i][3]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[4 + i] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        *reinterpret_cast<uint4*>(o0 + q * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(o0 + 8 * COUT + q * 32) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  if (p.stats == nullptr) return;
+  // per-channel partials of this block: sum over the 8 fragment rows (shuffles), then over the 8 warps (fixed order)
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      float a = ssum[nb][j], q = ssq[nb][j];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (g == 0) {
+        const int ch = pw_channel(nb, 2 * t + j);
+        s_red[warp][ch][0] = a;
+        s_red[warp][ch][1] = q;
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * 2; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) a += s_red[w][i >> 1][i & 1];
+    p.stats[(((long long)n * gridDim.x + chunk) * COUT) * 2 + i] = a;
+  }
+}
+
+struct PwPlan {
+  bool ok;
+  int taps, OD, OH, OW, tiles, tiles_per_block, chunks, mt;
+};
+
+PwPlan plan_pw(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
+  PwPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  const bool shape = Cin == 32 && (Cout == 32 || Cout == 64) && ((k == 1 && stride == 1) || (k == 2 && stride == 2));
+  if (!shape || n <= 0 || n > 65535) return pl;
+  if (stride == 2 && ((D | H | W) & 1)) return pl;
+  pl.taps = k == 1 ? 1 : 8;
+  pl.OD = D / stride; pl.OH = H / stride; pl.OW = W / stride;
+  const long long M = (long long)pl.OD * pl.OH * pl.OW;
+  pl.mt = 1;
+  if (pl.OW % 8 != 0 || M % (16 * pl.mt) != 0 || (long long)D * H * W * 32 >= (1ll << 31)) return pl;
+  pl.tiles = (int)(M / 16);
+  // 8 warps x 8 iterations of MT tiles per block when the frame is large enough
+  int tpb = 64 * pl.mt;
+  while (tpb > pl.mt && pl.tiles % tpb != 0) tpb >>= 1;
+  if (pl.tiles % tpb != 0) return pl;
+  pl.tiles_per_block = tpb;
+  pl.chunks = pl.tiles / tpb;
+  pl.ok = true;
+  return pl;
+}
+
+template <int COUT, int TAPS, int MT>
+int launch_pw(const PwParams& p, int chunks, int n, cudaStream_t st) {
+  const size_t smem = (size_t)TAPS * 2 * (COUT / 8) * 32 * sizeof(uint2);
+  conv_pw_kernel<COUT, TAPS, MT><<<dim3(chunks, n), 256, smem, st>>>(p);
+  NM_CHECK_LAUNCH("conv3d_pw");
+  return NM_OK;
+}
+
+}  // namespace
+
+extern "C" int nm_conv3d_pw_supported(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
+  return plan_pw(n, D, H, W, Cin, Cout, k, stride).ok ? 1 : 0;
+}
+
+extern "C" int nm_conv3d_pw_stats_chunks(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
+  const PwPlan pl = plan_pw(n, D, H, W, Cin, Cout, k, stride);
+  return pl.ok ? pl.chunks : 0;
+}
+
+extern "C" size_t nm_conv3d_pw_packed_bytes(int Cin, int Cout, int k) {
+  return (size_t)(k == 1 ? 1 : 8) * 2 * (Cout / 8) * 32 * sizeof(uint2);
+}
+
+extern "C" int nm_pack_conv_pw_weights(const float* weight, int Cin, int Cout, int k, void* packed, void* stream) {
+  NM_CHECK_ARG(weight && packed, "nm_pack_conv_pw_weights: null pointer");
+  NM_CHECK_ARG(Cin == 32 && (Cout == 32 || Cout == 64) && (k == 1 || k == 2),
+               "nm_pack_conv_pw_weights: Cin=%d Cout=%d k=%d unsupported", Cin, Cout, k);
+  pack_pw_kernel<<<16, 256, 0, (cudaStream_t)stream>>>(weight, Cout, k == 1 ? 1 : 8, (uint2*)packed);
+  NM_CHECK_LAUNCH("pack_conv_pw_weights");
+  return NM_OK;
+}
+
+extern "C" int nm_conv3d_pw(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H,
+                            int W, int Cin, int Cout, int k, int stride, const float* in_scale, const float* in_shift,
+                            int in_act, float* stats_partial, void* stream) {
+  NM_CHECK_ARG(x && packed_w && bias && out, "nm_conv3d_pw: null pointer");
+  NM_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "nm_conv3d_pw: in_scale and in_shift go together");
+  if (n == 0) return NM_OK;
+  const PwPlan pl = plan_pw(n, D, H, W, Cin, Cout, k, stride);
+  NM_CHECK_ARG(pl.ok, "nm_conv3d_pw: unsupported shape n=%d %dx%dx%d Cin=%d Cout=%d k=%d s=%d (see nm_conv3d_pw_supported)",
+               n, D, H, W, Cin, Cout, k, stride);
+  PwParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const act_t*)x; p.wfrag = (const uint2*)packed_w; p.bias = bias; p.out = (act_t*)out;
+  p.in_scale = in_scale; p.in_shift = in_shift; p.in_act = in_act; p.stats = stats_partial;
+  p.H = H; p.W = W; p.OH = pl.OH; p.OW = pl.OW;
+  p.in_frame = (long long)D * H * W * 32;
+  p.out_frame = (long long)pl.OD * pl.OH * pl.OW * Cout;
+  p.tiles_per_block = pl.tiles_per_block;
+  p.ow_magic = 0xffffffffu / (uint32_t)pl.OW + 1u;
+  p.oh_magic = 0xffffffffu / (uint32_t)pl.OH + 1u;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pl.taps == 8 && Cout == 32) return launch_pw<32, 8, 1>(p, pl.chunks, n, st);
+  if (pl.taps == 8 && Cout == 64) return launch_pw<64, 8, 1>(p, pl.chunks, n, st);
+  if (pl.taps == 1 && Cout == 32) return launch_pw<32, 1, 1>(p, pl.chunks, n, st);
+  return launch_pw<64, 1, 1>(p, pl.chunks, n, st);
+}

@@ -54,8 +54,10 @@ def _feature_net(in_channels, out_channels, grid_size):
 
 def run_feature_net(net: nn.Sequential, occ: torch.Tensor) -> torch.Tensor:
     """occ (n, G, G, G) fp32 -> act (n, G/4, G/4, G/4, C)."""
-    x = net[0].run_coordconv(occ)
-    for block in list(net)[1:]:
+    # the first layer's GroupNorm + LeakyReLU is applied inside the pool conv that follows
+    raw, a, b = net[0].run_coordconv_raw(occ)
+    x = net[1].run(raw, in_affine=(a, b))
+    for block in list(net)[2:]:
         x = block.run(x)
     return x
 

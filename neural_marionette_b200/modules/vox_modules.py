@@ -27,7 +27,14 @@ class _ActModule(nn.Module):
             return ops.act_to_ncdhw(self.run(ops.ncdhw_to_act(x)))
 
 
-def conv_gn_lrelu(x, conv, gn):
+def conv_gn_lrelu(x, conv, gn, in_affine=None):
+    """LeakyReLU(GN(conv(x))); with in_affine = (scale, shift) x is a RAW conv output whose GroupNorm + LeakyReLU is
+    applied inside this conv's operand path when the kernel supports it, else by a separate pass."""
+    if in_affine is not None:
+        if ops.can_fuse_input(x, conv):
+            raw, a, b = ops.conv3d(x, conv, gn, in_affine=(in_affine[0], in_affine[1], True))
+            return ops.affine_act(raw, a, b, True)
+        x = ops.affine_act(x, in_affine[0], in_affine[1], True)
     raw, a, b = ops.conv3d(x, conv, gn)
     return ops.affine_act(raw, a, b, True)
 
@@ -46,9 +53,14 @@ class Basic3DBlock(_ActModule):
 
     def run_coordconv(self, occ):
         """occ (n, G, G, G) fp32 occupancy; the 3 coordinate channels are synthesised in-kernel."""
+        raw, a, b = self.run_coordconv_raw(occ)
+        return ops.affine_act(raw, a, b, True)
+
+    def run_coordconv_raw(self, occ):
+        """-> (raw conv output, GroupNorm scale, shift): the consumer applies the normalisation + LeakyReLU."""
         raw = ops.first_conv(occ, self.block[0])
         a, b = ops.gn_scale_shift(raw, self.block[1])
-        return ops.affine_act(raw, a, b, True)
+        return raw, a, b
 
 
 class Res3DBlock(_ActModule):
@@ -88,8 +100,8 @@ class Pool3DBlock(_ActModule):
             nn.Conv3d(input_plane, input_plane, kernel_size=pool_size, stride=pool_size, padding=0),
             _norm(input_plane), nn.LeakyReLU())
 
-    def run(self, x):
-        return conv_gn_lrelu(x, self.stride_conv[0], self.stride_conv[1])
+    def run(self, x, in_affine=None):
+        return conv_gn_lrelu(x, self.stride_conv[0], self.stride_conv[1], in_affine)
 
 
 class Upsample3DBlock(_ActModule):

@@ -73,6 +73,16 @@ def packed_conv_weight(conv: torch.nn.Conv3d) -> torch.Tensor:
     return _cached(conv, "packed", [conv.weight], build)
 
 
+def packed_pw_weight(conv: torch.nn.Conv3d) -> torch.Tensor:
+    def build():
+        w = conv.weight.detach().float().contiguous()
+        co, ci, k = w.shape[0], w.shape[1], w.shape[2]
+        out = torch.empty(L.query("nm_conv3d_pw_packed_bytes", ci, co, k), dtype=torch.uint8, device=w.device)
+        L.call("nm_pack_conv_pw_weights", L.ptr(w), ci, co, k, L.ptr(out), L.stream())
+        return out
+    return _cached(conv, "packed_pw", [conv.weight], build)
+
+
 def f32(module, name: str) -> torch.Tensor:
     p = getattr(module, name)
     return _cached(module, "f32_" + name, [p], lambda: p.detach().float().contiguous())
@@ -121,8 +131,17 @@ def _tc_ok(conv, Cin):
 def can_fuse_input(x: torch.Tensor, conv: torch.nn.Conv3d) -> bool:
     """True when conv3d(x, conv, in_affine=...) can apply the producer's GroupNorm (+LeakyReLU) on the fly."""
     n, D, H, W, Cin = x.shape
+    if _pw_ok(x, conv):
+        return True
     return _tc_ok(conv, Cin) and bool(L.query("nm_conv3d_can_fuse_input", n, D, H, W, Cin, conv.out_channels,
                                               conv.kernel_size[0], conv.stride[0]))
+
+
+def _pw_ok(x, conv) -> bool:
+    """The memory-pipe-oriented mma.sync kernel covers this layer (Cin = 32 pool / 1x1 convs)."""
+    n, D, H, W, Cin = x.shape
+    k, s = conv.kernel_size[0], conv.stride[0]
+    return conv.padding[0] == 0 and bool(L.query("nm_conv3d_pw_supported", n, D, H, W, Cin, conv.out_channels, k, s))
 
 
 def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
@@ -140,15 +159,22 @@ def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNo
         out = conv3d_direct(x, conv)
         return (out,) + gn_scale_shift(out, gn) if gn is not None else out
     out = torch.empty(n, D // s, H // s, W // s, Cout, dtype=ACT_DTYPE, device=x.device)
-    pw, pb = packed_conv_weight(conv), f32(conv, "bias")
-    chunks = L.query("nm_conv3d_stats_chunks", n, D, H, W, Cin, Cout, k, s) if gn is not None else 0
+    pointwise = _pw_ok(x, conv)
+    pw, pb = packed_pw_weight(conv) if pointwise else packed_conv_weight(conv), f32(conv, "bias")
+    chunks = 0
+    if gn is not None:
+        chunks = L.query("nm_conv3d_pw_stats_chunks" if pointwise else "nm_conv3d_stats_chunks", n, D, H, W, Cin, Cout, k, s)
     partial = None
     if chunks > 0:
         partial = workspace(n * chunks * Cout * 8, x.device, "gn").view(torch.float32)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    if in_affine is None:
+    if pointwise:
+        ia = in_affine if in_affine is not None else (None, None, False)
+        L.call("nm_conv3d_pw", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
+               L.ptr(ia[0]), L.ptr(ia[1]), int(ia[2]), L.ptr(partial), L.stream())
+    elif in_affine is None:
         L.call("nm_conv3d_tc", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
                L.ptr(partial), L.stream())
     else:

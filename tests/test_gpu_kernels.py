@@ -165,6 +165,41 @@ def test_conv3d_fused_input_groupnorm(ops, n, grid, cin, cout):
     assert rel_err(got.float().cpu(), ref.float().cpu()) < 2e-3
 
 
+@pytest.mark.parametrize("n,grid,cout,k,stride", [(2, 16, 32, 2, 2), (1, 32, 32, 2, 2), (3, 8, 64, 1, 1),
+                                                 (2, 16, 64, 1, 1), (5, 16, 32, 1, 1)])
+def test_conv3d_pointwise_fused_input(ops, n, grid, cout, k, stride):
+    """Cin = 32 pool / 1x1 convs on the memory-pipe kernel: plain, and with the producer's GroupNorm + LeakyReLU
+    applied in registers; GroupNorm statistics of the output from the accumulators."""
+    g = torch.Generator().manual_seed(grid * 3 + cout + k)
+    conv = torch.nn.Conv3d(32, cout, k, stride, 0)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (32 * k ** 3) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g))
+    gn_out = torch.nn.GroupNorm(cout // 16, cout).cuda()
+    x = torch.randn(n, 32, grid, grid, grid, generator=g) * 1.5 + 0.3
+    raw_in = to_act(x)
+    assert ops._pw_ok(raw_in, conv) and ops.can_fuse_input(raw_in, conv)
+    ref = F.conv3d(x.half().float(), conv.weight.detach().half().float(), conv.bias.detach(), stride=stride)
+    conv = conv.cuda()
+    assert rel_err(from_act(ops.conv3d(raw_in, conv)), ref) < 2e-3
+    a = (0.5 + torch.rand(n, 32, generator=g)).cuda()
+    b = torch.randn(n, 32, generator=g).cuda()
+    act_in = F.leaky_relu(x.half().float() * a.cpu()[:, :, None, None, None] + b.cpu()[:, :, None, None, None], 0.01)
+    ref2 = F.conv3d(act_in.half().float(), conv.weight.detach().cpu().half().float(), conv.bias.detach().cpu(),
+                    stride=stride)
+    got, ga, gb = ops.conv3d(raw_in, conv, gn_out, in_affine=(a, b, True))
+    torch.cuda.synchronize()
+    assert rel_err(from_act(got), ref2) < 2e-3
+    ra, rb = ops.gn_scale_shift(got, gn_out)
+    assert (ga - ra).abs().max() <= 2e-3 * ra.abs().max() and (gb - rb).abs().max() <= 2e-3 * (1 + rb.abs().max())
+    # no activation: pure affine
+    got3 = ops.conv3d(raw_in, conv, in_affine=(a, b, False))
+    lin_in = x.half().float() * a.cpu()[:, :, None, None, None] + b.cpu()[:, :, None, None, None]
+    ref3 = F.conv3d(lin_in.half().float(), conv.weight.detach().cpu().half().float(), conv.bias.detach().cpu(),
+                    stride=stride)
+    assert rel_err(from_act(got3), ref3) < 2e-3
+
+
 def test_first_conv_coordconv(ops):
     for G, cout in [(16, 32), (32, 64)]:
         g = torch.Generator().manual_seed(G + cout)
