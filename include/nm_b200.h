@@ -86,8 +86,11 @@ int nm_conv3d_pw(const void* x, const void* packed_w, const float* bias, void* o
  * `tables` is built once per weight set by nm_first_conv_prepare. linspace: torch.linspace(-1,1,G) fp32. */
 size_t nm_first_conv_tables_bytes(int Cout);
 int nm_first_conv_prepare(const float* weight, int Cout, void* tables, void* stream);
+int nm_first_conv_stats_chunks(int G);
+/* stats_partial: null, or [n][nm_first_conv_stats_chunks(G)][Cout][2] per-channel (sum, sum of squares) partials of
+ * the output for nm_groupnorm_finalize (the GroupNorm that follows, modules/vox_modules.py:14). */
 int nm_first_conv_k5(const float* occ, const void* tables, const float* bias, const float* linspace, int n, int G,
-                     int Cout, void* out, void* stream);
+                     int Cout, void* out, float* stats_partial, void* stream);
 
 /* ---- GroupNorm / pointwise ---------------------------------------------------------------------------
  * nn.GroupNorm(C//16, C) statistics (modules/vox_modules.py:14,...) folded to per-(sample, channel)

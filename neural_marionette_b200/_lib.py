@@ -50,7 +50,8 @@ PROTOTYPES = {
     "nm_conv_transpose3d_k2s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_first_conv_tables_bytes": (_sz, [_i]),
     "nm_first_conv_prepare": (_i, [_vp, _i, _vp, _vp]),
-    "nm_first_conv_k5": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nm_first_conv_stats_chunks": (_i, [_i]),
+    "nm_first_conv_k5": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nm_gn_workspace_bytes": (_sz, [_i, _i, _i]),
     "nm_groupnorm_scale_shift": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
     "nm_affine_act": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -89,8 +89,10 @@ __constant__ int c_first_row_off[26] = {0, 1, 2, 3, 4, 12, 13, 14, 15, 16, 24, 2
 template <int COUT>
 __global__ void __launch_bounds__(256, 2)
 first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_tab, const uint2* __restrict__ wfrag,
-                  const float* __restrict__ bias, const float* __restrict__ lin, int G, act_t* __restrict__ out) {
+                  const float* __restrict__ bias, const float* __restrict__ lin, int G, act_t* __restrict__ out,
+                  float* __restrict__ stats /* [n][blocks per frame][COUT][2] or null */) {
   extern __shared__ __align__(16) uint32_t dyn_smem[];
+  __shared__ float s_red[8][COUT][2];
   // halo_w[R][HW]: row R = hx*12 + hy, half index i = z + 2 (z = -2 .. G+5 and zero padding up to 2*HW)
   // hb[R][HBW]: bit i of the row: halo value != 0
   // win[zt][hx*13 + hyp]: 12-bit occupancy window of z tile zt, rows (hx, hyp) | (hx, hyp+1)  (hyp = 0..10)
@@ -177,10 +179,15 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
   const uint32_t* halo_lane = halo_w + (lx * 12 + yw) * HW + (g >> 1) + t;   // + row offset * HW + z0 / 2
   const int sh = (g & 1) * 16;
 
+  float ssum[8], ssq[8];                                    // GroupNorm statistics of channels chb + t*8 + i
 #pragma unroll 1
   for (int pass = 0; pass < COUT / 16; pass++) {            // (32-channel group, M-tile)
     const int chb = (pass >> 1) * 32, mt = pass & 1;
     const int ya = yw + 2 * mt;
+    if (mt == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) ssum[i] = ssq[i] = 0.f;
+    }
     const float liny0 = __ldg(lin + y0 + ya), liny1 = __ldg(lin + y0 + ya + 1);
     const int yl0 = axis_class(y0 + ya, G) - axis_class(y0, G), yl1 = axis_class(y0 + ya + 1, G) - axis_class(y0, G);
     const float4* tab0 = tab + ((xl * NYL + yl0) * 5) * COUT + chb + t;
@@ -191,11 +198,27 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
     const uint32_t* win_p = win_lane + 2 * mt;
     const uint32_t* halo_p = halo_lane + 2 * mt * HW;
     float linz = __ldg(lin + g);
+    // GroupNorm statistics: M-tiles without occupancy hits are pure kb + kz * lin[z]: their sum and sum of squares
+    // follow from (count, sum lin, sum lin^2) of the tiles seen since the coefficients were loaded (3 FMAs per
+    // M-tile instead of 32); M-tiles with hits accumulate their accumulators explicitly.
+    float e_cnt = 0.f, e_s1 = 0.f, e_s2 = 0.f;
+    auto fold_stats = [&]() {
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float b_ = kb[h][i], z_ = kz[h][i];
+          ssum[i] += fmaf(e_cnt, b_, z_ * e_s1);
+          ssq[i] += fmaf(e_cnt * b_, b_, fmaf(2.f * b_ * z_, e_s1, z_ * z_ * e_s2));
+        }
+      e_cnt = e_s1 = e_s2 = 0.f;
+    };
 #pragma unroll 1
     for (int zt = 0; zt < NZT; zt++) {
       const int z0 = zt * 8;
       if (zt <= 1 || zt == NZT - 1) {
         // this thread's boundary class changes only at the first, second and last z tile
+        if (e_cnt != 0.f) fold_stats();
         const int cz = axis_class(z0 + g, G);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -215,11 +238,14 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
         c[i >> 1][i & 1] = fmaf(kz[0][i], linz, kb[0][i]);
         c[i >> 1][2 + (i & 1)] = fmaf(kz[1][i], linz, kb[1][i]);
       }
+      const float linz_cur = linz;
       linz = __ldg(lin + min(z0 + 8 + g, G - 1));           // next tile's
       // occupancy channel
+      bool hit;
       {
         const uint32_t rowmask = __ballot_sync(0xffffffffu, lane < 25 && win_p[zt * 104] != 0);
         uint32_t km = (rowmask | (rowmask >> 1)) & 0x1555555u;      // bit 2s: K step s has a non-empty window row
+        hit = km != 0;
         while (km) {
           const int s2 = __ffs(km) - 1;                             // 2 * s
           km &= km - 1;
@@ -235,6 +261,20 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
           for (int nb = 0; nb < 4; nb++) mma_m16n8k16(c[nb], a, __ldg(wf + nb * 32));
         }
       }
+      if (stats != nullptr) {
+        if (hit) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const float v0 = c[i >> 1][i & 1], v1 = c[i >> 1][2 + (i & 1)];
+            ssum[i] += v0 + v1;
+            ssq[i] = fmaf(v0, v0, fmaf(v1, v1, ssq[i]));
+          }
+        } else {
+          e_cnt += 1.f;
+          e_s1 += linz_cur;
+          e_s2 = fmaf(linz_cur, linz_cur, e_s2);
+        }
+      }
       // thread (g, t) holds channels t*8 .. t*8+7 of voxel g in both y rows: two 512-byte coalesced warp stores
       uint32_t pk[8];
 #pragma unroll
@@ -248,6 +288,30 @@ first_conv_kernel(const float* __restrict__ occ, const float4* __restrict__ cls_
       *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(dst + (long long)G * COUT) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     }
+    if (e_cnt != 0.f) fold_stats();
+    if (stats != nullptr && mt == 1) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        float a = ssum[i], q = ssq[i];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g == 0) {
+          s_red[warp][chb + t * 8 + i][0] = a;
+          s_red[warp][chb + t * 8 + i][1] = q;
+        }
+      }
+    }
+  }
+  if (stats == nullptr) return;
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * 2; i += 256) {       // fixed-order fold of the 8 warps: deterministic
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) a += s_red[w][i >> 1][i & 1];
+    stats[(((long long)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * COUT * 2 + i] = a;
   }
 }
 
@@ -338,8 +402,10 @@ extern "C" int nm_first_conv_prepare(const float* weight, int Cout, void* tables
   return NM_OK;
 }
 
+extern "C" int nm_first_conv_stats_chunks(int G) { return (G / 8) * (G / 4); }
+
 extern "C" int nm_first_conv_k5(const float* occ, const void* tables, const float* bias, const float* linspace,
-                                int n, int G, int Cout, void* out, void* stream) {
+                                int n, int G, int Cout, void* out, float* stats_partial, void* stream) {
   NM_CHECK_ARG(occ && tables && bias && linspace && out, "nm_first_conv_k5: null pointer");
   NM_CHECK_ARG(G % 8 == 0 && G >= 8, "nm_first_conv_k5: grid %d must be a multiple of 8", G);
   if (n == 0) return NM_OK;
@@ -357,9 +423,9 @@ extern "C" int nm_first_conv_k5(const float* occ, const void* tables, const floa
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (Cout == 32) {
-    first_conv_kernel<32><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out);
+    first_conv_kernel<32><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out, stats_partial);
   } else if (Cout == 64) {
-    first_conv_kernel<64><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out);
+    first_conv_kernel<64><<<grid, 256, smem, st>>>(occ, t, wf, bias, linspace, G, (act_t*)out, stats_partial);
   } else {
     NM_CHECK_ARG(false, "nm_first_conv_k5: Cout=%d unsupported", Cout);
   }

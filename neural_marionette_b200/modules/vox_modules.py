@@ -58,9 +58,7 @@ class Basic3DBlock(_ActModule):
 
     def run_coordconv_raw(self, occ):
         """-> (raw conv output, GroupNorm scale, shift): the consumer applies the normalisation + LeakyReLU."""
-        raw = ops.first_conv(occ, self.block[0])
-        a, b = ops.gn_scale_shift(raw, self.block[1])
-        return raw, a, b
+        return ops.first_conv(occ, self.block[0], self.block[1])
 
 
 class Res3DBlock(_ActModule):

@@ -220,8 +220,9 @@ def conv_transpose3d(x: torch.Tensor, conv: torch.nn.ConvTranspose3d) -> torch.T
     return out
 
 
-def first_conv(occ: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
-    """occ (n, G, G, G) fp32 -> act (n, G, G, G, Cout): CoordConv k5 layer with analytic coordinate channels."""
+def first_conv(occ: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None):
+    """occ (n, G, G, G) fp32 -> act (n, G, G, G, Cout): CoordConv k5 layer with analytic coordinate channels.
+    With `gn`: returns (raw, scale, shift) of the GroupNorm that follows, statistics from the kernel's accumulators."""
     _need_cuda(occ)
     n, G = occ.shape[0], occ.shape[1]
     Cout = conv.out_channels
@@ -233,9 +234,17 @@ def first_conv(occ: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
         return t
     tables = _cached(conv, "first_tables", [conv.weight], build)
     out = torch.empty(n, G, G, G, Cout, dtype=ACT_DTYPE, device=occ.device)
+    chunks = L.query("nm_first_conv_stats_chunks", G) if gn is not None else 0
+    partial = workspace(n * chunks * Cout * 8, occ.device, "gn").view(torch.float32) if chunks else None
     L.call("nm_first_conv_k5", L.ptr(occ), L.ptr(tables), L.ptr(f32(conv, "bias")), L.ptr(linspace(G, occ.device)),
-           n, G, Cout, L.ptr(out), L.stream())
-    return out
+           n, G, Cout, L.ptr(out), L.ptr(partial), L.stream())
+    if gn is None:
+        return out
+    a = torch.empty(n, Cout, dtype=torch.float32, device=occ.device)
+    b = torch.empty_like(a)
+    L.call("nm_groupnorm_finalize", L.ptr(partial), n, G ** 3, Cout, gn.num_groups, chunks, L.ptr(f32(gn, "weight")),
+           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+    return out, a, b
 
 
 # ------------------------------------------------------------------ GroupNorm / pointwise

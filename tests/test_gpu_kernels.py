@@ -209,6 +209,11 @@ def test_first_conv_coordconv(ops):
         ref = conv(O.add_coord_channels(occ)).detach()
         got = from_act(ops.first_conv(occ[:, 0].contiguous().cuda(), conv.cuda()))
         assert rel_err(got, ref) < 2e-3
+        # GroupNorm statistics from the kernel's accumulators == statistics of the stored output
+        gn = torch.nn.GroupNorm(cout // 16, cout).cuda()
+        raw, a, b = ops.first_conv(occ[:, 0].contiguous().cuda(), conv, gn)
+        a2, b2 = ops.gn_scale_shift(raw, gn)
+        assert (a - a2).abs().max() <= 2e-3 * a2.abs().max() and (b - b2).abs().max() <= 2e-3 * (1 + b2.abs().max())
 
 
 def test_conv_transpose(ops):

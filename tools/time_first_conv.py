@@ -25,4 +25,10 @@ for cout in (32, 64):
     ev1.record(); torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / 10
     gb = out.numel() * 2 / 1e9
+    gn = torch.nn.GroupNorm(cout // 16, cout).cuda()
+    for _ in range(3): ops.first_conv(occ, conv, gn)
+    ev0.record()
+    for _ in range(10): ops.first_conv(occ, conv, gn)
+    ev1.record(); torch.cuda.synchronize()
+    print(f"   with GroupNorm statistics + finalize: {ev0.elapsed_time(ev1) / 10:.3f} ms")
     print(f"Cout={cout} n={n}: {ms:.3f} ms  {ms / n * 1e3:.2f} us/frame  write {gb / ms * 1e3:.0f} GB/s  rel err {err:.2e}")
