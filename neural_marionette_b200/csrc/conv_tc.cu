@@ -584,6 +584,7 @@ constexpr int kPGroups = 5;    // 5 x 96 TMEM columns = 480 <= 512
 // Cin = 128 so that the 27 x kchunks resident weight tiles still fit); MMA N = 3 * PN.
 constexpr int kSlab3EpiWarps = 8;
 constexpr int kSlab3Threads = 64 + 32 * kSlab3EpiWarps;
+constexpr int kSlab3Ring = 8;        // max halo-slice ring depth (Cin = 32 has room for 8 slots, Cin = 64 for 4)
 constexpr int kSlab3XformWarps = 4;   // extra warps (only launched when the input transform is fused)
 
 template <int BK, int PN>
@@ -600,12 +601,12 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   uint8_t* s_out = s_ring + (size_t)ring * p.slot_bytes;               // [2][stage_bytes], 1 KiB aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 2 * stage_bytes);
   uint64_t* full = bars;                  // [ring]   slice landed
-  uint64_t* empty = full + kSlabRing;     // [ring]   slice consumed
-  uint64_t* pfull = empty + kSlabRing;    // [groups] P group complete
+  uint64_t* empty = full + kSlab3Ring;     // [ring]   slice consumed
+  uint64_t* pfull = empty + kSlab3Ring;    // [groups] P group complete
   uint64_t* pempty = pfull + kPGroups;    // [groups] P group drained
   uint64_t* wfull = pempty + kPGroups;    // [1]
   uint64_t* ready = wfull + 1;            // [ring]   slice transformed (fused input GroupNorm / LeakyReLU)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kSlabRing);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kSlab3Ring);
   float* s_ab = reinterpret_cast<float*>(tmem_slot + 4);   // [2][Cin] scale | shift of the current sample
   const bool xform = p.in_scale != nullptr;
 
@@ -622,9 +623,9 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_b) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_o) : "memory");
-    for (int s = 0; s < kSlabRing; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kSlab3Ring; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < kPGroups; s++) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], kSlab3EpiWarps); }
-    for (int s = 0; s < kSlabRing; s++) mbar_init(&ready[s], kSlab3XformWarps);
+    for (int s = 0; s < kSlab3Ring; s++) mbar_init(&ready[s], kSlab3XformWarps);
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -682,27 +683,36 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
             sh[k] = s_ab[p.cin + kc * BK + lc * 8 + k];
           }
           const uint32_t cbase = smem_u32(base) + (uint32_t)kc * p.chunk_bytes;   // shared-space address
-          int hh = r0 / kHaloW, ww = r0 % kHaloW;          // rstep rows further = (rstep / 10, rstep % 10) steps
-          for (int r = r0; r < kHaloW * kHaloH; r += rstep) {
-            const int h = ih * 16 - 1 + hh, w = iw * 8 - 1 + ww;
-            if ((unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W) {
-              const int pc = lc ^ (row_bytes == 128 ? (r & 7) : ((r >> 1) & 3));
-              const uint32_t addr = cbase + r * row_bytes + pc * 16;
-              uint4 raw = lds128(addr);
-              half8 hv = *reinterpret_cast<half8*>(&raw);
-              float f[8];
-              nm_unpack8(hv, f);
+          // fp32 affine, fp16 LeakyReLU (max(y, 0.01 y) on the rounded value); two rows in flight per thread
+          auto xf = [&](uint4 raw) -> uint4 {
+            const uint32_t in[4] = {raw.x, raw.y, raw.z, raw.w};
+            uint32_t o[4];
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                const float v = fmaf(f[k], sc[k], sh[k]);
-                f[k] = p.in_act ? nm_lrelu(v) : v;
-              }
-              hv = nm_pack8(f);
-              sts128(addr, *reinterpret_cast<uint4*>(&hv));
+            for (int k = 0; k < 4; k++) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[k]));
+              __half2 hv = __floats2half2_rn(fmaf(f.x, sc[2 * k], sh[2 * k]), fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]));
+              if (p.in_act) hv = __hmax2(hv, __hmul2(hv, __float2half2_rn(0.01f)));
+              o[k] = *reinterpret_cast<uint32_t*>(&hv);
             }
-            ww += rstep % kHaloW;
-            hh += rstep / kHaloW;
-            if (ww >= kHaloW) { ww -= kHaloW; hh++; }
+            return make_uint4(o[0], o[1], o[2], o[3]);
+          };
+          auto row_addr = [&](int r, bool& ok) -> uint32_t {
+            const int hh = r / kHaloW, ww = r - hh * kHaloW;
+            const int h = ih * 16 - 1 + hh, w = iw * 8 - 1 + ww;
+            ok = r < kHaloW * kHaloH && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+            const int pc = lc ^ (row_bytes == 128 ? (r & 7) : ((r >> 1) & 3));
+            return cbase + r * row_bytes + pc * 16;
+          };
+          for (int r = r0; r < kHaloW * kHaloH; r += 2 * rstep) {
+            bool ok0, ok1;
+            const uint32_t a0 = row_addr(r, ok0), a1 = row_addr(r + rstep, ok1);
+            uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+            if (ok0) v0 = lds128(a0);
+            if (ok1) v1 = lds128(a1);
+            v0 = xf(v0);
+            v1 = xf(v1);
+            if (ok0) sts128(a0, v0);
+            if (ok1) sts128(a1, v1);
           }
         }
         fence_async_smem();                              // generic-proxy writes -> visible to the UMMA reads
@@ -801,18 +811,48 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     uint32_t q0 = 0;                                     // global index of slice 0 of the current column
     uint32_t n_out = 0;                                  // output tiles staged so far (staging buffer parity)
     const bool is_issuer = warp == 2 && lane == 0;       // the thread that owns the TMA-store bulk groups
+    // this thread's 16-byte chunks in the staging tile (swizzled like the store tensor map): constant per thread
+    constexpr int row_b = PN * 2;                        // 64 B (SWIZZLE_64B) or 32 B (SWIZZLE_32B)
+    uint32_t st_off[CW / 8];
+#pragma unroll
+    for (int c8 = 0; c8 < CW / 8; c8++) {
+      const uint32_t off = (uint32_t)row * row_b + (uint32_t)(chalf * CW + c8 * 8) * 2;
+      st_off[c8] = off ^ (((off >> 7) & (row_b == 64 ? 3u : 1u)) << 4);
+    }
+    const uint32_t s_out_u32 = smem_u32(s_out);
     for (int col = col0; col < n_cols; col += col_step, q0 += p.D) {
       int t = col;
       const int iw = t % p.nw; t /= p.nw;
       const int ih = t % p.nh; t /= p.nh;
       const int n = t;
       // Event s = "group P(s) complete".  It finishes out(s-1) (needs P(s)[2]) and starts out(s)
-      // (P(s-1)[0] + P(s)[1]); after its TMEM loads P(s-1) is dead and is handed back to the MMA warp
+      // (P(s-1)[0] + P(s)[1] + bias); after its TMEM loads P(s-1) is dead and is handed back to the MMA warp
       // BEFORE the arithmetic / stores, so the issue loop runs up to kPGroups-1 slices ahead of the stores.
       float partial[CW];
       float ssum[CW], ssq[CW];                           // fused GroupNorm statistics of this thread's row
 #pragma unroll
       for (int c = 0; c < CW; c++) { ssum[c] = 0.f; ssq[c] = 0.f; }
+      // statistics, fp16 pack, swizzled staging tile, one TMA store per tile (direct per-thread 16-byte stores
+      // touched 16 cache lines per warp instruction and ran at ~1 TB/s)
+      auto emit = [&](const float (&f)[CW], int od) {
+#pragma unroll
+        for (int c = 0; c < CW; c++) { ssum[c] += f[c]; ssq[c] = fmaf(f[c], f[c], ssq[c]); }
+        const uint32_t boff = (n_out & 1) * stage_bytes;
+        if (is_issuer) bulk_wait_read<1>();              // the store that last read this buffer has drained
+        named_bar_sync(1, 32 * kSlab3EpiWarps);
+#pragma unroll
+        for (int c8 = 0; c8 < CW / 8; c8++) {
+          const half8 hv = nm_pack8(f + c8 * 8);
+          sts128(s_out_u32 + boff + st_off[c8], *reinterpret_cast<const uint4*>(&hv));
+        }
+        fence_async_smem();
+        named_bar_sync(1, 32 * kSlab3EpiWarps);
+        if (is_issuer && !(p.debug & 1)) {
+          tma_store_5d(&p.tmap_o, s_out + boff, part * PN, iw * 8, ih * 16, od, n);
+          bulk_commit();
+        }
+        n_out++;
+      };
       for (int sl = 0; sl < p.D; sl++) {
         const uint32_t q = q0 + sl;
         mbar_wait(&pfull[q % kPGroups], (q / kPGroups) & 1);
@@ -837,40 +877,15 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
           if (sl == p.D - 1) mbar_arrive(&pempty[q % kPGroups]);
         }
         // out(sl-1) is complete now; out(D-1) completes together with the last event
-        for (int fin = (sl >= 1 ? 0 : 1); fin < (sl == p.D - 1 ? 2 : 1); fin++) {
+        if (sl >= 1) {
           float f[CW];
-          if (fin == 0) {
 #pragma unroll
-            for (int c = 0; c < CW; c++) f[c] = partial[c] + __uint_as_float(ra[c]) + bias[c];
-          } else {
-#pragma unroll
-            for (int c = 0; c < CW; c++) f[c] = __uint_as_float(rb[c]) + __uint_as_float(rc[c]) + bias[c];
-          }
-#pragma unroll
-          for (int c = 0; c < CW; c++) { ssum[c] += f[c]; ssq[c] = fmaf(f[c], f[c], ssq[c]); }
-          const int od = fin == 0 ? sl - 1 : sl;
-          // stage the tile in shared memory (swizzled like the store tensor map), then one TMA store: the
-          // direct per-thread 16-byte stores touched 16 cache lines per warp instruction and ran at ~1 TB/s
-          uint8_t* buf = s_out + (n_out & 1) * stage_bytes;
-          if (is_issuer) bulk_wait_read<1>();            // the store that last read this buffer has drained
-          named_bar_sync(1, 32 * kSlab3EpiWarps);
-          constexpr int row_b = PN * 2;                  // 64 B (SWIZZLE_64B) or 32 B (SWIZZLE_32B)
-#pragma unroll
-          for (int c0 = 0; c0 < CW; c0 += 8) {
-            const uint32_t off = (uint32_t)row * row_b + (uint32_t)(chalf * CW + c0) * 2;
-            const uint32_t sw = off ^ (((off >> 7) & (row_b == 64 ? 3u : 1u)) << 4);
-            *reinterpret_cast<half8*>(buf + sw) = nm_pack8(f + c0);
-          }
-          fence_async_smem();
-          named_bar_sync(1, 32 * kSlab3EpiWarps);
-          if (is_issuer && !(p.debug & 1)) {
-            tma_store_5d(&p.tmap_o, buf, part * PN, iw * 8, ih * 16, od, n);
-            bulk_commit();
-          }
-          n_out++;
+          for (int c = 0; c < CW; c++) f[c] = partial[c] + __uint_as_float(ra[c]);
+          emit(f, sl - 1);
         }
 #pragma unroll
-        for (int c = 0; c < CW; c++) partial[c] = __uint_as_float(rb[c]) + __uint_as_float(rc[c]);
+        for (int c = 0; c < CW; c++) partial[c] = (__uint_as_float(rb[c]) + __uint_as_float(rc[c])) + bias[c];
+        if (sl == p.D - 1) emit(partial, sl);
       }
       if (p.stats) {
         // column done: fold the 32 rows of this warp (fixed butterfly order -> deterministic) and emit one
@@ -967,7 +982,7 @@ ConvPlan plan_conv(int n, int D, int H, int W, int Cin, int Cout, int k, int str
   pl.use3 = slab_mode >= 2 && pl.kch <= 2 && Cout % pl.pn == 0 && Cout <= 128;
   const size_t w_bytes = (size_t)27 * pl.kch * (pl.use3 ? pl.pn : pl.ntile) * pl.bk * 2;
   pl.chunk_bytes = ((kHaloW * kHaloH * pl.bk * 2 + 1023) / 1024) * 1024;
-  pl.ring = kSlabRing;
+  pl.ring = pl.use3 ? kSlab3Ring : kSlabRing;
   const size_t extra = 1024 + 40 * 8 + 16 + 2 * 256 * 4 + (pl.use3 ? (size_t)2 * kTileM * pl.pn * 2 : 0);
   if (pl.use3)
     while (pl.ring > 2 && w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra > 227 * 1024) pl.ring--;
@@ -995,10 +1010,11 @@ extern "C" int nm_conv3d_stats_chunks(int n, int D, int H, int W, int Cin, int C
 
 // 1 when nm_conv3d_tc_fused can apply the producer's GroupNorm scale/shift (+LeakyReLU) to its input on the fly
 extern "C" int nm_conv3d_can_fuse_input(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
-  // Measured on B200: the in-smem transform pays off when a slice carries enough MMA work to hide it and is not
-  // repeated by many output-channel parts: Cin = 64 (one 128-byte k-chunk), Cout <= 64.  For Cin = 32 (dec.11)
-  // and Cin = 128 with 8 parts the separate HBM-bound affine pass is faster.
+  // Measured on B200 (320 frames): the in-smem transform pays off when the slice is not repeated by many
+  // output-channel parts: 32->32 @64^3 4.95 ms plain + 2.23 ms affine pass vs 5.59 ms fused; 64->64 @32^3 1.95 + 0.69 vs
+  // 2.05.  For Cin = 128 (8 parts of 16 channels) the separate HBM-bound affine pass is faster.
   const ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, k, stride);
+  if (pl.slab && pl.use3 && pl.kch == 1 && pl.bk == 32 && Cout <= 32) return 1;
   return pl.slab && pl.use3 && pl.kch == 1 && pl.bk == 64 && Cout <= 64 ? 1 : 0;
 }
 

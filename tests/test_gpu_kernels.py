@@ -139,7 +139,8 @@ def test_conv3d_tc(ops, n, grid, cin, cout, k, stride):
         assert (a - a2).abs().max() <= 2e-3 * a2.abs().max() and (b - b2).abs().max() <= 2e-3 * (1 + b2.abs().max())
 
 
-@pytest.mark.parametrize("n,grid,cin,cout", [(2, 16, 64, 64), (1, 32, 64, 32), (3, 16, 64, 64)])
+@pytest.mark.parametrize("n,grid,cin,cout", [(2, 16, 64, 64), (1, 32, 64, 32), (3, 16, 64, 64), (2, 16, 32, 32),
+                                             (1, 32, 32, 32)])
 def test_conv3d_fused_input_groupnorm(ops, n, grid, cin, cout):
     """conv(LeakyReLU(GroupNorm(raw))) with the normalisation applied inside the conv's operand path."""
     g = torch.Generator().manual_seed(cin * 7 + cout)
@@ -149,7 +150,7 @@ def test_conv3d_fused_input_groupnorm(ops, n, grid, cin, cout):
     a = (0.5 + torch.rand(n, cin, generator=g)).cuda()
     b = torch.randn(n, cin, generator=g).cuda()
     assert ops.can_fuse_input(raw_in, conv)
-    assert not ops.can_fuse_input(to_act(torch.zeros(1, 32, 16, 16, 16)), torch.nn.Conv3d(32, 32, 3, 1, 1).cuda())
+    assert not ops.can_fuse_input(to_act(torch.zeros(1, 128, 16, 16, 16)), torch.nn.Conv3d(128, 64, 3, 1, 1).cuda())
     ref_in = ops.affine_act(raw_in, a, b, True)                       # separate pass (rounds to fp16)
     ref, ra, rb = ops.conv3d(ref_in, conv, gn_out)
     got, ga, gb = ops.conv3d(raw_in, conv, gn_out, in_affine=(a, b, True))
