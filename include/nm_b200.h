@@ -138,8 +138,10 @@ int nm_gaussian_render(const float* keypoints, int n, int K, int g, const float*
                        float* gaussians, void* stream);
 /* adjust_combined_representation (kypt_detector.py:381,404-408): 1x1 conv over cat[gauss_t, first_feature,
  * gauss_0, coords] + LeakyReLU, with the clip-constant part hoisted.  first_feature: act (n_clips, g^3, 128);
- * keypoints (n, K, 4) or gaussians (n, K, g^3) with n = n_clips*frames_per_clip; base_ws: n_clips*g^3*128 fp32;
+ * keypoints (n, K, 4) or gaussians (n, K, g^3) with n = n_clips*frames_per_clip; base_ws:
+ * nm_decoder_adjust_workspace_bytes(n_clips, g) bytes (the per-clip fp32 base + packed weight fragments);
  * out: act (n, g^3, 128). */
+size_t nm_decoder_adjust_workspace_bytes(int n_clips, int g);
 int nm_decoder_adjust(const void* first_feature, const float* keypoints, const float* gaussians, const float* weight,
                       const float* bias, int n_clips, int frames_per_clip, int g, int K, const float* linspace,
                       float gauss_width, float* base_ws, void* out, void* stream);

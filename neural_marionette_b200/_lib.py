@@ -66,6 +66,7 @@ PROTOTYPES = {
     "nm_heatmap_head": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _f, _vp, _vp, _vp, _vp,
                              _vp]),
     "nm_gaussian_render": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp]),
+    "nm_decoder_adjust_workspace_bytes": (_sz, [_i, _i]),
     "nm_decoder_adjust": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _f, _vp, _vp, _vp]),
     "nm_hsvrnn_step": (_i, [C.POINTER(HsvrnnWeights), _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -209,130 +209,212 @@ gaussian_render_kernel(const float* __restrict__ keypoints, int K, int g, const 
 //   base[clip][s][co] = b[co] + W[:,K:K+F] ff[clip][s] + W[:,K+F:2K+F] gauss_0[clip][s] + W[:,2K+F:] coords(s)
 //   out[frame][s][co] = lrelu(base[clip][s][co] + W[:, :K] gauss_t[frame][s])
 // Gaussians are recomputed from the keypoints (separable exps) unless a gaussians tensor is passed.
-template <int CO, int FD>
-__global__ void __launch_bounds__(256)
-adjust_base_kernel(const act_t* __restrict__ ff /* (clips, S, FD) */, const float* __restrict__ kp /* (n,K,4) */,
-                   const float* __restrict__ gs /* optional (n,K,S) */, int frames_per_clip,
-                   const float* __restrict__ w, const float* __restrict__ bias, int K, int g,
-                   const float* __restrict__ lin, float gauss_width, float* __restrict__ base) {
-  extern __shared__ float smem[];
-  const int ld = 2 * K + FD + 3;
-  float* s_w = smem;                 // [CO][FD + K + 3] (columns K .. end of W)
-  float* s_e = s_w + CO * (FD + K + 3);  // [K][3][32]
-  float* s_i = s_e + KMAX * 3 * 32;  // [K]
-  const int clip = blockIdx.y;
-  const int S = g * g * g;
-  const int wcols = FD + K + 3;
-  // gauss_0 = the gaussians of the clip's first frame (kypt_detector.py:406: gaussians[:, 0])
-  const float* kp0 = kp ? kp + (long long)clip * frames_per_clip * K * 4 : nullptr;
-  const float* g0 = gs ? gs + (long long)clip * frames_per_clip * K * S : nullptr;
-  for (int i = threadIdx.x; i < CO * wcols; i += 256) s_w[i] = w[(i / wcols) * ld + K + (i % wcols)];
-  if (!g0) {
-    for (int i = threadIdx.x; i < K * 3 * g; i += 256) {
-      const int k = i / (3 * g), a = (i / g) % 3, j = i % g;
-      const float d = lin[j] - kp0[k * 4 + a];
-      s_e[(k * 3 + a) * 32 + j] = expf(-(d * d) / gauss_width);
+// Both parts run on mma.sync (m16n8k16, fp16 operands, fp32 accumulate) with the fragment tricks of conv_pw.cu: the
+// K order is permuted so that the 8 consecutive feature channels a lane loads with one 16-byte load are the K slots
+// it owns in two k-steps, and the fragment columns are permuted so that a lane owns 4 consecutive output channels
+// (16-byte base loads / stores, 8-byte fp16 stores).  The Gaussian operand is evaluated straight into the A fragment
+// from the separable exp tables.  coords and bias stay fp32 (CUDA cores).
+constexpr int kAdjCO = 128, kAdjFD = 128, kAdjNB = kAdjCO / 8;
+constexpr int kAdjFragG = 2 * kAdjNB * 32;                 // uint2 per Gaussian weight block (K <= 32: 2 k-steps)
+constexpr int kAdjFragFF = (kAdjFD / 16) * kAdjNB * 32;    // first-feature block (8 k-steps)
+
+// output channel of fragment column c (0..7) of n-block nb
+__host__ __device__ inline int adj_channel(int nb, int c) { return (nb >> 1) * 16 + (c >> 1) * 4 + (nb & 1) * 2 + (c & 1); }
+
+// frags: [gauss_t (2 k-steps)][gauss_0 (2)][first_feature (8)] x [16 n-blocks][32 lanes]; xyzb[co] = (Wx, Wy, Wz, bias)
+__global__ void adjust_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias, int K, int ld,
+                                   uint2* __restrict__ frags, float4* __restrict__ xyzb) {
+  const int total = 2 * kAdjFragG + kAdjFragFF;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int lane = i & 31, g = lane >> 2, t = lane & 3;
+    int rest = i >> 5;
+    const int nb = rest % kAdjNB; rest /= kAdjNB;          // rest = k-step over the three blocks
+    const int co = adj_channel(nb, g);
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int j = e & 1, hi = e >> 1;
+      int col;
+      bool ok = true;
+      if (rest < 4) {                                      // Gaussian blocks: k = s*16 + 2t + j + 8*hi
+        const int k = (rest & 1) * 16 + 2 * t + j + 8 * hi;
+        ok = k < K;
+        col = (rest < 2 ? 0 : K + kAdjFD) + k;
+      } else {                                             // first feature: ci = m*32 + t*8 + s*4 + hi*2 + j
+        const int ks = rest - 4, m = ks >> 1, sst = ks & 1;
+        col = K + m * 32 + t * 8 + sst * 4 + hi * 2 + j;
+      }
+      v[e] = ok ? w[(long long)co * ld + col] : 0.f;
     }
-    for (int i = threadIdx.x; i < K; i += 256) s_i[i] = kp0[i * 4 + 3];
+    __half2 b0 = __floats2half2_rn(v[0], v[1]), b1 = __floats2half2_rn(v[2], v[3]);
+    frags[i] = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
   }
-  __syncthreads();
-  // thread -> (voxel, output-channel quarter): 4 threads per voxel, CO/4 outputs each
-  const int q = threadIdx.x & 3;
-  const int s = blockIdx.x * 64 + (threadIdx.x >> 2);
-  if (s >= S) return;
-  const int z = s % g, y = (s / g) % g, x = s / (g * g);
-  constexpr int PER = CO / 4;
-  float acc[PER];
-#pragma unroll
-  for (int j = 0; j < PER; j++) acc[j] = bias[q * PER + j];
-  const half8* p = reinterpret_cast<const half8*>(ff + ((long long)clip * S + s) * FD);
-  for (int c8 = 0; c8 < FD / 8; c8++) {
-    float v[8];
-    nm_unpack8(p[c8], v);
-#pragma unroll
-    for (int j = 0; j < PER; j++) {
-      const float* wr = s_w + (q * PER + j) * wcols + c8 * 8;
-#pragma unroll
-      for (int e = 0; e < 8; e++) acc[j] = fmaf(v[e], wr[e], acc[j]);
-    }
+  for (int co = blockIdx.x * blockDim.x + threadIdx.x; co < kAdjCO; co += gridDim.x * blockDim.x) {
+    const float* wr = w + (long long)co * ld + 2 * K + kAdjFD;
+    xyzb[co] = make_float4(wr[0], wr[1], wr[2], bias[co]);
   }
-  for (int k = 0; k < K; k++) {
-    float gv;
-    if (g0) gv = g0[(long long)k * S + s];
-    else gv = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + y]) * s_e[(k * 3 + 2) * 32 + z] * s_i[k];
-#pragma unroll
-    for (int j = 0; j < PER; j++) acc[j] = fmaf(gv, s_w[(q * PER + j) * wcols + FD + k], acc[j]);
-  }
-  const float cx = lin[x], cy = lin[y], cz = lin[z];
-#pragma unroll
-  for (int j = 0; j < PER; j++) {
-    const float* wr = s_w + (q * PER + j) * wcols + FD + K;
-    acc[j] = fmaf(cx, wr[0], fmaf(cy, wr[1], fmaf(cz, wr[2], acc[j])));
-  }
-  float* dst = base + ((long long)clip * S + s) * CO + q * PER;
-#pragma unroll
-  for (int j = 0; j < PER; j++) dst[j] = acc[j];
 }
 
-template <int CO>
+__device__ __forceinline__ void adj_mma(float (&c)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                        const uint32_t a3, const uint2 b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+}
+
+// Gaussian A fragments (2 k-steps) of one M-tile: rows r0 / r1 are voxels s0 / s1 of frame `gn`
+struct GaussSrc {
+  const float* s_e;     // [K][3][32] separable exps (keypoint mode)
+  const float* s_i;     // [K] intensities
+  const float* gs;      // gaussians tensor of this frame (K, S) or null
+  int K, g, S;
+};
+__device__ __forceinline__ void gauss_frags(const GaussSrc& q, int s0, int s1, int t, uint32_t (&a)[2][4]) {
+  const int z0 = s0 % q.g, y0 = (s0 / q.g) % q.g, x0 = s0 / (q.g * q.g);
+  const int z1 = s1 % q.g, y1 = (s1 / q.g) % q.g, x1 = s1 / (q.g * q.g);
+#pragma unroll
+  for (int st = 0; st < 2; st++)
+#pragma unroll
+    for (int hi = 0; hi < 2; hi++) {
+      float v[2][2];
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const int k = st * 16 + 2 * t + j + 8 * hi;
+        if (k < q.K) {
+          if (q.gs) {
+            v[0][j] = q.gs[(long long)k * q.S + s0];
+            v[1][j] = q.gs[(long long)k * q.S + s1];
+          } else {
+            const float* e = q.s_e + k * 96;
+            v[0][j] = ((1.0f * e[x0]) * e[32 + y0]) * e[64 + z0] * q.s_i[k];
+            v[1][j] = ((1.0f * e[x1]) * e[32 + y1]) * e[64 + z1] * q.s_i[k];
+          }
+        } else {
+          v[0][j] = v[1][j] = 0.f;
+        }
+      }
+      __half2 h0 = __floats2half2_rn(v[0][0], v[0][1]), h1 = __floats2half2_rn(v[1][0], v[1][1]);
+      a[st][hi * 2] = *reinterpret_cast<uint32_t*>(&h0);       // a0 / a2: row g
+      a[st][hi * 2 + 1] = *reinterpret_cast<uint32_t*>(&h1);   // a1 / a3: row g + 8
+    }
+}
+
+__device__ __forceinline__ void stage_exps(const float* kp /* (K,4) of one frame */, int K, int g, const float* lin,
+                                           float gauss_width, float* s_e, float* s_i) {
+  for (int i = threadIdx.x; i < K * 3 * g; i += 256) {
+    const int k = i / (3 * g), a = (i / g) % 3, j = i % g;
+    const float d = lin[j] - kp[k * 4 + a];
+    s_e[(k * 3 + a) * 32 + j] = expf(-(d * d) / gauss_width);
+  }
+  for (int i = threadIdx.x; i < K; i += 256) s_i[i] = kp[i * 4 + 3];
+}
+
+// base[clip][s][co] (fp32): one block = 128 voxels of one clip, one M-tile per warp
 __global__ void __launch_bounds__(256)
-adjust_frame_kernel(const float* __restrict__ base, const float* __restrict__ kp /* (n,K,4) */,
-                    const float* __restrict__ gs /* optional (n,K,S) */, const float* __restrict__ w, int ld,
-                    int K, int g, int frames_per_clip, const float* __restrict__ lin, float gauss_width,
-                    act_t* __restrict__ out) {
-  // block: 64 voxels of one frame; thread <-> (voxel slot tid / 16, 8 output channels tid % 16), four rounds of 16
-  // voxels.  W^T [K][CO] and the Gaussian values of the 64 voxels are staged in shared memory; base reads and
-  // output stores are 16/32-byte vectors, contiguous across the 16 threads of a voxel.
-  __shared__ float s_wt[KMAX * CO];      // [K][CO]
+adjust_base_kernel(const act_t* __restrict__ ff /* (clips, S, 128) */, const float* __restrict__ kp /* (n,K,4) */,
+                   const float* __restrict__ gs /* optional (n,K,S) */, int frames_per_clip,
+                   const uint2* __restrict__ frags, const float4* __restrict__ xyzb, int K, int g,
+                   const float* __restrict__ lin, float gauss_width, float* __restrict__ base) {
+  extern __shared__ __align__(16) uint2 s_frag[];          // [gauss_0 (2)][first_feature (8)] k-steps
   __shared__ float s_e[KMAX * 3 * 32];
   __shared__ float s_i[KMAX];
-  __shared__ float s_g[64 * KMAX];       // [voxel][K]
+  const int clip = blockIdx.y;
+  const int S = g * g * g;
+  for (int i = threadIdx.x; i < kAdjFragG + kAdjFragFF; i += 256) s_frag[i] = __ldg(frags + kAdjFragG + i);
+  // gauss_0 = the gaussians of the clip's first frame (kypt_detector.py:406: gaussians[:, 0])
+  if (!gs) stage_exps(kp + (long long)clip * frames_per_clip * K * 4, K, g, lin, gauss_width, s_e, s_i);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gr = lane >> 2, t = lane & 3;
+  const int s0 = (blockIdx.x * 8 + warp) * 16 + gr, s1 = s0 + 8;
+  if (s0 - gr >= S) return;
+  // accumulators start as bias + W_xyz coords
+  float c[kAdjNB][4];
+  {
+    const float cx0 = lin[s0 / (g * g)], cy0 = lin[(s0 / g) % g], cz0 = lin[s0 % g];
+    const float cx1 = lin[s1 / (g * g)], cy1 = lin[(s1 / g) % g], cz1 = lin[s1 % g];
+#pragma unroll
+    for (int nb = 0; nb < kAdjNB; nb++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) {
+        const float4 k = __ldg(xyzb + adj_channel(nb, 2 * t + j));
+        c[nb][j] = fmaf(cx0, k.x, fmaf(cy0, k.y, fmaf(cz0, k.z, k.w)));
+        c[nb][2 + j] = fmaf(cx1, k.x, fmaf(cy1, k.y, fmaf(cz1, k.z, k.w)));
+      }
+  }
+  GaussSrc q{s_e, s_i, gs ? gs + (long long)clip * frames_per_clip * K * S : nullptr, K, g, S};
+  uint32_t a[2][4];
+  gauss_frags(q, s0, s1, t, a);
+#pragma unroll
+  for (int st = 0; st < 2; st++)
+#pragma unroll
+    for (int nb = 0; nb < kAdjNB; nb++) adj_mma(c[nb], a[st][0], a[st][1], a[st][2], a[st][3], s_frag[(st * kAdjNB + nb) * 32 + lane]);
+  const uint4* f0 = reinterpret_cast<const uint4*>(ff + ((long long)clip * S + s0) * kAdjFD + t * 8);
+  const uint4* f1 = reinterpret_cast<const uint4*>(ff + ((long long)clip * S + s1) * kAdjFD + t * 8);
+#pragma unroll
+  for (int m = 0; m < kAdjFD / 32; m++) {
+    const uint4 r0 = __ldg(f0 + m * 4), r1 = __ldg(f1 + m * 4);
+    const uint2* fr = s_frag + kAdjFragG + (2 * m) * kAdjNB * 32 + lane;
+#pragma unroll
+    for (int nb = 0; nb < kAdjNB; nb++) {
+      adj_mma(c[nb], r0.x, r1.x, r0.y, r1.y, fr[nb * 32]);
+      adj_mma(c[nb], r0.z, r1.z, r0.w, r1.w, fr[(kAdjNB + nb) * 32]);
+    }
+  }
+  float* b0 = base + ((long long)clip * S + s0) * kAdjCO + t * 4;
+#pragma unroll
+  for (int m = 0; m < kAdjNB / 2; m++) {
+    *reinterpret_cast<float4*>(b0 + m * 16) = make_float4(c[2 * m][0], c[2 * m][1], c[2 * m + 1][0], c[2 * m + 1][1]);
+    *reinterpret_cast<float4*>(b0 + 8 * kAdjCO + m * 16) = make_float4(c[2 * m][2], c[2 * m][3], c[2 * m + 1][2], c[2 * m + 1][3]);
+  }
+}
+
+// out[frame][s][co] = lrelu(base[clip][s][co] + W[:, :K] gauss_t[frame][s]); one block = TILES*128 voxels of a frame
+__global__ void __launch_bounds__(256)
+adjust_frame_kernel(const float* __restrict__ base, const float* __restrict__ kp /* (n,K,4) */,
+                    const float* __restrict__ gs /* optional (n,K,S) */, const uint2* __restrict__ frags, int K, int g,
+                    int frames_per_clip, int tiles_per_warp, const float* __restrict__ lin, float gauss_width,
+                    act_t* __restrict__ out) {
+  __shared__ __align__(16) uint2 s_frag[kAdjFragG];
+  __shared__ float s_e[KMAX * 3 * 32];
+  __shared__ float s_i[KMAX];
   const int n = blockIdx.y, clip = n / frames_per_clip;
   const int S = g * g * g;
-  for (int i = threadIdx.x; i < CO * K; i += 256) s_wt[(i % K) * CO + i / K] = w[(i / K) * ld + (i % K)];
-  if (!gs) {
-    for (int i = threadIdx.x; i < K * 3 * g; i += 256) {
-      const int k = i / (3 * g), a = (i / g) % 3, j = i % g;
-      const float d = lin[j] - kp[((long long)n * K + k) * 4 + a];
-      s_e[(k * 3 + a) * 32 + j] = expf(-(d * d) / gauss_width);
-    }
-    for (int i = threadIdx.x; i < K; i += 256) s_i[i] = kp[((long long)n * K + i) * 4 + 3];
-  }
+  for (int i = threadIdx.x; i < kAdjFragG; i += 256) s_frag[i] = __ldg(frags + i);
+  if (!gs) stage_exps(kp + (long long)n * K * 4, K, g, lin, gauss_width, s_e, s_i);
   __syncthreads();
-  const int s0 = blockIdx.x * 64;
-  for (int i = threadIdx.x; i < 64 * K; i += 256) {
-    const int v = i / K, k = i % K, s = s0 + v;
-    float gv = 0.f;
-    if (s < S) {
-      if (gs) gv = gs[((long long)n * K + k) * S + s];
-      else {
-        const int z = s % g, y = (s / g) % g, x = s / (g * g);
-        gv = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + y]) * s_e[(k * 3 + 2) * 32 + z] * s_i[k];
-      }
-    }
-    s_g[v * KMAX + k] = gv;
-  }
-  __syncthreads();
-  const int c8 = threadIdx.x & 15;
-#pragma unroll 1
-  for (int round = 0; round < 4; round++) {
-    const int v = round * 16 + (threadIdx.x >> 4), s = s0 + v;
-    if (s >= S) continue;
-    float acc[8];
-    const float4* bp = reinterpret_cast<const float4*>(base + ((long long)clip * S + s) * CO + c8 * 8);
-    const float4 b0 = bp[0], b1 = bp[1];
-    acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-    for (int k = 0; k < K; k++) {
-      const float gv = s_g[v * KMAX + k];
-      const float4 w0 = *reinterpret_cast<const float4*>(s_wt + k * CO + c8 * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(s_wt + k * CO + c8 * 8 + 4);
-      acc[0] = fmaf(gv, w0.x, acc[0]); acc[1] = fmaf(gv, w0.y, acc[1]); acc[2] = fmaf(gv, w0.z, acc[2]);
-      acc[3] = fmaf(gv, w0.w, acc[3]); acc[4] = fmaf(gv, w1.x, acc[4]); acc[5] = fmaf(gv, w1.y, acc[5]);
-      acc[6] = fmaf(gv, w1.z, acc[6]); acc[7] = fmaf(gv, w1.w, acc[7]);
-    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gr = lane >> 2, t = lane & 3;
+  GaussSrc q{s_e, s_i, gs ? gs + (long long)n * K * S : nullptr, K, g, S};
+  for (int it = 0; it < tiles_per_warp; it++) {
+    const int tile = (blockIdx.x * tiles_per_warp + it) * 8 + warp;
+    if (tile * 16 >= S) break;
+    const int s0 = tile * 16 + gr, s1 = s0 + 8;
+    float c[kAdjNB][4];
+    const float* b0 = base + ((long long)clip * S + s0) * kAdjCO + t * 4;
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = nm_lrelu(acc[j]);
-    *reinterpret_cast<half8*>(out + ((long long)n * S + s) * CO + c8 * 8) = nm_pack8(acc);
+    for (int m = 0; m < kAdjNB / 2; m++) {
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(b0 + m * 16));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(b0 + 8 * kAdjCO + m * 16));
+      c[2 * m][0] = v0.x; c[2 * m][1] = v0.y; c[2 * m + 1][0] = v0.z; c[2 * m + 1][1] = v0.w;
+      c[2 * m][2] = v1.x; c[2 * m][3] = v1.y; c[2 * m + 1][2] = v1.z; c[2 * m + 1][3] = v1.w;
+    }
+    uint32_t a[2][4];
+    gauss_frags(q, s0, s1, t, a);
+#pragma unroll
+    for (int st = 0; st < 2; st++)
+#pragma unroll
+      for (int nb = 0; nb < kAdjNB; nb++)
+        adj_mma(c[nb], a[st][0], a[st][1], a[st][2], a[st][3], s_frag[(st * kAdjNB + nb) * 32 + lane]);
+    act_t* o0 = out + ((long long)n * S + s0) * kAdjCO + t * 4;
+    const __half2 slope = __float2half2_rn(0.01f);
+#pragma unroll
+    for (int m = 0; m < kAdjNB / 2; m++) {
+      __half2 h[4] = {__floats2half2_rn(c[2 * m][0], c[2 * m][1]), __floats2half2_rn(c[2 * m + 1][0], c[2 * m + 1][1]),
+                      __floats2half2_rn(c[2 * m][2], c[2 * m][3]), __floats2half2_rn(c[2 * m + 1][2], c[2 * m + 1][3])};
+#pragma unroll
+      for (int e = 0; e < 4; e++) h[e] = __hmax2(h[e], __hmul2(h[e], slope));
+      *reinterpret_cast<uint2*>(o0 + m * 16) = make_uint2(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]));
+      *reinterpret_cast<uint2*>(o0 + 8 * kAdjCO + m * 16) = make_uint2(*reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+    }
   }
 }
 
@@ -383,32 +465,43 @@ extern "C" int nm_gaussian_render(const float* keypoints, int n, int K, int g, c
   return NM_OK;
 }
 
+extern "C" size_t nm_decoder_adjust_workspace_bytes(int n_clips, int g) {
+  return (size_t)n_clips * g * g * g * kAdjCO * sizeof(float) + (size_t)(2 * kAdjFragG + kAdjFragFF) * sizeof(uint2) +
+         (size_t)kAdjCO * sizeof(float4);
+}
+
 extern "C" int nm_decoder_adjust(const void* first_feature, const float* keypoints, const float* gaussians,
                                  const float* weight, const float* bias, int n_clips, int frames_per_clip, int g,
                                  int K, const float* linspace, float gauss_width, float* base_ws, void* out,
                                  void* stream) {
   NM_CHECK_ARG(first_feature && weight && bias && base_ws && out && linspace, "nm_decoder_adjust: null pointer");
   NM_CHECK_ARG(keypoints || gaussians, "nm_decoder_adjust: need keypoints or gaussians");
-  NM_CHECK_ARG(K <= KMAX && g <= 32, "nm_decoder_adjust: K=%d g=%d unsupported", K, g);
+  NM_CHECK_ARG(K <= KMAX && (g == 8 || g == 16 || g == 32), "nm_decoder_adjust: K=%d g=%d unsupported", K, g);
   if (n_clips == 0) return NM_OK;
-  constexpr int CO = 128, FD = 128;
   const int S = g * g * g;
   const float width = gauss_width;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = (size_t)(CO * (FD + K + 3) + KMAX * 3 * 32 + KMAX) * sizeof(float);
+  // workspace: [base fp32 (n_clips, S, 128)][packed weight fragments][(Wx, Wy, Wz, bias) per channel]
+  uint2* frags = reinterpret_cast<uint2*>(base_ws + (size_t)n_clips * S * kAdjCO);
+  float4* xyzb = reinterpret_cast<float4*>(frags + 2 * kAdjFragG + kAdjFragFF);
+  adjust_pack_kernel<<<8, 256, 0, st>>>(weight, bias, K, 2 * K + kAdjFD + 3, frags, xyzb);
+  NM_CHECK_LAUNCH("decoder_adjust(pack)");
+  const size_t smem = (size_t)(kAdjFragG + kAdjFragFF) * sizeof(uint2);
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(adjust_base_kernel<CO, FD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    NM_CHECK_CUDA(cudaFuncSetAttribute(adjust_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr = true;
   }
   const int n = n_clips * frames_per_clip;
-  adjust_base_kernel<CO, FD><<<dim3(nm_cdiv(S, 64), n_clips), 256, smem, st>>>(
-      (const act_t*)first_feature, gaussians ? nullptr : keypoints, gaussians, frames_per_clip, weight, bias, K, g,
-      linspace, width, base_ws);
+  const float* kp = gaussians ? nullptr : keypoints;
+  adjust_base_kernel<<<dim3(S / 128, n_clips), 256, smem, st>>>((const act_t*)first_feature, kp, gaussians,
+                                                                 frames_per_clip, frags, xyzb, K, g, linspace, width,
+                                                                 base_ws);
   NM_CHECK_LAUNCH("decoder_adjust(base)");
-  adjust_frame_kernel<CO><<<dim3(nm_cdiv(S, 64), n), 256, 0, st>>>(base_ws, gaussians ? nullptr : keypoints, gaussians, weight,
-                                                                   2 * K + FD + 3, K, g, frames_per_clip, linspace,
-                                                                   width, (act_t*)out);
+  const int tiles_per_warp = S >= 4096 ? 4 : 1;
+  adjust_frame_kernel<<<dim3(S / (128 * tiles_per_warp), n), 256, 0, st>>>(base_ws, kp, gaussians, frags, K, g,
+                                                                            frames_per_clip, tiles_per_warp, linspace,
+                                                                            width, (act_t*)out);
   NM_CHECK_LAUNCH("decoder_adjust(frame)");
   return NM_OK;
 }

@@ -378,7 +378,8 @@ def decoder_adjust(ff_act, conv: torch.nn.Conv3d, frames_per_clip: int, g: int, 
     n = B * frames_per_clip
     dev = ff_act.device
     out = torch.empty(n, g, g, g, conv.out_channels, dtype=ACT_DTYPE, device=dev)
-    base = workspace(B * g ** 3 * conv.out_channels * 4, dev, "adjust")
+    assert conv.out_channels == 128 and conv.in_channels == 128 + 2 * K + 3
+    base = workspace(L.query("nm_decoder_adjust_workspace_bytes", B, g), dev, "adjust")
     w = f32(conv, "weight").reshape(conv.out_channels, -1)
     L.call("nm_decoder_adjust", L.ptr(ff_act), L.ptr(keypoints), L.ptr(gaussians), L.ptr(w), L.ptr(f32(conv, "bias")),
            B, frames_per_clip, g, K, L.ptr(linspace(g, dev)), gauss_width(sigma, g), L.ptr(base), L.ptr(out),
