@@ -67,6 +67,17 @@ int nm_conv3d_direct(const void* x, const float* weight, const float* bias, void
  * permuted to tap-major (8, Cin, Cout) */
 int nm_conv_transpose3d_k2s2(const void* x, const float* weight, const float* bias, void* out, int n, int D, int H,
                              int W, int Cin, int Cout, void* stream);
+/* k3 conv whose input is the 2x trilinear up-sampling (align_corners = False) of x_lo (n, D/2, H/2, W/2, Cin): the
+ * up-sampled tensor is never written - the halo slices of the tcgen05 kernel are interpolated in shared memory from
+ * low-resolution planes (reference: nn.Upsample(scale_factor=2, mode='trilinear') + nn.Conv3d(k3) in
+ * build_voxel_decoder, model/kypt_detector.py:385-396).  (D, H, W) is the OUTPUT extent.  Optional fused input
+ * transform act(x_lo*in_scale+in_shift) and fused GroupNorm statistics as for nm_conv3d_tc_fused (chunks from
+ * nm_conv3d_stats_chunks(n, D, H, W, Cin, Cout, 3, 1)).  packed_w from nm_pack_conv_weights. */
+int nm_conv3d_up2x_supported(int n, int D, int H, int W, int Cin, int Cout);
+int nm_conv3d_tc_up2x(const void* x_lo, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
+                      int Cin, int Cout, const float* in_scale, const float* in_shift, int in_act,
+                      float* stats_partial, void* stream);
+
 /* Pointwise-shaped convolutions with Cin = 32 on mma.sync, organised around the memory pipe: Conv3d(k2, s2) of
  * Pool3DBlock (modules/vox_modules.py:49-61) and the 1x1 skip convolution of Res3DBlock (modules/vox_modules.py:35-38),
  * Cout in {32, 64}.  Optional fused input transform act(x*in_scale+in_shift) with in_scale/in_shift (n, Cin) fp32 (the

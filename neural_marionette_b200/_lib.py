@@ -39,6 +39,8 @@ PROTOTYPES = {
     "nm_conv3d_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "nm_conv3d_stats_chunks": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_can_fuse_input": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_up2x_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_tc_up2x": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
     "nm_conv3d_pw_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_pw_stats_chunks": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_pw_packed_bytes": (_sz, [_i, _i, _i]),

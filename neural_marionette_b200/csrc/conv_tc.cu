@@ -587,7 +587,15 @@ constexpr int kSlab3Threads = 64 + 32 * kSlab3EpiWarps;
 constexpr int kSlab3Ring = 8;        // max halo-slice ring depth (Cin = 32 has room for 8 slots, Cin = 64 for 4)
 constexpr int kSlab3XformWarps = 4;   // extra warps (only launched when the input transform is fused)
 
-template <int BK, int PN>
+// UP: the conv input is the 2x trilinear up-sampling (align_corners = False) of a low-resolution tensor that is
+// never materialised: TMA brings (10 x 6)-row low-resolution planes into a small ring and the transform warps
+// interpolate every halo slice from two planes directly into the swizzled operand layout (tmap_a then describes the
+// low-resolution tensor; BK = 64, one k-chunk).
+constexpr int kLoRing = 4;
+constexpr int kLoRows = 10 * 6;              // low-resolution box: 10 (h) x 6 (w) rows of 64 channels
+constexpr int kLoBytes = kLoRows * 128;      // 7680
+
+template <int BK, int PN, bool UP = false>
 __global__ void __launch_bounds__(kSlab3Threads + 32 * kSlab3XformWarps, 1)
 conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -598,7 +606,8 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   uint8_t* s_w = smem;                                                 // [kh*3+kw][kc][kd][PN rows][BK]
   uint8_t* s_ring = smem + w_bytes;
   constexpr int stage_bytes = kTileM * PN * 2;                         // one output tile (128 rows x PN fp16)
-  uint8_t* s_out = s_ring + (size_t)ring * p.slot_bytes;               // [2][stage_bytes], 1 KiB aligned
+  uint8_t* s_lo = s_ring + (size_t)ring * p.slot_bytes;                // UP: [kLoRing][kLoBytes] low-res planes
+  uint8_t* s_out = s_lo + (UP ? kLoRing * kLoBytes : 0);               // [2][stage_bytes], 1 KiB aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + 2 * stage_bytes);
   uint64_t* full = bars;                  // [ring]   slice landed
   uint64_t* empty = full + kSlab3Ring;     // [ring]   slice consumed
@@ -606,9 +615,11 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   uint64_t* pempty = pfull + kPGroups;    // [groups] P group drained
   uint64_t* wfull = pempty + kPGroups;    // [1]
   uint64_t* ready = wfull + 1;            // [ring]   slice transformed (fused input GroupNorm / LeakyReLU)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ready + kSlab3Ring);
+  uint64_t* full_lo = ready + kSlab3Ring; // [kLoRing] UP: low-res plane landed
+  uint64_t* empty_lo = full_lo + kLoRing; // [kLoRing] UP: low-res plane dead
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_lo + kLoRing);
   float* s_ab = reinterpret_cast<float*>(tmem_slot + 4);   // [2][Cin] scale | shift of the current sample
-  const bool xform = p.in_scale != nullptr;
+  const bool xform = UP || p.in_scale != nullptr;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.N * p.nh * p.nw;
@@ -626,6 +637,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     for (int s = 0; s < kSlab3Ring; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < kPGroups; s++) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], kSlab3EpiWarps); }
     for (int s = 0; s < kSlab3Ring; s++) mbar_init(&ready[s], kSlab3XformWarps);
+    for (int s = 0; s < kLoRing; s++) { mbar_init(&full_lo[s], 1); mbar_init(&empty_lo[s], kSlab3XformWarps); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -642,7 +654,121 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     __trap();
   }
 
-  if (warp >= 2 + kSlab3EpiWarps) {
+  if (UP && warp >= 2 + kSlab3EpiWarps) {
+    // ===================== up-sampling operand producer (warps 10..13) =====================
+    // Output slice d blends the low-res planes near = d>>1 and far = near -/+ 1 (clamped) with weights 0.75 / 0.25
+    // (PyTorch trilinear, align_corners = False); the same rule applies along h and w.  Work item = (halo row hh,
+    // 16-byte channel chunk c): 24 plane loads -> depth + h blends for the 6 box columns -> the 10 halo columns of
+    // that row, written at the TMA-128B-swizzle position.  Rows / columns outside the tensor are the conv's zero
+    // padding.  With a fused prologue the producer's GroupNorm scale/shift (+LeakyReLU) is applied to each plane
+    // in place when it lands.
+    const int tid = threadIdx.x - 32 * (2 + kSlab3EpiWarps);
+    const bool fused = p.in_scale != nullptr;
+    const int Dl = p.D >> 1, Hl = p.H >> 1;
+    const __half2 q25 = __float2half2_rn(0.25f);
+    auto lerp = [&](const uint4& a, const uint4& b) -> uint4 {      // a + 0.25 (b - a)
+      uint4 r;
+      const __half2* pa = reinterpret_cast<const __half2*>(&a);
+      const __half2* pb = reinterpret_cast<const __half2*>(&b);
+      __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) pr[i] = __hfma2(q25, __hsub2(pb[i], pa[i]), pa[i]);
+      return r;
+    };
+    uint32_t fill = 0;                                    // slices produced so far (ring position)
+    uint32_t planes = 0;                                  // global index of plane 0 of the current column
+    int cur_n = -1;
+    const uint32_t lo_base = smem_u32(s_lo), ring_base = smem_u32(s_ring);
+    for (int col = col0; col < n_cols; col += col_step, planes += Dl) {
+      int t = col;
+      const int iw = t % p.nw; t /= p.nw;
+      const int ih = t % p.nh; t /= p.nh;
+      const int n = t;
+      if (fused && n != cur_n) {
+        named_bar_sync(2, 32 * kSlab3XformWarps);
+        for (int i = tid; i < p.cin; i += 32 * kSlab3XformWarps) {
+          s_ab[i] = p.in_scale[(long long)n * p.cin + i];
+          s_ab[p.cin + i] = p.in_shift[(long long)n * p.cin + i];
+        }
+        named_bar_sync(2, 32 * kSlab3XformWarps);
+        cur_n = n;
+      }
+      int landed = 0;                                     // planes of this column already waited for
+      for (int d = 0; d < p.D; d++, fill++) {
+        const int pn = d >> 1, pf = min(max(pn + ((d & 1) ? 1 : -1), 0), Dl - 1);
+        const int need = max(pn, pf);
+        while (landed <= need) {
+          const uint32_t g = planes + landed;
+          mbar_wait(&full_lo[g % kLoRing], (g / kLoRing) & 1);
+          if (fused) {
+            const uint32_t pb = lo_base + (g % kLoRing) * kLoBytes;
+            for (int i = tid; i < kLoRows * 8; i += 32 * kSlab3XformWarps) {
+              const int c = i & 7;
+              const uint32_t addr = pb + i * 16;
+              const uint4 raw = lds128(addr);
+              const uint32_t in[4] = {raw.x, raw.y, raw.z, raw.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in[k]));
+                __half2 hv = __floats2half2_rn(fmaf(f.x, s_ab[c * 8 + 2 * k], s_ab[p.cin + c * 8 + 2 * k]),
+                                               fmaf(f.y, s_ab[c * 8 + 2 * k + 1], s_ab[p.cin + c * 8 + 2 * k + 1]));
+                if (p.in_act) hv = __hmax2(hv, __hmul2(hv, __float2half2_rn(0.01f)));
+                o[k] = *reinterpret_cast<uint32_t*>(&hv);
+              }
+              sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
+            }
+            named_bar_sync(2, 32 * kSlab3XformWarps);
+          }
+          landed++;
+        }
+        const int slot = fill % ring;
+        mbar_wait(&empty[slot], ((fill / ring) & 1) ^ 1);
+        const uint32_t sbase = ring_base + (uint32_t)slot * p.slot_bytes;
+        const uint32_t lo_n = lo_base + ((planes + pn) % kLoRing) * kLoBytes;
+        const uint32_t lo_f = lo_base + ((planes + pf) % kLoRing) * kLoBytes;
+        for (int item = tid; item < kHaloH * 8; item += 32 * kSlab3XformWarps) {
+          const int hh = item >> 3, c = item & 7;
+          const int hf = ih * 16 - 1 + hh;
+          const uint32_t orow = sbase + (uint32_t)(hh * kHaloW) * 128;
+          const uint4 zero = make_uint4(0, 0, 0, 0);
+          if ((unsigned)hf >= (unsigned)p.H) {
+#pragma unroll
+            for (int ww = 0; ww < kHaloW; ww++) sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), zero);
+            continue;
+          }
+          const int hn = hf >> 1, hfar = min(max(hn + ((hf & 1) ? 1 : -1), 0), Hl - 1);
+          const uint32_t on = (uint32_t)((hn - (ih * 8 - 1)) * 6) * 128 + c * 16;
+          const uint32_t of = (uint32_t)((hfar - (ih * 8 - 1)) * 6) * 128 + c * 16;
+          uint4 v[6];
+#pragma unroll
+          for (int w = 0; w < 6; w++) {
+            const uint4 a = lds128(lo_n + on + w * 128), b = lds128(lo_f + on + w * 128);
+            const uint4 e = lds128(lo_n + of + w * 128), f = lds128(lo_f + of + w * 128);
+            v[w] = lerp(lerp(a, b), lerp(e, f));
+          }
+#pragma unroll
+          for (int ww = 0; ww < kHaloW; ww++) {
+            // halo column ww <-> w = iw*8 - 1 + ww: near box column (ww+1)>>1, far = near +1 (ww even) / -1 (ww odd)
+            const int nr = (ww + 1) >> 1, fr = (ww & 1) ? nr - 1 : nr + 1;
+            uint4 o;
+            if ((ww == 0 && iw == 0) || (ww == kHaloW - 1 && iw == p.nw - 1)) o = zero;               // conv padding
+            else if ((ww == 1 && iw == 0) || (ww == kHaloW - 2 && iw == p.nw - 1)) o = v[nr];          // clamped far
+            else o = lerp(v[nr], v[fr]);
+            sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), o);
+          }
+        }
+        fence_async_smem();                              // generic-proxy writes -> visible to the UMMA reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&ready[slot]);
+          // plane x is last read by slice min(2x + 2, D - 1)
+          if (d >= 2 && !(d & 1)) mbar_arrive(&empty_lo[(planes + ((d - 2) >> 1)) % kLoRing]);
+          if (d == p.D - 1) mbar_arrive(&empty_lo[(planes + Dl - 1) % kLoRing]);
+        }
+      }
+    }
+  } else if (warp >= 2 + kSlab3EpiWarps) {
     // ===================== input transform (warps 10..13, only with a fused prologue) =====================
     // The GroupNorm affine (+LeakyReLU) of the producing layer is applied to each halo slice in place, once,
     // before the 9 x kchunks x BK/16 MMAs read it: the activated tensor never exists in HBM.  Rows outside the
@@ -739,6 +865,15 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         const int iw = t % p.nw; t /= p.nw;
         const int ih = t % p.nh; t /= p.nh;
         const int n = t;
+        if constexpr (UP) {
+          for (int pl = 0; pl < (p.D >> 1); pl++, fill++) {
+            const int slot = fill % kLoRing;
+            mbar_wait(&empty_lo[slot], ((fill / kLoRing) & 1) ^ 1);
+            mbar_expect_tx(&full_lo[slot], (uint32_t)kLoBytes);
+            tma_load_5d(s_lo + (size_t)slot * kLoBytes, &p.tmap_a, &full_lo[slot], 0, iw * 4 - 1, ih * 8 - 1, pl, n);
+          }
+          continue;
+        }
         for (int dz = 0; dz < p.D; dz++, fill++) {
           const int slot = fill % ring;
           mbar_wait(&empty[slot], ((fill / ring) & 1) ^ 1);
@@ -800,7 +935,6 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     const int quad = warp & 3;
     const int chalf = (warp - 2) >> 2;                   // 0: columns [0, CW), 1: [CW, PN)
     const int row = quad * 32 + lane;
-    const int rx = row & 7, ry = row >> 3;
     const uint32_t lane_addr = ((uint32_t)(quad * 32) << 16) + (uint32_t)(chalf * CW);
     float bias[CW];
 #pragma unroll
@@ -970,7 +1104,7 @@ int slab_mode_env() {
   return slab_mode;
 }
 // Which kernel serves this conv, and how many GroupNorm partial chunks per sample it can emit (0 = none).
-struct ConvPlan { bool slab, use3; int bk, kch, ntile, pn, ring, chunk_bytes; size_t need; int stats_chunks; };
+struct ConvPlan { bool slab, use3; int bk, kch, ntile, pn, ring, chunk_bytes; size_t need, w_bytes, extra; int stats_chunks; };
 ConvPlan plan_conv(int n, int D, int H, int W, int Cin, int Cout, int k, int stride) {
   ConvPlan pl;
   memset(&pl, 0, sizeof(pl));
@@ -983,10 +1117,11 @@ ConvPlan plan_conv(int n, int D, int H, int W, int Cin, int Cout, int k, int str
   const size_t w_bytes = (size_t)27 * pl.kch * (pl.use3 ? pl.pn : pl.ntile) * pl.bk * 2;
   pl.chunk_bytes = ((kHaloW * kHaloH * pl.bk * 2 + 1023) / 1024) * 1024;
   pl.ring = pl.use3 ? kSlab3Ring : kSlabRing;
-  const size_t extra = 1024 + 40 * 8 + 16 + 2 * 256 * 4 + (pl.use3 ? (size_t)2 * kTileM * pl.pn * 2 : 0);
+  const size_t extra = 1024 + 48 * 8 + 16 + 2 * 256 * 4 + (pl.use3 ? (size_t)2 * kTileM * pl.pn * 2 : 0);
   if (pl.use3)
     while (pl.ring > 2 && w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra > 227 * 1024) pl.ring--;
   pl.need = w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra;
+  pl.w_bytes = w_bytes; pl.extra = extra;
   pl.slab = slab_mode && k == 3 && stride == 1 && Cin >= 32 && Cin % pl.bk == 0 && W % 8 == 0 && H % 16 == 0 &&
             pl.need <= 227 * 1024;
   if (pl.slab) {
@@ -1028,9 +1163,47 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
                             stats_partial, stream);
 }
 
+namespace {
+int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
+                   int Cin, int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
+                   float* stats_partial, void* stream, bool up);
+// up-sampling mode needs the slab3<64, 32> kernel with 3 slice slots + the low-resolution plane ring
+bool up2x_ok(int n, int D, int H, int W, int Cin, int Cout) {
+  if ((D | H | W) & 1) return false;
+  const ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, 3, 1);
+  return pl.slab && pl.use3 && pl.bk == 64 && pl.kch == 1 && pl.pn == 32 &&
+         pl.w_bytes + (size_t)3 * pl.chunk_bytes + kLoRing * kLoBytes + pl.extra <= 227 * 1024;
+}
+}  // namespace
+
 extern "C" int nm_conv3d_tc_fused(const void* x, const void* packed_w, const float* bias, void* out, int n, int D,
                                   int H, int W, int Cin, int Cout, int k, int stride, const float* in_scale,
                                   const float* in_shift, int in_act, float* stats_partial, void* stream) {
+  return conv3d_tc_impl(x, packed_w, bias, out, n, D, H, W, Cin, Cout, k, stride, in_scale, in_shift, in_act,
+                        stats_partial, stream, false);
+}
+
+// 1 when nm_conv3d_tc_up2x serves a k3 conv with (D, H, W) OUTPUT extent
+extern "C" int nm_conv3d_up2x_supported(int n, int D, int H, int W, int Cin, int Cout) {
+  return up2x_ok(n, D, H, W, Cin, Cout) ? 1 : 0;
+}
+
+// out = conv3d_k3(upsample2x_trilinear(act(x_lo * in_scale + in_shift))), x_lo: (n, D/2, H/2, W/2, Cin); the
+// up-sampled tensor is never written (reference: nn.Upsample(scale_factor=2, mode='trilinear') followed by
+// nn.Conv3d(k3) in build_voxel_decoder, model/kypt_detector.py:385-396).  in_scale / in_shift may be null.
+extern "C" int nm_conv3d_tc_up2x(const void* x_lo, const void* packed_w, const float* bias, void* out, int n, int D,
+                                 int H, int W, int Cin, int Cout, const float* in_scale, const float* in_shift,
+                                 int in_act, float* stats_partial, void* stream) {
+  NM_CHECK_ARG(up2x_ok(n, D, H, W, Cin, Cout), "nm_conv3d_tc_up2x: unsupported shape n=%d out %dx%dx%d Cin=%d Cout=%d", n,
+               D, H, W, Cin, Cout);
+  return conv3d_tc_impl(x_lo, packed_w, bias, out, n, D, H, W, Cin, Cout, 3, 1, in_scale, in_shift, in_act,
+                        stats_partial, stream, true);
+}
+
+namespace {
+int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
+                   int Cin, int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
+                   float* stats_partial, void* stream, bool up) {
   NM_CHECK_ARG(x && packed_w && bias && out, "nm_conv3d_tc: null pointer");
   NM_CHECK_ARG((stride == 1 && (k == 1 || k == 3)) || (stride == 2 && k == 2), "nm_conv3d_tc: k=%d stride=%d unsupported",
                k, stride);
@@ -1044,7 +1217,11 @@ extern "C" int nm_conv3d_tc_fused(const void* x, const void* packed_w, const flo
     return NM_ERR_DRIVER;
   }
   // ---- slab-walking kernels: k3, weights resident in smem
-  const ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, k, stride);
+  ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, k, stride);
+  if (up) {
+    pl.ring = 3;
+    pl.need = pl.w_bytes + (size_t)3 * pl.chunk_bytes + kLoRing * kLoBytes + pl.extra;
+  }
   NM_CHECK_ARG(!stats_partial || pl.stats_chunks > 0, "nm_conv3d_tc: this shape cannot fuse GroupNorm statistics");
   NM_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "nm_conv3d_tc: in_scale and in_shift go together");
   NM_CHECK_ARG(!in_scale || (pl.slab && pl.use3 && Cin <= 256),
@@ -1068,9 +1245,15 @@ extern "C" int nm_conv3d_tc_fused(const void* x, const void* packed_w, const flo
                                (cuuint64_t)D * H * W * Cin * 2};
       cuuint32_t box[5] = {(cuuint32_t)bk, kHaloW, kHaloH, 1, 1};
       cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+      if (up) {   // the low-resolution tensor, (10 x 6)-row planes, linear rows (read by the transform warps)
+        dims[1] = W / 2; dims[2] = H / 2; dims[3] = D / 2;
+        strides[1] = (cuuint64_t)(W / 2) * Cin * 2; strides[2] = (cuuint64_t)(H / 2) * (W / 2) * Cin * 2;
+        strides[3] = (cuuint64_t)(D / 2) * (H / 2) * (W / 2) * Cin * 2;
+        box[1] = 6; box[2] = 10;
+      }
       CUresult r = encode(&q.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)x, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, up ? CU_TENSOR_MAP_SWIZZLE_NONE : swz,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab): cuTensorMapEncodeTiled(A) failed with %d", (int)r); return NM_ERR_DRIVER; }
       cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 27};
       cuuint64_t wstrides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
@@ -1105,10 +1288,12 @@ extern "C" int nm_conv3d_tc_fused(const void* x, const void* packed_w, const flo
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           slab3_attr = true;
         }
-        const int threads3 = kSlab3Threads + (in_scale ? 32 * kSlab3XformWarps : 0);
-        if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+        const int threads3 = kSlab3Threads + (in_scale || up ? 32 * kSlab3XformWarps : 0);
+        if (up) conv3d_slab3_kernel<64, 32, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+        else if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         else conv3d_slab3_kernel<32, 32><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
       } else if (bk == 64) conv3d_slab_kernel<64><<<grid, 192, need, (cudaStream_t)stream>>>(q);
@@ -1210,3 +1395,4 @@ extern "C" int nm_conv3d_tc_fused(const void* x, const void* packed_w, const flo
   NM_CHECK_LAUNCH("conv3d_tc");
   return NM_OK;
 }
+}  // namespace

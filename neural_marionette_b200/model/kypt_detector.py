@@ -184,10 +184,13 @@ class KyptToVoxNet(nn.Module):
                 x = ops.upsample2x(x)
                 raw, a, b = ops.conv3d(x, dec[1], dec[2])
                 raw, a, b = self._conv_after_gn(raw, a, b, dec[4], dec[5])
-                # GroupNorm affine + LeakyReLU on the low-resolution tensor (HBM-bound, 8x fewer elements than the
-                # output), then the half2 interpolation kernel: fewer instructions than the fused variant
-                x = ops.upsample2x(ops.affine_act(raw, a, b, True))
-                raw, a, b = ops.conv3d(x, dec[8], dec[9])
+                if ops.can_conv_up2x(raw, dec[8]):
+                    # GroupNorm + LeakyReLU + trilinear up-sampling all happen inside the conv's operand path: the
+                    # 64-channel 64^3 tensor (33.5 MB / frame) is never written
+                    raw, a, b = ops.conv3d_up2x(raw, dec[8], dec[9], in_affine=(a, b, True))
+                else:
+                    x = ops.upsample2x(ops.affine_act(raw, a, b, True))
+                    raw, a, b = ops.conv3d(x, dec[8], dec[9])
                 raw, a, b = self._conv_after_gn(raw, a, b, dec[11], dec[12])
                 tgt = target[b0:b1].view(n, G, G, G) if target is not None else None
                 ops.final_recon(raw, a, b, dec[14], first_frame[b0:b1], T, sharpness, translation, target=tgt,

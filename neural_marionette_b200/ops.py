@@ -196,6 +196,42 @@ def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNo
     return out, a, b
 
 
+def can_conv_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d) -> bool:
+    n, D, H, W, Cin = x_lo.shape
+    return conv.kernel_size[0] == 3 and conv.stride[0] == 1 and conv.padding[0] == 1 and \
+        bool(L.query("nm_conv3d_up2x_supported", n, 2 * D, 2 * H, 2 * W, Cin, conv.out_channels))
+
+
+def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
+    """conv3d_k3(upsample2x_trilinear(act(x_lo*scale+shift))) without materialising the up-sampled tensor.
+    x_lo act (n, D, H, W, Cin) -> raw (n, 2D, 2H, 2W, Cout) [, GroupNorm scale, shift]."""
+    _need_cuda(x_lo)
+    n, D, H, W, Cin = x_lo.shape
+    Cout = conv.out_channels
+    assert can_conv_up2x(x_lo, conv) and x_lo.dtype == ACT_DTYPE and x_lo.is_contiguous()
+    out = torch.empty(n, 2 * D, 2 * H, 2 * W, Cout, dtype=ACT_DTYPE, device=x_lo.device)
+    pw, pb = packed_conv_weight(conv), f32(conv, "bias")
+    chunks = L.query("nm_conv3d_stats_chunks", n, 2 * D, 2 * H, 2 * W, Cin, Cout, 3, 1) if gn is not None else 0
+    partial = workspace(n * chunks * Cout * 8, x_lo.device, "gn").view(torch.float32) if chunks else None
+    ia = in_affine if in_affine is not None else (None, None, False)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    L.call("nm_conv3d_tc_up2x", L.ptr(x_lo), L.ptr(pw), L.ptr(pb), L.ptr(out), n, 2 * D, 2 * H, 2 * W, Cin, Cout,
+           L.ptr(ia[0]), L.ptr(ia[1]), int(ia[2]), L.ptr(partial), L.stream())
+    if PROFILE is not None:
+        e1.record()
+        flops = 2.0 * n * 8 * D * H * W * Cout * Cin * 27
+        PROFILE.setdefault((n, 2 * D, Cin, Cout, 3, 1, flops), []).append((e0, e1))
+    if gn is None:
+        return out
+    a = torch.empty(n, Cout, dtype=torch.float32, device=x_lo.device)
+    b = torch.empty_like(a)
+    L.call("nm_groupnorm_finalize", L.ptr(partial), n, 8 * D * H * W, Cout, gn.num_groups, chunks,
+           L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+    return out, a, b
+
+
 def conv3d_direct(x: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
     """CUDA-core cross-check of conv3d (tests only)."""
     n, D, H, W, Cin = x.shape

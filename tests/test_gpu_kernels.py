@@ -166,6 +166,38 @@ def test_conv3d_fused_input_groupnorm(ops, n, grid, cin, cout):
     assert rel_err(got.float().cpu(), ref.float().cpu()) < 2e-3
 
 
+@pytest.mark.parametrize("n,grid,cout,fused", [(2, 16, 32, True), (1, 32, 32, False), (3, 16, 64, True), (1, 32, 64, True)])
+def test_conv3d_upsample_fused(ops, n, grid, cout, fused):
+    """conv3d_k3(upsample2x(LeakyReLU(GN(raw)))) with the up-sampled tensor interpolated inside the conv's operand
+    path: against the two-kernel device path and against torch (F.interpolate trilinear + conv3d)."""
+    g = torch.Generator().manual_seed(grid + cout)
+    conv = torch.nn.Conv3d(64, cout, 3, 1, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (64 * 27) ** 0.5)
+    gn_out = torch.nn.GroupNorm(cout // 16, cout).cuda()
+    lo = grid // 2
+    x = torch.randn(n, 64, lo, lo, lo, generator=g) * 1.5 + 0.3
+    raw = to_act(x)
+    a = (0.5 + torch.rand(n, 64, generator=g)).cuda()
+    b = torch.randn(n, 64, generator=g).cuda()
+    conv = conv.cuda()
+    assert ops.can_conv_up2x(raw, conv)
+    if fused:
+        act = ops.affine_act(raw, a, b, True)
+        got, ga, gb = ops.conv3d_up2x(raw, conv, gn_out, in_affine=(a, b, True))
+    else:
+        act = raw
+        got, ga, gb = ops.conv3d_up2x(raw, conv, gn_out)
+    two, ta, tb = ops.conv3d(ops.upsample2x(act), conv, gn_out)
+    ref = F.conv3d(F.interpolate(from_act(act), scale_factor=2.0, mode="trilinear", align_corners=False),
+                   conv.weight.detach().cpu().half().float(), conv.bias.detach().cpu(), padding=1)
+    torch.cuda.synchronize()
+    assert rel_err(from_act(two), ref) < 3e-3
+    assert rel_err(from_act(got), ref) < 3e-3
+    assert rel_err(from_act(got), from_act(two)) < 3e-3
+    assert (ga - ta).abs().max() <= 3e-3 * ta.abs().max() and (gb - tb).abs().max() <= 3e-3 * (1 + tb.abs().max())
+
+
 @pytest.mark.parametrize("n,grid,cout,k,stride", [(2, 16, 32, 2, 2), (1, 32, 32, 2, 2), (3, 8, 64, 1, 1),
                                                  (2, 16, 64, 1, 1), (5, 16, 32, 1, 1)])
 def test_conv3d_pointwise_fused_input(ops, n, grid, cout, k, stride):
