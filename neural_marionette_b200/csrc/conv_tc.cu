@@ -727,35 +727,45 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         const uint32_t sbase = ring_base + (uint32_t)slot * p.slot_bytes;
         const uint32_t lo_n = lo_base + ((planes + pn) % kLoRing) * kLoBytes;
         const uint32_t lo_f = lo_base + ((planes + pf) % kLoRing) * kLoBytes;
-        for (int item = tid; item < kHaloH * 8; item += 32 * kSlab3XformWarps) {
-          const int hh = item >> 3, c = item & 7;
-          const int hf = ih * 16 - 1 + hh;
-          const uint32_t orow = sbase + (uint32_t)(hh * kHaloW) * 128;
-          const uint4 zero = make_uint4(0, 0, 0, 0);
-          if ((unsigned)hf >= (unsigned)p.H) {
-#pragma unroll
-            for (int ww = 0; ww < kHaloW; ww++) sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), zero);
-            continue;
-          }
-          const int hn = hf >> 1, hfar = min(max(hn + ((hf & 1) ? 1 : -1), 0), Hl - 1);
-          const uint32_t on = (uint32_t)((hn - (ih * 8 - 1)) * 6) * 128 + c * 16;
-          const uint32_t of = (uint32_t)((hfar - (ih * 8 - 1)) * 6) * 128 + c * 16;
-          uint4 v[6];
+        // item = (pair of halo rows 2j, 2j+1, chunk c): h = ih*16 - 1 + 2j is odd (= 2m+1) and h + 1 = 2m+2, so both
+        // rows interpolate between the same low-res rows m and m+1 (near / far swapped): the 24 plane loads and the
+        // 12 depth blends are shared
+        for (int item = tid; item < (kHaloH / 2) * 8; item += 32 * kSlab3XformWarps) {
+          const int j = item >> 3, c = item & 7;
+          const int h0 = ih * 16 - 1 + 2 * j;                        // first row of the pair (may be -1)
+          const int m = (h0 + 1) / 2 - 1;                            // h0 = 2m + 1
+          const int ma = min(max(m, 0), Hl - 1), mb = min(m + 1, Hl - 1);
+          const uint32_t oa = (uint32_t)((ma - (ih * 8 - 1)) * 6) * 128 + c * 16;
+          const uint32_t ob = (uint32_t)((mb - (ih * 8 - 1)) * 6) * 128 + c * 16;
+          uint4 va[6], vb[6];                                        // depth-blended low-res rows m and m+1
 #pragma unroll
           for (int w = 0; w < 6; w++) {
-            const uint4 a = lds128(lo_n + on + w * 128), b = lds128(lo_f + on + w * 128);
-            const uint4 e = lds128(lo_n + of + w * 128), f = lds128(lo_f + of + w * 128);
-            v[w] = lerp(lerp(a, b), lerp(e, f));
+            va[w] = lerp(lds128(lo_n + oa + w * 128), lds128(lo_f + oa + w * 128));
+            vb[w] = lerp(lds128(lo_n + ob + w * 128), lds128(lo_f + ob + w * 128));
           }
+          const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int ww = 0; ww < kHaloW; ww++) {
-            // halo column ww <-> w = iw*8 - 1 + ww: near box column (ww+1)>>1, far = near +1 (ww even) / -1 (ww odd)
-            const int nr = (ww + 1) >> 1, fr = (ww & 1) ? nr - 1 : nr + 1;
-            uint4 o;
-            if ((ww == 0 && iw == 0) || (ww == kHaloW - 1 && iw == p.nw - 1)) o = zero;               // conv padding
-            else if ((ww == 1 && iw == 0) || (ww == kHaloW - 2 && iw == p.nw - 1)) o = v[nr];          // clamped far
-            else o = lerp(v[nr], v[fr]);
-            sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), o);
+          for (int r2 = 0; r2 < 2; r2++) {
+            const int hh = 2 * j + r2, hf = h0 + r2;
+            const uint32_t orow = sbase + (uint32_t)(hh * kHaloW) * 128;
+            if ((unsigned)hf >= (unsigned)p.H) {                     // conv padding row
+#pragma unroll
+              for (int ww = 0; ww < kHaloW; ww++) sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), zero);
+              continue;
+            }
+            uint4 v[6];                                              // row 2m+1: near m, far m+1; row 2m+2: near m+1, far m
+#pragma unroll
+            for (int w = 0; w < 6; w++) v[w] = r2 == 0 ? lerp(va[w], vb[w]) : lerp(vb[w], va[w]);
+#pragma unroll
+            for (int ww = 0; ww < kHaloW; ww++) {
+              // halo column ww <-> w = iw*8 - 1 + ww: near box column (ww+1)>>1, far = near +1 (ww even) / -1 (ww odd)
+              const int nr = (ww + 1) >> 1, fr = (ww & 1) ? nr - 1 : nr + 1;
+              uint4 o;
+              if ((ww == 0 && iw == 0) || (ww == kHaloW - 1 && iw == p.nw - 1)) o = zero;               // conv padding
+              else if ((ww == 1 && iw == 0) || (ww == kHaloW - 2 && iw == p.nw - 1)) o = v[nr];          // clamped far
+              else o = lerp(v[nr], v[fr]);
+              sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), o);
+            }
           }
         }
         fence_async_smem();                              // generic-proxy writes -> visible to the UMMA reads
