@@ -1004,15 +1004,20 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         const uint32_t g_cur = lane_addr + (q % kPGroups) * (3 * PN);
         const uint32_t g_prev = lane_addr + ((q + kPGroups - 1) % kPGroups) * (3 * PN);
         uint32_t ra[CW], rb[CW], rc[CW];
-        if (sl >= 1) {
+        if (sl >= 1 && !(p.debug & 24)) {
           if constexpr (CW == 16) { tmem_ld16(g_cur + 2 * PN, ra); tmem_ld16(g_prev, rc); }
           else { tmem_ld8(g_cur + 2 * PN, ra); tmem_ld8(g_prev, rc); }
         } else {
 #pragma unroll
           for (int c = 0; c < CW; c++) { ra[c] = 0u; rc[c] = 0u; }
         }
-        if constexpr (CW == 16) tmem_ld16(g_cur + PN, rb);
-        else tmem_ld8(g_cur + PN, rb);
+        if (!(p.debug & 8)) {
+          if constexpr (CW == 16) tmem_ld16(g_cur + PN, rb);
+          else tmem_ld8(g_cur + PN, rb);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CW; c++) rb[c] = 0u;
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();

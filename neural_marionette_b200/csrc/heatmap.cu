@@ -21,49 +21,85 @@ __device__ __forceinline__ float softplus1(float x) {
   return x > 20.f ? x : log1pf(expf(x));
 }
 
-// Phase 1 (parallel over voxels): heat-map values.  grid = (g^3 / 256, n); one voxel per thread.
+// Phase 1 (parallel over voxels): heat-map values on mma.sync (m16n8k16, fp16 operands, fp32 accumulate).
+// grid = (g^3 / 512, n); a warp owns M-tiles of 16 consecutive voxels, K = C feature channels, N = 24 keypoints (3
+// n-blocks).  The K order is permuted so that the 8 consecutive channels a lane loads with one 16-byte load are the
+// K slots it owns in two k-steps (as in conv_pw.cu); the 1x1 conv weights are packed into B fragments once per block.
 //   mode 0: heat = lrelu(w1 f + b1);  mode 1: heat = softplus(pw0 * lrelu(w1 f + b1) + pw1 * prev[clip] + pb)
+__device__ __forceinline__ void head_mma(float (&c)[4], const uint32_t a0, const uint32_t a1, const uint32_t a2,
+                                         const uint32_t a3, const uint2 b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b.x), "r"(b.y));
+}
+
 template <int C>
 __global__ void __launch_bounds__(256)
 head_heat_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, const float* __restrict__ b1,
                  int K, int S, int mode, const float* __restrict__ prev, int frames_per_clip, float pw0, float pw1,
                  float pb, float* __restrict__ heat) {
-  extern __shared__ float smem[];
-  float* s_w = smem;                       // [K][C]
-  float* s_b = s_w + KMAX * C;             // [K]
+  constexpr int KS = C / 16, NB = KMAX / 8;
+  // the fp32 weights are split into fp16 hi + lo parts (two MMAs per k-step): the heat-maps keep fp32-weight accuracy
+  __shared__ __align__(16) uint2 s_frag[KS * NB * 32];
+  __shared__ __align__(16) uint2 s_frag_lo[KS * NB * 32];
+  __shared__ float s_b[KMAX];
   const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < K * C; i += 256) s_w[i] = w1[i];
-  for (int i = threadIdx.x; i < K; i += 256) s_b[i] = b1[i];
-  __syncthreads();
-  const int s = blockIdx.x * 256 + threadIdx.x;
-  if (s >= S) return;
-  float acc[KMAX];
+  // k-step ks = 2m + s of the 32-channel group m: slot (2t + j + 8 hi) <-> channel m*32 + t*8 + s*4 + hi*2 + j
+  for (int i = threadIdx.x; i < KS * NB * 32; i += 256) {
+    const int lane = i & 31, nb = (i >> 5) % NB, ks = (i >> 5) / NB;
+    const int g = lane >> 2, t = lane & 3, k = nb * 8 + g;
+    const int c0 = (ks >> 1) * 32 + t * 8 + (ks & 1) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k < K) {
 #pragma unroll
-  for (int k = 0; k < KMAX; k++) acc[k] = 0.f;
-  const half8* p = reinterpret_cast<const half8*>(feature + ((long long)n * S + s) * C);
-#pragma unroll 2
-  for (int c8 = 0; c8 < C / 8; c8++) {
-    float v[8];
-    nm_unpack8(p[c8], v);
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-      if (k < K) {
-        const float4 wa = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8);
-        const float4 wb = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 8 + 4);
-        acc[k] = fmaf(v[0], wa.x, fmaf(v[1], wa.y, fmaf(v[2], wa.z, fmaf(v[3], wa.w, acc[k]))));
-        acc[k] = fmaf(v[4], wb.x, fmaf(v[5], wb.y, fmaf(v[6], wb.z, fmaf(v[7], wb.w, acc[k]))));
-      }
+      for (int e = 0; e < 4; e++) v[e] = w1[k * C + c0 + e];
     }
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    s_frag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    __half2 l0 = __floats2half2_rn(v[0] - f0.x, v[1] - f0.y), l1 = __floats2half2_rn(v[2] - f1.x, v[3] - f1.y);
+    s_frag_lo[i] = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
   }
+  for (int i = threadIdx.x; i < KMAX; i += 256) s_b[i] = i < K ? b1[i] : 0.f;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float* pv = prev ? prev + (long long)(n / frames_per_clip) * K * S : nullptr;
   float* hm_out = heat + (long long)n * K * S;
+#pragma unroll 1
+  for (int it = 0; it < 4; it++) {
+    const int s0 = ((blockIdx.x * 4 + it) * 8 + warp) * 16;
+    if (s0 >= S) break;
+    float c[NB][4];
 #pragma unroll
-  for (int k = 0; k < KMAX; k++) {
-    if (k < K) {
-      float h = nm_lrelu(acc[k] + s_b[k]);
-      if (mode == 1) h = softplus1(fmaf(pw0, h, fmaf(pw1, pv[(long long)k * S + s], pb)));
-      hm_out[(long long)k * S + s] = h;
+    for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+      for (int j = 0; j < 2; j++) c[nb][j] = c[nb][2 + j] = s_b[nb * 8 + 2 * t + j];
+    const uint4* f0 = reinterpret_cast<const uint4*>(feature + ((long long)n * S + s0 + g) * C + t * 8);
+    const uint4* f1 = f0 + 8 * (C / 8);
+#pragma unroll
+    for (int m = 0; m < C / 32; m++) {
+      const uint4 r0 = __ldg(f0 + m * 4), r1 = __ldg(f1 + m * 4);
+      const uint2* fr = s_frag + (2 * m) * NB * 32 + lane;
+      const uint2* fl = s_frag_lo + (2 * m) * NB * 32 + lane;
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) {
+        head_mma(c[nb], r0.x, r1.x, r0.y, r1.y, fl[nb * 32]);
+        head_mma(c[nb], r0.z, r1.z, r0.w, r1.w, fl[(NB + nb) * 32]);
+        head_mma(c[nb], r0.x, r1.x, r0.y, r1.y, fr[nb * 32]);
+        head_mma(c[nb], r0.z, r1.z, r0.w, r1.w, fr[(NB + nb) * 32]);
+      }
     }
+#pragma unroll
+    for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int k = nb * 8 + 2 * t + (e & 1), s = s0 + g + (e >> 1) * 8;
+        if (k < K) {
+          float h = nm_lrelu(c[nb][e]);
+          if (mode == 1) h = softplus1(fmaf(pw0, h, fmaf(pw1, pv[(long long)k * S + s], pb)));
+          hm_out[(long long)k * S + s] = h;
+        }
+      }
   }
 }
 
@@ -430,13 +466,12 @@ extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float
   if (n == 0) return NM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int S = g * g * g;
-  const size_t smem1 = (size_t)(KMAX * C + KMAX) * sizeof(float);
-  dim3 grid1(nm_cdiv(S, 256), n);
+  dim3 grid1(nm_cdiv(S, 512), n);
   if (C == 128) {
-    head_heat_kernel<128><<<grid1, 256, smem1, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
+    head_heat_kernel<128><<<grid1, 256, 0, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
                                                      pw0, pw1, pb, heat);
   } else if (C == 256) {
-    head_heat_kernel<256><<<grid1, 256, smem1, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
+    head_heat_kernel<256><<<grid1, 256, 0, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
                                                      pw0, pw1, pb, heat);
   } else {
     NM_CHECK_ARG(false, "nm_heatmap_head: C=%d unsupported", C);
