@@ -78,19 +78,23 @@ int nm_conv3d_tc_up2x(const void* x_lo, const void* packed_w, const float* bias,
                       int Cin, int Cout, const float* in_scale, const float* in_shift, int in_act,
                       float* stats_partial, void* stream);
 
-/* Pointwise-shaped convolutions with Cin = 32 on mma.sync, organised around the memory pipe: Conv3d(k2, s2) of
- * Pool3DBlock (modules/vox_modules.py:49-61) and the 1x1 skip convolution of Res3DBlock (modules/vox_modules.py:35-38),
- * Cout in {32, 64}.  Optional fused input transform act(x*in_scale+in_shift) with in_scale/in_shift (n, Cin) fp32 (the
- * producer's GroupNorm folded to scale/shift; in_act != 0: LeakyReLU 0.01) and fused GroupNorm statistics of the
- * output: stats_partial [n][chunks][Cout][2] for nm_groupnorm_finalize, chunks = nm_conv3d_pw_stats_chunks(...).
+/* Pointwise-shaped convolutions with Cin in {32, 64} on mma.sync, organised around the memory pipe: Conv3d(k2, s2) of
+ * Pool3DBlock (modules/vox_modules.py:49-61) and the 1x1 skip convolution of Res3DBlock (modules/vox_modules.py:35-38);
+ * shapes: nm_conv3d_pw_supported.  Optional fused input transform
+ *     input = act(x*in_scale + in_shift) [+ x2*in_scale2 + in_shift2]
+ * (scales/shifts (n, Cin) fp32: a producer's GroupNorm folded to scale/shift; in_act != 0: LeakyReLU 0.01 on the first
+ * term; x2: a second tensor of x's shape - the other branch of a Res3DBlock, modules/vox_modules.py:40-47 - added as
+ * is when in_scale2 is null) and fused GroupNorm statistics of the output: stats_partial [n][chunks][Cout][2] for
+ * nm_groupnorm_finalize, chunks = nm_conv3d_pw_stats_chunks(...).
  * packed_w comes from nm_pack_conv_pw_weights (weight: the nn.Conv3d (Cout, Cin, k, k, k) fp32 tensor). */
 int nm_conv3d_pw_supported(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);
+int nm_conv3d_pw_dual_supported(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);  /* x2 allowed */
 int nm_conv3d_pw_stats_chunks(int n, int D, int H, int W, int Cin, int Cout, int k, int stride);
 size_t nm_conv3d_pw_packed_bytes(int Cin, int Cout, int k);
 int nm_pack_conv_pw_weights(const float* weight, int Cin, int Cout, int k, void* packed, void* stream);
 int nm_conv3d_pw(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W, int Cin,
-                 int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
-                 float* stats_partial, void* stream);
+                 int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act, const void* x2,
+                 const float* in_scale2, const float* in_shift2, float* stats_partial, void* stream);
 
 /* First layer: add_coord_channels (utils/kypt_detector_utils.py:4-26) + Conv3d(1+3, Cout, k5, pad 2)
  * (model/kypt_detector.py:266).  occ: (n, G, G, G) fp32; weight (Cout, 4, 5, 5, 5) fp32; out: act (n,G,G,G,Cout).

@@ -56,8 +56,11 @@ def run_feature_net(net: nn.Sequential, occ: torch.Tensor) -> torch.Tensor:
     """occ (n, G, G, G) fp32 -> act (n, G/4, G/4, G/4, C)."""
     # the first layer's GroupNorm + LeakyReLU is applied inside the pool conv that follows
     raw, a, b = net[0].run_coordconv_raw(occ)
-    x = net[1].run(raw, in_affine=(a, b))
-    for block in list(net)[2:]:
+    x = net[1].run(raw, in_affine=(a, b, True))
+    # the two normalised branches of the first Res3DBlock are summed inside the second pool conv
+    raw, a, b, x2, a2, b2 = net[2].run_raw(x)
+    x = net[3].run(raw, in_affine=(a, b, False, x2, a2, b2))
+    for block in list(net)[4:]:
         x = block.run(x)
     return x
 

@@ -28,13 +28,19 @@ class _ActModule(nn.Module):
 
 
 def conv_gn_lrelu(x, conv, gn, in_affine=None):
-    """LeakyReLU(GN(conv(x))); with in_affine = (scale, shift) x is a RAW conv output whose GroupNorm + LeakyReLU is
-    applied inside this conv's operand path when the kernel supports it, else by a separate pass."""
+    """LeakyReLU(GN(conv(input))).  Without in_affine the input is x.  With in_affine = (scale, shift, act[, x2, scale2,
+    shift2]) x is a RAW conv output and input = act(x*scale+shift) [+ x2*scale2+shift2]; that is applied inside this
+    conv's operand path when the kernel supports it, else by a separate pass."""
     if in_affine is not None:
-        if ops.can_fuse_input(x, conv):
-            raw, a, b = ops.conv3d(x, conv, gn, in_affine=(in_affine[0], in_affine[1], True))
+        dual = len(in_affine) > 3 and in_affine[3] is not None
+        if ops.can_fuse_input2(x, conv) if dual else ops.can_fuse_input(x, conv):
+            raw, a, b = ops.conv3d(x, conv, gn, in_affine=in_affine)
             return ops.affine_act(raw, a, b, True)
-        x = ops.affine_act(x, in_affine[0], in_affine[1], True)
+        if dual:
+            x = ops.affine_act(x, in_affine[0], in_affine[1], in_affine[2], x2=in_affine[3], a2=in_affine[4],
+                               b2=in_affine[5])
+        else:
+            x = ops.affine_act(x, in_affine[0], in_affine[1], in_affine[2])
     raw, a, b = ops.conv3d(x, conv, gn)
     return ops.affine_act(raw, a, b, True)
 
@@ -77,6 +83,12 @@ class Res3DBlock(_ActModule):
                 nn.Conv3d(in_planes, out_planes, kernel_size=1, stride=1, padding=0), _norm(out_planes))
 
     def run(self, x):
+        raw, a, b, x2, a2, b2 = self.run_raw(x)
+        return ops.affine_act(raw, a, b, False, x2=x2, a2=a2, b2=b2)
+
+    def run_raw(self, x):
+        """-> (raw, scale, shift, x2, scale2, shift2) with block output = raw*scale+shift + x2*scale2+shift2 (x2 as is
+        when scale2 is None): a consumer that can apply this in its operand path avoids one pass over the tensor."""
         raw1, a1, b1 = ops.conv3d(x, self.res_branch[0], self.res_branch[1])
         if ops.can_fuse_input(raw1, self.res_branch[3]):
             # GroupNorm + LeakyReLU of the first conv applied inside the second conv's operand path
@@ -84,9 +96,9 @@ class Res3DBlock(_ActModule):
         else:
             raw, a, b = ops.conv3d(ops.affine_act(raw1, a1, b1, True), self.res_branch[3], self.res_branch[4])
         if len(self.skip_con) == 0:
-            return ops.affine_act(raw, a, b, False, x2=x)
+            return raw, a, b, x, None, None
         sraw, sa, sb = ops.conv3d(x, self.skip_con[0], self.skip_con[1])
-        return ops.affine_act(raw, a, b, False, x2=sraw, a2=sa, b2=sb)
+        return raw, a, b, sraw, sa, sb
 
 
 class Pool3DBlock(_ActModule):

@@ -144,10 +144,18 @@ def _pw_ok(x, conv) -> bool:
     return conv.padding[0] == 0 and bool(L.query("nm_conv3d_pw_supported", n, D, H, W, Cin, conv.out_channels, k, s))
 
 
+def can_fuse_input2(x: torch.Tensor, conv: torch.nn.Conv3d) -> bool:
+    """True when conv3d(x, conv, in_affine=(a, b, act, x2, a2, b2)) can sum two normalised tensors on the fly."""
+    n, D, H, W, Cin = x.shape
+    return conv.padding[0] == 0 and bool(L.query("nm_conv3d_pw_dual_supported", n, D, H, W, Cin, conv.out_channels,
+                                                 conv.kernel_size[0], conv.stride[0]))
+
+
 def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
     """act (n, D, H, W, Cin) -> raw conv output act (n, OD, OH, OW, Cout); bias included.
     `in_affine` = (scale, shift, act): x is the RAW output of the previous conv and act(x*scale+shift) is applied
-    inside the kernel's operand path (only when can_fuse_input(x, conv)).
+    inside the kernel's operand path (only when can_fuse_input(x, conv)); (scale, shift, act, x2, scale2, shift2)
+    additionally adds x2*scale2+shift2 (x2 as is when scale2 is None) - only when can_fuse_input2(x, conv).
     With `gn`: returns (raw, scale, shift) of the GroupNorm that follows; the statistics come out of the conv
     epilogue when the kernel supports it (no extra pass over the output), else from a reduction kernel."""
     _need_cuda(x)
@@ -171,9 +179,12 @@ def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNo
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
     if pointwise:
-        ia = in_affine if in_affine is not None else (None, None, False)
+        ia = tuple(in_affine) if in_affine is not None else (None, None, False)
+        ia = ia + (None, None, None) if len(ia) == 3 else ia
+        assert ia[3] is None or (ia[3].shape == x.shape and ia[3].is_contiguous())
         L.call("nm_conv3d_pw", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
-               L.ptr(ia[0]), L.ptr(ia[1]), int(ia[2]), L.ptr(partial), L.stream())
+               L.ptr(ia[0]), L.ptr(ia[1]), int(ia[2]), L.ptr(ia[3]), L.ptr(ia[4]), L.ptr(ia[5]), L.ptr(partial),
+               L.stream())
     elif in_affine is None:
         L.call("nm_conv3d_tc", L.ptr(x), L.ptr(pw), L.ptr(pb), L.ptr(out), n, D, H, W, Cin, Cout, k, s,
                L.ptr(partial), L.stream())

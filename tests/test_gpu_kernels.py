@@ -198,28 +198,31 @@ def test_conv3d_upsample_fused(ops, n, grid, cout, fused):
     assert (ga - ta).abs().max() <= 3e-3 * ta.abs().max() and (gb - tb).abs().max() <= 3e-3 * (1 + tb.abs().max())
 
 
-@pytest.mark.parametrize("n,grid,cout,k,stride", [(2, 16, 32, 2, 2), (1, 32, 32, 2, 2), (3, 8, 64, 1, 1),
-                                                 (2, 16, 64, 1, 1), (5, 16, 32, 1, 1)])
-def test_conv3d_pointwise_fused_input(ops, n, grid, cout, k, stride):
-    """Cin = 32 pool / 1x1 convs on the memory-pipe kernel: plain, and with the producer's GroupNorm + LeakyReLU
-    applied in registers; GroupNorm statistics of the output from the accumulators."""
-    g = torch.Generator().manual_seed(grid * 3 + cout + k)
-    conv = torch.nn.Conv3d(32, cout, k, stride, 0)
+@pytest.mark.parametrize("n,grid,cin,cout,k,stride", [(2, 16, 32, 32, 2, 2), (1, 32, 32, 32, 2, 2), (3, 8, 32, 64, 1, 1),
+                                                     (2, 16, 32, 64, 1, 1), (5, 16, 32, 32, 1, 1), (2, 16, 64, 64, 2, 2),
+                                                     (1, 32, 64, 64, 2, 2), (3, 16, 64, 128, 1, 1), (2, 8, 64, 64, 1, 1)])
+def test_conv3d_pointwise_fused_input(ops, n, grid, cin, cout, k, stride):
+    """Cin = 32 / 64 pool / 1x1 convs on the memory-pipe kernel: plain, with the producer's GroupNorm + LeakyReLU
+    applied in registers, and (64->64 pool) with the two normalised branches of a Res3DBlock summed on the fly;
+    GroupNorm statistics of the output from the accumulators."""
+    g = torch.Generator().manual_seed(grid * 3 + cin + cout + k)
+    conv = torch.nn.Conv3d(cin, cout, k, stride, 0)
     with torch.no_grad():
-        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (32 * k ** 3) ** 0.5)
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (cin * k ** 3) ** 0.5)
         conv.bias.copy_(torch.randn(cout, generator=g))
     gn_out = torch.nn.GroupNorm(cout // 16, cout).cuda()
-    x = torch.randn(n, 32, grid, grid, grid, generator=g) * 1.5 + 0.3
+    x = torch.randn(n, cin, grid, grid, grid, generator=g) * 1.5 + 0.3
     raw_in = to_act(x)
     assert ops._pw_ok(raw_in, conv) and ops.can_fuse_input(raw_in, conv)
-    ref = F.conv3d(x.half().float(), conv.weight.detach().half().float(), conv.bias.detach(), stride=stride)
+    wh, bias = conv.weight.detach().half().float(), conv.bias.detach().clone()
+    ref = F.conv3d(x.half().float(), wh, bias, stride=stride)
     conv = conv.cuda()
     assert rel_err(from_act(ops.conv3d(raw_in, conv)), ref) < 2e-3
-    a = (0.5 + torch.rand(n, 32, generator=g)).cuda()
-    b = torch.randn(n, 32, generator=g).cuda()
-    act_in = F.leaky_relu(x.half().float() * a.cpu()[:, :, None, None, None] + b.cpu()[:, :, None, None, None], 0.01)
-    ref2 = F.conv3d(act_in.half().float(), conv.weight.detach().cpu().half().float(), conv.bias.detach().cpu(),
-                    stride=stride)
+    a = (0.5 + torch.rand(n, cin, generator=g)).cuda()
+    b = torch.randn(n, cin, generator=g).cuda()
+    bc = lambda v: v.cpu()[:, :, None, None, None]                        # noqa: E731
+    lin_in = x.half().float() * bc(a) + bc(b)
+    ref2 = F.conv3d(F.leaky_relu(lin_in, 0.01).half().float(), wh, bias, stride=stride)
     got, ga, gb = ops.conv3d(raw_in, conv, gn_out, in_affine=(a, b, True))
     torch.cuda.synchronize()
     assert rel_err(from_act(got), ref2) < 2e-3
@@ -227,10 +230,18 @@ def test_conv3d_pointwise_fused_input(ops, n, grid, cout, k, stride):
     assert (ga - ra).abs().max() <= 2e-3 * ra.abs().max() and (gb - rb).abs().max() <= 2e-3 * (1 + rb.abs().max())
     # no activation: pure affine
     got3 = ops.conv3d(raw_in, conv, in_affine=(a, b, False))
-    lin_in = x.half().float() * a.cpu()[:, :, None, None, None] + b.cpu()[:, :, None, None, None]
-    ref3 = F.conv3d(lin_in.half().float(), conv.weight.detach().cpu().half().float(), conv.bias.detach().cpu(),
-                    stride=stride)
-    assert rel_err(from_act(got3), ref3) < 2e-3
+    assert rel_err(from_act(got3), F.conv3d(lin_in.half().float(), wh, bias, stride=stride)) < 2e-3
+    if ops.can_fuse_input2(raw_in, conv):
+        x2 = torch.randn(n, cin, grid, grid, grid, generator=g)
+        a2 = (0.5 + torch.rand(n, cin, generator=g)).cuda()
+        b2 = torch.randn(n, cin, generator=g).cuda()
+        for a2_, b2_ in ((a2, b2), (None, None)):
+            second = x2.half().float() * bc(a2_) + bc(b2_) if a2_ is not None else x2.half().float()
+            ref4 = F.conv3d((lin_in + second).half().float(), wh, bias, stride=stride)
+            got4 = ops.conv3d(raw_in, conv, in_affine=(a, b, False, to_act(x2), a2_, b2_))
+            assert rel_err(from_act(got4), ref4) < 2e-3
+    else:
+        assert not (cin == 64 and k == 2)
 
 
 def test_first_conv_coordconv(ops):
