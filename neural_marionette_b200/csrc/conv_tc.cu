@@ -730,7 +730,9 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         // item = (pair of halo rows 2j, 2j+1, chunk c): h = ih*16 - 1 + 2j is odd (= 2m+1) and h + 1 = 2m+2, so both
         // rows interpolate between the same low-res rows m and m+1 (near / far swapped): the 24 plane loads and the
         // 12 depth blends are shared
-        for (int item = tid; item < (kHaloH / 2) * 8; item += 32 * kSlab3XformWarps) {
+        // 72 items on the first three producer warps: the fourth shares its SM sub-partition with the MMA-issuing
+        // warp (warp 1) and only takes part in the barriers, so that it does not compete for issue slots
+        for (int item = tid < 96 ? tid : 9999; item < (kHaloH / 2) * 8; item += 96) {
           const int j = item >> 3, c = item & 7;
           const int h0 = ih * 16 - 1 + 2 * j;                        // first row of the pair (may be -1)
           const int m = (h0 + 1) / 2 - 1;                            // h0 = 2m + 1
