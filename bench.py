@@ -231,10 +231,12 @@ def main():
                 "kernel": ("conv3d_slab3_kernel" if slab3 else "conv3d_tc_kernel") + " (nm_conv3d_tc, tcgen05 implicit GEMM)",
                 "layer": f"n={tn} grid={tD} Cin={tci} Cout={tco} k={tk} s={ts}", "achieved": ach,
                 "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of the dec.8 launch from the ncu --set full capture in
-                # profiles/r01_conv_slab3_final.md: 16.41 GB for 320 frames = 51.3 MB/frame (algorithmic: 33.5 MB in
-                # + 16.8 MB out per frame)
-                "traffic": 51.29e6 * tn if (tD, tci, tco, tk) == (64, 64, 32, 3) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch (dec.8 with the up-sampling produced in its
+                # operand path) from the ncu pass in profiles/r01_step_launches_v3.md: 1.40 GB read + 5.34 GB written
+                # for 320 frames = 21.08 MB/frame (algorithmic: 4.19 MB low-resolution input + 16.78 MB output)
+                "traffic": 21.08e6 * tn if (tD, tci, tco, tk) == (64, 64, 32, 3) else None,
+                "note": "dec.8: conv3d_k3(upsample2x(LeakyReLU(GroupNorm(x)))) in one kernel; FLOPs counted are the "
+                        "conv's only" if (tD, tci, tco, tk) == (64, 64, 32, 3) else None,
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "launch_ms": t_ms / cnt, "share_of_step": t_ms / (ms * args.steps),
                 "all_tc_convs": {"achieved": tot_flop / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / (ms * args.steps)},
