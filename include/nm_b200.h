@@ -96,6 +96,16 @@ int nm_conv3d_pw(const void* x, const void* packed_w, const float* bias, void* o
                  int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act, const void* x2,
                  const float* in_scale2, const float* in_shift2, float* stats_partial, void* stream);
 
+/* ConvTranspose3d(k2, s2) with Cin = 32 on mma.sync (Upsample3DBlock, modules/vox_modules.py:63-75); weight is the
+ * nn.ConvTranspose3d (Cin, Cout, 2, 2, 2) fp32 tensor; x (n, D, H, W, Cin) -> out (n, 2D, 2H, 2W, Cout); optional
+ * GroupNorm statistics of the output as in nm_conv3d_pw. */
+int nm_conv_transpose3d_pw_supported(int n, int D, int H, int W, int Cin, int Cout);
+int nm_conv_transpose3d_pw_stats_chunks(int n, int D, int H, int W, int Cin, int Cout);
+size_t nm_conv_transpose3d_pw_packed_bytes(int Cin, int Cout);
+int nm_pack_conv_transpose3d_pw_weights(const float* weight, int Cin, int Cout, void* packed, void* stream);
+int nm_conv_transpose3d_pw(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
+                           int Cin, int Cout, float* stats_partial, void* stream);
+
 /* First layer: add_coord_channels (utils/kypt_detector_utils.py:4-26) + Conv3d(1+3, Cout, k5, pad 2)
  * (model/kypt_detector.py:266).  occ: (n, G, G, G) fp32; weight (Cout, 4, 5, 5, 5) fp32; out: act (n,G,G,G,Cout).
  * `tables` is built once per weight set by nm_first_conv_prepare. linspace: torch.linspace(-1,1,G) fp32. */

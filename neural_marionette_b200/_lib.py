@@ -41,6 +41,11 @@ PROTOTYPES = {
     "nm_conv3d_can_fuse_input": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_up2x_supported": (_i, [_i, _i, _i, _i, _i, _i]),
     "nm_conv3d_tc_up2x": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "nm_conv_transpose3d_pw_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "nm_conv_transpose3d_pw_stats_chunks": (_i, [_i, _i, _i, _i, _i, _i]),
+    "nm_conv_transpose3d_pw_packed_bytes": (_sz, [_i, _i]),
+    "nm_pack_conv_transpose3d_pw_weights": (_i, [_vp, _i, _i, _vp, _vp]),
+    "nm_conv_transpose3d_pw": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "nm_conv3d_pw_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_pw_dual_supported": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_pw_stats_chunks": (_i, [_i, _i, _i, _i, _i, _i, _i, _i]),

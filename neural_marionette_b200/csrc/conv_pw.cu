@@ -256,6 +256,148 @@ __global__ void __launch_bounds__(256, (COUT >= 128 || CIN >= 64) ? 1 : 2) conv_
   }
 }
 
+// ConvTranspose3d(k2, s2), Cin = 32 (Upsample3DBlock, reference modules/vox_modules.py:63-75): every input voxel
+// feeds the 8 output voxels (2x+dx, 2y+dy, 2z+dz) through 8 independent 1x1 convs.  One M-tile = 16 input voxels,
+// loaded once (two 16-byte loads per lane, same K permutation as above); per tap 2 x NB MMAs and 16-byte stores of
+// 8 consecutive channels.  GroupNorm statistics of the output from the accumulators.
+// wfrag[(tap*2 + s)][nb][lane]; weight is the nn.ConvTranspose3d (Cin, Cout, 2, 2, 2) tensor.
+__global__ void pack_pwT_kernel(const float* __restrict__ w, int Cout, uint2* __restrict__ wfrag) {
+  const int NB = Cout / 8;
+  const int total = 8 * 2 * NB * 32;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int lane = i & 31, nb = (i >> 5) % NB, ks = (i >> 5) / NB, s = ks & 1, tap = ks >> 1;
+    const int g = lane >> 2, t = lane & 3, co = pw_channel(nb, g);
+    auto wv = [&](int ci) -> float { return w[((long long)ci * Cout + co) * 8 + tap]; };
+    const int c0 = t * 8 + s * 4;
+    __half2 b0 = __floats2half2_rn(wv(c0), wv(c0 + 1));
+    __half2 b1 = __floats2half2_rn(wv(c0 + 2), wv(c0 + 3));
+    wfrag[i] = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+  }
+}
+
+struct PwTParams {
+  const act_t* x;
+  const uint2* wfrag;
+  const float* bias;
+  act_t* out;
+  float* stats;            // [n][chunks][COUT][2] or null
+  int H, W;                // input dims (D implied)
+  long long in_frame, out_frame;
+  int tiles_per_block;
+  uint32_t w_magic, h_magic;
+};
+
+template <int COUT>
+__global__ void __launch_bounds__(256) convT_pw_kernel(const PwTParams p) {
+  constexpr int NB = COUT / 8;
+  extern __shared__ __align__(16) uint2 s_w[];           // [8 taps * 2][NB][32]
+  __shared__ float s_red[8][COUT][2];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int i = threadIdx.x; i < 16 * NB * 32; i += 256) s_w[i] = __ldg(p.wfrag + i);
+  float bia[NB][2];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) {
+    bia[nb][0] = __ldg(p.bias + pw_channel(nb, 2 * t));
+    bia[nb][1] = __ldg(p.bias + pw_channel(nb, 2 * t + 1));
+  }
+  float ssum[NB][2], ssq[NB][2];
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++) ssum[nb][0] = ssum[nb][1] = ssq[nb][0] = ssq[nb][1] = 0.f;
+  __syncthreads();
+  const act_t* xin = p.x + (long long)n * p.in_frame + t * 8;
+  act_t* xout = p.out + (long long)n * p.out_frame + t * 8;
+  const int OH = 2 * p.H, OW = 2 * p.W;
+#pragma unroll 1
+  for (int tl = warp; tl < p.tiles_per_block; tl += 8) {
+    const int v0 = (chunk * p.tiles_per_block + tl) * 16 + g;
+    uint4 a[2];
+    long long obase[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const int v = v0 + r * 8;
+      a[r] = __ldg(reinterpret_cast<const uint4*>(xin + (long long)v * 32));
+      const int q = (int)__umulhi((uint32_t)v, p.w_magic);      // v / W
+      const int z = v - q * p.W;
+      const int x = (int)__umulhi((uint32_t)q, p.h_magic);      // q / H
+      const int y = q - x * p.H;
+      obase[r] = (((long long)(2 * x) * OH + 2 * y) * OW + 2 * z) * COUT;
+    }
+#pragma unroll
+    for (int tap = 0; tap < 8; tap++) {
+      float c[NB][4];
+#pragma unroll
+      for (int nb = 0; nb < NB; nb++) {
+        c[nb][0] = c[nb][2] = bia[nb][0];
+        c[nb][1] = c[nb][3] = bia[nb][1];
+        mma_m16n8k16(c[nb], a[0].x, a[1].x, a[0].y, a[1].y, s_w[((tap * 2) * NB + nb) * 32 + lane]);
+        mma_m16n8k16(c[nb], a[0].z, a[1].z, a[0].w, a[1].w, s_w[((tap * 2 + 1) * NB + nb) * 32 + lane]);
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+          const float u0 = c[nb][j], u1 = c[nb][2 + j];
+          ssum[nb][j] += u0 + u1;
+          ssq[nb][j] = fmaf(u0, u0, fmaf(u1, u1, ssq[nb][j]));
+        }
+      }
+      const long long toff = ((long long)(((tap >> 2) & 1) * OH + ((tap >> 1) & 1)) * OW + (tap & 1)) * COUT;
+#pragma unroll
+      for (int q = 0; q < NB / 4; q++) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          __half2 h0 = __floats2half2_rn(c[4 * q + i][0], c[4 * q + i][1]);
+          __half2 h1 = __floats2half2_rn(c[4 * q + i][2], c[4 * q + i][3]);
+          pk[i] = *reinterpret_cast<uint32_t*>(&h0);
+          pk[4 + i] = *reinterpret_cast<uint32_t*>(&h1);
+        }
+        *reinterpret_cast<uint4*>(xout + obase[0] + toff + q * 32) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(xout + obase[1] + toff + q * 32) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+  }
+  if (p.stats == nullptr) return;
+#pragma unroll
+  for (int nb = 0; nb < NB; nb++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      float a_ = ssum[nb][j], q = ssq[nb][j];
+#pragma unroll
+      for (int o = 4; o < 32; o <<= 1) {
+        a_ += __shfl_xor_sync(0xffffffffu, a_, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (g == 0) {
+        const int ch = pw_channel(nb, 2 * t + j);
+        s_red[warp][ch][0] = a_;
+        s_red[warp][ch][1] = q;
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * 2; i += 256) {
+    float a_ = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) a_ += s_red[w][i >> 1][i & 1];
+    p.stats[(((long long)n * gridDim.x + chunk) * COUT) * 2 + i] = a_;
+  }
+}
+
+struct PwTPlan { bool ok; int tiles, tiles_per_block, chunks; };
+PwTPlan plan_pwT(int n, int D, int H, int W, int Cin, int Cout) {
+  PwTPlan pl;
+  memset(&pl, 0, sizeof(pl));
+  const long long M = (long long)D * H * W;
+  if (Cin != 32 || (Cout != 32 && Cout != 64) || n <= 0 || n > 65535 || W % 8 != 0 || M % 16 != 0 ||
+      M * 8 * Cout >= (1ll << 40))
+    return pl;
+  pl.tiles = (int)(M / 16);
+  int tpb = 8;                                        // one M-tile per warp: many small blocks (frames are tiny)
+  while (tpb > 1 && pl.tiles % tpb != 0) tpb >>= 1;
+  pl.tiles_per_block = tpb;
+  pl.chunks = pl.tiles / tpb;
+  pl.ok = true;
+  return pl;
+}
+
 struct PwPlan {
   bool ok;
   int taps, OD, OH, OW, tiles, tiles_per_block, chunks;
@@ -363,4 +505,48 @@ extern "C" int nm_conv3d_pw(const void* x, const void* packed_w, const float* bi
   if (pl.taps == 8) return x2 ? launch_pw<64, 64, 8, true>(p, pl.chunks, n, st) : launch_pw<64, 64, 8>(p, pl.chunks, n, st);
   if (Cout == 64) return launch_pw<64, 64, 1>(p, pl.chunks, n, st);
   return launch_pw<64, 128, 1>(p, pl.chunks, n, st);
+}
+
+extern "C" int nm_conv_transpose3d_pw_supported(int n, int D, int H, int W, int Cin, int Cout) {
+  return plan_pwT(n, D, H, W, Cin, Cout).ok ? 1 : 0;
+}
+
+extern "C" int nm_conv_transpose3d_pw_stats_chunks(int n, int D, int H, int W, int Cin, int Cout) {
+  const PwTPlan pl = plan_pwT(n, D, H, W, Cin, Cout);
+  return pl.ok ? pl.chunks : 0;
+}
+
+extern "C" size_t nm_conv_transpose3d_pw_packed_bytes(int Cin, int Cout) {
+  return (size_t)8 * 2 * (Cout / 8) * 32 * sizeof(uint2);
+}
+
+extern "C" int nm_pack_conv_transpose3d_pw_weights(const float* weight, int Cin, int Cout, void* packed, void* stream) {
+  NM_CHECK_ARG(weight && packed, "nm_pack_conv_transpose3d_pw_weights: null pointer");
+  NM_CHECK_ARG(Cin == 32 && (Cout == 32 || Cout == 64), "nm_pack_conv_transpose3d_pw_weights: Cin=%d Cout=%d unsupported", Cin, Cout);
+  pack_pwT_kernel<<<16, 256, 0, (cudaStream_t)stream>>>(weight, Cout, (uint2*)packed);
+  NM_CHECK_LAUNCH("pack_conv_transpose3d_pw_weights");
+  return NM_OK;
+}
+
+extern "C" int nm_conv_transpose3d_pw(const void* x, const void* packed_w, const float* bias, void* out, int n, int D,
+                                      int H, int W, int Cin, int Cout, float* stats_partial, void* stream) {
+  NM_CHECK_ARG(x && packed_w && bias && out, "nm_conv_transpose3d_pw: null pointer");
+  if (n == 0) return NM_OK;
+  const PwTPlan pl = plan_pwT(n, D, H, W, Cin, Cout);
+  NM_CHECK_ARG(pl.ok, "nm_conv_transpose3d_pw: unsupported shape n=%d %dx%dx%d Cin=%d Cout=%d", n, D, H, W, Cin, Cout);
+  PwTParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = (const act_t*)x; p.wfrag = (const uint2*)packed_w; p.bias = bias; p.out = (act_t*)out; p.stats = stats_partial;
+  p.H = H; p.W = W;
+  p.in_frame = (long long)D * H * W * Cin;
+  p.out_frame = (long long)D * H * W * 8 * Cout;
+  p.tiles_per_block = pl.tiles_per_block;
+  p.w_magic = 0xffffffffu / (uint32_t)W + 1u;
+  p.h_magic = 0xffffffffu / (uint32_t)H + 1u;
+  const size_t smem = nm_conv_transpose3d_pw_packed_bytes(Cin, Cout);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cout == 32) convT_pw_kernel<32><<<dim3(pl.chunks, n), 256, smem, st>>>(p);
+  else convT_pw_kernel<64><<<dim3(pl.chunks, n), 256, smem, st>>>(p);
+  NM_CHECK_LAUNCH("conv_transpose3d_pw");
+  return NM_OK;
 }

@@ -126,8 +126,7 @@ class Upsample3DBlock(_ActModule):
             _norm(out_planes), nn.LeakyReLU())
 
     def run(self, x, skip=None):
-        raw = ops.conv_transpose3d(x, self.block[0])
-        a, b = ops.gn_scale_shift(raw, self.block[1])
+        raw, a, b = ops.conv_transpose3d(x, self.block[0], self.block[1])
         return ops.affine_act(raw, a, b, True, x2=skip)
 
 

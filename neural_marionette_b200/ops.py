@@ -254,17 +254,36 @@ def conv3d_direct(x: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
     return out
 
 
-def conv_transpose3d(x: torch.Tensor, conv: torch.nn.ConvTranspose3d) -> torch.Tensor:
+def conv_transpose3d(x: torch.Tensor, conv: torch.nn.ConvTranspose3d, gn: Optional[torch.nn.GroupNorm] = None):
+    """ConvTranspose3d(k2, s2): act (n, D, H, W, Cin) -> raw (n, 2D, 2H, 2W, Cout) [, GroupNorm scale, shift]."""
     n, D, H, W, Cin = x.shape
     Cout = conv.out_channels
     assert conv.kernel_size[0] == 2 and conv.stride[0] == 2 and tuple(conv.output_padding) == (0, 0, 0), \
         "only ConvTranspose3d(k2, s2, output_padding 0) is implemented (grid sizes divisible by 32)"
     out = torch.empty(n, 2 * D, 2 * H, 2 * W, Cout, dtype=ACT_DTYPE, device=x.device)
+    if L.query("nm_conv_transpose3d_pw_supported", n, D, H, W, Cin, Cout):
+        def build():
+            t = torch.empty(L.query("nm_conv_transpose3d_pw_packed_bytes", Cin, Cout), dtype=torch.uint8, device=x.device)
+            L.call("nm_pack_conv_transpose3d_pw_weights", L.ptr(conv.weight.detach().float().contiguous()), Cin, Cout,
+                   L.ptr(t), L.stream())
+            return t
+        pw = _cached(conv, "packed_pwT", [conv.weight], build)
+        chunks = L.query("nm_conv_transpose3d_pw_stats_chunks", n, D, H, W, Cin, Cout) if gn is not None else 0
+        partial = workspace(n * chunks * Cout * 8, x.device, "gn").view(torch.float32) if chunks else None
+        L.call("nm_conv_transpose3d_pw", L.ptr(x), L.ptr(pw), L.ptr(f32(conv, "bias")), L.ptr(out), n, D, H, W, Cin,
+               Cout, L.ptr(partial), L.stream())
+        if gn is None:
+            return out
+        a = torch.empty(n, Cout, dtype=torch.float32, device=x.device)
+        b = torch.empty_like(a)
+        L.call("nm_groupnorm_finalize", L.ptr(partial), n, 8 * D * H * W, Cout, gn.num_groups, chunks,
+               L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+        return out, a, b
     wt = _cached(conv, "tapmajor", [conv.weight],
                  lambda: conv.weight.detach().float().permute(2, 3, 4, 0, 1).reshape(8, Cin, Cout).contiguous())
     L.call("nm_conv_transpose3d_k2s2", L.ptr(x), L.ptr(wt), L.ptr(f32(conv, "bias")), L.ptr(out),
            n, D, H, W, Cin, Cout, L.stream())
-    return out
+    return (out,) + gn_scale_shift(out, gn) if gn is not None else out
 
 
 def first_conv(occ: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None):

@@ -260,13 +260,21 @@ def test_first_conv_coordconv(ops):
         assert (a - a2).abs().max() <= 2e-3 * a2.abs().max() and (b - b2).abs().max() <= 2e-3 * (1 + b2.abs().max())
 
 
-def test_conv_transpose(ops):
-    g = torch.Generator().manual_seed(3)
-    conv = torch.nn.ConvTranspose3d(72, 48, 2, 2)
-    x = torch.randn(3, 72, 2, 2, 2, generator=g)
-    ref = conv(x.half().float()).detach()
-    got = from_act(ops.conv_transpose3d(to_act(x), conv.cuda()))
+@pytest.mark.parametrize("n,cin,cout,g", [(3, 72, 48, 2), (2, 32, 64, 8), (5, 32, 32, 8), (1, 32, 64, 16)])
+def test_conv_transpose(ops, n, cin, cout, g):
+    gen = torch.Generator().manual_seed(3 + cin + g)
+    conv = torch.nn.ConvTranspose3d(cin, cout, 2, 2)
+    x = torch.randn(n, cin, g, g, g, generator=gen)
+    wh = conv.weight.detach().half().float() if cin == 32 else conv.weight.detach()   # mma path: fp16 weights
+    ref = F.conv_transpose3d(x.half().float(), wh, conv.bias.detach(), stride=2)
+    conv = conv.cuda()
+    got = from_act(ops.conv_transpose3d(to_act(x), conv))
     assert rel_err(got, ref) < 2e-3
+    gn = torch.nn.GroupNorm(cout // 16, cout).cuda()
+    raw, a, b = ops.conv_transpose3d(to_act(x), conv, gn)
+    a2, b2 = ops.gn_scale_shift(raw, gn)
+    assert torch.equal(raw, ops.conv_transpose3d(to_act(x), conv))
+    assert (a - a2).abs().max() <= 2e-3 * a2.abs().max() and (b - b2).abs().max() <= 2e-3 * (1 + b2.abs().max())
 
 
 # ------------------------------------------------------------------------------------------------ pointwise
