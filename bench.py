@@ -244,7 +244,7 @@ def main():
                               "ms_per_launch": round(v[0] / v[1], 4),
                               "tflops": round(k[6] * v[1] / (v[0] / 1e3) / 1e12, 1),
                               "share_of_step": round(v[0] / (ms * args.steps), 4)}
-                             for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:12]]}
+                             for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:30]]}
 
     line = {
         "metric": "voxel frames/sec keypoint detection", "value": value, "unit": "frames/s", "n_gpus": world,

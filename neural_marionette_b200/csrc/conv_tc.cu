@@ -1139,7 +1139,11 @@ ConvPlan plan_conv(int n, int D, int H, int W, int Cin, int Cout, int k, int str
     while (pl.ring > 2 && w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra > 227 * 1024) pl.ring--;
   pl.need = w_bytes + (size_t)pl.ring * pl.kch * pl.chunk_bytes + extra;
   pl.w_bytes = w_bytes; pl.extra = extra;
-  pl.slab = slab_mode && k == 3 && stride == 1 && Cin >= 32 && Cin % pl.bk == 0 && W % 8 == 0 && H % 16 == 0 &&
+  // Measured (B200, 320 frames): with N = Cout >= 128 the tap-streaming kernel amortises the shared-memory A-operand
+  // read over a wide MMA and wins over 16-channel slab3 parts: 128->128 @16^3 1.17 vs 1.32 ms, @32^3 (64 clips) 1.87
+  // vs 2.11 ms.  (128->64: 8.0 vs 5.1 ms, 64->128: 0.63 vs 0.51 ms - those stay on slab3.)
+  const bool wide = Cin >= 128 && Cout >= 128;
+  pl.slab = slab_mode && !wide && k == 3 && stride == 1 && Cin >= 32 && Cin % pl.bk == 0 && W % 8 == 0 && H % 16 == 0 &&
             pl.need <= 227 * 1024;
   if (pl.slab) {
     pl.stats_chunks = pl.use3 ? (H / 16) * (W / 8) * 4 : 0;
