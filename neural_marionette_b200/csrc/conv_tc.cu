@@ -392,7 +392,9 @@ struct ConvSlabParams {
   const float* in_shift;  //        i.e. the GroupNorm (+LeakyReLU) of the producing layer applied on the halo
   int in_act;             //        slice in shared memory (zero padding preserved); (n, Cin) fp32 each
   int cin;
-  const float* bias;
+  int cin_off;            // slab3: first input channel of this launch (split-K over two launches: Cin = 128)
+  int accum;              // slab3: add the existing contents of `out` (the partial sum of the previous launch)
+  const float* bias;      // may be null (second split-K launch)
   act_t* out;
 };
 
@@ -867,8 +869,8 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       for (int tap = 0; tap < 27; tap++) {
         const int kd = tap / 9, khw = tap % 9;
         for (int kc = 0; kc < p.kchunks; kc++)
-          tma_load_3d(s_w + (size_t)((khw * p.kchunks + kc) * 3 + kd) * w_tile_bytes, &p.tmap_b, wfull, kc * BK,
-                      part * PN, tap);
+          tma_load_3d(s_w + (size_t)((khw * p.kchunks + kc) * 3 + kd) * w_tile_bytes, &p.tmap_b, wfull,
+                      p.cin_off + kc * BK, part * PN, tap);
       }
       uint32_t fill = 0;
       const uint32_t slice_tx = (uint32_t)(kHaloW * kHaloH * BK * 2 * p.kchunks);
@@ -893,7 +895,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
           mbar_expect_tx(&full[slot], slice_tx);
           for (int kc = 0; kc < p.kchunks; kc++)
             tma_load_5d(s_ring + (size_t)slot * p.slot_bytes + (size_t)kc * p.chunk_bytes, &p.tmap_a, &full[slot],
-                        kc * BK, iw * 8 - 1, ih * 16 - 1, dz, n);
+                        p.cin_off + kc * BK, iw * 8 - 1, ih * 16 - 1, dz, n);
         }
       }
     }
@@ -952,7 +954,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
 #pragma unroll
     for (int j = 0; j < CW; j++) {
       const int ch = part * PN + chalf * CW + j;
-      bias[j] = ch < p.cout ? __ldg(p.bias + ch) : 0.f;
+      bias[j] = (p.bias && ch < p.cout) ? __ldg(p.bias + ch) : 0.f;
     }
     uint32_t q0 = 0;                                     // global index of slice 0 of the current column
     uint32_t n_out = 0;                                  // output tiles staged so far (staging buffer parity)
@@ -980,7 +982,25 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       for (int c = 0; c < CW; c++) { ssum[c] = 0.f; ssq[c] = 0.f; }
       // statistics, fp16 pack, swizzled staging tile, one TMA store per tile (direct per-thread 16-byte stores
       // touched 16 cache lines per warp instruction and ran at ~1 TB/s)
-      auto emit = [&](const float (&f)[CW], int od) {
+      // split-K second launch: the partial sum the first launch left in `out` (fp16) is added; its loads are issued
+      // before the wait for the P group so that their latency overlaps it
+      uint4 pvq[CW / 8];
+      auto load_prev = [&](int od) {
+        const act_t* prev = p.out + ((((long long)n * p.D + od) * p.H + ih * 16 + (row >> 3)) * p.W + iw * 8 + (row & 7)) * p.cout +
+                            part * PN + chalf * CW;
+#pragma unroll
+        for (int c8 = 0; c8 < CW / 8; c8++) pvq[c8] = *reinterpret_cast<const uint4*>(prev + c8 * 8);
+      };
+      auto emit = [&](float (&f)[CW], int od) {
+        if (p.accum) {
+#pragma unroll
+          for (int c8 = 0; c8 < CW / 8; c8++) {
+            float pv[8];
+            nm_unpack8(*reinterpret_cast<const half8*>(&pvq[c8]), pv);
+#pragma unroll
+            for (int k = 0; k < 8; k++) f[c8 * 8 + k] += pv[k];
+          }
+        }
 #pragma unroll
         for (int c = 0; c < CW; c++) { ssum[c] += f[c]; ssq[c] = fmaf(f[c], f[c], ssq[c]); }
         const uint32_t boff = (n_out & 1) * stage_bytes;
@@ -1001,6 +1021,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       };
       for (int sl = 0; sl < p.D; sl++) {
         const uint32_t q = q0 + sl;
+        if (p.accum && sl >= 1) load_prev(sl - 1);
         mbar_wait(&pfull[q % kPGroups], (q / kPGroups) & 1);
         tc_fence_after();
         const uint32_t g_cur = lane_addr + (q % kPGroups) * (3 * PN);
@@ -1036,7 +1057,10 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         }
 #pragma unroll
         for (int c = 0; c < CW; c++) partial[c] = (__uint_as_float(rb[c]) + __uint_as_float(rc[c])) + bias[c];
-        if (sl == p.D - 1) emit(partial, sl);
+        if (sl == p.D - 1) {
+          if (p.accum) load_prev(sl);
+          emit(partial, sl);
+        }
       }
       if (p.stats) {
         // column done: fold the 32 rows of this warp (fixed butterfly order -> deterministic) and emit one
@@ -1187,7 +1211,7 @@ extern "C" int nm_conv3d_tc(const void* x, const void* packed_w, const float* bi
 namespace {
 int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
                    int Cin, int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
-                   float* stats_partial, void* stream, bool up);
+                   float* stats_partial, void* stream, bool up, int cin_total = 0, int cin_off = 0, int accum = 0);
 // up-sampling mode needs the slab3<64, 32> kernel with 3 slice slots + the low-resolution plane ring
 bool up2x_ok(int n, int D, int H, int W, int Cin, int Cout) {
   if ((D | H | W) & 1) return false;
@@ -1224,8 +1248,24 @@ extern "C" int nm_conv3d_tc_up2x(const void* x_lo, const void* packed_w, const f
 namespace {
 int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void* out, int n, int D, int H, int W,
                    int Cin, int Cout, int k, int stride, const float* in_scale, const float* in_shift, int in_act,
-                   float* stats_partial, void* stream, bool up) {
-  NM_CHECK_ARG(x && packed_w && bias && out, "nm_conv3d_tc: null pointer");
+                   float* stats_partial, void* stream, bool up, int cin_total, int cin_off, int accum) {
+  NM_CHECK_ARG(x && packed_w && (bias || accum) && out, "nm_conv3d_tc: null pointer");
+  if (cin_total == 0) cin_total = Cin;
+  // Split-K over two launches for Cin = 128 -> Cout <= 64 (dec.1): with both 64-channel chunks of the weights
+  // resident a CTA can only serve 16 output channels (N = 48 per MMA, 58 cycles for 24 cycles of tensor work); one
+  // chunk at a time allows 32-channel parts (N = 96, 92 cycles for 48).  The second launch adds the fp16 partial sum
+  // the first one left in `out`; GroupNorm statistics come from the second.
+  if (!up && !in_scale && cin_total == Cin && Cin == 128 && Cout % 32 == 0 && Cout <= 64 && k == 3 && stride == 1 && n > 0 &&
+      !getenv("NM_NO_SPLITK")) {
+    const ConvPlan half = plan_conv(n, D, H, W, 64, Cout, k, stride);
+    if (half.slab && half.use3 && half.pn == 32) {
+      const int rc = conv3d_tc_impl(x, packed_w, bias, out, n, D, H, W, 64, Cout, k, stride, nullptr, nullptr, 0, nullptr,
+                                    stream, false, 128, 0, 0);
+      if (rc != NM_OK) return rc;
+      return conv3d_tc_impl(x, packed_w, nullptr, out, n, D, H, W, 64, Cout, k, stride, nullptr, nullptr, 0,
+                            stats_partial, stream, false, 128, 64, 1);
+    }
+  }
   NM_CHECK_ARG((stride == 1 && (k == 1 || k == 3)) || (stride == 2 && k == 2), "nm_conv3d_tc: k=%d stride=%d unsupported",
                k, stride);
   NM_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && Cout <= 256 && Cin >= 16, "nm_conv3d_tc: Cin=%d Cout=%d unsupported", Cin,
@@ -1260,24 +1300,26 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
       { const char* dbg = getenv("NM_SLAB_DEBUG"); q.debug = dbg ? atoi(dbg) : 0; }
       q.bias = bias; q.out = (act_t*)out; q.stats = use3 ? stats_partial : nullptr;
       q.in_scale = in_scale; q.in_shift = in_shift; q.in_act = in_act; q.cin = Cin;
+      q.cin_off = cin_off; q.accum = accum;
+      NM_CHECK_ARG(cin_total == Cin || use3, "nm_conv3d_tc: split-K needs the slab3 kernel");
       const CUtensorMapSwizzle swz = bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-      cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
-      cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2,
-                               (cuuint64_t)D * H * W * Cin * 2};
+      const cuuint64_t ct = (cuuint64_t)cin_total;
+      cuuint64_t dims[5] = {ct, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)n};
+      cuuint64_t strides[4] = {ct * 2, (cuuint64_t)W * ct * 2, (cuuint64_t)H * W * ct * 2, (cuuint64_t)D * H * W * ct * 2};
       cuuint32_t box[5] = {(cuuint32_t)bk, kHaloW, kHaloH, 1, 1};
       cuuint32_t estr[5] = {1, 1, 1, 1, 1};
       if (up) {   // the low-resolution tensor, (10 x 6)-row planes, linear rows (read by the transform warps)
         dims[1] = W / 2; dims[2] = H / 2; dims[3] = D / 2;
-        strides[1] = (cuuint64_t)(W / 2) * Cin * 2; strides[2] = (cuuint64_t)(H / 2) * (W / 2) * Cin * 2;
-        strides[3] = (cuuint64_t)(D / 2) * (H / 2) * (W / 2) * Cin * 2;
+        strides[1] = (cuuint64_t)(W / 2) * ct * 2; strides[2] = (cuuint64_t)(H / 2) * (W / 2) * ct * 2;
+        strides[3] = (cuuint64_t)(D / 2) * (H / 2) * (W / 2) * ct * 2;
         box[1] = 6; box[2] = 10;
       }
       CUresult r = encode(&q.tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, (void*)x, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, up ? CU_TENSOR_MAP_SWIZZLE_NONE : swz,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab): cuTensorMapEncodeTiled(A) failed with %d", (int)r); return NM_ERR_DRIVER; }
-      cuuint64_t wdims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 27};
-      cuuint64_t wstrides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * Cout * 2};
+      cuuint64_t wdims[3] = {ct, (cuuint64_t)Cout, 27};
+      cuuint64_t wstrides[2] = {ct * 2, ct * Cout * 2};
       cuuint32_t wbox[3] = {(cuuint32_t)bk, (cuuint32_t)(use3 ? pn : ntile), 1};
       cuuint32_t westr[3] = {1, 1, 1};
       r = encode(&q.tmap_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)packed_w, wdims, wstrides, wbox, westr,
