@@ -597,7 +597,8 @@ constexpr int kLoRing = 4;
 constexpr int kLoRows = 10 * 6;              // low-resolution box: 10 (h) x 6 (w) rows of 64 channels
 constexpr int kLoBytes = kLoRows * 128;      // 7680
 
-template <int BK, int PN, bool UP = false>
+// ACC: split-K second launch - the epilogue adds the partial sum already in `out`.
+template <int BK, int PN, bool UP = false, bool ACC = false>
 __global__ void __launch_bounds__(kSlab3Threads + 32 * kSlab3XformWarps, 1)
 conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -908,39 +909,95 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     const uint32_t ring_lo = desc_lo(smem_u32(s_ring)), w_lo = desc_lo(smem_u32(s_w));
     const uint32_t slot_step = (uint32_t)p.slot_bytes >> 4, chunk_step = (uint32_t)p.chunk_bytes >> 4;
     constexpr uint32_t w_step = (uint32_t)(3 * w_tile_bytes) >> 4;       // one (khw, kc) B tile = 3 kd tiles
-    mbar_wait(wfull, 0);
-    uint32_t q = 0;                                      // global slice counter (ring + P-group position)
-    for (int col = col0; col < n_cols; col += col_step) {
-      for (int sl = 0; sl < p.D; sl++, q++) {
-        mbar_wait(xform ? &ready[q % ring] : &full[q % ring], (q / ring) & 1);
-        mbar_wait(&pempty[q % kPGroups], ((q / kPGroups) & 1) ^ 1);
+    if (xform) {
+      // With an in-kernel operand producer (fused GroupNorm / up-sampling) the plain loop is faster [measured: dec.8
+      // with fused up-sampling 9.0 vs 9.4 ms, dec.11 with fused GroupNorm 5.4 vs 6.0 ms]: the burstier stream of the
+      // pipelined variant below starves the producer warps.
+      mbar_wait(wfull, 0);
+      uint32_t q = 0;                                    // global slice counter (ring + P-group position)
+      for (int col = col0; col < n_cols; col += col_step) {
+        for (int sl = 0; sl < p.D; sl++, q++) {
+          mbar_wait(&ready[q % ring], (q / ring) & 1);
+          mbar_wait(&pempty[q % kPGroups], ((q / kPGroups) & 1) ^ 1);
+          tc_fence_after();
+          __syncwarp();
+          if (elect_one()) {
+            const uint32_t tmem_d = (q % kPGroups) * (3 * PN);
+            const uint32_t slot_lo = ring_lo + (q % ring) * slot_step;
+            uint32_t blo = w_lo;
+            if (!(p.debug & 2))
+#pragma unroll
+            for (int t9 = 0; t9 < 9; t9++) {
+              const uint32_t tap_lo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
+#pragma unroll 1
+              for (int kc = 0; kc < p.kchunks; kc++) {
+                const uint32_t alo = tap_lo + kc * chunk_step;
+                if (t9 == 0 && kc == 0) umma_f16(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc, 0u);
+                else umma_f16_acc(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc);
+#pragma unroll
+                for (int k = 1; k < BK / 16; k++)
+                  umma_f16_acc(tmem_d, desc64(hi_a, alo + 2 * k), desc64(hi_b, blo + 2 * k), idesc);
+                blo += w_step;
+              }
+            }
+            umma_commit(&empty[q % ring]);
+            umma_commit(&pfull[q % kPGroups]);
+          }
+          __syncwarp();
+        }
+      }
+    } else
+    // One elected thread runs the whole issue loop.  The waits for slice q+1 (operand slice landed / transformed,
+    // TMEM group drained) are taken BEFORE the last tap of slice q is issued, while the tensor pipe still has queued
+    // MMAs: the barrier round trip no longer drains the pipe at every slice boundary.
+    if (elect_one()) {
+      mbar_wait(wfull, 0);
+      uint32_t q = 0;                                    // global slice counter (ring + P-group position)
+      auto wait_slice = [&](uint32_t qq) {
+        mbar_wait(&full[qq % ring], (qq / ring) & 1);
+        mbar_wait(&pempty[qq % kPGroups], ((qq / kPGroups) & 1) ^ 1);
         tc_fence_after();
-        __syncwarp();
-        if (elect_one()) {
+      };
+      auto issue_tap = [&](int t9, uint32_t tmem_d, uint32_t slot_lo, uint32_t& blo) {
+        const uint32_t tap_lo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
+#pragma unroll 1
+        for (int kc = 0; kc < p.kchunks; kc++) {
+          const uint32_t alo = tap_lo + kc * chunk_step;
+          if (t9 == 0 && kc == 0) umma_f16(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc, 0u);
+          else umma_f16_acc(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc);
+#pragma unroll
+          for (int k = 1; k < BK / 16; k++)
+            umma_f16_acc(tmem_d, desc64(hi_a, alo + 2 * k), desc64(hi_b, blo + 2 * k), idesc);
+          blo += w_step;
+        }
+      };
+      // non-blocking variant: true when both barriers of slice qq have already completed
+      auto try_slice = [&](uint32_t qq) -> bool {
+        if (!mbar_try_wait(&full[qq % ring], (qq / ring) & 1)) return false;
+        if (!mbar_try_wait(&pempty[qq % kPGroups], ((qq / kPGroups) & 1) ^ 1)) return false;
+        tc_fence_after();
+        return true;
+      };
+      bool ready_now = false;
+      for (int col = col0; col < n_cols; col += col_step) {
+        for (int sl = 0; sl < p.D; sl++, q++) {
+          if (!ready_now) wait_slice(q);
           const uint32_t tmem_d = (q % kPGroups) * (3 * PN);
           const uint32_t slot_lo = ring_lo + (q % ring) * slot_step;
           uint32_t blo = w_lo;
-          if (!(p.debug & 2))
+          const bool has_next = sl + 1 < p.D || col + col_step < n_cols;
+          if (!(p.debug & 2)) {
 #pragma unroll
-          for (int t9 = 0; t9 < 9; t9++) {
-            const uint32_t tap_lo = slot_lo + (uint32_t)(((t9 / 3) * kHaloW + (t9 % 3)) * (BK * 2 / 16));
-#pragma unroll 1
-            for (int kc = 0; kc < p.kchunks; kc++) {
-              const uint32_t alo = tap_lo + kc * chunk_step;
-              if (t9 == 0 && kc == 0) umma_f16(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc, 0u);
-              else umma_f16_acc(tmem_d, desc64(hi_a, alo), desc64(hi_b, blo), idesc);
-#pragma unroll
-              for (int k = 1; k < BK / 16; k++)
-                umma_f16_acc(tmem_d, desc64(hi_a, alo + 2 * k), desc64(hi_b, blo + 2 * k), idesc);
-              blo += w_step;
-            }
+            for (int t9 = 0; t9 < 8; t9++) issue_tap(t9, tmem_d, slot_lo, blo);
           }
+          ready_now = has_next && try_slice(q + 1);      // if it is not there yet, block after this slice's commits
+          if (!(p.debug & 2)) issue_tap(8, tmem_d, slot_lo, blo);
           umma_commit(&empty[q % ring]);
           umma_commit(&pfull[q % kPGroups]);
         }
-        __syncwarp();
       }
     }
+    __syncwarp();
   } else {
     // ===================== epilogue (warps 2..9) =====================
     // The epilogue (TMEM -> registers, 3-block sum, fp16 pack, store) is what bounds the low-K layers
@@ -984,15 +1041,15 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       // touched 16 cache lines per warp instruction and ran at ~1 TB/s)
       // split-K second launch: the partial sum the first launch left in `out` (fp16) is added; its loads are issued
       // before the wait for the P group so that their latency overlaps it
-      uint4 pvq[CW / 8];
+      uint4 pvq[ACC ? CW / 8 : 1];
       auto load_prev = [&](int od) {
         const act_t* prev = p.out + ((((long long)n * p.D + od) * p.H + ih * 16 + (row >> 3)) * p.W + iw * 8 + (row & 7)) * p.cout +
                             part * PN + chalf * CW;
 #pragma unroll
-        for (int c8 = 0; c8 < CW / 8; c8++) pvq[c8] = *reinterpret_cast<const uint4*>(prev + c8 * 8);
+        for (int c8 = 0; c8 < (ACC ? CW / 8 : 0); c8++) pvq[c8] = *reinterpret_cast<const uint4*>(prev + c8 * 8);
       };
       auto emit = [&](float (&f)[CW], int od) {
-        if (p.accum) {
+        if constexpr (ACC) {
 #pragma unroll
           for (int c8 = 0; c8 < CW / 8; c8++) {
             float pv[8];
@@ -1021,7 +1078,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       };
       for (int sl = 0; sl < p.D; sl++) {
         const uint32_t q = q0 + sl;
-        if (p.accum && sl >= 1) load_prev(sl - 1);
+        if (ACC && sl >= 1) load_prev(sl - 1);
         mbar_wait(&pfull[q % kPGroups], (q / kPGroups) & 1);
         tc_fence_after();
         const uint32_t g_cur = lane_addr + (q % kPGroups) * (3 * PN);
@@ -1058,7 +1115,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
 #pragma unroll
         for (int c = 0; c < CW; c++) partial[c] = (__uint_as_float(rb[c]) + __uint_as_float(rc[c])) + bias[c];
         if (sl == p.D - 1) {
-          if (p.accum) load_prev(sl);
+          if (ACC) load_prev(sl);
           emit(partial, sl);
         }
       }
@@ -1352,10 +1409,14 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           slab3_attr = true;
         }
         const int threads3 = kSlab3Threads + (in_scale || up ? 32 * kSlab3XformWarps : 0);
-        if (up) conv3d_slab3_kernel<64, 32, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+        if (accum) {
+          NM_CHECK_ARG(bk == 64 && pn == 32 && !up && !in_scale, "nm_conv3d_tc: split-K accumulation needs slab3<64, 32>");
+          conv3d_slab3_kernel<64, 32, false, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+        } else if (up) conv3d_slab3_kernel<64, 32, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         else if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         else conv3d_slab3_kernel<32, 32><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
