@@ -1053,7 +1053,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       // statistics, fp16 pack, swizzled staging tile, one TMA store per tile (direct per-thread 16-byte stores
       // touched 16 cache lines per warp instruction and ran at ~1 TB/s)
       // split-K second launch: the partial sum the first launch left in `out` (fp16) is added; its loads are issued
-      // before the wait for the P group so that their latency overlaps it
+      // one output slice ahead
       uint4 pvq[ACC ? CW / 8 : 1];
       auto load_prev = [&](int od) {
         const act_t* prev = p.out + ((((long long)n * p.D + od) * p.H + ih * 16 + (row >> 3)) * p.W + iw * 8 + (row & 7)) * p.cout +
@@ -1070,6 +1070,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
 #pragma unroll
             for (int k = 0; k < 8; k++) f[c8 * 8 + k] += pv[k];
           }
+          if (od + 1 < p.D) load_prev(od + 1);           // for the next output slice: a whole slice period ahead
         }
 #pragma unroll
         for (int c = 0; c < CW; c++) { ssum[c] += f[c]; ssq[c] = fmaf(f[c], f[c], ssq[c]); }
@@ -1089,9 +1090,9 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         }
         n_out++;
       };
+      if (ACC) load_prev(0);
       for (int sl = 0; sl < p.D; sl++) {
         const uint32_t q = q0 + sl;
-        if (ACC && sl >= 1) load_prev(sl - 1);
         // with producer warps in the CTA the eight epilogue warps back off between polls (isolated launch of the
         // fused 32->32 layer: 5.97 -> 5.12 ms; inside the full step the effect is within run-to-run noise)
         if (xform) mbar_wait_backoff(&pfull[q % kPGroups], (q / kPGroups) & 1, 100u);
@@ -1131,7 +1132,6 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
 #pragma unroll
         for (int c = 0; c < CW; c++) partial[c] = (__uint_as_float(rb[c]) + __uint_as_float(rc[c])) + bias[c];
         if (sl == p.D - 1) {
-          if (ACC) load_prev(sl);
           emit(partial, sl);
         }
       }
