@@ -24,10 +24,11 @@ from ..utils.kypt_detector_utils import (get_graph_consistency_loss, get_graph_t
                                          get_temporal_separation_loss, get_volume_fitting_loss,
                                          sparsity_loss_from_means)
 
-# Frames pushed through the conv stack per pass.  Bounds activation memory (the widest tensor is the decoder's
-# up-sampled 64 ch @ G^3 input = 33.5 MB/frame at G = 64 -> ~11 GB at 320 frames) while keeping every launch large:
-# measured on B200 (B = 64, T = 20): 20 frames/pass 369 ms/step, 60 -> 281, 120 -> 263, 320 -> 251, 1280 -> 250.
-FRAME_CHUNK = int(__import__("os").environ.get("NM_FRAME_CHUNK", "320"))
+# Frames pushed through the conv stack per pass.  Bounds activation memory (the widest tensors are 32 ch @ G^3 =
+# 16.8 MB/frame at G = 64 -> ~11 GB each at 640 frames, ~45 GB live) while keeping every launch large: the hour-glass
+# levels <= 8^3 are launch-latency bound, so bigger passes amortise them.  Measured on one B200 (B = 64, T = 20, same
+# GPU): 320 frames/pass 168.5 ms/step, 640 -> 166.9, 1280 -> 166.3.
+FRAME_CHUNK = int(__import__("os").environ.get("NM_FRAME_CHUNK", "640"))
 
 
 def _no_training(module):
