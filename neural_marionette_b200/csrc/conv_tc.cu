@@ -600,7 +600,8 @@ constexpr int kPGroups = 5;    // 5 x 96 TMEM columns = 480 <= 512
 constexpr int kSlab3EpiWarps = 8;
 constexpr int kSlab3Threads = 64 + 32 * kSlab3EpiWarps;
 constexpr int kSlab3Ring = 8;        // max halo-slice ring depth (Cin = 32 has room for 8 slots, Cin = 64 for 4)
-constexpr int kSlab3XformWarps = 4;   // extra warps (only launched when the input transform is fused)
+constexpr int kSlab3XformWarps = 6;   // max extra warps (only launched when the input transform is fused); the
+                                      // number actually launched comes from blockDim (512 threads x 128 registers)
 
 // UP: the conv input is the 2x trilinear up-sampling (align_corners = False) of a low-resolution tensor that is
 // never materialised: TMA brings (10 x 6)-row low-resolution planes into a small ring and the transform warps
@@ -636,6 +637,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_lo + kLoRing);
   float* s_ab = reinterpret_cast<float*>(tmem_slot + 4);   // [2][Cin] scale | shift of the current sample
   const bool xform = UP || p.in_scale != nullptr;
+  const int nxw = ((int)blockDim.x - kSlab3Threads) >> 5;   // transform / producer warps launched (0, 4 or 6)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_cols = p.N * p.nh * p.nw;
@@ -652,8 +654,8 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_o) : "memory");
     for (int s = 0; s < kSlab3Ring; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < kPGroups; s++) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], kSlab3EpiWarps); }
-    for (int s = 0; s < kSlab3Ring; s++) mbar_init(&ready[s], kSlab3XformWarps);
-    for (int s = 0; s < kLoRing; s++) { mbar_init(&full_lo[s], 1); mbar_init(&empty_lo[s], kSlab3XformWarps); }
+    for (int s = 0; s < kSlab3Ring; s++) mbar_init(&ready[s], nxw);
+    for (int s = 0; s < kLoRing; s++) { mbar_init(&full_lo[s], 1); mbar_init(&empty_lo[s], nxw); }
     mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -701,12 +703,12 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       const int ih = t % p.nh; t /= p.nh;
       const int n = t;
       if (fused && n != cur_n) {
-        named_bar_sync(2, 32 * kSlab3XformWarps);
-        for (int i = tid; i < p.cin; i += 32 * kSlab3XformWarps) {
+        named_bar_sync(2, 32 * nxw);
+        for (int i = tid; i < p.cin; i += 32 * nxw) {
           s_ab[i] = p.in_scale[(long long)n * p.cin + i];
           s_ab[p.cin + i] = p.in_shift[(long long)n * p.cin + i];
         }
-        named_bar_sync(2, 32 * kSlab3XformWarps);
+        named_bar_sync(2, 32 * nxw);
         cur_n = n;
       }
       int landed = 0;                                     // planes of this column already waited for
@@ -718,7 +720,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
           mbar_wait(&full_lo[g % kLoRing], (g / kLoRing) & 1);
           if (fused) {
             const uint32_t pb = lo_base + (g % kLoRing) * kLoBytes;
-            for (int i = tid; i < kLoRows * 8; i += 32 * kSlab3XformWarps) {
+            for (int i = tid; i < kLoRows * 8; i += 32 * nxw) {
               const int c = i & 7;
               const uint32_t addr = pb + i * 16;
               const uint4 raw = lds128(addr);
@@ -734,7 +736,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
               }
               sts128(addr, make_uint4(o[0], o[1], o[2], o[3]));
             }
-            named_bar_sync(2, 32 * kSlab3XformWarps);
+            named_bar_sync(2, 32 * nxw);
           }
           landed++;
         }
@@ -807,7 +809,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
     const int tid = threadIdx.x - 32 * (2 + kSlab3EpiWarps);
     // thread <-> (logical 16-byte channel chunk lc, rows r0, r0 + rstep, ...): a warp covers whole rows
     const int lc = tid % cpr, r0 = tid / cpr;
-    constexpr int rstep = 32 * kSlab3XformWarps / cpr;
+    const int rstep = 32 * nxw / cpr;
     uint32_t fill = 0;
     int cur_n = -1;
     for (int col = col0; col < n_cols; col += col_step) {
@@ -816,12 +818,12 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       const int ih = t % p.nh; t /= p.nh;
       const int n = t;
       if (n != cur_n) {                                  // (re)load this sample's scale / shift
-        named_bar_sync(2, 32 * kSlab3XformWarps);
-        for (int i = tid; i < p.cin; i += 32 * kSlab3XformWarps) {
+        named_bar_sync(2, 32 * nxw);
+        for (int i = tid; i < p.cin; i += 32 * nxw) {
           s_ab[i] = p.in_scale[(long long)n * p.cin + i];
           s_ab[p.cin + i] = p.in_shift[(long long)n * p.cin + i];
         }
-        named_bar_sync(2, 32 * kSlab3XformWarps);
+        named_bar_sync(2, 32 * nxw);
         cur_n = n;
       }
       for (int dz = 0; dz < p.D; dz++, fill++) {
@@ -1428,7 +1430,10 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           slab3_attr = true;
         }
-        const int threads3 = kSlab3Threads + (in_scale || up ? 32 * kSlab3XformWarps : 0);
+        static int xw_env = -1;
+        if (xw_env < 0) { const char* e = getenv("NM_XFORM_WARPS"); xw_env = e ? atoi(e) : 6; if (xw_env != 4) xw_env = 6; }
+        // the up-sampling producer uses three warps (+ one idle); the in-place transform takes 4 or 6
+        const int threads3 = kSlab3Threads + (up ? 32 * 4 : (in_scale ? 32 * xw_env : 0));
         if (accum) {
           NM_CHECK_ARG(bk == 64 && pn == 32 && !up && !in_scale, "nm_conv3d_tc: split-K accumulation needs slab3<64, 32>");
           conv3d_slab3_kernel<64, 32, false, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
