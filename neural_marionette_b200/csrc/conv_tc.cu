@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 namespace {
 
@@ -748,45 +749,64 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         // item = (pair of halo rows 2j, 2j+1, chunk c): h = ih*16 - 1 + 2j is odd (= 2m+1) and h + 1 = 2m+2, so both
         // rows interpolate between the same low-res rows m and m+1 (near / far swapped): the 24 plane loads and the
         // 12 depth blends are shared
-        // 72 items on the first three producer warps: the fourth shares its SM sub-partition with the MMA-issuing
-        // warp (warp 1) and only takes part in the barriers, so that it does not compete for issue slots
-        for (int item = tid < 96 ? tid : 9999; item < (kHaloH / 2) * 8; item += 96) {
-          const int j = item >> 3, c = item & 7;
+        // Work split: with 4 producer warps, 72 (pair, chunk) items on the first three; with 6 warps, 144 (pair, chunk,
+        // half of the 10 halo columns) items on five.  The warp that shares its SM sub-partition with the MMA-issuing
+        // warp (producer warp 3 = warp 13) only takes part in the barriers, so that it does not compete for issue slots.
+        const int pw = tid >> 5;                                     // producer warp index
+        const int wtid = pw < 3 ? tid : (pw == 3 ? -1 : tid - 32);   // worker thread id, -1: idle warp
+        const bool split = nxw >= 6;
+        const int n_items = split ? (kHaloH / 2) * 16 : (kHaloH / 2) * 8;
+        const int n_workers = split ? 160 : 96;
+        for (int item = wtid >= 0 ? wtid : 99999; item < n_items; item += n_workers) {
+          const int j = split ? item >> 4 : item >> 3, c = split ? (item >> 1) & 7 : item & 7;
+          const int half = split ? item & 1 : 2;                     // 0: columns 0..4, 1: 5..9, 2: all ten
           const int h0 = ih * 16 - 1 + 2 * j;                        // first row of the pair (may be -1)
           const int m = (h0 + 1) / 2 - 1;                            // h0 = 2m + 1
           const int ma = min(max(m, 0), Hl - 1), mb = min(m + 1, Hl - 1);
           const uint32_t oa = (uint32_t)((ma - (ih * 8 - 1)) * 6) * 128 + c * 16;
           const uint32_t ob = (uint32_t)((mb - (ih * 8 - 1)) * 6) * 128 + c * 16;
-          uint4 va[6], vb[6];                                        // depth-blended low-res rows m and m+1
-#pragma unroll
-          for (int w = 0; w < 6; w++) {
-            va[w] = lerp(lds128(lo_n + oa + w * 128), lds128(lo_f + oa + w * 128));
-            vb[w] = lerp(lds128(lo_n + ob + w * 128), lds128(lo_f + ob + w * 128));
-          }
           const uint4 zero = make_uint4(0, 0, 0, 0);
+          // W0 .. W0+NW-1: box columns needed; WW0 .. WW0+NWW-1: halo columns produced
+          auto run = [&](auto W0c, auto NWc, auto WW0c, auto NWWc) {
+            constexpr int W0 = decltype(W0c)::value, NW = decltype(NWc)::value, WW0 = decltype(WW0c)::value,
+                          NWW = decltype(NWWc)::value;
+            uint4 va[NW], vb[NW];                                    // depth-blended low-res rows m and m+1
 #pragma unroll
-          for (int r2 = 0; r2 < 2; r2++) {
-            const int hh = 2 * j + r2, hf = h0 + r2;
-            const uint32_t orow = sbase + (uint32_t)(hh * kHaloW) * 128;
-            if ((unsigned)hf >= (unsigned)p.H) {                     // conv padding row
-#pragma unroll
-              for (int ww = 0; ww < kHaloW; ww++) sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), zero);
-              continue;
+            for (int w = 0; w < NW; w++) {
+              va[w] = lerp(lds128(lo_n + oa + (W0 + w) * 128), lds128(lo_f + oa + (W0 + w) * 128));
+              vb[w] = lerp(lds128(lo_n + ob + (W0 + w) * 128), lds128(lo_f + ob + (W0 + w) * 128));
             }
-            uint4 v[6];                                              // row 2m+1: near m, far m+1; row 2m+2: near m+1, far m
 #pragma unroll
-            for (int w = 0; w < 6; w++) v[w] = r2 == 0 ? lerp(va[w], vb[w]) : lerp(vb[w], va[w]);
+            for (int r2 = 0; r2 < 2; r2++) {
+              const int hh = 2 * j + r2, hf = h0 + r2;
+              const uint32_t orow = sbase + (uint32_t)(hh * kHaloW) * 128;
+              if ((unsigned)hf >= (unsigned)p.H) {                   // conv padding row
 #pragma unroll
-            for (int ww = 0; ww < kHaloW; ww++) {
-              // halo column ww <-> w = iw*8 - 1 + ww: near box column (ww+1)>>1, far = near +1 (ww even) / -1 (ww odd)
-              const int nr = (ww + 1) >> 1, fr = (ww & 1) ? nr - 1 : nr + 1;
-              uint4 o;
-              if ((ww == 0 && iw == 0) || (ww == kHaloW - 1 && iw == p.nw - 1)) o = zero;               // conv padding
-              else if ((ww == 1 && iw == 0) || (ww == kHaloW - 2 && iw == p.nw - 1)) o = v[nr];          // clamped far
-              else o = lerp(v[nr], v[fr]);
-              sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), o);
+                for (int k = 0; k < NWW; k++) sts128(orow + (WW0 + k) * 128 + ((c ^ ((hh * kHaloW + WW0 + k) & 7)) << 4), zero);
+                continue;
+              }
+              uint4 v[NW];                                           // row 2m+1: near m, far m+1; row 2m+2: near m+1, far m
+#pragma unroll
+              for (int w = 0; w < NW; w++) v[w] = r2 == 0 ? lerp(va[w], vb[w]) : lerp(vb[w], va[w]);
+#pragma unroll
+              for (int k = 0; k < NWW; k++) {
+                // halo column ww <-> w = iw*8 - 1 + ww: near box column (ww+1)>>1, far = near +1 (ww even) / -1 (ww odd)
+                const int ww = WW0 + k;
+                const int nr = ((ww + 1) >> 1) - W0, fr = (ww & 1) ? nr - 1 : nr + 1;
+                uint4 o;
+                if ((ww == 0 && iw == 0) || (ww == kHaloW - 1 && iw == p.nw - 1)) o = zero;             // conv padding
+                else if ((ww == 1 && iw == 0) || (ww == kHaloW - 2 && iw == p.nw - 1)) o = v[nr];        // clamped far
+                else o = lerp(v[nr], v[fr]);
+                sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), o);
+              }
             }
-          }
+          };
+          using I0 = std::integral_constant<int, 0>; using I2 = std::integral_constant<int, 2>;
+          using I4 = std::integral_constant<int, 4>; using I5 = std::integral_constant<int, 5>;
+          using I6 = std::integral_constant<int, 6>; using I10 = std::integral_constant<int, 10>;
+          if (half == 0) run(I0{}, I4{}, I0{}, I5{});                // halo columns 0..4 use box columns 0..3
+          else if (half == 1) run(I2{}, I4{}, I5{}, I5{});           // halo columns 5..9 use box columns 2..5
+          else run(I0{}, I6{}, I0{}, I10{});
         }
         fence_async_smem();                              // generic-proxy writes -> visible to the UMMA reads
         __syncwarp();
@@ -1432,7 +1452,9 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
         }
         static int xw_env = -1;
         if (xw_env < 0) { const char* e = getenv("NM_XFORM_WARPS"); xw_env = e ? atoi(e) : 6; if (xw_env != 4) xw_env = 6; }
-        // the up-sampling producer uses three warps (+ one idle); the in-place transform takes 4 or 6
+        // the up-sampling producer runs on 4 warps (3 working): with 6 (5 working, 144 finer items) dec.8 got slower
+        // [measured, same GPU: 20.4 -> 24.6 ms per 640 frames] - more producer threads take issue slots and shared-memory
+        // bandwidth from the MMA / epilogue warps; the in-place transform gains from 6 (13.2 -> 11.6 ms)
         const int threads3 = kSlab3Threads + (up ? 32 * 4 : (in_scale ? 32 * xw_env : 0));
         if (accum) {
           NM_CHECK_ARG(bk == 64 && pn == 32 && !up && !in_scale, "nm_conv3d_tc: split-K accumulation needs slab3<64, 32>");
