@@ -990,7 +990,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       uint32_t q = 0;                                    // global slice counter (ring + P-group position)
       auto wait_slice = [&](uint32_t qq) {
         mbar_wait(&full[qq % ring], (qq / ring) & 1);
-        mbar_wait(&pempty[qq % kPGroups], ((qq / kPGroups) & 1) ^ 1);
+        if (!(p.debug & 256)) mbar_wait(&pempty[qq % kPGroups], ((qq / kPGroups) & 1) ^ 1);
         tc_fence_after();
       };
       auto issue_tap = [&](int t9, uint32_t tmem_d, uint32_t slot_lo, uint32_t& blo) {
@@ -1009,7 +1009,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       // non-blocking variant: true when both barriers of slice qq have already completed
       auto try_slice = [&](uint32_t qq) -> bool {
         if (!mbar_try_wait(&full[qq % ring], (qq / ring) & 1)) return false;
-        if (!mbar_try_wait(&pempty[qq % kPGroups], ((qq / kPGroups) & 1) ^ 1)) return false;
+        if (!(p.debug & 256) && !mbar_try_wait(&pempty[qq % kPGroups], ((qq / kPGroups) & 1) ^ 1)) return false;
         tc_fence_after();
         return true;
       };
@@ -1144,6 +1144,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
           if (sl >= 1) mbar_arrive(&pempty[(q + kPGroups - 1) % kPGroups]);
           if (sl == p.D - 1) mbar_arrive(&pempty[q % kPGroups]);
         }
+        if (p.debug & 128) continue;                     // ablation: handshakes only
         // out(sl-1) is complete now; out(D-1) completes together with the last event
         if (sl >= 1) {
           float f[CW];
