@@ -104,8 +104,9 @@ head_heat_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1
 }
 
 // Phase 2 (one CTA per frame): marginals of the heat-maps -> soft-argmax keypoints -> Gaussian re-render.
-// heat: (n, K, g^3) fp32 written by head_heat_kernel.  g in {8, 16, 32}: a warp's 32 consecutive voxels share x;
-// y is constant over runs of min(g, 32) lanes.  No float atomics: the result is bit-reproducible.
+// heat: (n, K, g^3) fp32 written by head_heat_kernel, g in {8, 16, 32}.  Per keypoint a thread reads z rows of g
+// floats (16-byte loads): the row sum feeds the x and y marginals, the row itself is accumulated into per-thread z
+// partials that are folded through shared memory in a fixed order.  No float atomics: bit-reproducible run to run.
 __global__ void __launch_bounds__(256)
 head_reduce_kernel(int K, int g, const float* __restrict__ lin, float gauss_width, const float* __restrict__ heat,
                    float* __restrict__ keypoints, float* __restrict__ gaussians, float* __restrict__ heat_mean) {
@@ -113,63 +114,59 @@ head_reduce_kernel(int K, int g, const float* __restrict__ lin, float gauss_widt
   float* s_m = smem;                       // [3][K][32] raw marginal sums along x, y, z
   float* s_kp = s_m + 3 * KMAX * 32;       // [K][4]
   float* s_e = s_kp + KMAX * 4;            // [K][3][32] separable gaussian factors
-  float* s_px = s_e + KMAX * 3 * 32;       // [8 warps][K]        per-iteration warp partials (x)
-  float* s_py = s_px + 8 * KMAX;           // [8 warps][K][4]     (y: one per run of `run` lanes)
-  float* s_pz = s_py + 8 * KMAX * 4;       // [8 warps][K][32]    (z)
+  float* s_row = s_e + KMAX * 3 * 32;      // [g*g] row sums of the current keypoint
+  float* s_part = s_row + 32 * 32;         // [256 / g][g] partial z marginals
+  float* s_z = s_part + 256;               // [256][g + 1] per-thread z partials, rows padded by one float
   const int n = blockIdx.x;
-  const int S = g * g * g;
-  for (int i = threadIdx.x; i < 3 * KMAX * 32; i += 256) s_m[i] = 0.f;
-  __syncthreads();
-
-  const float* hm_out = heat + (long long)n * K * S;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int run = g < 32 ? g : 32;          // lanes that share y
-  const int runs = 32 / run;                // y rows per warp
-
-  // voxel s = (x*g + y)*g + z ; consecutive threads -> consecutive s (coalesced heat-map rows)
-  for (int s0 = 0; s0 < S; s0 += 256) {
-    const int s = s0 + threadIdx.x;        // S is a multiple of 256 for g >= 8
+  const int S = g * g * g, GG = g * g, gp = g + 1;
+  const int lg = g == 8 ? 3 : (g == 16 ? 4 : 5);
+  const int parts = 256 >> lg;             // thread groups per z value in the z-marginal fold
+  for (int k = 0; k < K; k++) {
+    const float* vol = heat + ((long long)n * K + k) * S;
+    float zacc[32];
 #pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-      if (k < K) {
-        const float h = hm_out[(long long)k * S + s];     // written by head_heat_kernel
-        {
-          // warp-level partial sums (shuffles only: deterministic)
-          float hy = h;                                    // y: segmented sum over runs of `run` lanes
-          for (int o = 1; o < run; o <<= 1) hy += __shfl_xor_sync(0xffffffffu, hy, o);
-          float hz = h;                                    // z: sum over lanes with equal lane % g
-          for (int o = run; o < 32; o <<= 1) hz += __shfl_xor_sync(0xffffffffu, hz, o);
-          float hx = hy;                                   // x: whole warp
-          for (int o = run; o < 32; o <<= 1) hx += __shfl_xor_sync(0xffffffffu, hx, o);
-          if (lane == 0) s_px[warp * KMAX + k] = hx;
-          if ((lane % run) == 0) s_py[(warp * KMAX + k) * 4 + lane / run] = hy;
-          if (lane < run) s_pz[(warp * KMAX + k) * 32 + lane] = hz;
+    for (int i = 0; i < 32; i++) zacc[i] = 0.f;
+    for (int r = threadIdx.x; r < GG; r += 256) {
+      const float4* row = reinterpret_cast<const float4*>(vol + (long long)r * g);
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        if (q < g / 4) {
+          const float4 v = row[q];                                 // written by head_heat_kernel
+          sum += v.x; sum += v.y; sum += v.z; sum += v.w;
+          zacc[4 * q] += v.x; zacc[4 * q + 1] += v.y; zacc[4 * q + 2] += v.z; zacc[4 * q + 3] += v.w;
         }
       }
+      s_row[r] = sum;
     }
+#pragma unroll
+    for (int i = 0; i < 32; i++)
+      if (i < g) s_z[threadIdx.x * gp + i] = zacc[i];
+    __syncthreads();
     {
-      // fold the 8 warps' partials into the marginals in a fixed order (no float atomics: results are
-      // bit-reproducible run to run, which the reference's callers rely on via cudnn.deterministic)
-      __syncthreads();
-      for (int i = threadIdx.x; i < K * (1 + 32); i += 256) {
-        const int k = i / 33, j = i % 33;
-        if (j == 32) {
-          for (int w = 0; w < 8; w++) {
-            const int sw = s0 + w * 32;                    // first voxel of warp w in this iteration
-            s_m[(0 * KMAX + k) * 32 + sw / (g * g)] += s_px[w * KMAX + k];
-            for (int r = 0; r < runs; r++)
-              s_m[(1 * KMAX + k) * 32 + ((sw + r * run) / g) % g] += s_py[(w * KMAX + k) * 4 + r];
-          }
-        } else if (j < run) {
-          float t = 0.f;
-          for (int w = 0; w < 8; w++) t += s_pz[(w * KMAX + k) * 32 + j];
-          s_m[(2 * KMAX + k) * 32 + j] += t;
+      // z marginal: thread (part, z) folds the partials of threads part, part + parts, ...; x / y from the row sums
+      const int z = threadIdx.x & (g - 1), part = threadIdx.x >> lg;
+      float t = 0.f;
+      for (int u = part; u < 256; u += parts) t += s_z[u * gp + z];
+      s_part[part * g + z] = t;
+      if (threadIdx.x < g) {
+        float mx = 0.f, my = 0.f;
+        for (int j = 0; j < g; j++) {
+          mx += s_row[threadIdx.x * g + j];                        // x = threadIdx.x, sum over y
+          my += s_row[j * g + threadIdx.x];                        // y = threadIdx.x, sum over x
         }
+        s_m[(0 * KMAX + k) * 32 + threadIdx.x] = mx;
+        s_m[(1 * KMAX + k) * 32 + threadIdx.x] = my;
       }
-      __syncthreads();
     }
+    __syncthreads();
+    if (threadIdx.x < g) {
+      float t = 0.f;
+      for (int q = 0; q < parts; q++) t += s_part[q * g + threadIdx.x];
+      s_m[(2 * KMAX + k) * 32 + threadIdx.x] = t;
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- soft-argmax (utils/kypt_detector_utils.py:28-55)
   if (threadIdx.x < K) {
@@ -208,10 +205,16 @@ head_reduce_kernel(int K, int g, const float* __restrict__ lin, float gauss_widt
   }
   __syncthreads();
   float* go = gaussians + (long long)n * K * S;
-  for (int i = threadIdx.x; i < K * S; i += 256) {
-    const int k = i / S, s = i % S;
-    const int z = s % g, y = (s / g) % g, x = s / (g * g);
-    go[i] = (s_e[(k * 3 + 0) * 32 + x] * s_e[(k * 3 + 1) * 32 + y]) * s_e[(k * 3 + 2) * 32 + z] * s_kp[k * 4 + 3];
+  // one z row (k, x, y) per thread iteration, 16-byte stores; same multiplication order as before: ((ex*ey)*ez)*I
+  for (int r = threadIdx.x; r < K * GG; r += 256) {
+    const int k = r / GG, xy = r - k * GG, x = xy >> lg, y = xy & (g - 1);
+    const float exy = s_e[(k * 3 + 0) * 32 + x] * s_e[(k * 3 + 1) * 32 + y];
+    const float inten_k = s_kp[k * 4 + 3];
+    const float* ez = s_e + (k * 3 + 2) * 32;
+    float4* dst = reinterpret_cast<float4*>(go + (long long)r * g);
+    for (int q = 0; q < g / 4; q++)
+      dst[q] = make_float4((exy * ez[4 * q]) * inten_k, (exy * ez[4 * q + 1]) * inten_k, (exy * ez[4 * q + 2]) * inten_k,
+                           (exy * ez[4 * q + 3]) * inten_k);
   }
 }
 
@@ -478,7 +481,7 @@ extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float
   }
   NM_CHECK_LAUNCH("heatmap_head(heat)");
   if (mode == 0) return NM_OK;
-  const size_t smem2 = (size_t)(3 * KMAX * 32 + KMAX * 4 + KMAX * 3 * 32 + 8 * KMAX * (1 + 4 + 32)) * sizeof(float);
+  const size_t smem2 = (size_t)(3 * KMAX * 32 + KMAX * 4 + KMAX * 3 * 32 + 32 * 32 + 256 + 256 * 33) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(head_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
