@@ -235,10 +235,17 @@ gaussian_render_kernel(const float* __restrict__ keypoints, int K, int g, const 
   for (int i = threadIdx.x; i < K; i += 256) s_i[i] = kp[i * 4 + 3];
   __syncthreads();
   float* go = gaussians + (long long)n * K * S;
-  for (int i = threadIdx.x; i < K * S; i += 256) {
-    const int k = i / S, s = i % S;
-    const int z = s % g, y = (s / g) % g, x = s / (g * g);
-    go[i] = ((1.0f * s_e[(k * 3 + 0) * 32 + x]) * s_e[(k * 3 + 1) * 32 + y]) * s_e[(k * 3 + 2) * 32 + z] * s_i[k];
+  // one z row (k, x, y) per thread iteration, 16-byte stores; multiplication order ((ex*ey)*ez)*I as in the reference
+  const int GG = g * g;
+  for (int r = threadIdx.x; r < K * GG; r += 256) {
+    const int k = r / GG, xy = r - k * GG, x = xy / g, y = xy - x * g;
+    const float exy = (1.0f * s_e[(k * 3 + 0) * 32 + x]) * s_e[(k * 3 + 1) * 32 + y];
+    const float inten = s_i[k];
+    const float* ez = s_e + (k * 3 + 2) * 32;
+    float4* dst = reinterpret_cast<float4*>(go + (long long)r * g);
+    for (int q = 0; q < g / 4; q++)
+      dst[q] = make_float4((exy * ez[4 * q]) * inten, (exy * ez[4 * q + 1]) * inten, (exy * ez[4 * q + 2]) * inten,
+                           (exy * ez[4 * q + 3]) * inten);
   }
 }
 
@@ -495,7 +502,7 @@ extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float
 extern "C" int nm_gaussian_render(const float* keypoints, int n, int K, int g, const float* linspace,
                                   float gauss_width, float* gaussians, void* stream) {
   NM_CHECK_ARG(keypoints && linspace && gaussians, "nm_gaussian_render: null pointer");
-  NM_CHECK_ARG(K <= KMAX && g <= 32, "nm_gaussian_render: K=%d g=%d unsupported", K, g);
+  NM_CHECK_ARG(K <= KMAX && g <= 32 && g % 4 == 0, "nm_gaussian_render: K=%d g=%d unsupported", K, g);
   if (n == 0) return NM_OK;
   const float width = gauss_width;
   gaussian_render_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(keypoints, K, g, linspace, width, gaussians);
