@@ -102,6 +102,21 @@ def test_detector_batched_vs_oracle_and_chunking():
     out["recon"][out["recon"] < 0.5] = 0
 
 
+def test_detector_is_bit_reproducible():
+    """Two runs on the same input give identical bits (no float atomics, fixed reduction orders, fixed MMA order):
+    the reference's callers set cudnn.deterministic = True and compare runs."""
+    G, B, T = 64, 2, 3
+    hp = O.default_hparams(grid_size=G)
+    net, _ = build(hp, 43)
+    vox, _ = clips(6000, B, T, 20000, G)
+    with torch.no_grad():
+        a = net.kypt_detector(vox)
+        b = net.kypt_detector(vox)
+    for key in ("heatmaps", "keypoints", "recon", "first_feature", "affinity", "vol_fit_reg", "sparsity_loss"):
+        assert torch.equal(a[key], b[key]), key
+    assert float(a["recon_loss"]) == float(b["recon_loss"])
+
+
 def test_generate_vs_reference_golden(golden_dir):
     z = np.load(os.path.join(golden_dir, "generate_g32.npz"))
     hp = O.default_hparams(grid_size=32)
