@@ -29,6 +29,8 @@ from ..utils.kypt_detector_utils import (get_graph_consistency_loss, get_graph_t
 # levels <= 8^3 are launch-latency bound, so bigger passes amortise them.  Measured on one B200 (B = 64, T = 20, same
 # GPU): 320 frames/pass 168.5 ms/step, 640 -> 166.9, 1280 -> 166.3.
 FRAME_CHUNK = int(__import__("os").environ.get("NM_FRAME_CHUNK", "640"))
+# Run the once-per-clip spatio-temporal branch on an auxiliary stream next to the per-frame encoder (0 disables).
+ST_OVERLAP = __import__("os").environ.get("NM_ST_OVERLAP", "1") != "0"
 
 
 def _no_training(module):
@@ -96,10 +98,21 @@ class VoxToKyptNet(nn.Module):
         seq = seq.float().contiguous()
         sigma = float(self.sigmas[0])
         with torch.no_grad():
-            # once per clip: spatio-temporal heat-map from the frame mean (never updated for const_intensity 3)
-            st = run_feature_net(self.extract_spatio_temporal_features, ops.mean_over_frames(seq))
-            prev = ops.heatmap_head(st, self.extract_spatio_temporal_heatmaps_from_features[0], K, mode=0)
-            del st
+            # once per clip: spatio-temporal heat-map from the frame mean (never updated for const_intensity 3).
+            # Its ~170 mostly small launches run on an auxiliary stream, next to the per-frame encoder of the first
+            # pass; the per-frame head waits for it.
+            main = torch.cuda.current_stream(seq.device)
+            side = ops.side_stream(seq.device) if ST_OVERLAP else main
+            if side is not main:
+                side.wait_stream(main)
+            with torch.cuda.stream(side):
+                st = run_feature_net(self.extract_spatio_temporal_features, ops.mean_over_frames(seq))
+                prev = ops.heatmap_head(st, self.extract_spatio_temporal_heatmaps_from_features[0], K, mode=0)
+                del st
+            if side is not main:
+                prev.record_stream(main)
+                seq.record_stream(side)
+            st_pending = side is not main
             frames = seq.view(B * T, G, G, G)
             heat = torch.empty(B * T, K, g, g, g, dtype=torch.float32, device=seq.device)
             kps = torch.empty(B * T, K, 4, dtype=torch.float32, device=seq.device)
@@ -112,6 +125,9 @@ class VoxToKyptNet(nn.Module):
                 feat = run_feature_net(self.extract_features, frames[b0 * T:b1 * T])
                 ff_act[b0:b1] = feat.view(b1 - b0, T, g, g, g, self.feat_dim)[:, 0]
                 sl = slice(b0 * T, b1 * T)
+                if st_pending:
+                    main.wait_stream(side)
+                    st_pending = False
                 ops.heatmap_head(feat, self.extract_heatmaps_from_features[0], K, mode=1, prev=prev[b0:b1],
                                  frames_per_clip=T, prop=self.propagate_heatmaps[0], sigma=sigma,
                                  want_gaussians=want_gaussians,

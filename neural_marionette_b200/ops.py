@@ -25,9 +25,9 @@ def _need_cuda(*ts):
 
 
 def workspace(nbytes: int, device, slot: str = "default") -> torch.Tensor:
-    """Grow-only byte scratch per (device, slot).  Kernels on one stream run in order, so a
-    scratch buffer may be reused by the next launch."""
-    key = (str(device), slot)
+    """Grow-only byte scratch per (device, slot, stream).  Kernels on one stream run in order, so a
+    scratch buffer may be reused by the next launch; each stream has its own buffers."""
+    key = (str(device), slot, torch.cuda.current_stream(device).cuda_stream)
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
@@ -36,6 +36,15 @@ def workspace(nbytes: int, device, slot: str = "default") -> torch.Tensor:
 
 
 _linspace = {}
+_side_streams = {}
+
+
+def side_stream(device) -> "torch.cuda.Stream":
+    """One auxiliary stream per device (used to overlap the once-per-clip branch with the per-frame encoder)."""
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 def linspace(n: int, device) -> torch.Tensor:
@@ -43,6 +52,7 @@ def linspace(n: int, device) -> torch.Tensor:
     key = (n, str(device))
     if key not in _linspace:
         _linspace[key] = torch.linspace(-1.0, 1.0, n, device=device)
+        torch.cuda.current_stream(device).synchronize()      # built once; readable from any stream afterwards
     return _linspace[key]
 
 
