@@ -920,7 +920,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
             const int slot = fill % kLoRing;
             mbar_wait(&empty_lo[slot], ((fill / kLoRing) & 1) ^ 1);
             mbar_expect_tx(&full_lo[slot], (uint32_t)kLoBytes);
-            tma_load_5d(s_lo + (size_t)slot * kLoBytes, &p.tmap_a, &full_lo[slot], 0, iw * 4 - 1, ih * 8 - 1, pl, n);
+            tma_load_5d(s_lo + (size_t)slot * kLoBytes, &p.tmap_a, &full_lo[slot], p.cin_off, iw * 4 - 1, ih * 8 - 1, pl, n);
           }
           continue;
         }
@@ -1311,6 +1311,7 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
 // up-sampling mode needs the slab3<64, 32> kernel with 3 slice slots + the low-resolution plane ring
 bool up2x_ok(int n, int D, int H, int W, int Cin, int Cout) {
   if ((D | H | W) & 1) return false;
+  if (Cin == 128) Cin = 64;   // split-K: two launches over 64-channel slices of the low-resolution tensor
   const ConvPlan pl = plan_conv(n, D, H, W, Cin, Cout, 3, 1);
   return pl.slab && pl.use3 && pl.bk == 64 && pl.kch == 1 && pl.pn == 32 &&
          pl.w_bytes + (size_t)3 * pl.chunk_bytes + kLoRing * kLoBytes + pl.extra <= 227 * 1024;
@@ -1337,6 +1338,16 @@ extern "C" int nm_conv3d_tc_up2x(const void* x_lo, const void* packed_w, const f
                                  int in_act, float* stats_partial, void* stream) {
   NM_CHECK_ARG(up2x_ok(n, D, H, W, Cin, Cout), "nm_conv3d_tc_up2x: unsupported shape n=%d out %dx%dx%d Cin=%d Cout=%d", n,
                D, H, W, Cin, Cout);
+  if (Cin == 128) {
+    // split-K (see conv3d_tc_impl): both launches interpolate their 64-channel slice of the low-resolution tensor
+    NM_CHECK_ARG(!in_scale, "nm_conv3d_tc_up2x: the fused input transform is not implemented for Cin = 128");
+    if (n == 0) return NM_OK;
+    const int rc = conv3d_tc_impl(x_lo, packed_w, bias, out, n, D, H, W, 64, Cout, 3, 1, nullptr, nullptr, 0, nullptr, stream,
+                                  true, 128, 0, 0);
+    if (rc != NM_OK) return rc;
+    return conv3d_tc_impl(x_lo, packed_w, nullptr, out, n, D, H, W, 64, Cout, 3, 1, nullptr, nullptr, 0, stats_partial,
+                          stream, true, 128, 64, 1);
+  }
   return conv3d_tc_impl(x_lo, packed_w, bias, out, n, D, H, W, Cin, Cout, 3, 1, in_scale, in_shift, in_act,
                         stats_partial, stream, true);
 }
@@ -1449,6 +1460,7 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           slab3_attr = true;
         }
         static int xw_env = -1;
@@ -1458,8 +1470,9 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
         // bandwidth from the MMA / epilogue warps; the in-place transform gains from 6 (13.2 -> 11.6 ms)
         const int threads3 = kSlab3Threads + (up ? 32 * 4 : (in_scale ? 32 * xw_env : 0));
         if (accum) {
-          NM_CHECK_ARG(bk == 64 && pn == 32 && !up && !in_scale, "nm_conv3d_tc: split-K accumulation needs slab3<64, 32>");
-          conv3d_slab3_kernel<64, 32, false, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+          NM_CHECK_ARG(bk == 64 && pn == 32 && !in_scale, "nm_conv3d_tc: split-K accumulation needs slab3<64, 32>");
+          if (up) conv3d_slab3_kernel<64, 32, true, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
+          else conv3d_slab3_kernel<64, 32, false, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         } else if (up) conv3d_slab3_kernel<64, 32, true><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         else if (pn == 16) conv3d_slab3_kernel<64, 16><<<grid, threads3, need, (cudaStream_t)stream>>>(q);
         else if (bk == 64) conv3d_slab3_kernel<64, 32><<<grid, threads3, need, (cudaStream_t)stream>>>(q);

@@ -31,6 +31,8 @@ from ..utils.kypt_detector_utils import (get_graph_consistency_loss, get_graph_t
 FRAME_CHUNK = int(__import__("os").environ.get("NM_FRAME_CHUNK", "640"))
 # Run the once-per-clip spatio-temporal branch on an auxiliary stream next to the per-frame encoder (0 disables).
 ST_OVERLAP = __import__("os").environ.get("NM_ST_OVERLAP", "1") != "0"
+# Interpolate the first decoder up-sampling inside the dec.1 conv as well (0: separate up-sampling kernel).
+UP_DEC1 = __import__("os").environ.get("NM_UP_DEC1", "1") != "0"
 
 
 def _no_training(module):
@@ -201,8 +203,10 @@ class KyptToVoxNet(nn.Module):
                 gs = gaussians[b0:b1].float().contiguous().view(n, K, g, g, g) if keypoints is None else None
                 x = ops.decoder_adjust(first_feature_act[b0:b1], self.adjust_combined_representation[0], T, g, K,
                                        sigma, keypoints=kp, gaussians=gs)
-                x = ops.upsample2x(x)
-                raw, a, b = ops.conv3d(x, dec[1], dec[2])
+                if UP_DEC1 and ops.can_conv_up2x(x, dec[1]):
+                    raw, a, b = ops.conv3d_up2x(x, dec[1], dec[2])     # up-sampling inside the conv's operand path
+                else:
+                    raw, a, b = ops.conv3d(ops.upsample2x(x), dec[1], dec[2])
                 raw, a, b = self._conv_after_gn(raw, a, b, dec[4], dec[5])
                 if ops.can_conv_up2x(raw, dec[8]):
                     # GroupNorm + LeakyReLU + trilinear up-sampling all happen inside the conv's operand path: the

@@ -166,20 +166,21 @@ def test_conv3d_fused_input_groupnorm(ops, n, grid, cin, cout):
     assert rel_err(got.float().cpu(), ref.float().cpu()) < 2e-3
 
 
-@pytest.mark.parametrize("n,grid,cout,fused", [(2, 16, 32, True), (1, 32, 32, False), (3, 16, 64, True), (1, 32, 64, True)])
-def test_conv3d_upsample_fused(ops, n, grid, cout, fused):
+@pytest.mark.parametrize("n,grid,cin,cout,fused", [(2, 16, 64, 32, True), (1, 32, 64, 32, False), (3, 16, 64, 64, True),
+                                                   (1, 32, 64, 64, True), (2, 16, 128, 64, False), (1, 32, 128, 64, False)])
+def test_conv3d_upsample_fused(ops, n, grid, cin, cout, fused):
     """conv3d_k3(upsample2x(LeakyReLU(GN(raw)))) with the up-sampled tensor interpolated inside the conv's operand
     path: against the two-kernel device path and against torch (F.interpolate trilinear + conv3d)."""
-    g = torch.Generator().manual_seed(grid + cout)
-    conv = torch.nn.Conv3d(64, cout, 3, 1, 1)
+    g = torch.Generator().manual_seed(grid + cout + cin)
+    conv = torch.nn.Conv3d(cin, cout, 3, 1, 1)
     with torch.no_grad():
-        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (64 * 27) ** 0.5)
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (cin * 27) ** 0.5)
     gn_out = torch.nn.GroupNorm(cout // 16, cout).cuda()
     lo = grid // 2
-    x = torch.randn(n, 64, lo, lo, lo, generator=g) * 1.5 + 0.3
+    x = torch.randn(n, cin, lo, lo, lo, generator=g) * 1.5 + 0.3
     raw = to_act(x)
-    a = (0.5 + torch.rand(n, 64, generator=g)).cuda()
-    b = torch.randn(n, 64, generator=g).cuda()
+    a = (0.5 + torch.rand(n, cin, generator=g)).cuda()
+    b = torch.randn(n, cin, generator=g).cuda()
     conv = conv.cuda()
     assert ops.can_conv_up2x(raw, conv)
     if fused:
