@@ -365,6 +365,10 @@ final_recon_kernel(const act_t* __restrict__ x, const float* __restrict__ a, con
   const int clip = n / frames_per_clip;
   const int sub = threadIdx.x % LPV;
   float loss = 0.f;
+  // this lane's 8 channels never change: scale / shift / weight live in registers (24 shared loads per chunk less)
+  float ra[8], rb[8], rw[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { ra[k] = sa[sub * 8 + k]; rb[k] = sb[sub * 8 + k]; rw[k] = sw[sub * 8 + k]; }
   const half8* base = reinterpret_cast<const half8*>(x + (long long)n * S * C);
   // A group of LPV lanes handles LPV consecutive voxels per iteration: lane `sub` loads channel chunk `sub` of
   // each of them, the partial dot products are transpose-reduced so that lane j ends up with the full sum of
@@ -372,13 +376,18 @@ final_recon_kernel(const act_t* __restrict__ x, const float* __restrict__ a, con
   const int groups_per_block = 256 / LPV;
   for (int v0 = (blockIdx.x * groups_per_block + threadIdx.x / LPV) * LPV; v0 < S; v0 += gridDim.x * groups_per_block * LPV) {
     float part[LPV];
+    half8 raw[LPV];
+#pragma unroll
+    for (int j = 0; j < LPV; j++) raw[j] = base[(long long)(v0 + j) * LPV + sub];   // all loads in flight first
+    const float ff = first_frame[(long long)clip * S + v0 + sub];
+    const float tt = target ? target[(long long)n * S + v0 + sub] : 0.f;
 #pragma unroll
     for (int j = 0; j < LPV; j++) {
       float f[8];
-      nm_unpack8(base[(long long)(v0 + j) * LPV + sub], f);
+      nm_unpack8(raw[j], f);
       float acc = 0.f;
 #pragma unroll
-      for (int k = 0; k < 8; k++) acc = fmaf(nm_lrelu(fmaf(f[k], sa[sub * 8 + k], sb[sub * 8 + k])), sw[sub * 8 + k], acc);
+      for (int k = 0; k < 8; k++) acc = fmaf(nm_lrelu(fmaf(f[k], ra[k], rb[k])), rw[k], acc);
       part[j] = acc;
     }
     // recursive halving inside the LPV-lane group: after it, lane `sub` holds the total of voxel `sub`
@@ -393,11 +402,11 @@ final_recon_kernel(const act_t* __restrict__ x, const float* __restrict__ a, con
       }
     }
     const int s = v0 + sub;
-    const float z = sharp * (tanhf(part[0] + bias) + first_frame[(long long)clip * S + s] - trans);
+    const float z = sharp * (tanhf(part[0] + bias) + ff - trans);
     const float r = 1.0f / (1.0f + expf(-z));
     recon[(long long)n * S + s] = r;
     if (target) {
-      const float t = target[(long long)n * S + s];
+      const float t = tt;
       loss -= t * fmaxf(logf(r), -100.f) + (1.f - t) * fmaxf(logf(1.f - r), -100.f);
     }
   }
