@@ -29,6 +29,11 @@ from ..utils.kypt_detector_utils import (get_graph_consistency_loss, get_graph_t
 # levels <= 8^3 are launch-latency bound, so bigger passes amortise them.  Measured on one B200 (B = 64, T = 20, same
 # GPU): 320 frames/pass 168.5 ms/step, 640 -> 166.9, 1280 -> 166.3.
 FRAME_CHUNK = int(__import__("os").environ.get("NM_FRAME_CHUNK", "640"))
+
+
+def frames_per_pass(grid_size: int) -> int:
+    """FRAME_CHUNK is quoted for grid 64^3; other grids keep the same activation footprint (G = 128: 80 frames)."""
+    return max(1, FRAME_CHUNK * 64 ** 3 // grid_size ** 3)
 # Run the once-per-clip spatio-temporal branch on an auxiliary stream next to the per-frame encoder (0 disables).
 ST_OVERLAP = __import__("os").environ.get("NM_ST_OVERLAP", "1") != "0"
 # Interpolate the first decoder up-sampling inside the dec.1 conv as well (0: separate up-sampling kernel).
@@ -121,7 +126,7 @@ class VoxToKyptNet(nn.Module):
             gss = torch.empty(B * T, K, g, g, g, dtype=torch.float32, device=seq.device) if want_gaussians else None
             hmean = torch.empty(B * T, K, dtype=torch.float32, device=seq.device)
             ff_act = torch.empty(B, g, g, g, self.feat_dim, dtype=ops.ACT_DTYPE, device=seq.device)
-            clips = max(1, FRAME_CHUNK // T)
+            clips = max(1, frames_per_pass(G) // T)
             for b0 in range(0, B, clips):
                 b1 = min(B, b0 + clips)
                 feat = run_feature_net(self.extract_features, frames[b0 * T:b1 * T])
@@ -195,7 +200,7 @@ class KyptToVoxNet(nn.Module):
             bce = torch.empty(B, T, dtype=torch.float32, device=dev) if target is not None else None
             if target is not None:
                 target = target.float().contiguous()
-            clips = max(1, FRAME_CHUNK // T)
+            clips = max(1, frames_per_pass(G) // T)
             for b0 in range(0, B, clips):
                 b1 = min(B, b0 + clips)
                 n = (b1 - b0) * T

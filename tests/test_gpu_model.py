@@ -80,7 +80,7 @@ def test_detector_batched_vs_oracle_and_chunking():
     vox, vox_ref = clips(5000, B, T, 20000, G)
     old = kd.FRAME_CHUNK
     try:
-        kd.FRAME_CHUNK = 5          # forces clip-sized chunks (one clip per pass)
+        kd.FRAME_CHUNK = 0          # forces clip-sized chunks (one clip per pass)
         with torch.no_grad():
             hm, kp, gs, ff = net.kypt_detector.vox_to_kypt(vox)
             rec = net.kypt_detector.kypt_to_vox(gs, ff, vox[:, 0])
