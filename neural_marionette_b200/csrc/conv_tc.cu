@@ -694,6 +694,24 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
       for (int i = 0; i < 4; i++) pr[i] = __hfma2(q25, __hsub2(pb[i], pa[i]), pa[i]);
       return r;
     };
+    const __half2 q75 = __float2half2_rn(0.75f);
+    auto scale4 = [&](const uint4& a, const __half2 f) -> uint4 {
+      uint4 r;
+      const __half2* pa = reinterpret_cast<const __half2*>(&a);
+      __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) pr[i] = __hmul2(pa[i], f);
+      return r;
+    };
+    auto add4 = [&](const uint4& a, const uint4& b) -> uint4 {
+      uint4 r;
+      const __half2* pa = reinterpret_cast<const __half2*>(&a);
+      const __half2* pb = reinterpret_cast<const __half2*>(&b);
+      __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; i++) pr[i] = __hadd2(pa[i], pb[i]);
+      return r;
+    };
     uint32_t fill = 0;                                    // slices produced so far (ring position)
     uint32_t planes = 0;                                  // global index of plane 0 of the current column
     int cur_n = -1;
@@ -788,6 +806,11 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
               uint4 v[NW];                                           // row 2m+1: near m, far m+1; row 2m+2: near m+1, far m
 #pragma unroll
               for (int w = 0; w < NW; w++) v[w] = r2 == 0 ? lerp(va[w], vb[w]) : lerp(vb[w], va[w]);
+              // along w every box column is the near operand of two halo columns and the far operand of up to two:
+              // 0.75 v and 0.25 v once per column, then one add per output (22 instead of 40 half2 ops per channel pair)
+              uint4 t75[NW], t25[NW];
+#pragma unroll
+              for (int w = 0; w < NW; w++) { t75[w] = scale4(v[w], q75); t25[w] = scale4(v[w], q25); }
 #pragma unroll
               for (int k = 0; k < NWW; k++) {
                 // halo column ww <-> w = iw*8 - 1 + ww: near box column (ww+1)>>1, far = near +1 (ww even) / -1 (ww odd)
@@ -796,7 +819,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
                 uint4 o;
                 if ((ww == 0 && iw == 0) || (ww == kHaloW - 1 && iw == p.nw - 1)) o = zero;             // conv padding
                 else if ((ww == 1 && iw == 0) || (ww == kHaloW - 2 && iw == p.nw - 1)) o = v[nr];        // clamped far
-                else o = lerp(v[nr], v[fr]);
+                else o = add4(t75[nr], t25[fr]);
                 sts128(orow + ww * 128 + ((c ^ ((hh * kHaloW + ww) & 7)) << 4), o);
               }
             }
