@@ -130,3 +130,47 @@ def test_generate(golden_dir):
                                     eps_gen=torch.from_numpy(z["eps_gen"]))
     np.testing.assert_allclose(out["keypoints"].numpy(), z["keypoints"], atol=5e-5)
     np.testing.assert_allclose(out["gen"][..., ::2, ::2, ::2].numpy(), z["gen_sub_f16"].astype(np.float32), atol=3e-3)
+
+
+# ---- plain-C oracle (oracle/nm_oracle_c.c): same fixtures, no numpy in the arithmetic ------------------------------
+def test_c_oracle_voxelize_hashes(golden_dir):
+    from oracle import c_oracle as C
+    cases = json.load(open(os.path.join(golden_dir, "voxelize_hashes.json")))
+    clips = {}
+    for c in cases:
+        key = (c["seed"], c["N"])
+        if key not in clips:
+            T = 1 + max(x["t"] for x in cases if x["seed"] == c["seed"])
+            raw = O.synthetic_clip(c["seed"], T, c["N"])
+            clips[key] = (raw, C.episodic_normalization(raw))
+            assert np.array_equal(clips[key][1], O.episodic_normalization(raw))        # float64, bit for bit
+        g = C.voxelize(clips[key][1][c["t"]], c["G"])
+        assert int(g.sum()) == c["occupied"]
+        assert hashlib.sha256(g.tobytes()).hexdigest() == c["sha256"]
+
+
+def test_c_oracle_real_geometry_and_clip(golden_dir):
+    from oracle import c_oracle as C
+    z = np.load(os.path.join(golden_dir, "voxelize_obj.npz"))
+    g = C.normalize_voxelize_clip(z["obj_points_f32"][None], 64, scale=0.8)[0]
+    assert int(g.sum()) == int(z["obj_occupied"])
+    assert np.array_equal(np.packbits(g.astype(np.uint8).ravel()), z["obj_grid_packed"])
+    raw = O.synthetic_clip(77, 3, 5000)
+    for kw in (dict(), dict(scale=0.8, x_trans=0.05, z_trans=0.1)):
+        want = O.voxelize_clip(O.episodic_normalization(raw, **kw), 32)
+        assert np.array_equal(C.normalize_voxelize_clip(raw, 32, **kw), want)
+
+
+def test_c_oracle_edge_cases():
+    from oracle import c_oracle as C
+    assert C.voxelize(np.zeros((0, 3)), 8).sum() == 0
+    p = np.array([[0.0, 0.0, 0.0]] * 5 + [[np.nextafter(1.0, 0.0)] * 3, [-1.0, -1.0, -1.0]])
+    g = C.voxelize(p, 8)[0]
+    assert g.sum() == 3 and g[7, 7, 7] == 1 and g[0, 0, 0] == 1 and g[3, 3, 3] == 1
+    with pytest.raises(IndexError):
+        C.voxelize(np.array([[1.5, 0.0, 0.0]]), 8)
+    with pytest.raises(ValueError):
+        C.episodic_normalization(np.zeros((0, 4, 3), np.float32))
+    # extra columns (normals) are ignored, utils/dataset_utils.py:27
+    q = np.concatenate([p, np.ones((len(p), 3))], 1)
+    assert np.array_equal(C.voxelize(q, 8), g[None])
