@@ -194,6 +194,34 @@ int nm_hsvrnn_decode_pose(const nm_hsvrnn_weights* w, const float* dec_in, const
 int nm_hsvrnn_bone_offsets(const float* keypoints, const int* parents, const float* offset_param, int B, int T, int K,
                            float* out, void* stream);
 
+/* ---- consumers of the path's outputs -----------------------------------------------
+ * utils/eval_utils.py:29-56 `voxel_chamfer_distance`: per-frame symmetric chamfer distance between the occupied
+ * voxels of gt (n, G, G, G; non-zero = occupied) and of recon (>= 0.5 = occupied; binarised IN PLACE when
+ * binarize_recon != 0, as :37-38 do), coordinates idx / ((G-1)/2) - 1.  out (n) fp32; a frame whose gt or recon
+ * is empty gives NaN and sets bit 0 of *err_flag (torch raises there).  occupied_out (optional): (n, 2) int32
+ * voxel counts.  n <= 65535 per call. */
+size_t nm_voxel_chamfer_workspace_bytes(int n, int G);
+int nm_voxel_chamfer(const float* gt, float* recon, int n, int G, int binarize_recon, float* out, int* occupied_out,
+                     int* err_flag, void* workspace, void* stream);
+/* utils/eval_utils.py:60-90 `semantic_scores`: rows of keypoints (F, K, 4) with intensity < threshold are
+ * overwritten IN PLACE by (1e4, 1e4, 1e4, 1) (:68-69); idx_out (F, Kgt) int64 = nearest detected keypoint of
+ * every ground-truth joint gt_keypoints (F, Kgt, 3); hist (Kgt, K) int32 = its histogram over the F frames. */
+int nm_semantic_nearest(float* keypoints, const float* gt_keypoints, int F, int K, int Kgt, float threshold,
+                        long long* idx_out, int* hist, void* stream);
+/* vis_retarget.py:21-62 `extract_skin_weights`: points (N, 3), keypoints (K, 4), parents (K) int32, root =
+ * priority.indices[0]; skin_out (N, K) fp32 (two non-zeros per row); nearest_out (optional, N) int32 = the chosen
+ * bone; bit 0 of *err_flag is set when the parent walk over invalid joints does not terminate. */
+int nm_skin_weights(const float* points, int N, const float* keypoints, const int* parents, int K, int root,
+                    float hardness, float threshold, float* skin_out, int* nearest_out, int* err_flag, void* stream);
+/* vis_retarget.py:279-287,:300: forward kinematics of the retargeted skeleton.  R (T, K, 3, 3), offset (K, 3),
+ * root_pos (T, 3), order = priority.indices, parents (K) int32 -> pos_out (T, K, 3), clipped to [-1, 1] if clip. */
+int nm_retarget_fk(const float* R, const float* offset, const float* root_pos, const int* order, const int* parents,
+                   int T, int K, int clip, float* pos_out, void* stream);
+/* vis_retarget.py:263-270,:315-322: linear blend skinning.  points (N, 3), joints (K, 3), R_inv (K, 3, 3) or NULL
+ * (identity), T3x4 (T, K, 3, 4) = [R | pos], skin (N, K) -> out (T, N, 3). */
+int nm_linear_blend_skinning(const float* points, int N, const float* joints, const float* R_inv, const float* T3x4,
+                             const float* skin, int T, int K, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,6 +80,12 @@ PROTOTYPES = {
                             _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nm_hsvrnn_decode_pose": (_i, [C.POINTER(HsvrnnWeights), _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "nm_hsvrnn_bone_offsets": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nm_voxel_chamfer_workspace_bytes": (_sz, [_i, _i]),
+    "nm_voxel_chamfer": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "nm_semantic_nearest": (_i, [_vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "nm_skin_weights": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "nm_retarget_fk": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "nm_linear_blend_skinning": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
 }
 
 _lib = None

@@ -528,3 +528,67 @@ def hsvrnn_bone_offsets(keypoints, parents, offset_param) -> torch.Tensor:
     L.call("nm_hsvrnn_bone_offsets", L.ptr(keypoints), L.ptr(parents), L.ptr(offset_param), B, T, K, L.ptr(out),
            L.stream())
     return out
+
+
+# ------------------------------------------------------------------ consumers of the path's outputs
+def voxel_chamfer(gt: torch.Tensor, recon: torch.Tensor, binarize: bool = True, frames_per_call: int = 256):
+    """gt, recon (n, G, G, G) fp32 dense -> (chamfer (n) fp32, occupied (n, 2) int32, err int32 scalar tensor).
+    `recon` is binarised in place when `binarize` (utils/eval_utils.py:37-38)."""
+    _need_cuda(gt)
+    n, G = gt.shape[0], gt.shape[-1]
+    out = torch.empty(n, dtype=torch.float32, device=gt.device)
+    occ = torch.empty(n, 2, dtype=torch.int32, device=gt.device)
+    err = torch.zeros(1, dtype=torch.int32, device=gt.device)
+    step = max(1, min(frames_per_call, 65535))
+    ws = workspace(L.query("nm_voxel_chamfer_workspace_bytes", min(n, step), G), gt.device, "voxel_chamfer")
+    for s in range(0, n, step):
+        m = min(step, n - s)
+        L.call("nm_voxel_chamfer", L.ptr(gt[s:s + m]), L.ptr(recon[s:s + m]), m, G, int(binarize), L.ptr(out[s:s + m]),
+               L.ptr(occ[s:s + m]), L.ptr(err), L.ptr(ws), L.stream())
+    return out, occ, err
+
+
+def semantic_nearest(keypoints: torch.Tensor, gt_keypoints: torch.Tensor, threshold: float = 0.2):
+    """keypoints (F, K, 4) fp32 (masked in place), gt_keypoints (F, Kgt, 3) -> (idx (F, Kgt) int64, hist (Kgt, K) int32)."""
+    _need_cuda(keypoints)
+    F, K = keypoints.shape[0], keypoints.shape[1]
+    Kgt = gt_keypoints.shape[1]
+    idx = torch.empty(F, Kgt, dtype=torch.int64, device=keypoints.device)
+    hist = torch.empty(Kgt, K, dtype=torch.int32, device=keypoints.device)
+    L.call("nm_semantic_nearest", L.ptr(keypoints), L.ptr(gt_keypoints), F, K, Kgt, float(threshold), L.ptr(idx),
+           L.ptr(hist), L.stream())
+    return idx, hist
+
+
+def skin_weights(points: torch.Tensor, keypoints: torch.Tensor, parents: torch.Tensor, root: int, hardness: float,
+                 threshold: float):
+    """points (N, 3), keypoints (K, 4) fp32, parents (K) int32 -> (skin (N, K) fp32, nearest (N) int32, err)."""
+    _need_cuda(points)
+    N, K = points.shape[0], keypoints.shape[0]
+    skin = torch.empty(N, K, dtype=torch.float32, device=points.device)
+    near = torch.empty(N, dtype=torch.int32, device=points.device)
+    err = torch.zeros(1, dtype=torch.int32, device=points.device)
+    L.call("nm_skin_weights", L.ptr(points), N, L.ptr(keypoints), L.ptr(parents), K, int(root), float(hardness),
+           float(threshold), L.ptr(skin), L.ptr(near), L.ptr(err), L.stream())
+    return skin, near, err
+
+
+def retarget_fk(R: torch.Tensor, offset: torch.Tensor, root_pos: torch.Tensor, order: torch.Tensor,
+                parents: torch.Tensor, clip: bool = True) -> torch.Tensor:
+    """R (T, K, 3, 3), offset (K, 3), root_pos (T, 3), order / parents (K) int32 -> (T, K, 3)."""
+    _need_cuda(R)
+    T, K = R.shape[0], R.shape[1]
+    pos = torch.empty(T, K, 3, dtype=torch.float32, device=R.device)
+    L.call("nm_retarget_fk", L.ptr(R), L.ptr(offset), L.ptr(root_pos), L.ptr(order), L.ptr(parents), T, K, int(clip),
+           L.ptr(pos), L.stream())
+    return pos
+
+
+def linear_blend_skinning(points, joints, R_inv, T3x4, skin) -> torch.Tensor:
+    """points (N, 3), joints (K, 3), R_inv (K, 3, 3) | None, T3x4 (T, K, 3, 4), skin (N, K) -> (T, N, 3)."""
+    _need_cuda(points)
+    N, (T, K) = points.shape[0], T3x4.shape[:2]
+    out = torch.empty(T, N, 3, dtype=torch.float32, device=points.device)
+    L.call("nm_linear_blend_skinning", L.ptr(points), N, L.ptr(joints), L.ptr(R_inv), L.ptr(T3x4), L.ptr(skin), T, K,
+           L.ptr(out), L.stream())
+    return out
