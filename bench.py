@@ -207,6 +207,13 @@ def main():
         step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
 
+        # SURVEY.md §8(d) config #2 asks for the encoder-only figure next to the full forward: voxelize + VoxToKyptNet
+        # (ST branch, per-frame encoder, heat-map head, soft-argmax, Gaussian render) without decoder and losses
+        def step_encoder():
+            return det.vox_to_kypt(ops.normalize_voxelize(raw_dev, G, check=False))
+        step_encoder()
+        ms_enc = timed(step_encoder, args.steps)
+
     frames_total = world * B * T
     value = frames_total / (ms / 1e3)
     e2e = frames_total / (ms_e2e / 1e3)
@@ -257,6 +264,9 @@ def main():
         "gpu_launches_note": "C-ABI calls inside the timed region (each enqueues >= 1 of our kernels)",
         "model_tflops": world * (B * (GF_ST_CLIP + T * (GF_ENC_FRAME + GF_DEC_FRAME))) / (ms / 1e3) / 1e3
         if G == 64 else None,
+        "encoder_only": {"value": world * B * T / (ms_enc / 1e3), "unit": "frames/s", "ms_per_step": ms_enc,
+                         "workload": "voxelize + VoxToKyptNet.forward (no decoder, no losses), same clips",
+                         "model_tflops": world * B * (GF_ST_CLIP + T * GF_ENC_FRAME) / (ms_enc / 1e3) / 1e3 if G == 64 else None},
         "roofline": roof,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -151,3 +151,47 @@ class HSVRNNBVH(nn.Module):
                 gen.append(f.view(B, K, 4))
             return dict(keypoints_cond=torch.stack(cond, dim=1)[..., :4],
                         keypoints_gen=torch.stack(gen, dim=1)[..., :4])
+
+    def interpolate(self, keypoints, affinity, sample_num=32, sample_rate=10, eps=None):
+        """Key-frame interpolation with `sample_num` hypotheses — the loop the reference keeps inline in
+        `vis_interpolation.py:86-136`, on the fused step kernels (one `nm_hsvrnn_step` per frame plus one
+        `nm_hsvrnn_decode_pose` per key frame instead of ~40 module calls; no host sync inside the loop).
+        keypoints (1, T, K, 4) detected on the clip; key frames are `t % sample_rate == 0` and the last frame.
+        eps optional (T, 2, sample_num, Z): [t, 0] the posterior (key frame) / prior (in-between) draw, [t, 1] the
+        prior draw "for choosing".  Returns dict(keypoints (1, T, K, 4) with the first frame's intensities,
+        picks (n_key, 2) int64: surviving hypothesis / emitted hypothesis per key frame)."""
+        self._guard()
+        B, T, K, _ = keypoints.shape
+        if B != 1:
+            raise ValueError("interpolate works on one clip (the reference's loop expands it to sample_num hypotheses)")
+        dev = keypoints.device
+        self._ensure_skeleton(affinity)
+        order, parents = self._tree(dev)
+        Z, S = self.nlatent_kypt, int(sample_num)
+        with torch.no_grad():
+            kp = keypoints.float().contiguous()
+            w = ops.hsvrnn_weight_struct(self)
+            offset = ops.hsvrnn_bone_offsets(kp, parents, ops.f32(self, "offset_param")).expand(S, -1, -1).contiguous()
+            h = self.init_kypt_rnn_state.detach().float().expand(S, -1).contiguous()
+            selected, pending, picks = [], [], []
+            for t in range(T):
+                kp_flat = kp[:, t].reshape(1, -1).expand(S, -1).contiguous()
+                e = eps[t].float() if eps is not None else torch.randn(2, S, Z, device=dev)
+                if t % sample_rate == 0 or t == T - 1:
+                    h_new, f, _, _, _, prior = ops.hsvrnn_step(w, h, kp_flat, e[0:1].contiguous(), offset, order, parents,
+                                                               K, True, want_prior=True)
+                    zc = prior[:, :Z] + prior[:, Z:] * e[1]
+                    fc, _ = ops.hsvrnn_decode_pose(w, torch.cat([h, zc], dim=-1).contiguous(), offset, order, parents, K)
+                    i = (f - kp_flat).pow(2).sum(dim=-1).argmin()
+                    j = (fc - f[i][None]).pow(2).sum(dim=-1).argmin()
+                    h = h_new[i][None].expand(S, -1).contiguous()      # GRU(cat[f_i, z_i], h_i) == the collapsed update
+                    pending.append(kp_flat)
+                    selected += [s[j].view(K, 4) for s in pending]
+                    pending = []
+                    picks.append(torch.stack([i, j]))
+                else:
+                    h, f, *_ = ops.hsvrnn_step(w, h, None, e[0].contiguous(), offset, order, parents, K, False)
+                    pending.append(f)
+            sel = torch.stack(selected, dim=0)[None].clone()
+            sel[0, :, :, -1] = sel[0, 0, :, -1]
+            return dict(keypoints=sel, picks=torch.stack(picks, dim=0))

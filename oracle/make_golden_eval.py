@@ -115,6 +115,52 @@ alt = np.einsum('nk,tkij,kjl,nl->tni', ref_w.astype(np.float64), M, Binv, ph)[..
 assert np.abs(alt - lbs).max() <= 1e-9
 report["fk_lbs"] = "oracle == homogeneous-matrix formulation (<= 1e-9)"
 
+# ---- key-frame interpolation: the loop of vis_interpolation.py:86-135 executed verbatim on the reference network ----
+import pickle           # noqa: E402
+import textwrap         # noqa: E402
+from torch.distributions import Normal   # noqa: E402
+from model.neural_marionette import NeuralMarionette   # noqa: E402  (the reference)
+
+opt = pickle.load(open(os.path.join(REF, "pretrained/aist/opt.pickle"), "rb"))
+hp = O.default_hparams()
+sd = O.synthetic_state_dict(hp, seed=21)
+network = NeuralMarionette(opt).eval()
+network.anneal(1)
+network.load_state_dict(sd, strict=True)
+Ti, sample_num, sample_rate, Z = 12, 16, 5, hp.nlatent_kypt
+gk = torch.Generator().manual_seed(7)
+ikp = torch.cat([torch.rand(1, Ti, 24, 3, generator=gk) * 1.2 - 0.6, torch.rand(1, Ti, 24, 1, generator=gk)], dim=-1)
+ikp = ikp + 0.02 * torch.arange(Ti).float()[None, :, None, None]
+ieps = torch.randn(Ti, 2, sample_num, Z, generator=gk)
+queue = []
+for t in range(Ti):
+    queue += [ieps[t, 0], ieps[t, 1]] if (t % sample_rate == 0 or t == Ti - 1) else [ieps[t, 0]]
+
+
+class QueuedNormal(Normal):
+    """Normal whose rsample() consumes the injected draws: loc + eps * scale is what Normal.rsample computes."""
+    def rsample(self, sample_shape=torch.Size()):
+        return self.loc + queue.pop(0) * self.scale
+
+
+lines = open(os.path.join(REF, "vis_interpolation.py")).read().split("\n")[85:136]     # :86-136
+assert lines[0].strip().startswith("_ = network.dyna_module.encode") and "selected_keypoints[0, :, :, -1]" in lines[-1]
+ns = dict(network=network, torch=torch, Normal=QueuedNormal, keypoints=ikp.clone(), T=Ti, K=24, sample_num=sample_num,
+          sample_rate=sample_rate)
+with torch.no_grad():
+    ns["affinity"] = network.kypt_detector.get_affinity()
+    exec(textwrap.dedent("\n".join(lines)), ns)
+    assert not queue
+    skeleton = (network.dyna_module.A, network.dyna_module.priority, network.dyna_module.parents)
+    ora_sel, picks = O.dyna_interpolate(ikp, skeleton, sd, hp, sample_num, sample_rate, ieps)
+d = float((ns["selected_keypoints"] - ora_sel).abs().max())
+assert d <= 5e-6, d
+report["interpolation"] = "oracle vs reference loop max |diff| = %.2e (T=%d, %d hypotheses, key frames every %d), picks %s" % (
+    d, Ti, sample_num, sample_rate, picks)
+np.savez_compressed(os.path.join(GOLD, "interpolation.npz"), seed=21, kp=ikp.numpy(), eps=ieps.numpy(),
+                    sample_num=sample_num, sample_rate=sample_rate, selected=ns["selected_keypoints"].numpy(),
+                    picks=np.array(picks))
+
 np.savez_compressed(
     os.path.join(GOLD, "eval_retarget.npz"),
     vc_soft=soft.numpy().astype(np.float16), vc_seeds=np.array([300, T, 4000, G, B]),

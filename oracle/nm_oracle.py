@@ -695,6 +695,49 @@ def dyna_generate(keypoints_cond, skeleton, sd, hp, Ttot, Tcond, eps_cond=None, 
                 h_last=h)
 
 
+def dyna_interpolate(keypoints, skeleton, sd, hp, sample_num, sample_rate, eps, prefix="dyna_module"):
+    """vis_interpolation.py:90-137 — key-frame interpolation with ``sample_num`` hypotheses: at key frames
+    (``t % sample_rate == 0`` or the last frame) every hypothesis draws one posterior sample, the one nearest to the
+    detected keypoints survives (state, latent and pose collapse onto it) and the pending in-between poses of the
+    hypothesis whose *prior* sample lands nearest to it are emitted; between key frames the prior is rolled out.
+    keypoints (1, T, K, 4); eps (T, 2, sample_num, Z) replaces the rsample draws in call order ([t, 0]: posterior at
+    key frames / prior otherwise, [t, 1]: the prior draw "for choosing").  Returns (selected (1, T, K, 4), picks)."""
+    _, T, K, _ = keypoints.shape
+    _, priority, parents = skeleton
+    order = priority.indices
+    h = sd[prefix + ".init_kypt_rnn_state"].expand(sample_num, -1)                           # :90
+    offset = bone_offsets(keypoints, parents, sd, prefix).expand(sample_num, -1, -1, -1)     # :91
+    selected, pending, picks = [], [], []
+    for t in range(T):
+        kp_flat = keypoints[:, t].reshape(1, -1).expand(sample_num, -1)                      # :96-97
+        if t % sample_rate == 0 or t == T - 1:
+            qm, qs = _mlp(torch.cat([h, kp_flat], dim=-1), sd, prefix + ".extract_post_dist").chunk(2, dim=-1)
+            qs = _softplus_std(qs)
+            pm, ps = prior_params(h, sd, prefix)
+            z = qm + qs * eps[t, 0]                                                          # :106
+            zc = pm + ps * eps[t, 1]                                                         # :108
+            f, _ = decode_pose(torch.cat([h, z], dim=-1), offset, order, parents, sd, K, prefix)
+            fc, _ = decode_pose(torch.cat([h, zc], dim=-1), offset, order, parents, sd, K, prefix)
+            i = (f - kp_flat).pow(2).sum(dim=-1).argmin()                                    # :111-112
+            f = f[i][None].expand(sample_num, -1)
+            z = z[i][None].expand(sample_num, -1)
+            h = h[i][None].expand(sample_num, -1)
+            j = (fc - f).pow(2).sum(dim=-1).argmin()                                         # :116-117
+            pending.append(kp_flat)
+            selected += [s[j].view(K, 4) for s in pending]                                   # :118-120
+            pending = []
+            picks.append((int(i), int(j)))
+        else:
+            pm, ps = prior_params(h, sd, prefix)
+            z = pm + ps * eps[t, 0]
+            f, _ = decode_pose(torch.cat([h, z], dim=-1), offset, order, parents, sd, K, prefix)
+            pending.append(f)                                                                # :129
+        h = gru_cell(torch.cat([f, z], dim=-1), h, sd, prefix + ".kypt_rnn_cell")            # :131-132
+    sel = torch.stack(selected, dim=0)[None].clone()
+    sel[0, :, :, -1] = sel[0, 0, :, -1]                                                      # :135
+    return sel, picks
+
+
 # ----------------------------------------------------------------------------
 # C11 façade: NeuralMarionette.forward / generate
 # ----------------------------------------------------------------------------

@@ -478,3 +478,21 @@ def test_dynamics_large_batch_matches_small():
         small = net.dyna_module.generate(kp[:40], aff, Ttot=4, Tcond=2, eps_cond=ec[:, :, :40].contiguous(),
                                          eps_gen=eg[:, :40].contiguous())
     assert (big["keypoints_gen"][:40] - small["keypoints_gen"]).abs().max() < 1e-5
+
+
+def test_dynamics_interpolation_golden(golden_dir):
+    """Key-frame interpolation (vis_interpolation.py:86-136) against the reference's own loop (tests/golden/interpolation.npz)."""
+    z = np.load(os.path.join(golden_dir, "interpolation.npz"))
+    net, sd, hp = _dyna_setup(int(z["seed"]))
+    kp = torch.from_numpy(z["kp"]).cuda()
+    with torch.no_grad():
+        aff = net.kypt_detector.get_affinity()
+        out = net.dyna_module.interpolate(kp, aff, sample_num=int(z["sample_num"]), sample_rate=int(z["sample_rate"]),
+                                          eps=torch.from_numpy(z["eps"]).cuda())
+    assert out["picks"].cpu().tolist() == z["picks"].tolist()
+    assert out["keypoints"].shape == z["selected"].shape
+    assert (out["keypoints"].cpu() - torch.from_numpy(z["selected"])).abs().max() < 5e-4
+    # key frames return the detected keypoints themselves (with frame 0's intensities)
+    assert torch.equal(out["keypoints"][0, 0, :, :3], kp[0, 0, :, :3])
+    with pytest.raises(ValueError):
+        net.dyna_module.interpolate(kp.repeat(2, 1, 1, 1), aff)

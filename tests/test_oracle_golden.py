@@ -174,3 +174,15 @@ def test_c_oracle_edge_cases():
     # extra columns (normals) are ignored, utils/dataset_utils.py:27
     q = np.concatenate([p, np.ones((len(p), 3))], 1)
     assert np.array_equal(C.voxelize(q, 8), g[None])
+
+
+def test_interpolation_fixture(golden_dir):
+    """oracle.dyna_interpolate replays the reference's vis_interpolation.py loop (fixture written from the reference)."""
+    z = np.load(os.path.join(golden_dir, "interpolation.npz"))
+    hp = O.default_hparams()
+    sd = O.synthetic_state_dict(hp, seed=int(z["seed"]))
+    skeleton = O.skeleton_from_affinity(O.get_affinity(sd, hp))
+    sel, picks = O.dyna_interpolate(torch.from_numpy(z["kp"]), skeleton, sd, hp, int(z["sample_num"]), int(z["sample_rate"]),
+                                    torch.from_numpy(z["eps"]))
+    assert [list(p) for p in picks] == z["picks"].tolist()
+    assert (sel - torch.from_numpy(z["selected"])).abs().max() <= 5e-6
