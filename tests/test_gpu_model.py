@@ -186,3 +186,50 @@ def test_stress_resolution_g128_vs_oracle():
         rec = net.kypt_detector.kypt_to_vox.decode(net.kypt_detector.vox_to_kypt.detect(vox)["first_feature_act"],
                                                    vox[:, 0], keypoints=kp[:, :1], sigma=1.5)
     assert rec.shape == (1, 1, 1, G, G, G) and bool(torch.isfinite(rec).all())
+
+
+def test_full_size_config2_properties():
+    """BASELINE.json configs[1] at its full size (64 clips x 20 frames x 20 000 points, grid 64^3) through
+    size-independent properties: occupancy bit-exact against the oracle on every distinct clip; duplicated clips give
+    identical bits wherever they sit in the batch (clips are independent: GroupNorm is per sample, reductions have a
+    fixed order); permuting the clips permutes the outputs; value ranges of the reference's definitions; one clip
+    checked against the CPU oracle within the north-star tolerances."""
+    import neural_marionette_b200 as nm
+    G, B, T, N, D = 64, 64, 20, 20000, 4
+    hp = O.default_hparams(grid_size=G)
+    net, sd = build(hp, 47)
+    distinct = np.stack([O.synthetic_clip(7000 + d, T, N) for d in range(D)], 0)
+    owner = np.array([(3 * b + b // 7) % D for b in range(B)])              # duplicates spread over both 32-clip passes
+    raw = distinct[owner]
+    vox = nm.voxelize_raw_clips(raw, G)
+    assert vox.shape == (B, T, 1, G, G, G)
+    ref_vox = np.stack([O.voxelize_clip(O.episodic_normalization(distinct[d]), G) for d in range(D)], 0)
+    first = [int(np.argmax(owner == d)) for d in range(D)]
+    for d in range(D):
+        assert np.array_equal(vox[first[d]].cpu().numpy(), ref_vox[d])      # bit-exact occupancy
+    assert torch.equal(vox, vox[torch.as_tensor(first)][torch.as_tensor(owner)])
+    with torch.no_grad():
+        out = net.kypt_detector(vox)
+        kp, hm, rec = out["keypoints"], out["heatmaps"], out["recon"]
+        assert kp.shape == (B, T, 24, 4) and hm.shape == (B, T, 24, 16, 16, 16) and rec.shape == vox.shape
+        # value ranges: soft-argmax coordinates inside the cube, intensities in (0, 1], Softplus heat-maps > 0, sigmoid
+        assert float(kp[..., :3].abs().max()) < 1.0 and float(kp[..., 3].min()) > 0.0 and float(kp[..., 3].max()) <= 1.0
+        assert float(kp[..., 3].amax(dim=-1).min()) > 0.999                 # the brightest keypoint of a frame has I ~ 1
+        assert float(hm.min()) > 0.0 and float(rec.min()) >= 0.0 and float(rec.max()) <= 1.0
+        assert all(bool(torch.isfinite(out[k]).all()) for k in ("recon_loss", "vol_fit_reg", "separation_loss",
+                                                                 "sparsity_loss", "graph_traj_loss"))
+        # duplicates: identical bits for every copy of a clip
+        rep = torch.as_tensor(first, device=kp.device)[torch.as_tensor(owner, device=kp.device)]
+        for key in ("keypoints", "heatmaps", "first_feature"):
+            assert torch.equal(out[key], out[key][rep]), key
+        assert torch.equal(rec[40:], rec[rep[40:]])
+        # permutation equivariance
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(3)).cuda()
+        out_p = net.kypt_detector(vox[perm].contiguous())
+        assert torch.equal(out_p["keypoints"], kp[perm]) and torch.equal(out_p["heatmaps"], hm[perm])
+        # one full clip against the CPU oracle (north-star tolerances)
+        ref = O.detector_forward(torch.from_numpy(ref_vox[0])[None], sd, hp)
+    b0 = first[0]
+    assert (kp[b0].cpu() - ref["keypoints"][0]).abs().max() <= KP_TOL
+    assert float((hm[b0].cpu() - ref["heatmaps"][0]).abs().max() / ref["heatmaps"].max()) <= HM_TOL
+    assert (rec[b0].cpu() - ref["recon"][0]).abs().mean() <= 5e-3
