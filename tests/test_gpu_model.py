@@ -233,3 +233,35 @@ def test_full_size_config2_properties():
     assert (kp[b0].cpu() - ref["keypoints"][0]).abs().max() <= KP_TOL
     assert float((hm[b0].cpu() - ref["heatmaps"][0]).abs().max() / ref["heatmaps"].max()) <= HM_TOL
     assert (rec[b0].cpu() - ref["recon"][0]).abs().mean() <= 5e-3
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """`graph.capture_detector*`: the captured launch sequence replays to the same bits as the eager call, also on a
+    different input of the same shape (config #1 shape is launch-bound; the graph removes the launch gaps)."""
+    from neural_marionette_b200 import graph as NG
+    import neural_marionette_b200 as nm
+    G, B, T = 32, 1, 4
+    hp = O.default_hparams(grid_size=G)
+    net, _ = build(hp, 53)
+    det = net.kypt_detector
+    raw_a = torch.from_numpy(O.synthetic_clip(8100, T, 20000))[None].cuda()
+    raw_b = torch.from_numpy(O.synthetic_clip(8101, T, 20000))[None].cuda()
+    vox_a, vox_b = (nm.voxelize_raw_clips(r, G) for r in (raw_a, raw_b))
+    with torch.no_grad():
+        eager_a, eager_b = det(vox_a), det(vox_b)
+    cap = NG.capture_detector(det, vox_a)
+    for vox, eager in ((vox_a, eager_a), (vox_b, eager_b), (vox_a, eager_a)):
+        got = cap(vox)
+        for key in ("keypoints", "heatmaps", "recon", "first_feature", "recon_loss", "vol_fit_reg", "sparsity_loss",
+                    "graph_traj_loss"):
+            assert torch.equal(got[key], eager[key]), key
+    cap2 = NG.capture_detector_from_points(det, raw_a, G)
+    got = cap2(raw_b)
+    assert torch.equal(got["voxel"], vox_b) and torch.equal(got["keypoints"], eager_b["keypoints"])
+    assert torch.equal(got["recon"], eager_b["recon"])
+    with pytest.raises(ValueError):
+        cap(vox_a[:, :2])
+    # eager calls still work after captures (scratch buffers are per stream)
+    with torch.no_grad():
+        again = det(vox_b)
+    assert torch.equal(again["keypoints"], eager_b["keypoints"])
