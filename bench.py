@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--cpu-baseline-frames", type=int, default=20,
                     help="frames of the ONE clip the CPU arm processes per step (default = a full clip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="detector", choices=["detector", "generate"],
+                    help="detector = configs[1] (default, the headline); generate = configs[2] shape: "
+                         "NeuralMarionette.generate (detector on Tcond frames + HSVRNN roll-out + decode of the rest)")
     return ap.parse_args()
 
 
@@ -110,8 +113,11 @@ def cpu_reference_run(args, steps, warmup, frames):
         for i in range(warmup + steps):
             t0 = time.perf_counter()
             vox = torch.from_numpy(O.voxelize_clip(O.episodic_normalization(raw), args.grid))[None]
-            out = O.detector_forward(vox, sd, hp)
-            float(out["recon_loss"])
+            if args.workload == "generate":
+                float(O.marionette_generate(vox, sd, hp)["gen"][:, -1].mean())
+            else:
+                out = O.detector_forward(vox, sd, hp)
+                float(out["recon_loss"])
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
@@ -132,6 +138,11 @@ def main():
                            "statistics / heads / losses",
               "parallelism": f"clip-sharded x{world}, no data-path collective"}
 
+    if args.workload == "generate":
+        Tc = 5   # opt.pickle / dataset/config.py:55-56 (oracle.default_hparams().Tcond)
+        config["workload"] = (f"NeuralMarionette.generate (voxelize + detector on Tcond={Tc} frames + {T}-step HSVRNN "
+                              f"roll-out + decode of the {T - Tc} generated frames) on {B} synthetic clips x {T} frames "
+                              f"x {N} pts per GPU, grid {G}^3, K=24")
     if args.impl == "reference":
         if rank != 0:
             return
@@ -143,7 +154,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config,
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                             "sample": f"1 clip x {frames} frames per step (voxelize + detector forward; same per-frame work "
+                             "sample": f"1 clip x {frames} frames per step (voxelize + {args.workload}; same per-frame work "
                                        f"as the GPU arm)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -179,6 +190,17 @@ def main():
         out = det(vox)
         kp = out["keypoints"].cpu()
         return kp, float(out["recon_loss"])
+
+    if args.workload == "generate":
+        act = {"detector": True, "learner": True}
+        with torch.no_grad():
+            net(ops.normalize_voxelize(raw_dev[:2], G, check=False), act)      # builds the skeleton once, as the reference requires
+        def step_resident():  # noqa: F811
+            return net.generate(ops.normalize_voxelize(raw_dev, G, check=False), act)
+
+        def step_e2e():  # noqa: F811
+            out = net.generate(ops.normalize_voxelize(raw_host.to(dev, non_blocking=True), G, check=False), act)
+            return out["keypoints"].cpu(), float(out["gen"][:, -1].mean())
 
     from neural_marionette_b200.parallel import barrier, max_over_ranks
 
@@ -262,8 +284,10 @@ def main():
                 "d2h_bytes_per_step": int(B * T * 24 * 4 * 4 + 4), "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "gpu_launches_note": "C-ABI calls inside the timed region (each enqueues >= 1 of our kernels)",
-        "model_tflops": world * (B * (GF_ST_CLIP + T * (GF_ENC_FRAME + GF_DEC_FRAME))) / (ms / 1e3) / 1e3
-        if G == 64 else None,
+        "model_tflops": (world * (B * (GF_ST_CLIP + T * (GF_ENC_FRAME + GF_DEC_FRAME))) / (ms / 1e3) / 1e3
+                         if args.workload == "detector" else
+                         world * B * (GF_ST_CLIP + hp.Tcond * (GF_ENC_FRAME + GF_DEC_FRAME) + (T - hp.Tcond) * GF_DEC_FRAME)
+                         / (ms / 1e3) / 1e3) if G == 64 else None,
         "encoder_only": {"value": world * B * T / (ms_enc / 1e3), "unit": "frames/s", "ms_per_step": ms_enc,
                          "workload": "voxelize + VoxToKyptNet.forward (no decoder, no losses), same clips",
                          "model_tflops": world * B * (GF_ST_CLIP + T * GF_ENC_FRAME) / (ms_enc / 1e3) / 1e3 if G == 64 else None},
@@ -272,7 +296,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         fps, t, cores = cpu_reference_run(args, 2, 1, args.cpu_baseline_frames)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                "sample": f"1 clip x {args.cpu_baseline_frames} frames (voxelize + detector forward), "
+                                "sample": f"1 clip x {args.cpu_baseline_frames} frames (voxelize + {args.workload}), "
                                           f"1 warm-up + 2 timed reps of {t:.1f} s; same per-frame work as the GPU arm"}
     if rank == 0:
         print(json.dumps(line))

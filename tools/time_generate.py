@@ -31,3 +31,7 @@ with torch.no_grad():
     gen_kp = net.dyna_module.generate(kp, aff, Ttot=T, Tcond=5)["keypoints_gen"]
     print("decode_from_dyna (15) %.1f ms" % timeit(lambda: net.kypt_detector.decode_from_dyna(gen_kp, det["first_feature"], vox[:, 0])))
     print("dyna.encode T=20      %.1f ms" % timeit(lambda: net.dyna_module.encode(net.kypt_detector(vox)["keypoints"] if False else kp.repeat(1, 4, 1, 1), aff)))
+    # key-frame interpolation (vis_interpolation.py shape: T = 21, key frames every 10) with many hypotheses
+    kp21 = kp[:1].repeat(1, 5, 1, 1)[:, :21].contiguous()
+    for S in (32, 512, 4096):
+        print("dyna.interpolate T=21 S=%-5d %.2f ms" % (S, timeit(lambda: net.dyna_module.interpolate(kp21, aff, sample_num=S, sample_rate=10))))
