@@ -223,6 +223,23 @@ def can_conv_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d) -> bool:
         bool(L.query("nm_conv3d_up2x_supported", n, 2 * D, 2 * H, 2 * W, Cin, conv.out_channels))
 
 
+def conv3d_input_grad(grad_out: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
+    """dL/dx of a stride-1 "same" Conv3d (k = 1 or 3): the conv of dL/dy with the spatially flipped taps and the
+    in / out channels swapped - it runs on the forward tensor-core kernels (first brick of the config #4 backward;
+    DESIGN.md §7).  grad_out act (n, D, H, W, Cout) -> act (n, D, H, W, Cin)."""
+    k = conv.kernel_size[0]
+    if conv.stride[0] != 1 or k not in (1, 3) or conv.padding[0] != (k - 1) // 2 or conv.groups != 1:
+        raise NotImplementedError("conv3d_input_grad: stride-1 'same' convolutions with k in (1, 3) only")
+
+    def build():
+        mirror = torch.nn.Conv3d(conv.out_channels, conv.in_channels, k, stride=1, padding=(k - 1) // 2, bias=True)
+        mirror = mirror.to(conv.weight.device).requires_grad_(False)
+        mirror.weight.copy_(conv.weight.detach().flip(2, 3, 4).transpose(0, 1))
+        mirror.bias.zero_()
+        return mirror
+    return conv3d(grad_out, _cached(conv, "dgrad_mirror", [conv.weight], build))
+
+
 def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
     """conv3d_k3(upsample2x_trilinear(act(x_lo*scale+shift))) without materialising the up-sampled tensor.
     x_lo act (n, D, H, W, Cin) -> raw (n, 2D, 2H, 2W, Cout) [, GroupNorm scale, shift]."""

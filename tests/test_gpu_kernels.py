@@ -496,3 +496,25 @@ def test_dynamics_interpolation_golden(golden_dir):
     assert torch.equal(out["keypoints"][0, 0, :, :3], kp[0, 0, :, :3])
     with pytest.raises(ValueError):
         net.dyna_module.interpolate(kp.repeat(2, 1, 1, 1), aff)
+
+
+@pytest.mark.parametrize("n,grid,cin,cout,k", [(1, 32, 64, 32, 3), (2, 16, 32, 32, 3), (1, 16, 128, 64, 3),
+                                              (2, 16, 64, 64, 3), (1, 16, 32, 64, 1)])
+def test_conv3d_input_grad(ops, n, grid, cin, cout, k):
+    """dL/dx of the decoder / encoder conv shapes on the forward tensor-core kernels (flipped, transposed weights)
+    against torch.nn.grad.conv3d_input on the CPU (fp16-rounded operands, fp32 accumulation)."""
+    g = torch.Generator().manual_seed(grid + cin + 7 * cout + k)
+    conv = torch.nn.Conv3d(cin, cout, k, 1, (k - 1) // 2)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (cout * k ** 3) ** 0.5)
+    gy = torch.randn(n, cout, grid, grid, grid, generator=g)
+    ref = torch.nn.grad.conv3d_input((n, cin, grid, grid, grid), conv.weight.detach().half().float(), gy.half().float(),
+                                     padding=(k - 1) // 2)
+    conv = conv.cuda()
+    got = from_act(ops.conv3d_input_grad(to_act(gy), conv))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 2e-3
+    # the mirrored weights follow an in-place update of the parameter (optimizer step)
+    with torch.no_grad():
+        conv.weight.mul_(2.0)
+    assert rel_err(from_act(ops.conv3d_input_grad(to_act(gy), conv)), 2 * ref) < 2e-3
