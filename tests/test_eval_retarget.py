@@ -161,3 +161,22 @@ def test_gpu_skin_weights_invalid_root_raises():
     with pytest.raises(RuntimeError):
         RT.extract_skin_weights(kp, Priority(None, torch.tensor([0, 1, 2, 3])), torch.tensor([0, 0, 0, 2]),
                                 np.random.rand(10, 3).astype(np.float32), kp)
+
+
+def test_evaluate_final_matches_reference_arithmetic(tmp_path):
+    """utils/eval_utils.py:12-27: pure host arithmetic (the CSV files go to <result_dir>/semantic|chamfer)."""
+    from neural_marionette_b200.utils import eval_utils as U
+    rng = np.random.default_rng(0)
+    counts = rng.integers(0, 50, size=(17, 24)).astype(np.float64)
+    counts[:, 0] += 1
+    counts *= 600.0 / counts.sum(1, keepdims=True)            # every gt joint was matched in the same number of frames
+    want = (counts / counts[0].sum()).max(axis=-1)
+    got = U.evaluate_final("semantic", {"semantic": counts.copy()}, result_dir=str(tmp_path))
+    assert got == want.mean()
+    assert np.allclose(np.loadtxt(tmp_path / "semantic" / "semantic_result.csv", delimiter=","), want)
+    per_clip = [[0.0012], [0.0034], [0.0005]]
+    got = U.evaluate_final("voxel_chamfer", {"voxel_chamfer": per_clip}, result_dir=str(tmp_path))
+    assert got == np.array(per_clip).mean() * 1e4
+    assert np.allclose(np.loadtxt(tmp_path / "chamfer" / "chamfer_result.csv", delimiter=","), np.array(per_clip)[:, 0])
+    with pytest.raises(ValueError):
+        U.evaluate_final("nope", {})
