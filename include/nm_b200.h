@@ -222,6 +222,16 @@ int nm_retarget_fk(const float* R, const float* offset, const float* root_pos, c
 int nm_linear_blend_skinning(const float* points, int N, const float* joints, const float* R_inv, const float* T3x4,
                              const float* skin, int T, int K, float* out, void* stream);
 
+/* ---- config #4 backward, first bricks --------------------------------------------------
+ * Weight gradient of a stride-1 3x3x3 "same" Conv3d (what autograd computes for vox_modules.py:8-47 /
+ * kypt_detector.py:417-460 layers): x act (n, D, H, W, Cin), grad_out act (n, D, H, W, Cout) ->
+ * dw (Cout, Cin, 3, 3, 3) fp32 in the nn.Conv3d weight layout, fully overwritten.  Cin, Cout multiples of 32 (<= 256),
+ * W in {16, 32, 48, 64}.  First version on mma.sync with a fixed-order split-K reduction (bit-reproducible).
+ * (The data gradient needs no entry point of its own: it is nm_conv3d_tc with flipped, transposed weights.) */
+size_t nm_conv3d_k3_wgrad_workspace_bytes(int n, int D, int H, int W, int Cin, int Cout);
+int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int n, int D, int H, int W, int Cin, int Cout, float* dw,
+                       void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,8 @@ PROTOTYPES = {
     "nm_skin_weights": (_i, [_vp, _i, _vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp, _vp]),
     "nm_retarget_fk": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "nm_linear_blend_skinning": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "nm_conv3d_k3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_k3_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib = None

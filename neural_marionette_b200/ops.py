@@ -240,6 +240,21 @@ def conv3d_input_grad(grad_out: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Te
     return conv3d(grad_out, _cached(conv, "dgrad_mirror", [conv.weight], build))
 
 
+def conv3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """dL/dW of a stride-1 3x3x3 "same" Conv3d: x act (n, D, H, W, Cin), grad_out act (n, D, H, W, Cout) ->
+    (Cout, Cin, 3, 3, 3) fp32 (the nn.Conv3d weight layout).  First version (mma.sync, fixed-order split-K)."""
+    _need_cuda(x, grad_out)
+    n, D, H, W, Cin = x.shape
+    Cout = grad_out.shape[-1]
+    assert grad_out.shape[:4] == x.shape[:4] and x.dtype == ACT_DTYPE and grad_out.dtype == ACT_DTYPE
+    assert x.is_contiguous() and grad_out.is_contiguous()
+    nbytes = L.query("nm_conv3d_k3_wgrad_workspace_bytes", n, D, H, W, Cin, Cout)
+    dw = torch.empty(Cout, Cin, 3, 3, 3, dtype=torch.float32, device=x.device)
+    ws = workspace(max(nbytes, 16), x.device, "wgrad")
+    L.call("nm_conv3d_k3_wgrad", L.ptr(x), L.ptr(grad_out), n, D, H, W, Cin, Cout, L.ptr(dw), L.ptr(ws), L.stream())
+    return dw
+
+
 def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
     """conv3d_k3(upsample2x_trilinear(act(x_lo*scale+shift))) without materialising the up-sampled tensor.
     x_lo act (n, D, H, W, Cin) -> raw (n, 2D, 2H, 2W, Cout) [, GroupNorm scale, shift]."""

@@ -518,3 +518,20 @@ def test_conv3d_input_grad(ops, n, grid, cin, cout, k):
     with torch.no_grad():
         conv.weight.mul_(2.0)
     assert rel_err(from_act(ops.conv3d_input_grad(to_act(gy), conv)), 2 * ref) < 2e-3
+
+
+@pytest.mark.parametrize("n,grid,cin,cout", [(1, 32, 64, 32), (2, 16, 32, 32), (1, 16, 128, 64), (3, 16, 64, 64),
+                                            (1, 64, 32, 32)])
+def test_conv3d_weight_grad(ops, n, grid, cin, cout):
+    """dL/dW of the stride-1 k3 convs against torch.nn.grad.conv3d_weight on the CPU (fp16-rounded operands, fp32
+    accumulation: K = n * grid^3 products per weight -> tolerance relative to the largest gradient entry)."""
+    g = torch.Generator().manual_seed(3 * grid + cin + 11 * cout)
+    x = torch.randn(n, cin, grid, grid, grid, generator=g)
+    gy = torch.randn(n, cout, grid, grid, grid, generator=g) / grid ** 1.5
+    ref = torch.nn.grad.conv3d_weight(x.half().float(), (cout, cin, 3, 3, 3), gy.half().float(), padding=1)
+    got = ops.conv3d_weight_grad(to_act(x), to_act(gy)).cpu()
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < 1e-3
+    assert torch.equal(got, ops.conv3d_weight_grad(to_act(x), to_act(gy)).cpu())      # fixed-order split-K
+    with pytest.raises(Exception):
+        ops.conv3d_weight_grad(to_act(x[:, :24]), to_act(gy))                          # Cin not a multiple of 32
