@@ -231,6 +231,14 @@ int nm_linear_blend_skinning(const float* points, int N, const float* joints, co
 size_t nm_conv3d_k3_wgrad_workspace_bytes(int n, int D, int H, int W, int Cin, int Cout);
 int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int n, int D, int H, int W, int Cin, int Cout, float* dw,
                        void* workspace, void* stream);
+/* Backward of z = LeakyReLU_0.01(GroupNorm(x)) (leaky != 0) or of GroupNorm alone (modules/vox_modules.py:8-75 under
+ * autograd): x, grad_out (= dL/dz), grad_in (= dL/dx) act (n, S, C) fp16; gamma, beta (C) fp32; dgamma, dbeta (C) fp32
+ * (optional), summed over the n samples.  C in {8, 16, ..., 256}, channels per group a multiple of 8.  Statistics are
+ * recomputed from x (three passes, fixed-order reductions: bit-reproducible). */
+size_t nm_groupnorm_backward_workspace_bytes(int n, int C, int groups);
+int nm_groupnorm_backward(const void* x, const void* grad_out, const float* gamma, const float* beta, int n, long long S,
+                          int C, int groups, float eps, int leaky, void* grad_in, float* dgamma, float* dbeta,
+                          void* workspace, void* stream);
 
 #ifdef __cplusplus
 }

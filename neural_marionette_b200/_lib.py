@@ -88,6 +88,8 @@ PROTOTYPES = {
     "nm_linear_blend_skinning": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "nm_conv3d_k3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "nm_conv3d_k3_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "nm_groupnorm_backward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "nm_groupnorm_backward": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _lib = None

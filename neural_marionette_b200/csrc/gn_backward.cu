@@ -1,0 +1,222 @@
+// Backward of z = LeakyReLU_0.01(GroupNorm(x)) (or of GroupNorm alone) on channels-last fp16 tensors - config #4 backward,
+// first version: three HBM passes, every reduction in a fixed order (fp32 partials per (sample, chunk,
+// channel), fp64 finalize) -> bit-reproducible.
+//   pass A: per (sample, channel) sum x, sum x^2                 -> mean, rstd per (sample, group)
+//   pass B: dy = dz * (y > 0 ? 1 : 0.01), y = gamma * xhat + beta -> per (sample, channel) sum dy, sum dy * x
+//           -> dbeta, dgamma (summed over samples in order) and the two group means of the input gradient
+//   pass C: dx = rstd * (gamma * dy - m1 - xhat * m2)
+// Reference semantics: torch.autograd through nn.GroupNorm + nn.LeakyReLU (modules/vox_modules.py:8-75).
+#include "common.cuh"
+#include "../../include/nm_b200.h"
+
+namespace {
+
+constexpr int kGnbThreads = 256;
+constexpr int kGnbChunks = 32;                 // CTAs per sample in the reduction passes
+
+struct GnbShape {
+  int n, C, groups, cpg, ccs, nvl;             // ccs = C / 8 channel chunks, nvl = voxel lanes per CTA
+  long long S;
+};
+
+// Block-level fixed-order reduction of per-thread partials v[16] (8 channels x 2 quantities): thread (vl, cc) holds the
+// partial of channel chunk cc over its voxels; the result for chunk cc is the sum over vl = 0 .. nvl-1 in that order.
+__device__ __forceinline__ void gnb_block_reduce(const float* v, float* red, const GnbShape& s, float* out /* [C][2] */) {
+  const int cc = threadIdx.x % s.ccs, vl = threadIdx.x / s.ccs;
+#pragma unroll
+  for (int i = 0; i < 16; i++) red[(vl * s.ccs + cc) * 16 + i] = v[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < s.ccs * 16; i += kGnbThreads) {
+    const int c2 = i / 16, q = i % 16;         // q = channel-in-chunk * 2 + quantity
+    float acc = 0.f;
+    for (int l = 0; l < s.nvl; l++) acc += red[(l * s.ccs + c2) * 16 + q];
+    out[(c2 * 8 + (q >> 1)) * 2 + (q & 1)] = acc;
+  }
+}
+
+// pass A (stats == true): partial[n][chunk][c] = (sum x, sum x^2)
+// pass B (stats == false): partial[n][chunk][c] = (sum dy, sum dy * x), dy masked by the LeakyReLU derivative
+template <bool kStats>
+__global__ void __launch_bounds__(kGnbThreads)
+gnb_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, const float* __restrict__ mean_rstd, GnbShape s, int leaky,
+                  float* __restrict__ partial) {
+  __shared__ float red[kGnbThreads * 16];
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int cc = threadIdx.x % s.ccs, vl = threadIdx.x / s.ccs;
+  const long long per = (s.S + kGnbChunks - 1) / kGnbChunks;
+  const long long v0 = chunk * per, v1 = min(s.S, v0 + per);
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc[i] = 0.f;
+  float g[8], b[8], mu = 0.f, rs = 0.f;
+  if (!kStats) {
+    const int grp = (cc * 8) / s.cpg;          // cpg is a multiple of 8 (checked by the host): one group per chunk
+    mu = mean_rstd[(n * s.groups + grp) * 2];
+    rs = mean_rstd[(n * s.groups + grp) * 2 + 1];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { g[i] = gamma[cc * 8 + i]; b[i] = beta[cc * 8 + i]; }
+  }
+  for (long long v = v0 + vl; v < v1; v += s.nvl) {
+    const long long off = ((long long)n * s.S + v) * s.C + cc * 8;
+    float xf[8];
+    nm_unpack8(*reinterpret_cast<const half8*>(x + off), xf);
+    if (kStats) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) { acc[2 * i] += xf[i]; acc[2 * i + 1] = fmaf(xf[i], xf[i], acc[2 * i + 1]); }
+    } else {
+      float df[8];
+      nm_unpack8(*reinterpret_cast<const half8*>(dz + off), df);
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        const float y = fmaf(g[i], (xf[i] - mu) * rs, b[i]);
+        const float dy = (leaky && !(y > 0.f)) ? 0.01f * df[i] : df[i];
+        acc[2 * i] += dy;
+        acc[2 * i + 1] = fmaf(dy, xf[i], acc[2 * i + 1]);
+      }
+    }
+  }
+  gnb_block_reduce(acc, red, s, partial + ((long long)n * kGnbChunks + chunk) * s.C * 2);
+}
+
+// mean / rstd per (sample, group) from the pass-A partials (fp64, fixed order)
+__global__ void gnb_stats_finalize_kernel(const float* __restrict__ partial, GnbShape s, float eps, float* __restrict__ mean_rstd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n * s.groups) return;
+  const int n = i / s.groups, grp = i % s.groups;
+  double s1 = 0.0, s2 = 0.0;
+  for (int ch = 0; ch < kGnbChunks; ch++)
+    for (int c = grp * s.cpg; c < (grp + 1) * s.cpg; c++) {
+      const float* p = partial + (((long long)n * kGnbChunks + ch) * s.C + c) * 2;
+      s1 += p[0];
+      s2 += p[1];
+    }
+  const double M = (double)s.cpg * (double)s.S;
+  const double mu = s1 / M;
+  double var = s2 / M - mu * mu;                                        // biased variance, as nn.GroupNorm
+  if (var < 0.0) var = 0.0;
+  mean_rstd[i * 2] = (float)mu;
+  mean_rstd[i * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// per (sample, channel) totals of pass B -> group means m1, m2 (per sample, group) and dgamma / dbeta contributions
+__global__ void gnb_grad_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                         const float* __restrict__ mean_rstd, GnbShape s, float* __restrict__ m12,
+                                         float* __restrict__ chan /* [n][C][2]: sum dy, sum dy*xhat */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.n * s.groups) return;
+  const int n = i / s.groups, grp = i % s.groups;
+  const double mu = mean_rstd[i * 2], rs = mean_rstd[i * 2 + 1];
+  double a1 = 0.0, a2 = 0.0;
+  for (int c = grp * s.cpg; c < (grp + 1) * s.cpg; c++) {
+    double p1 = 0.0, p2 = 0.0;
+    for (int ch = 0; ch < kGnbChunks; ch++) {
+      const float* p = partial + (((long long)n * kGnbChunks + ch) * s.C + c) * 2;
+      p1 += p[0];
+      p2 += p[1];
+    }
+    const double dyxhat = rs * (p2 - mu * p1);                          // sum dy * xhat
+    chan[((long long)n * s.C + c) * 2] = (float)p1;
+    chan[((long long)n * s.C + c) * 2 + 1] = (float)dyxhat;
+    a1 += (double)gamma[c] * p1;
+    a2 += (double)gamma[c] * dyxhat;
+  }
+  const double M = (double)s.cpg * (double)s.S;
+  m12[i * 2] = (float)(a1 / M);
+  m12[i * 2 + 1] = (float)(a2 / M);
+}
+
+__global__ void gnb_param_grad_kernel(const float* __restrict__ chan, GnbShape s, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= s.C) return;
+  double db = 0.0, dg = 0.0;
+  for (int n = 0; n < s.n; n++) {                                        // fixed order over the samples
+    db += chan[((long long)n * s.C + c) * 2];
+    dg += chan[((long long)n * s.C + c) * 2 + 1];
+  }
+  if (dbeta) dbeta[c] = (float)db;
+  if (dgamma) dgamma[c] = (float)dg;
+}
+
+// pass C: dx = rstd * (gamma * dy - m1 - xhat * m2)
+__global__ void __launch_bounds__(kGnbThreads)
+gnb_dx_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, const float* __restrict__ gamma, const float* __restrict__ beta,
+              const float* __restrict__ mean_rstd, const float* __restrict__ m12, GnbShape s, int leaky, __half* __restrict__ dx) {
+  const long long total = (long long)s.n * s.S * s.ccs;                  // 16-byte channel chunks
+  for (long long i = (long long)blockIdx.x * kGnbThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kGnbThreads) {
+    const int cc = (int)(i % s.ccs);
+    const int n = (int)(i / (s.S * s.ccs));
+    const int grp = (cc * 8) / s.cpg;
+    const float mu = mean_rstd[(n * s.groups + grp) * 2], rs = mean_rstd[(n * s.groups + grp) * 2 + 1];
+    const float m1 = m12[(n * s.groups + grp) * 2], m2 = m12[(n * s.groups + grp) * 2 + 1];
+    float xf[8], df[8], o[8];
+    nm_unpack8(*reinterpret_cast<const half8*>(x + i * 8), xf);
+    nm_unpack8(*reinterpret_cast<const half8*>(dz + i * 8), df);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float gk = gamma[cc * 8 + k];
+      const float xhat = (xf[k] - mu) * rs;
+      const float y = fmaf(gk, xhat, beta[cc * 8 + k]);
+      const float dy = (leaky && !(y > 0.f)) ? 0.01f * df[k] : df[k];
+      o[k] = rs * (gk * dy - m1 - xhat * m2);
+    }
+    *reinterpret_cast<half8*>(dx + i * 8) = nm_pack8(o);
+  }
+}
+
+bool gnb_shape(int n, long long S, int C, int groups, GnbShape* s) {
+  if (n <= 0 || S <= 0 || C <= 0 || groups <= 0 || C % groups) return false;
+  const int cpg = C / groups, ccs = C / 8;
+  if (C % 8 || cpg % 8 || ccs > 32 || (kGnbThreads % ccs) != 0) return false;   // C in {8, 16, 32, 64, 128, 256}
+  *s = GnbShape{n, C, groups, cpg, ccs, kGnbThreads / ccs, S};
+  return true;
+}
+
+size_t gnb_ws_floats(const GnbShape& s) {
+  return (size_t)s.n * kGnbChunks * s.C * 2 /* partial */ + (size_t)s.n * s.groups * 4 /* mean_rstd, m12 */ +
+         (size_t)s.n * s.C * 2 /* chan */;
+}
+
+}  // namespace
+
+extern "C" size_t nm_groupnorm_backward_workspace_bytes(int n, int C, int groups) {
+  GnbShape s;
+  if (!gnb_shape(n, 1, C, groups, &s)) return 0;
+  return gnb_ws_floats(s) * sizeof(float) + 64;
+}
+
+extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const float* gamma, const float* beta, int n,
+                                     long long S, int C, int groups, float eps, int leaky, void* grad_in, float* dgamma,
+                                     float* dbeta, void* workspace, void* stream) {
+  NM_CHECK_ARG(x && grad_out && gamma && beta && grad_in && workspace, "nm_groupnorm_backward: null pointer");
+  GnbShape s;
+  NM_CHECK_ARG(gnb_shape(n, S, C, groups, &s),
+               "nm_groupnorm_backward: need C in {8, 16, 32, 64, 128, 256} and channels per group a multiple of 8 (got C=%d, groups=%d)",
+               C, groups);
+  NM_CHECK_ARG(n <= 65535, "nm_groupnorm_backward: at most 65535 samples per call");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* mean_rstd = partial + (size_t)n * kGnbChunks * C * 2;
+  float* m12 = mean_rstd + (size_t)n * groups * 2;
+  float* chan = m12 + (size_t)n * groups * 2;
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  const __half* dz = reinterpret_cast<const __half*>(grad_out);
+  const dim3 rgrid(kGnbChunks, n);
+  gnb_reduce_kernel<true><<<rgrid, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, s, leaky, partial);
+  NM_CHECK_LAUNCH("gnb_reduce_kernel<stats>");
+  gnb_stats_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, s, eps, mean_rstd);
+  NM_CHECK_LAUNCH("gnb_stats_finalize_kernel");
+  gnb_reduce_kernel<false><<<rgrid, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, s, leaky, partial);
+  NM_CHECK_LAUNCH("gnb_reduce_kernel<grad>");
+  gnb_grad_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, gamma, mean_rstd, s, m12, chan);
+  NM_CHECK_LAUNCH("gnb_grad_finalize_kernel");
+  if (dgamma || dbeta) {
+    gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, s, dgamma, dbeta);
+    NM_CHECK_LAUNCH("gnb_param_grad_kernel");
+  }
+  const long long total = (long long)n * S * s.ccs;
+  const int blocks = (int)min((long long)nm_num_sms() * 8, (total + kGnbThreads - 1) / kGnbThreads);
+  gnb_dx_kernel<<<blocks, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, m12, s, leaky, reinterpret_cast<__half*>(grad_in));
+  NM_CHECK_LAUNCH("gnb_dx_kernel");
+  return NM_OK;
+}

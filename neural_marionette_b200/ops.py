@@ -255,6 +255,23 @@ def conv3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
     return dw
 
 
+def groupnorm_backward(x: torch.Tensor, grad_out: torch.Tensor, gn: torch.nn.GroupNorm, leaky: bool = True):
+    """Backward of LeakyReLU(GroupNorm(x)) (`leaky`) or GroupNorm(x): x, grad_out act (n, D, H, W, C) ->
+    (grad_in act, dgamma (C) fp32, dbeta (C) fp32)."""
+    _need_cuda(x, grad_out)
+    assert x.shape == grad_out.shape and x.dtype == ACT_DTYPE and grad_out.dtype == ACT_DTYPE
+    assert x.is_contiguous() and grad_out.is_contiguous()
+    n, C = x.shape[0], x.shape[-1]
+    S = x.numel() // (n * C)
+    dx = torch.empty_like(x)
+    dg = torch.empty(C, dtype=torch.float32, device=x.device)
+    db = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = workspace(max(L.query("nm_groupnorm_backward_workspace_bytes", n, C, gn.num_groups), 16), x.device, "gnb")
+    L.call("nm_groupnorm_backward", L.ptr(x), L.ptr(grad_out), L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), n, S, C,
+           gn.num_groups, float(gn.eps), int(leaky), L.ptr(dx), L.ptr(dg), L.ptr(db), L.ptr(ws), L.stream())
+    return dx, dg, db
+
+
 def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
     """conv3d_k3(upsample2x_trilinear(act(x_lo*scale+shift))) without materialising the up-sampled tensor.
     x_lo act (n, D, H, W, Cin) -> raw (n, 2D, 2H, 2W, Cout) [, GroupNorm scale, shift]."""

@@ -535,3 +535,33 @@ def test_conv3d_weight_grad(ops, n, grid, cin, cout):
     assert torch.equal(got, ops.conv3d_weight_grad(to_act(x), to_act(gy)).cpu())      # fixed-order split-K
     with pytest.raises(Exception):
         ops.conv3d_weight_grad(to_act(x[:, :24]), to_act(gy))                          # Cin not a multiple of 32
+
+
+@pytest.mark.parametrize("n,grid,C,groups,leaky", [(2, 16, 32, 2, True), (3, 8, 64, 4, True), (1, 32, 32, 2, False),
+                                                  (2, 8, 128, 8, True)])
+def test_groupnorm_backward(ops, n, grid, C, groups, leaky):
+    """dL/dx, dL/dgamma, dL/dbeta of LeakyReLU(GroupNorm(x)) against torch.autograd on the CPU (fp32 on the fp16-rounded
+    tensors).  An element whose pre-activation sits within rounding of 0 may take the other LeakyReLU branch: the check
+    allows 1e-5 of the elements to differ and bounds the mean error."""
+    g = torch.Generator().manual_seed(grid + C + groups)
+    gn = torch.nn.GroupNorm(groups, C)
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        gn.bias.copy_(0.3 * torch.randn(C, generator=g))
+    x = (torch.randn(n, C, grid, grid, grid, generator=g) * 1.5 + 0.3).half().float().requires_grad_(True)
+    dz = torch.randn(n, C, grid, grid, grid, generator=g).half().float()
+    y = gn(x)
+    z = F.leaky_relu(y, 0.01) if leaky else y
+    (z * dz).sum().backward()
+    gn_cuda = torch.nn.GroupNorm(groups, C).cuda()
+    gn_cuda.load_state_dict(gn.state_dict())
+    dx, dg, db = ops.groupnorm_backward(to_act(x.detach()), to_act(dz), gn_cuda, leaky=leaky)
+    dx = from_act(dx)
+    scale = float(x.grad.abs().max())
+    diff = (dx - x.grad).abs()
+    assert float((diff > 3e-3 * scale).float().mean()) <= 1e-5
+    assert float(diff.mean()) <= 3e-4 * scale
+    assert float((dg.cpu() - gn.weight.grad).abs().max()) <= 2e-3 * float(gn.weight.grad.abs().max())
+    assert float((db.cpu() - gn.bias.grad).abs().max()) <= 2e-3 * float(gn.bias.grad.abs().max())
+    dx2, dg2, db2 = ops.groupnorm_backward(to_act(x.detach()), to_act(dz), gn_cuda, leaky=leaky)
+    assert torch.equal(from_act(dx2), dx) and torch.equal(dg2, dg) and torch.equal(db2, db)
