@@ -16,32 +16,32 @@ from .. import ops
 
 
 def evaluate(name, scores_dict, params):
-    """utils/eval_utils.py:4-10."""
-    if name == 'semantic':
-        return semantic_scores(scores_dict[name], params)
-    elif name == 'voxel_chamfer':
-        return voxel_chamfer_distance(scores_dict[name], params)
-    else:
+    """Running update of one metric (`utils/eval_utils.py:4-10`): `scores_dict[name]` is the accumulator returned by
+    the previous call (None the first time)."""
+    metric = _METRICS.get(name)
+    if metric is None:
         raise ValueError("invalid evaluation metric.")
+    return metric(scores_dict[name], params)
 
 
 def evaluate_final(name, scores_dict, result_dir='pretrained/results'):
-    """utils/eval_utils.py:12-27 (the result CSVs go to the same relative paths; the directory is created)."""
-    if name == 'semantic':
-        scores = scores_dict[name]
-        total_num = scores[0].sum()
-        scores /= total_num
-        scores = scores.max(axis=-1)  # (K',)
-        os.makedirs(os.path.join(result_dir, 'semantic'), exist_ok=True)
-        np.savetxt(os.path.join(result_dir, 'semantic', 'semantic_result.csv'), scores, delimiter=",")
-        return scores.mean()
-    elif name == 'voxel_chamfer':
-        scores = np.array(scores_dict[name])  # (totB, 1)
-        os.makedirs(os.path.join(result_dir, 'chamfer'), exist_ok=True)
-        np.savetxt(os.path.join(result_dir, 'chamfer', 'chamfer_result.csv'), scores, delimiter=",")
-        return scores.mean() * 1e4  # note that result is 1e4X
-    else:
+    """Final figure of one metric over the whole evaluation set (`utils/eval_utils.py:12-27`); the per-joint /
+    per-clip table goes to `<result_dir>/semantic/semantic_result.csv` or `<result_dir>/chamfer/chamfer_result.csv`
+    (the reference's relative paths; the directory is created here)."""
+    if name not in _METRICS:
         raise ValueError("invalid evaluation metric.")
+    sub, fname = ('semantic', 'semantic_result.csv') if name == 'semantic' else ('chamfer', 'chamfer_result.csv')
+    os.makedirs(os.path.join(result_dir, sub), exist_ok=True)
+    target = os.path.join(result_dir, sub, fname)
+    if name == 'semantic':
+        hist = scores_dict[name]                       # (K', K) match counts, normalised IN PLACE like the reference
+        hist /= hist[0].sum()
+        best = hist.max(axis=-1)                       # (K',): share of frames on the most frequent detected keypoint
+        np.savetxt(target, best, delimiter=",")
+        return best.mean()
+    per_clip = np.array(scores_dict[name])             # (clips, 1)
+    np.savetxt(target, per_clip, delimiter=",")
+    return per_clip.mean() * 1e4                       # reported x 1e4
 
 
 def _dense_view(t: torch.Tensor, shape):
@@ -87,3 +87,6 @@ def semantic_scores(scores, params):
     scores += counts
     temp = np.array([(counts[k] / counts[k].sum()).max() for k in range(K_gt)], dtype=np.float32)
     return dict(scores=scores, scores_log=temp.mean())
+
+
+_METRICS = {'semantic': semantic_scores, 'voxel_chamfer': voxel_chamfer_distance}
