@@ -115,3 +115,27 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(base, f)).read()
                 assert "oracle" not in src.replace("the oracle", ""), f"{f} references oracle/"
+
+
+def test_new_entry_points_reject_cpu_tensors():
+    """No CPU fallback anywhere: the §8f#4 consumers and the backward bricks raise on CPU tensors."""
+    import numpy as np
+    import torch
+    from neural_marionette_b200 import _lib, ops
+    from collections import namedtuple
+    from neural_marionette_b200.utils import retarget_utils as RT
+    Priority = namedtuple("Priority", ["values", "indices"])
+    a = torch.zeros(1, 8, 8, 8)
+    act = torch.zeros(1, 16, 16, 16, 32, dtype=ops.ACT_DTYPE)
+    calls = [lambda: ops.voxel_chamfer(a, a.clone()),
+             lambda: ops.semantic_nearest(torch.zeros(2, 4, 4), torch.zeros(2, 3, 3)),
+             lambda: ops.skin_weights(torch.zeros(5, 3), torch.zeros(4, 4), torch.zeros(4, dtype=torch.int32), 0, 8.0, 0.2),
+             lambda: ops.linear_blend_skinning(torch.zeros(5, 3), torch.zeros(4, 3), None, torch.zeros(2, 4, 3, 4), torch.zeros(5, 4)),
+             lambda: ops.conv3d_weight_grad(act, act),
+             lambda: ops.groupnorm_backward(act, act, torch.nn.GroupNorm(2, 32)),
+             lambda: ops.conv3d_input_grad(act, torch.nn.Conv3d(32, 32, 3, 1, 1)),
+             lambda: RT.extract_skin_weights(torch.zeros(1), Priority(None, torch.tensor([0, 1])), [0, 0],
+                                             np.zeros((3, 3), np.float32), torch.zeros(2, 4))]
+    for fn in calls:
+        with pytest.raises(_lib.NmError, match="CUDA tensors"):
+            fn()
