@@ -25,7 +25,12 @@ def lib():
         L.nmo_voxelize_f64.argtypes = [f64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, f32p]
         L.nmo_normalize_voxelize_clip.argtypes = [f32p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.c_double,
                                                   ctypes.c_double, ctypes.c_double, f64p, f32p]
-        for fn in (L.nmo_episodic_normalization_f32, L.nmo_voxelize_f64, L.nmo_normalize_voxelize_clip):
+        L.nmo_voxel_chamfer_frame.argtypes = [f32p, f32p, ctypes.c_int, f64p]
+        L.nmo_semantic_nearest_frame.argtypes = [f32p, f32p, ctypes.c_int, ctypes.c_int, ctypes.c_float,
+                                                 ctypes.POINTER(ctypes.c_int)]
+        L.nmo_semantic_nearest_frame.restype = None
+        for fn in (L.nmo_episodic_normalization_f32, L.nmo_voxelize_f64, L.nmo_normalize_voxelize_clip,
+                   L.nmo_voxel_chamfer_frame):
             fn.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -65,3 +70,21 @@ def normalize_voxelize_clip(raw: np.ndarray, G: int, scale=1.0, x_trans=0.0, z_t
     if rc:
         raise IndexError("point outside [-1, 1)" if rc == 2 else "empty clip")
     return grids
+
+
+def voxel_chamfer_frame(gt: np.ndarray, recon: np.ndarray) -> float:
+    gt = np.ascontiguousarray(gt, dtype=np.float32)
+    recon = np.ascontiguousarray(recon, dtype=np.float32)
+    out = ctypes.c_double()
+    if lib().nmo_voxel_chamfer_frame(_p(gt, ctypes.c_float), _p(recon, ctypes.c_float), gt.shape[-1], ctypes.byref(out)):
+        raise IndexError("empty gt or recon")
+    return out.value
+
+
+def semantic_nearest_frame(kypt: np.ndarray, gt: np.ndarray, threshold: float = 0.2) -> np.ndarray:
+    kypt = np.ascontiguousarray(kypt, dtype=np.float32)
+    gt = np.ascontiguousarray(gt, dtype=np.float32)
+    idx = np.empty(gt.shape[0], dtype=np.int32)
+    lib().nmo_semantic_nearest_frame(_p(kypt, ctypes.c_float), _p(gt, ctypes.c_float), kypt.shape[0], gt.shape[0], threshold,
+                                     _p(idx, ctypes.c_int))
+    return idx

@@ -76,3 +76,55 @@ int nmo_normalize_voxelize_clip(const float* raw, int T, size_t N, int G, double
   }
   return rc;
 }
+
+/* utils/eval_utils.py:43-46 for ONE frame: symmetric chamfer distance between the occupied voxels of gt (non-zero) and
+ * of recon (>= 0.5, the reference binarises first, :37-38).  Coordinates idx / ((G-1)/2) - 1 and squared distances in
+ * float32 as torch computes them; the two means are accumulated in double (torch sums float32 pairwise: agreement to
+ * ~1e-7 relative, the test allows 1e-6).  Returns 1 when either set is empty (torch raises there).  O(n_gt * n_recon). */
+int nmo_voxel_chamfer_frame(const float* gt, const float* recon, int G, double* out) {
+  const size_t S = (size_t)G * G * G;
+  size_t na = 0, nb = 0;
+  for (size_t i = 0; i < S; i++) { na += gt[i] != 0.0f; nb += recon[i] >= 0.5f; }
+  if (na == 0 || nb == 0) return 1;
+  const float half = (float)((G - 1) / 2.0);
+  double sum_a = 0.0, sum_b = 0.0;
+  for (int dir = 0; dir < 2; dir++) {
+    const float* q = dir ? recon : gt;
+    const float* t = dir ? gt : recon;
+    double acc = 0.0;
+    for (size_t i = 0; i < S; i++) {
+      if (!(dir ? q[i] >= 0.5f : q[i] != 0.0f)) continue;
+      const float qx = (float)(i / ((size_t)G * G)) / half - 1.0f, qy = (float)((i / G) % G) / half - 1.0f,
+                  qz = (float)(i % G) / half - 1.0f;
+      float best = 3.4e38f;
+      for (size_t j = 0; j < S; j++) {
+        if (!(dir ? t[j] != 0.0f : t[j] >= 0.5f)) continue;
+        const float dx = qx - ((float)(j / ((size_t)G * G)) / half - 1.0f), dy = qy - ((float)((j / G) % G) / half - 1.0f),
+                    dz = qz - ((float)(j % G) / half - 1.0f);
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best) best = d;
+      }
+      acc += (double)best;
+    }
+    if (dir) sum_b = acc / (double)nb; else sum_a = acc / (double)na;
+  }
+  *out = sum_a + sum_b;
+  return 0;
+}
+
+/* utils/eval_utils.py:65-81 for ONE frame: keypoints (K, 4) with intensity < threshold count as (1e4, 1e4, 1e4); idx_out[k']
+ * = the detected keypoint nearest to gt joint k' (first minimum, float32 distances summed x, y, z in that order). */
+void nmo_semantic_nearest_frame(const float* kypt, const float* gt, int K, int Kgt, float threshold, int* idx_out) {
+  for (int g = 0; g < Kgt; g++) {
+    float best = 0.0f;
+    int arg = 0;
+    for (int k = 0; k < K; k++) {
+      const int invalid = kypt[4 * k + 3] < threshold;
+      const float x = invalid ? 1e4f : kypt[4 * k], y = invalid ? 1e4f : kypt[4 * k + 1], z = invalid ? 1e4f : kypt[4 * k + 2];
+      const float dx = gt[3 * g] - x, dy = gt[3 * g + 1] - y, dz = gt[3 * g + 2] - z;
+      const float d = (dx * dx + dy * dy) + dz * dz;
+      if (k == 0 || d < best) { best = d; arg = k; }
+    }
+    idx_out[g] = arg;
+  }
+}

@@ -180,3 +180,19 @@ def test_evaluate_final_matches_reference_arithmetic(tmp_path):
     assert np.allclose(np.loadtxt(tmp_path / "chamfer" / "chamfer_result.csv", delimiter=","), np.array(per_clip)[:, 0])
     with pytest.raises(ValueError):
         U.evaluate_final("nope", {})
+
+
+def test_c_oracle_metrics_replay_reference_fixture(gold):
+    """Plain-C restatement (oracle/nm_oracle_c.c) of the two evaluation metrics against the reference-derived fixture."""
+    from oracle import c_oracle as C
+    vox, soft = _vc_inputs(gold)
+    B, T, G = vox.shape[0], vox.shape[1], vox.shape[-1]
+    per = np.array([C.voxel_chamfer_frame(vox[b, t, 0].numpy(), soft[b, t, 0].numpy()) for b in range(B) for t in range(T)])
+    assert np.allclose(per, gold["vc_ref_per_frame"], rtol=1e-6, atol=0)
+    assert np.allclose(per.reshape(B, T).mean(1), gold["vc_ref_scores"][:, 0], rtol=1e-6, atol=0)
+    kp, gt = gold["sem_kp"], gold["sem_gt"]
+    idx = np.stack([C.semantic_nearest_frame(kp.reshape(-1, *kp.shape[2:])[f], gt.reshape(-1, *gt.shape[2:])[f])
+                    for f in range(kp.shape[0] * kp.shape[1])])
+    assert np.array_equal(idx, gold["sem_ref_idx"])
+    with pytest.raises(IndexError):
+        C.voxel_chamfer_frame(np.zeros((8, 8, 8), np.float32), np.ones((8, 8, 8), np.float32))
