@@ -55,3 +55,70 @@ def gather_clip_outputs(local: torch.Tensor, n_clips_total: int) -> torch.Tensor
     parts = [torch.empty_like(buf) for _ in range(size)]
     dist.all_gather(parts, buf)
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+class GradientBuckets:
+    """Flat fp32 gradient storage + bucketed all-reduce for the data-parallel training step.
+
+    The parameters are laid out in REVERSE registration order (the order in which a backward pass produces their
+    gradients) in one flat buffer cut into `n_buckets` contiguous buckets of roughly equal size; `param.grad` of every
+    parameter is a view into it, so the wgrad kernels write straight into the communication buffer.  The backward
+    calls `ready(param)` as gradients are produced: when the last parameter of a bucket is ready its all-reduce (sum) is
+    launched asynchronously and overlaps the rest of the backward; `finish()` waits for all buckets and divides by the
+    world size.  Stage 1 of the reference trains 8 557 044 detector values (34.2 MB): 4 buckets of ≈ 8.6 MB, each
+    far above NCCL's latency floor over NVLink and small enough to overlap.  Backend: NCCL on GPUs, gloo in the CPU tests.
+    """
+
+    def __init__(self, params, n_buckets: int = 4, device=None):
+        self.params = [p for p in params if p.requires_grad][::-1]
+        if not self.params:
+            raise ValueError("GradientBuckets: no trainable parameters")
+        device = device if device is not None else self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        total = sum(sizes)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.bounds: List[Tuple[int, int]] = []            # [lo, hi) offsets of the buckets in `flat`
+        self._bucket_of, self._pending = {}, []
+        target, lo, off, b = total / max(1, n_buckets), 0, 0, 0
+        for p, n in zip(self.params, sizes):
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[id(p)] = b
+            off += n
+            last = p is self.params[-1]
+            if last or (off >= target * (b + 1) and b < n_buckets - 1):     # cumulative thresholds: balanced cuts
+                self.bounds.append((lo, off))
+                lo, b = off, b + 1
+        self._need = [0] * len(self.bounds)
+        for p in self.params:
+            self._need[self._bucket_of[id(p)]] += 1
+        self._left, self._work, self._launched = list(self._need), [None] * len(self.bounds), [False] * len(self.bounds)
+
+    def zero(self) -> None:
+        self.flat.zero_()
+        self._left, self._work, self._launched = list(self._need), [None] * len(self.bounds), [False] * len(self.bounds)
+
+    def ready(self, param) -> None:
+        """The gradient of `param` is complete on this rank."""
+        b = self._bucket_of[id(param)]
+        self._left[b] -= 1
+        if self._left[b] == 0:
+            self._launch(b)
+
+    def _launch(self, b: int) -> None:
+        if self._launched[b]:
+            return
+        self._launched[b] = True
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            lo, hi = self.bounds[b]
+            self._work[b] = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish(self) -> None:
+        """Launch whatever was not reported ready, wait for every bucket, average over the ranks."""
+        for b in range(len(self.bounds)):
+            self._launch(b)
+        for w in self._work:
+            if w is not None:
+                w.wait()
+        _, size = world()
+        if size > 1:
+            self.flat.div_(size)

@@ -57,3 +57,52 @@ def test_gloo_world2_gather_and_timing():
         assert p.exitcode == 0
     assert [r[1] for r in res] == [True, True]
     assert [r[2] for r in res] == [(0, 4), (4, 7)]
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Linear(5, 3), torch.nn.Linear(3, 11))
+    net[1].bias.requires_grad_(False)                       # frozen tensors (offset_param in the reference) are skipped
+    gb = P.GradientBuckets(net.parameters(), n_buckets=3)
+    trainable = [p for p in net.parameters() if p.requires_grad]
+    ok = sum(hi - lo for lo, hi in gb.bounds) == sum(p.numel() for p in trainable) and 2 <= len(gb.bounds) <= 3
+    ok = ok and gb.params[0] is trainable[-1]               # reverse order: the last layer's gradients come first
+    for step in range(2):
+        gb.zero()
+        for i, p in enumerate(gb.params):                   # "backward": rank r produces (r + 1) * (i + 1 + step) everywhere
+            p.grad.fill_(float((rank + 1) * (i + 1 + step)))
+            gb.ready(p)
+        gb.finish()
+        mean = sum(r + 1 for r in range(world)) / world
+        for i, p in enumerate(gb.params):
+            ok = ok and bool(torch.all(p.grad == mean * (i + 1 + step))) and p.grad.data_ptr() >= gb.flat.data_ptr()
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_gradient_buckets():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
+def test_gradient_buckets_single_process():
+    net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+    gb = P.GradientBuckets(net.parameters(), n_buckets=8)   # more buckets than tensors: one tensor per bucket at most
+    assert 1 <= len(gb.bounds) <= 4 and gb.bounds[0][0] == 0 and gb.bounds[-1][1] == gb.flat.numel()
+    assert all(a[1] == b[0] for a, b in zip(gb.bounds, gb.bounds[1:]))
+    for p in gb.params:
+        p.grad.fill_(2.0)
+        gb.ready(p)
+    gb.finish()                                             # world size 1: no collective, no scaling
+    assert bool(torch.all(gb.flat == 2.0))
