@@ -106,3 +106,25 @@ def test_gradient_buckets_single_process():
         gb.ready(p)
     gb.finish()                                             # world size 1: no collective, no scaling
     assert bool(torch.all(gb.flat == 2.0))
+
+
+def test_gradient_bucket_bounds_property():
+    """Whatever the tensor sizes and bucket count: buckets tile the flat buffer exactly, follow the reverse parameter order,
+    never split a tensor, and every `.grad` aliases its slice."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(1, 40), min_size=1, max_size=12), st.integers(1, 9))
+    def check(sizes, n_buckets):
+        params = [torch.nn.Parameter(torch.zeros(n)) for n in sizes]
+        gb = P.GradientBuckets(params, n_buckets=n_buckets)
+        assert gb.flat.numel() == sum(sizes) and 1 <= len(gb.bounds) <= min(n_buckets, len(sizes))
+        assert gb.bounds[0][0] == 0 and gb.bounds[-1][1] == sum(sizes)
+        assert all(a[1] == b[0] and a[0] < a[1] for a, b in zip(gb.bounds, gb.bounds[1:] + [(sum(sizes), None)]))
+        off = 0
+        for p in params[::-1]:
+            assert p.grad.data_ptr() == gb.flat.data_ptr() + 4 * off
+            lo, hi = gb.bounds[gb._bucket_of[id(p)]]
+            assert lo <= off and off + p.numel() <= hi
+            off += p.numel()
+    check()
