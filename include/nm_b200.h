@@ -222,23 +222,95 @@ int nm_retarget_fk(const float* R, const float* offset, const float* root_pos, c
 int nm_linear_blend_skinning(const float* points, int N, const float* joints, const float* R_inv, const float* T3x4,
                              const float* skin, int T, int K, float* out, void* stream);
 
-/* ---- config #4 backward, first bricks --------------------------------------------------
+/* ---- config #4 training step: backward kernels -----------------------------------------
  * Weight gradient of a stride-1 3x3x3 "same" Conv3d (what autograd computes for vox_modules.py:8-47 /
  * kypt_detector.py:417-460 layers): x act (n, D, H, W, Cin), grad_out act (n, D, H, W, Cout) ->
- * dw (Cout, Cin, 3, 3, 3) fp32 in the nn.Conv3d weight layout, fully overwritten.  Cin, Cout multiples of 32 (<= 256),
+ * dw (Cout, Cin, 3, 3, 3) fp32 in the nn.Conv3d weight layout, fully overwritten, multiplied by out_scale.  Cin, Cout multiples of 32 (<= 256),
  * W in {16, 32, 48, 64}.  First version on mma.sync with a fixed-order split-K reduction (bit-reproducible).
  * (The data gradient needs no entry point of its own: it is nm_conv3d_tc with flipped, transposed weights.) */
 size_t nm_conv3d_k3_wgrad_workspace_bytes(int n, int D, int H, int W, int Cin, int Cout);
-int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int n, int D, int H, int W, int Cin, int Cout, float* dw,
-                       void* workspace, void* stream);
+int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int n, int D, int H, int W, int Cin, int Cout,
+                       float out_scale, float* dw, void* workspace, void* stream);
 /* Backward of z = LeakyReLU_0.01(GroupNorm(x)) (leaky != 0) or of GroupNorm alone (modules/vox_modules.py:8-75 under
- * autograd): x, grad_out (= dL/dz), grad_in (= dL/dx) act (n, S, C) fp16; gamma, beta (C) fp32; dgamma, dbeta (C) fp32
- * (optional), summed over the n samples.  C in {8, 16, ..., 256}, channels per group a multiple of 8.  Statistics are
- * recomputed from x (three passes, fixed-order reductions: bit-reproducible). */
+ * autograd): x, grad_out (= dL/dz), grad_in (= dL/dx) act (n, S, C) fp16; gamma, beta (C) fp32.  Optional fp32 outputs,
+ * summed over the n samples and multiplied by out_scale (= 1 / loss scale): dgamma, dbeta (C) and dxsum (C) = the sum of
+ * grad_in over samples and voxels, i.e. the gradient of the bias of the convolution that produced x.  Streaming kernels
+ * for C in {8, 16, 32, 64, 128, 256} with 8 | channels per group; any other (C, groups) (the hour-glass's 48 / 72
+ * channels) on small tensors.  Statistics are recomputed from x; fixed-order reductions (bit-reproducible). */
 size_t nm_groupnorm_backward_workspace_bytes(int n, int C, int groups);
 int nm_groupnorm_backward(const void* x, const void* grad_out, const float* gamma, const float* beta, int n, long long S,
-                          int C, int groups, float eps, int leaky, void* grad_in, float* dgamma, float* dbeta,
-                          void* workspace, void* stream);
+                          int C, int groups, float eps, int leaky, float out_scale, void* grad_in, float* dgamma,
+                          float* dbeta, float* dxsum, void* workspace, void* stream);
+
+/* Weight gradient of the convolutions the slab kernel above does not cover - 1x1, k2/s2 "pool", ConvTranspose3d(k2, s2),
+ * k3 on small grids or with 48 / 72 channels (modules/vox_modules.py:12-68 under autograd):
+ *   dw[a][b][tap] = out_scale * sum_u small_side[u][a] * large_side[u * stride + tap - pad][b]
+ * nn.Conv3d: small_side = dL/dy (n, Ds, Hs, Ws, Cout), large_side = x -> dw (Cout, Cin, k, k, k);
+ * nn.ConvTranspose3d: small_side = x (n, Ds, Hs, Ws, Cin), large_side = dL/dy -> dw (Cin, Cout, 2, 2, 2).
+ * (k, stride) in {(1, 1), (3, 1), (2, 2)}; channels multiples of 8, <= 256.  mma.sync, fixed-order split-K. */
+size_t nm_conv3d_wgrad_gather_workspace_bytes(int n, int Ds, int Hs, int Ws, int Ca, int Cb, int k, int stride);
+int nm_conv3d_wgrad_gather(const void* small_side, const void* large_side, int n, int Ds, int Hs, int Ws, int Ca, int Cb,
+                           int k, int stride, float out_scale, float* dw, void* workspace, void* stream);
+
+/* Backward of nm_upsample2x without the fused prologue (nn.Upsample(scale 2, trilinear, align_corners=False),
+ * model/kypt_detector.py:427,441): grad_out act (n, 2D, 2H, 2W, C) -> grad_in act (n, D, H, W, C). */
+int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n, int D, int H, int W, int C, void* stream);
+
+/* Backward of nm_final_recon with the BCE (model/kypt_detector.py:410,453-457,:91-92).  x, a, b, w, bias, first_frame,
+ * recon (the saved forward output), target as in the forward; grad_bce (n) = dL/d(per-frame BCE mean).
+ * grad_act act (n, S, C) = grad_scale * dL/d(LeakyReLU(x*a+b)) (feed it to nm_groupnorm_backward with x);
+ * dw (C), dbias (1) fp32 = gradient of the 1x1 conv (not scaled). */
+size_t nm_final_recon_backward_workspace_bytes(int n);
+int nm_final_recon_backward(const void* x, const float* a, const float* b, const float* w, float bias,
+                            const float* first_frame, int frames_per_clip, float sharpness, float translation,
+                            const float* recon, const float* target, const float* grad_bce, float grad_scale,
+                            void* grad_act, float* dw, float* dbias, void* workspace, int n, int S, int C, void* stream);
+
+/* Backward of nm_heatmap_head (model/kypt_detector.py:273-297,336-343; utils/kypt_detector_utils.py:28-55).
+ * mode 1: inputs as the forward plus its saved outputs heat, keypoints, heat_mean; upstream gradients (each optional)
+ *   grad_keypoints (n, K, 4), grad_heat_mean (n, K), grad_heat (n, K, g^3).  Outputs: grad_feature act (n, g^3, C) times
+ *   grad_scale; dq_out (n, K, g^3) = dL/d(pre-Softplus map) (input of the mode-0 call); dw1 (K, C), db1 (K),
+ *   dprop (3) = gradient of the propagate conv (w0, w1, bias).
+ * mode 0 (spatio-temporal head, n = clips): upstream = pw1 * sum over the clip's frames of dq_in ((n*frames_per_clip, K,
+ *   g^3)) [+ grad_heat]; outputs grad_feature, dw1, db1. */
+size_t nm_heatmap_head_backward_workspace_bytes(int n, int C, int K);
+int nm_heatmap_head_backward(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K, int mode,
+                             const float* prev, int frames_per_clip, float pw0, float pw1, float pb, const float* linspace,
+                             const float* heat, const float* keypoints, const float* heat_mean,
+                             const float* grad_keypoints, const float* grad_heat_mean, const float* grad_heat,
+                             const float* dq_in, float grad_scale, void* grad_feature, float* dq_out, float* dw1,
+                             float* db1, float* dprop, void* workspace, void* stream);
+
+/* Backward of nm_decoder_adjust in keypoint mode (model/kypt_detector.py:381,404-408 + the Gaussian render,
+ * utils/kypt_detector_utils.py:57-90).  grad_out, out: act (n, g^3, 128) (out = the saved forward output; grad_out carries
+ * grad_scale).  Outputs: grad_first_feature act (n_clips, g^3, 128) times grad_scale; grad_keypoints (n, K, 4) fp32
+ * (through gauss_t of every frame and gauss_0 of the clip's first frame); dweight (128, 2K+131), dbias (128) fp32. */
+size_t nm_decoder_adjust_backward_workspace_bytes(int n_clips, int frames_per_clip);
+int nm_decoder_adjust_backward(const void* grad_out, const void* out, const void* first_feature, const float* keypoints,
+                               const float* weight, int n_clips, int frames_per_clip, int g, int K, const float* linspace,
+                               float gauss_width, float grad_scale, void* grad_first_feature, float* grad_keypoints,
+                               float* dweight, float* dbias, void* workspace, void* stream);
+
+/* Backward of nm_chamfer_vol_fit (utils/kypt_detector_utils.py:141-157): grad_out (n) -> grad_keypoints (n, K, 4). */
+size_t nm_chamfer_vol_fit_backward_workspace_bytes(int n, int K);
+int nm_chamfer_vol_fit_backward(const float* seq, const float* keypoints, const float* linspace, const float* grad_out,
+                                int n, int K, int G, float* grad_keypoints, void* workspace, void* stream);
+
+/* Weight gradient of the CoordConv first layer (add_coord_channels + Conv3d(4, Cout, k5, pad 2),
+ * utils/kypt_detector_utils.py:4-26, model/kypt_detector.py:266): occ (n, G, G, G) fp32 (any values: the
+ * spatio-temporal branch feeds the frame mean), grad_out act (n, G, G, G, Cout) -> dw (Cout, 4, 5, 5, 5) fp32 times
+ * out_scale.  The coordinate channels are never materialised: their sums follow from 125 positional bins of the
+ * moments of grad_out; the occupancy channel is a gather over the non-zero voxels. */
+size_t nm_first_conv_wgrad_workspace_bytes(int n, int Cout);
+int nm_first_conv_wgrad(const float* occ, const void* grad_out, const float* linspace, int n, int G, int Cout,
+                        float out_scale, float* dw, void* workspace, void* stream);
+
+/* Optimizer of the training loop (train.py:380-409: torch.optim.Adam(lr) with default betas / eps, no weight decay) as
+ * one launch over a flat parameter buffer.  grad is multiplied by grad_mul first (unscaling / averaging); when
+ * *skip_flag != 0 (set by nm_grad_nonfinite: some gradient is inf / NaN) the step leaves everything untouched. */
+int nm_grad_nonfinite(const float* grad, long long count, int* flag, void* stream);
+int nm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
+                 float beta2, float eps, int step, float grad_mul, const int* skip_flag, void* stream);
 
 #ifdef __cplusplus
 }

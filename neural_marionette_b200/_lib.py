@@ -87,9 +87,26 @@ PROTOTYPES = {
     "nm_retarget_fk": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "nm_linear_blend_skinning": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "nm_conv3d_k3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
-    "nm_conv3d_k3_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "nm_conv3d_k3_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nm_groupnorm_backward_workspace_bytes": (_sz, [_i, _i, _i]),
-    "nm_groupnorm_backward": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp]),
+    "nm_groupnorm_backward": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nm_conv3d_wgrad_gather_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_wgrad_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "nm_upsample2x_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nm_final_recon_backward_workspace_bytes": (_sz, [_i]),
+    "nm_final_recon_backward": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i,
+                                     _i, _vp]),
+    "nm_heatmap_head_backward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "nm_heatmap_head_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nm_decoder_adjust_backward_workspace_bytes": (_sz, [_i, _i]),
+    "nm_decoder_adjust_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nm_chamfer_vol_fit_backward_workspace_bytes": (_sz, [_i, _i]),
+    "nm_chamfer_vol_fit_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "nm_first_conv_wgrad_workspace_bytes": (_sz, [_i, _i]),
+    "nm_first_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "nm_grad_nonfinite": (_i, [_vp, _ll, _vp, _vp]),
+    "nm_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _i, _f, _vp, _vp]),
 }
 
 _lib = None

@@ -1,0 +1,1034 @@
+// Backward kernels of the detector's non-convolution stages and of its first layer (config #4 training step).
+// What torch.autograd computes for the reference, restated per stage:
+//   trilinear x2 up-sampling      model/kypt_detector.py:427,441           -> nm_upsample2x_backward
+//   decoder tail + BCE            model/kypt_detector.py:410,453-457,91-92 -> nm_final_recon_backward
+//   heat-map heads + soft-argmax  model/kypt_detector.py:273-297,336-343; utils/kypt_detector_utils.py:28-55
+//                                                                          -> nm_heatmap_head_backward
+//   Gaussian render + adjust conv utils/kypt_detector_utils.py:57-90; model/kypt_detector.py:381,404-408
+//                                                                          -> nm_decoder_adjust_backward
+//   chamfer volume-fitting loss   utils/kypt_detector_utils.py:141-157     -> nm_chamfer_vol_fit_backward
+//   CoordConv first layer         utils/kypt_detector_utils.py:4-26 + modules/vox_modules.py:12 -> nm_first_conv_wgrad
+//   Adam                          train.py:380-409 (torch.optim.Adam defaults) -> nm_adam_step
+// Activation gradients travel as fp16 multiplied by a loss scale (`grad_scale`); every fp32 output (parameter and
+// keypoint gradients) is divided by it again (`inv_scale`).  All reductions run in a fixed order: bit-reproducible.
+#include "common.cuh"
+#include "../../include/nm_b200.h"
+
+namespace {
+
+constexpr int KMAX = 24;
+
+// ------------------------------------------------------------------ trilinear x2 backward
+// d_in[i] = sum_{j in -1..2} w_j * g[clamp(2i + j)], w = (.25, .75, .75, .25) per axis (the transpose of PyTorch's
+// align_corners=False rule incl. its index clamping at the borders).  One thread per (input voxel, 8 channels).
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const __half* __restrict__ g, __half* __restrict__ dx, int D, int H, int W, int C, long long total8) {
+  const int c8n = C >> 3;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total8; i += (long long)gridDim.x * 256) {
+    const int c8 = (int)(i % c8n);
+    long long v = i / c8n;
+    const int w = (int)(v % W); v /= W;
+    const int h = (int)(v % H); v /= H;
+    const int d = (int)(v % D);
+    const long long n = v / D;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = 0.f;
+    const __half* gn = g + n * (8LL * D * H * W) * C + c8 * 8;
+#pragma unroll
+    for (int jd = -1; jd <= 2; jd++) {
+      const int od = min(max(2 * d + jd, 0), 2 * D - 1);
+      const float wd = (jd == -1 || jd == 2) ? 0.25f : 0.75f;
+#pragma unroll
+      for (int jh = -1; jh <= 2; jh++) {
+        const int oh = min(max(2 * h + jh, 0), 2 * H - 1);
+        const float wh = wd * ((jh == -1 || jh == 2) ? 0.25f : 0.75f);
+        const __half* row = gn + ((long long)od * (2 * H) + oh) * (2 * W) * C;
+#pragma unroll
+        for (int jw = -1; jw <= 2; jw++) {
+          const int ow = min(max(2 * w + jw, 0), 2 * W - 1);
+          const float ww = wh * ((jw == -1 || jw == 2) ? 0.25f : 0.75f);
+          float f[8];
+          nm_unpack8(*reinterpret_cast<const half8*>(row + (long long)ow * C), f);
+#pragma unroll
+          for (int k = 0; k < 8; k++) acc[k] = fmaf(ww, f[k], acc[k]);
+        }
+      }
+    }
+    reinterpret_cast<half8*>(dx)[i] = nm_pack8(acc);
+  }
+}
+
+// ------------------------------------------------------------------ decoder tail backward
+// forward: act = lrelu(x*a + b); x14 = w . act + bias; p = sigmoid(sharp * (tanh(x14) + ff - trans)); bce = mean BCE(p, y)
+// backward (PyTorch's binary_cross_entropy_backward: (p - y) / max(p (1 - p), 1e-12)):
+//   dx14 = gbce[n] / S * (p - y) * [p(1-p) / max(p(1-p), 1e-12)] * sharp * (1 - tanh^2(x14))
+//   dact[c] = w[c] * dx14 (written fp16, times grad_scale);  dw[c] = sum act[c] * dx14;  dbias = sum dx14
+constexpr int kFrbBlocks = 64;
+__global__ void __launch_bounds__(256)
+final_recon_bwd_kernel(const __half* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                       const float* __restrict__ w, float bias, const float* __restrict__ first_frame, int frames_per_clip,
+                       float sharp, float trans, const float* __restrict__ recon, const float* __restrict__ target,
+                       const float* __restrict__ gbce, float grad_scale, __half* __restrict__ dact,
+                       float* __restrict__ partial /* [n][blocks][33] */, int S) {
+  constexpr int C = 32;
+  const int n = blockIdx.y;
+  __shared__ float sa[C], sb[C], sw[C];
+  __shared__ float red[8][C + 1];
+  if (threadIdx.x < C) {
+    sa[threadIdx.x] = a[(long long)n * C + threadIdx.x];
+    sb[threadIdx.x] = b[(long long)n * C + threadIdx.x];
+    sw[threadIdx.x] = w[threadIdx.x];
+  }
+  __syncthreads();
+  const int clip = n / frames_per_clip;
+  const float gn = gbce[n] / (float)S;
+  float dw[C], db = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; c++) dw[c] = 0.f;
+  const half8* base = reinterpret_cast<const half8*>(x + (long long)n * S * C);
+  half8* obase = reinterpret_cast<half8*>(dact + (long long)n * S * C);
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < S; s += gridDim.x * 256) {
+    half8 raw[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) raw[j] = base[(long long)s * 4 + j];
+    float act[C];
+    float x14 = bias;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float f[8];
+      nm_unpack8(raw[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = j * 8 + k;
+        act[c] = nm_lrelu(fmaf(f[k], sa[c], sb[c]));
+        x14 = fmaf(act[c], sw[c], x14);
+      }
+    }
+    const float t = tanhf(x14);
+    const float p = recon[(long long)n * S + s], y = target[(long long)n * S + s];
+    (void)first_frame; (void)clip; (void)trans;                         // p already contains them (saved forward output)
+    const float pq = p * (1.f - p);
+    const float dx14 = gn * (p - y) * (pq / fmaxf(pq, 1e-12f)) * sharp * (1.f - t * t);
+    db += dx14;
+    const float ds = dx14 * grad_scale;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = j * 8 + k;
+        dw[c] = fmaf(act[c], dx14, dw[c]);
+        o[k] = sw[c] * ds;
+      }
+      obase[(long long)s * 4 + j] = nm_pack8(o);
+    }
+  }
+  // block reduction: butterfly inside the warp, then the 8 warps in order
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    const float v = nm_warp_sum(dw[c]);
+    if (lane == 0) red[warp][c] = v;
+  }
+  db = nm_warp_sum(db);
+  if (lane == 0) red[warp][C] = db;
+  __syncthreads();
+  if (threadIdx.x <= C) {
+    float tot = 0.f;
+    for (int k = 0; k < 8; k++) tot += red[k][threadIdx.x];
+    partial[((long long)n * gridDim.x + blockIdx.x) * (C + 1) + threadIdx.x] = tot;
+  }
+}
+
+// out[j] = scale * sum_r partial[r * ld + j], j < cols (fixed order, fp64)
+__global__ void reduce_cols_kernel(const float* __restrict__ partial, long long rows, int ld, int cols, float scale,
+                                   float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  double acc = 0.0;
+  for (long long r = 0; r < rows; r++) acc += (double)partial[r * ld + j];
+  out[j] = (float)(acc * (double)scale);
+}
+
+// ------------------------------------------------------------------ heat-map head backward
+// mode 1 (per-frame head): u = w1 f + b1; h = lrelu(u); q = pw0 h + pw1 prev + pb; hm = softplus(q);
+//   keypoints / heat_mean are functions of hm:  d hm[k][s] = A_k + sum_a B_ka lin[s_a]  (+ dheat[k][s]) with
+//     den_k = S (mean_k + 1e-6),  B_ka = dkp[k][a] / den_k,  A_k = dmean_k / S - sum_a B_ka kp[k][a],
+//     dmean_k = dkp[k][3] / (mx + 1e-6) + dmean_up[k] - [k == argmax] sum_j dkp[j][3] mean_j / (mx + 1e-6)^2
+//   dq = dhm * (1 - exp(-hm));  du = pw0 dq lrelu'(u)
+// mode 0 (spatio-temporal head): h = lrelu(u) is the output; dh[k][s] = pw1 * sum_t dq[clip*T + t][k][s]
+// outputs: dfeat = grad_scale * W1^T du (fp16), dq (mode 1), per-frame partials of dW1, db1, (dpw0, dpw1, dpb).
+template <int C>
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const __half* __restrict__ feature, const float* __restrict__ w1, const float* __restrict__ b1, int K, int g,
+                int mode, const float* __restrict__ prev, int frames_per_clip, float pw0, float pw1, float pb,
+                const float* __restrict__ lin, const float* __restrict__ heat, const float* __restrict__ kp,
+                const float* __restrict__ heat_mean, const float* __restrict__ dkp, const float* __restrict__ dmean_up,
+                const float* __restrict__ dheat, const float* __restrict__ dq_in, float grad_scale,
+                __half* __restrict__ dfeat, float* __restrict__ dq_out, float* __restrict__ pw_partial /* [n][K][C] */,
+                float* __restrict__ pb_partial /* [n][K] */, float* __restrict__ pp_partial /* [n][3] */) {
+  constexpr int TS = 64;                                   // voxels per tile
+  constexpr int FS = C + 1;                                // fp32 feature row stride (odd: conflict-free column reads)
+  constexpr int KPT = KMAX * C / 256;                      // dW1 accumulators per thread
+  extern __shared__ __align__(16) float smem[];
+  float* s_w = smem;                                       // [KMAX][C]
+  float* s_f = s_w + KMAX * C;                             // [TS][FS]
+  float* s_du = s_f + TS * FS;                             // [KMAX][TS]
+  float* s_co = s_du + KMAX * TS;                          // [KMAX][4]: A, Bx, By, Bz
+  float* s_red = s_co + KMAX * 4;                          // [256][3]
+  const int n = blockIdx.x, S = g * g * g;
+  const int clip = n / frames_per_clip;
+  for (int i = threadIdx.x; i < KMAX * C; i += 256) s_w[i] = (i / C) < K ? w1[i] : 0.f;
+  if (mode == 1 && threadIdx.x < KMAX) {
+    const int k = threadIdx.x;
+    float A = 0.f, B[3] = {0.f, 0.f, 0.f};
+    if (k < K) {
+      const float* hmn = heat_mean + (long long)n * K;
+      float mx = -INFINITY;
+      int jm = 0;
+      for (int j = 0; j < K; j++)
+        if (hmn[j] > mx) { mx = hmn[j]; jm = j; }            // first maximum, as torch.max
+      const float inv = 1.f / (mx + 1e-6f);
+      float dmean = dmean_up ? dmean_up[(long long)n * K + k] : 0.f;
+      if (dkp) {
+        dmean += dkp[((long long)n * K + k) * 4 + 3] * inv;
+        if (k == jm) {
+          float t = 0.f;
+          for (int j = 0; j < K; j++) t += dkp[((long long)n * K + j) * 4 + 3] * hmn[j];
+          dmean -= t * inv * inv;
+        }
+      }
+      const float den = (float)S * (hmn[k] + 1e-6f);
+      A = dmean / (float)S;
+      if (dkp)
+        for (int a = 0; a < 3; a++) {
+          B[a] = dkp[((long long)n * K + k) * 4 + a] / den;
+          A -= B[a] * kp[((long long)n * K + k) * 4 + a];
+        }
+    }
+    s_co[k * 4] = A; s_co[k * 4 + 1] = B[0]; s_co[k * 4 + 2] = B[1]; s_co[k * 4 + 3] = B[2];
+  }
+  __syncthreads();
+  float accw[KPT];
+#pragma unroll
+  for (int i = 0; i < KPT; i++) accw[i] = 0.f;
+  float accb = 0.f, sp0 = 0.f, sp1 = 0.f, sp2 = 0.f;
+  const int wc = threadIdx.x % C, wk0 = (threadIdx.x / C) * KPT;      // dW1 ownership: channel wc, keypoints wk0..
+  const __half* fbase = feature + (long long)n * S * C;
+  for (int s0 = 0; s0 < S; s0 += TS) {
+    // feature tile -> fp32 shared
+    for (int i = threadIdx.x; i < TS * (C / 8); i += 256) {
+      const int sl = i / (C / 8), c8 = i % (C / 8);
+      float f[8];
+      nm_unpack8(*reinterpret_cast<const half8*>(fbase + (long long)(s0 + sl) * C + c8 * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) s_f[sl * FS + c8 * 8 + k] = f[k];
+    }
+    __syncthreads();
+    {
+      // u, dq, du for 6 keypoints of one voxel
+      const int sl = threadIdx.x % TS, kg = threadIdx.x / TS, s = s0 + sl;
+      const int x = s / (g * g), y = (s / g) % g, z = s % g;
+      const float lx = lin[x], ly = lin[y], lz = lin[z];
+#pragma unroll
+      for (int kk = 0; kk < KMAX / 4; kk++) {
+        const int k = kg * (KMAX / 4) + kk;
+        float du = 0.f;
+        if (k < K) {
+          float u = b1[k];
+          const float* fr = s_f + sl * FS;
+          const float* wr = s_w + k * C;
+#pragma unroll 8
+          for (int c = 0; c < C; c++) u = fmaf(wr[c], fr[c], u);
+          const float slope = u > 0.f ? 1.f : 0.01f;
+          float dh;
+          if (mode == 1) {
+            const float h = u > 0.f ? u : 0.01f * u;
+            const float pv = prev[((long long)clip * K + k) * S + s];
+            const float hm = heat[((long long)n * K + k) * S + s];
+            float dhm = s_co[k * 4] + s_co[k * 4 + 1] * lx + s_co[k * 4 + 2] * ly + s_co[k * 4 + 3] * lz;
+            if (dheat) dhm += dheat[((long long)n * K + k) * S + s];
+            const float dq = dhm * (1.f - expf(-hm));
+            dq_out[((long long)n * K + k) * S + s] = dq;
+            sp0 = fmaf(dq, h, sp0);
+            sp1 = fmaf(dq, pv, sp1);
+            sp2 += dq;
+            dh = pw0 * dq;
+          } else {
+            dh = dheat ? dheat[((long long)n * K + k) * S + s] : 0.f;
+            if (dq_in) {
+              float t = 0.f;
+              for (int tt = 0; tt < frames_per_clip; tt++) t += dq_in[(((long long)n * frames_per_clip + tt) * K + k) * S + s];
+              dh = fmaf(pw1, t, dh);
+            }
+          }
+          du = dh * slope;
+        }
+        s_du[k * TS + sl] = du;
+      }
+    }
+    __syncthreads();
+    // dfeat[s][c] = grad_scale * sum_k du[k][s] w1[k][c]
+    for (int i = threadIdx.x; i < TS * (C / 8); i += 256) {
+      const int sl = i / (C / 8), c8 = i % (C / 8);
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) o[e] = 0.f;
+      for (int k = 0; k < K; k++) {
+        const float d = s_du[k * TS + sl];
+        const float* wr = s_w + k * C + c8 * 8;
+#pragma unroll
+        for (int e = 0; e < 8; e++) o[e] = fmaf(d, wr[e], o[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) o[e] *= grad_scale;
+      *reinterpret_cast<half8*>(dfeat + ((long long)n * S + s0 + sl) * C + c8 * 8) = nm_pack8(o);
+    }
+    // dW1[k][c] += sum_s du[k][s] f[s][c];  db1[k] += sum_s du[k][s]
+#pragma unroll
+    for (int i = 0; i < KPT; i++) {
+      const float* dr = s_du + (wk0 + i) * TS;
+      float t = 0.f;
+      for (int sl = 0; sl < TS; sl++) t = fmaf(dr[sl], s_f[sl * FS + wc], t);
+      accw[i] += t;
+    }
+    if (threadIdx.x < KMAX) {
+      float t = 0.f;
+      for (int sl = 0; sl < TS; sl++) t += s_du[threadIdx.x * TS + sl];
+      accb += t;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < KPT; i++)
+    if (wk0 + i < K) pw_partial[((long long)n * K + wk0 + i) * C + wc] = accw[i];
+  if (threadIdx.x < K) pb_partial[(long long)n * K + threadIdx.x] = accb;
+  if (mode == 1) {
+    s_red[threadIdx.x * 3] = sp0; s_red[threadIdx.x * 3 + 1] = sp1; s_red[threadIdx.x * 3 + 2] = sp2;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      float t = 0.f;
+      for (int i = 0; i < 256; i++) t += s_red[i * 3 + threadIdx.x];
+      pp_partial[(long long)n * 3 + threadIdx.x] = t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ decoder adjust + Gaussian render backward
+// forward: y = lrelu(W cat[G_t (K), ff (128), G_0 (K), coords (3)] + b), G[k][s] = ex[x] ey[y] ez[z] I_k
+// dz = dy / grad_scale * lrelu'(y).  Per frame: dG_t = W[:, :K]^T dz -> d keypoints (render backward), dW[:, :K], db.
+// Per clip (on sum_t dz): d first_feature, d keypoints of frame 0 (through G_0), dW[:, K:].
+constexpr int kAdjC = 128;
+constexpr int kAdjTS = 64;
+
+__device__ __forceinline__ void adj_stage_exps(const float* kp, int K, int g, const float* lin, float width, float* s_e, float* s_kp) {
+  for (int i = threadIdx.x; i < K * 3 * g; i += 256) {
+    const int k = i / (3 * g), a = (i / g) % 3, j = i % g;
+    const float d = lin[j] - kp[k * 4 + a];
+    s_e[(k * 3 + a) * 32 + j] = expf(-(d * d) / width);
+  }
+  for (int i = threadIdx.x; i < K * 4; i += 256) s_kp[i] = kp[i];
+}
+
+// dz tile -> shared, transposed [co][TS + 1]; frames = 1 (per-frame kernel) or T (sum over the clip's frames)
+__device__ __forceinline__ void adj_load_dz(const __half* dy, const __half* y, long long frame0, int frames, int S, int s0,
+                                            float inv_scale, float* s_dz) {
+  for (int i = threadIdx.x; i < kAdjTS * (kAdjC / 8); i += 256) {
+    const int sl = i / (kAdjC / 8), c8 = i % (kAdjC / 8);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) acc[e] = 0.f;
+    for (int t = 0; t < frames; t++) {
+      const long long off = ((frame0 + t) * S + s0 + sl) * kAdjC + c8 * 8;
+      float d[8], o[8];
+      nm_unpack8(*reinterpret_cast<const half8*>(dy + off), d);
+      nm_unpack8(*reinterpret_cast<const half8*>(y + off), o);
+#pragma unroll
+      for (int e = 0; e < 8; e++) acc[e] += o[e] > 0.f ? d[e] : 0.01f * d[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e++) s_dz[(c8 * 8 + e) * (kAdjTS + 1) + sl] = acc[e] * inv_scale;
+  }
+}
+
+// render backward accumulation for the keypoints owned by this thread (6 of them, one voxel)
+struct RenderAcc { float v[KMAX / 4][4]; };
+
+__device__ __forceinline__ void adj_gauss_tile(const float* s_e, const float* s_kp, int K, int g, int s0, float* s_G) {
+  for (int i = threadIdx.x; i < KMAX * kAdjTS; i += 256) {
+    const int k = i / kAdjTS, sl = i % kAdjTS, s = s0 + sl;
+    float v = 0.f;
+    if (k < K) {
+      const int x = s / (g * g), yy = (s / g) % g, z = s % g;
+      v = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + yy]) * s_e[(k * 3 + 2) * 32 + z] * s_kp[k * 4 + 3];
+    }
+    s_G[i] = v;
+  }
+}
+
+// dG[k][s] = sum_co W[co][col0 + k] dz[co][s] for this thread's 6 keypoints, accumulated into the render gradient
+__device__ __forceinline__ void adj_render_bwd(const float* s_wg /* [128][KMAX] */, const float* s_dz, const float* s_e,
+                                               const float* s_kp, const float* lin, int K, int g, int s0, float width,
+                                               RenderAcc& r) {
+  const int sl = threadIdx.x % kAdjTS, kg = threadIdx.x / kAdjTS, s = s0 + sl;
+  const int x = s / (g * g), yy = (s / g) % g, z = s % g;
+  const float lx = lin[x], ly = lin[yy], lz = lin[z];
+#pragma unroll
+  for (int kk = 0; kk < KMAX / 4; kk++) {
+    const int k = kg * (KMAX / 4) + kk;
+    if (k < K) {
+      float dG = 0.f;
+      for (int co = 0; co < kAdjC; co++) dG = fmaf(s_wg[co * KMAX + k], s_dz[co * (kAdjTS + 1) + sl], dG);
+      const float E = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + yy]) * s_e[(k * 3 + 2) * 32 + z];
+      const float gG = dG * E * s_kp[k * 4 + 3] * (2.f / width);
+      r.v[kk][0] = fmaf(gG, lx - s_kp[k * 4], r.v[kk][0]);
+      r.v[kk][1] = fmaf(gG, ly - s_kp[k * 4 + 1], r.v[kk][1]);
+      r.v[kk][2] = fmaf(gG, lz - s_kp[k * 4 + 2], r.v[kk][2]);
+      r.v[kk][3] = fmaf(dG, E, r.v[kk][3]);
+    }
+  }
+}
+
+// fold the per-thread render accumulators over the 64 voxel lanes of each keypoint group (fixed order)
+__device__ __forceinline__ void adj_render_store(const RenderAcc& r, float* s_tmp /* [256][24] */, int K, float* out /* [K][4] */) {
+#pragma unroll
+  for (int kk = 0; kk < KMAX / 4; kk++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) s_tmp[threadIdx.x * 24 + kk * 4 + q] = r.v[kk][q];
+  __syncthreads();
+  if (threadIdx.x < KMAX * 4) {
+    const int k = threadIdx.x / 4, q = threadIdx.x % 4, kg = k / (KMAX / 4), kk = k % (KMAX / 4);
+    float t = 0.f;
+    for (int sl = 0; sl < kAdjTS; sl++) t += s_tmp[(kg * kAdjTS + sl) * 24 + kk * 4 + q];
+    if (k < K) out[k * 4 + q] = t;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+adjust_bwd_frame_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const float* __restrict__ kp,
+                        const float* __restrict__ W, int ld, int K, int g, const float* __restrict__ lin, float width,
+                        float inv_scale, float* __restrict__ dkp /* [n][K][4] */, float* __restrict__ pwg /* [n][128][KMAX] */,
+                        float* __restrict__ pbias /* [n][128] */) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_wg = smem;                                     // [128][KMAX]
+  float* s_dz = s_wg + kAdjC * KMAX;                      // [128][TS + 1]
+  float* s_G = s_dz + kAdjC * (kAdjTS + 1);               // [KMAX][TS]
+  float* s_e = s_G + KMAX * kAdjTS;                       // [KMAX][3][32]
+  float* s_kp = s_e + KMAX * 96;                          // [KMAX][4]
+  float* s_tmp = s_kp + KMAX * 4;                         // [256][24]
+  const int n = blockIdx.x, S = g * g * g;
+  for (int i = threadIdx.x; i < kAdjC * KMAX; i += 256) {
+    const int co = i / KMAX, k = i % KMAX;
+    s_wg[i] = k < K ? W[(long long)co * ld + k] : 0.f;
+  }
+  adj_stage_exps(kp + (long long)n * K * 4, K, g, lin, width, s_e, s_kp);
+  __syncthreads();
+  RenderAcc r;
+#pragma unroll
+  for (int kk = 0; kk < KMAX / 4; kk++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) r.v[kk][q] = 0.f;
+  float accw[12], accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; i++) accw[i] = 0.f;
+  const int wco = threadIdx.x % kAdjC, wk0 = (threadIdx.x / kAdjC) * 12;
+  for (int s0 = 0; s0 < S; s0 += kAdjTS) {
+    adj_load_dz(dy, y, n, 1, S, s0, inv_scale, s_dz);
+    adj_gauss_tile(s_e, s_kp, K, g, s0, s_G);
+    __syncthreads();
+    adj_render_bwd(s_wg, s_dz, s_e, s_kp, lin, K, g, s0, width, r);
+    // dW[co][k] += sum_s dz[co][s] G[k][s];  db[co] += sum_s dz[co][s]
+    const float* dr = s_dz + wco * (kAdjTS + 1);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const float* gr = s_G + (wk0 + i) * kAdjTS;
+      float t = 0.f;
+      for (int sl = 0; sl < kAdjTS; sl++) t = fmaf(dr[sl], gr[sl], t);
+      accw[i] += t;
+    }
+    if (threadIdx.x < kAdjC) {
+      float t = 0.f;
+      for (int sl = 0; sl < kAdjTS; sl++) t += dr[sl];
+      accb += t;
+    }
+    __syncthreads();
+  }
+  adj_render_store(r, s_tmp, K, dkp + (long long)n * K * 4);
+#pragma unroll
+  for (int i = 0; i < 12; i++) pwg[((long long)n * kAdjC + wco) * KMAX + wk0 + i] = accw[i];
+  if (threadIdx.x < kAdjC) pbias[(long long)n * kAdjC + threadIdx.x] = accb;
+}
+
+// per clip, split over `splits` voxel ranges: works on dzs = sum over the clip's frames of dz
+__global__ void __launch_bounds__(256)
+adjust_bwd_clip_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ ff,
+                       const float* __restrict__ kp, const float* __restrict__ W, int ld, int K, int g, int frames_per_clip,
+                       const float* __restrict__ lin, float width, float inv_scale, float grad_scale,
+                       __half* __restrict__ dff /* [clips][S][128] */, float* __restrict__ dkp0 /* [clips][splits][K][4] */,
+                       float* __restrict__ pw /* [clips][splits][128][128 + KMAX + 3] */) {
+  extern __shared__ __align__(16) float smem[];
+  float* s_wff = smem;                                    // [128 co][128 c]
+  float* s_wg = s_wff + kAdjC * kAdjC;                    // [128][KMAX]  (gauss_0 columns)
+  float* s_dz = s_wg + kAdjC * KMAX;                      // [128][TS + 1]
+  float* s_ff = s_dz + kAdjC * (kAdjTS + 1);              // [TS][128]
+  float* s_G = s_ff + kAdjTS * kAdjC;                     // [KMAX][TS]
+  float* s_e = s_G + KMAX * kAdjTS;                       // [KMAX][3][32]
+  float* s_kp = s_e + KMAX * 96;                          // [KMAX][4]
+  float* s_tmp = s_kp + KMAX * 4;                         // [256][24]
+  const int clip = blockIdx.x, split = blockIdx.y, splits = gridDim.y, S = g * g * g;
+  const int per = S / splits;                             // multiple of TS (checked by the host)
+  for (int i = threadIdx.x; i < kAdjC * kAdjC; i += 256) s_wff[i] = W[(long long)(i / kAdjC) * ld + K + i % kAdjC];
+  for (int i = threadIdx.x; i < kAdjC * KMAX; i += 256) {
+    const int co = i / KMAX, k = i % KMAX;
+    s_wg[i] = k < K ? W[(long long)co * ld + K + kAdjC + k] : 0.f;
+  }
+  adj_stage_exps(kp + (long long)clip * frames_per_clip * K * 4, K, g, lin, width, s_e, s_kp);
+  __syncthreads();
+  RenderAcc r;
+#pragma unroll
+  for (int kk = 0; kk < KMAX / 4; kk++)
+#pragma unroll
+    for (int q = 0; q < 4; q++) r.v[kk][q] = 0.f;
+  float accf[64], accg[12], accx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 64; i++) accf[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; i++) accg[i] = 0.f;
+  const int wc = threadIdx.x % kAdjC, half_id = threadIdx.x / kAdjC;   // half_id: 0 / 1
+  for (int s0 = split * per; s0 < (split + 1) * per; s0 += kAdjTS) {
+    adj_load_dz(dy, y, (long long)clip * frames_per_clip, frames_per_clip, S, s0, inv_scale, s_dz);
+    adj_gauss_tile(s_e, s_kp, K, g, s0, s_G);
+    for (int i = threadIdx.x; i < kAdjTS * (kAdjC / 8); i += 256) {
+      const int sl = i / (kAdjC / 8), c8 = i % (kAdjC / 8);
+      float f[8];
+      nm_unpack8(*reinterpret_cast<const half8*>(ff + ((long long)clip * S + s0 + sl) * kAdjC + c8 * 8), f);
+#pragma unroll
+      for (int e = 0; e < 8; e++) s_ff[sl * kAdjC + c8 * 8 + e] = f[e];
+    }
+    __syncthreads();
+    adj_render_bwd(s_wg, s_dz, s_e, s_kp, lin, K, g, s0, width, r);
+    // d first_feature[s][c] = grad_scale * sum_co W[co][K + c] dzs[co][s]: thread (c = wc, 32 voxels)
+    for (int sl = half_id * 32; sl < half_id * 32 + 32; sl++) {
+      float t = 0.f;
+#pragma unroll 8
+      for (int co = 0; co < kAdjC; co++) t = fmaf(s_wff[co * kAdjC + wc], s_dz[co * (kAdjTS + 1) + sl], t);
+      dff[((long long)clip * S + s0 + sl) * kAdjC + wc] = __float2half_rn(t * grad_scale);
+    }
+    // dW[co][K + c] += sum_s dzs[co][s] ff[s][c]: thread (c = wc, co = half_id * 64 ...)
+#pragma unroll 4
+    for (int sl = 0; sl < kAdjTS; sl++) {
+      const float f = s_ff[sl * kAdjC + wc];
+#pragma unroll
+      for (int i = 0; i < 64; i++) accf[i] = fmaf(s_dz[(half_id * 64 + i) * (kAdjTS + 1) + sl], f, accf[i]);
+    }
+    // dW[co][K + 128 + k] += sum_s dzs[co][s] G0[k][s]  (co = wc, 12 keypoints);  coords: thread co = wc of half 0
+    {
+      const float* dr = s_dz + wc * (kAdjTS + 1);
+#pragma unroll
+      for (int i = 0; i < 12; i++) {
+        const float* gr = s_G + (half_id * 12 + i) * kAdjTS;
+        float t = 0.f;
+        for (int sl = 0; sl < kAdjTS; sl++) t = fmaf(dr[sl], gr[sl], t);
+        accg[i] += t;
+      }
+      if (half_id == 0) {
+        for (int sl = 0; sl < kAdjTS; sl++) {
+          const int s = s0 + sl;
+          const float d = dr[sl];
+          accx[0] = fmaf(d, lin[s / (g * g)], accx[0]);
+          accx[1] = fmaf(d, lin[(s / g) % g], accx[1]);
+          accx[2] = fmaf(d, lin[s % g], accx[2]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const long long part = (long long)clip * splits + split;
+  adj_render_store(r, s_tmp, K, dkp0 + part * K * 4);
+  constexpr int LDP = kAdjC + KMAX + 3;
+  float* o = pw + part * kAdjC * LDP;
+#pragma unroll
+  for (int i = 0; i < 64; i++) o[(long long)(half_id * 64 + i) * LDP + wc] = accf[i];
+#pragma unroll
+  for (int i = 0; i < 12; i++) o[(long long)wc * LDP + kAdjC + half_id * 12 + i] = accg[i];
+  if (half_id == 0)
+    for (int a = 0; a < 3; a++) o[(long long)wc * LDP + kAdjC + KMAX + a] = accx[a];
+}
+
+// dW (128, 2K + 131) and db (128) from the per-frame / per-clip partials; dkp[clip's frame 0] += sum over splits of dkp0
+__global__ void adjust_bwd_finalize_kernel(const float* __restrict__ pwg, const float* __restrict__ pbias, const float* __restrict__ pw,
+                                           const float* __restrict__ dkp0, int n, int parts, int clips, int splits,
+                                           int frames_per_clip, int K, float* __restrict__ dW, float* __restrict__ db,
+                                           float* __restrict__ dkp) {
+  const int ld = 2 * K + kAdjC + 3;
+  constexpr int LDP = kAdjC + KMAX + 3;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kAdjC * ld) {
+    const int co = i / ld, col = i % ld;
+    double acc = 0.0;
+    if (col < K) {
+      for (int f = 0; f < n; f++) acc += (double)pwg[((long long)f * kAdjC + co) * KMAX + col];
+    } else {
+      const int pc = col < K + kAdjC ? col - K : (col < 2 * K + kAdjC ? kAdjC + (col - K - kAdjC) : kAdjC + KMAX + (col - 2 * K - kAdjC));
+      for (int p = 0; p < parts; p++) acc += (double)pw[((long long)p * kAdjC + co) * LDP + pc];
+    }
+    dW[i] = (float)acc;
+  } else if (i < kAdjC * ld + kAdjC) {
+    const int co = i - kAdjC * ld;
+    double acc = 0.0;
+    for (int f = 0; f < n; f++) acc += (double)pbias[(long long)f * kAdjC + co];
+    db[co] = (float)acc;
+  } else if (i < kAdjC * ld + kAdjC + clips * K * 4) {
+    const int j = i - kAdjC * ld - kAdjC, clip = j / (K * 4), e = j % (K * 4);
+    float acc = 0.f;
+    for (int sp = 0; sp < splits; sp++) acc += dkp0[((long long)clip * splits + sp) * K * 4 + e];
+    dkp[(long long)clip * frames_per_clip * K * 4 + e] += acc;
+  }
+}
+
+// ------------------------------------------------------------------ chamfer volume-fitting loss backward
+// loss_n = sum_v o_v min_k |c_v - kp_k|^2 / sum_v o_v  ->  d kp_k = g_n / sum o * sum_{v: argmin = k} o_v 2 (kp_k - c_v)
+constexpr int kChbBlocks = 32;
+__global__ void __launch_bounds__(256)
+chamfer_bwd_kernel(const float* __restrict__ seq, const float* __restrict__ kp, int K, int G, const float* __restrict__ lin,
+                   float* __restrict__ partial /* [n][blocks][K*3 + 1] */) {
+  extern __shared__ float sm[];
+  float* s_kp = sm;                       // [K][3]
+  float* s_acc = sm + KMAX * 3;           // [K*3][256] thread-private columns
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < K * 3; i += 256) s_kp[i] = kp[((long long)n * K + i / 3) * 4 + i % 3];
+  for (int i = 0; i < K * 3; i++) s_acc[i * 256 + threadIdx.x] = 0.f;
+  __syncthreads();
+  const int S = G * G * G;
+  float osum = 0.f;
+  for (int s = blockIdx.x * 256 + threadIdx.x; s < S; s += gridDim.x * 256) {
+    const float o = seq[(long long)n * S + s];
+    if (o != 0.f) {
+      const float cx = lin[s / (G * G)], cy = lin[(s / G) % G], cz = lin[s % G];
+      float best = INFINITY;
+      int kb = 0;
+      for (int k = 0; k < K; k++) {
+        const float dx = cx - s_kp[k * 3], dy = cy - s_kp[k * 3 + 1], dz = cz - s_kp[k * 3 + 2];
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (d < best) { best = d; kb = k; }                                // first minimum, as torch.min
+      }
+      s_acc[(kb * 3) * 256 + threadIdx.x] += o * 2.f * (s_kp[kb * 3] - cx);
+      s_acc[(kb * 3 + 1) * 256 + threadIdx.x] += o * 2.f * (s_kp[kb * 3 + 1] - cy);
+      s_acc[(kb * 3 + 2) * 256 + threadIdx.x] += o * 2.f * (s_kp[kb * 3 + 2] - cz);
+      osum += o;
+    }
+  }
+  __syncthreads();
+  float* out = partial + ((long long)n * gridDim.x + blockIdx.x) * (K * 3 + 1);
+  for (int i = threadIdx.x; i < K * 3; i += 256) {
+    float t = 0.f;
+    for (int j = 0; j < 256; j++) t += s_acc[i * 256 + j];
+    out[i] = t;
+  }
+  __shared__ float red[8];
+  osum = nm_warp_sum(osum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = osum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; k++) t += red[k];
+    out[K * 3] = t;
+  }
+}
+
+__global__ void chamfer_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gout, int n, int K,
+                                            int blocks, float* __restrict__ dkp /* [n][K][4] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * K * 4) return;
+  const int f = i / (K * 4), k = (i / 4) % K, a = i % 4;
+  if (a == 3) { dkp[i] = 0.f; return; }
+  double acc = 0.0, os = 0.0;
+  for (int b = 0; b < blocks; b++) {
+    const float* p = partial + ((long long)f * blocks + b) * (K * 3 + 1);
+    acc += (double)p[k * 3 + a];
+    os += (double)p[K * 3];
+  }
+  dkp[i] = (float)((double)gout[f] * acc / os);
+}
+
+// ------------------------------------------------------------------ CoordConv first layer: weight gradient
+// dW[co][c][t] = sum_v dY[v][co] in_c[v + t - 2], t = (tx, ty, tz) in 0..4, in = cat[occ, x, y, z] zero-padded by 2.
+// Coordinate channels: in_a[v + t - 2] = lin[v_a + t_a - 2] inside the volume -> affine in the voxel index, so the sums
+// over the tap's in-bounds box follow from 125 bins (5 position classes per axis: 0, 1, interior, G-2, G-1) of the
+// moments (sum dY, sum x dY, sum y dY, sum z dY).  Occupancy channel: a gather over the occupied voxels.
+template <int C>
+__global__ void __launch_bounds__(256)
+first_wgrad_moments_kernel(const __half* __restrict__ dy, int G, float* __restrict__ bins /* [n][125][4][C] */) {
+  constexpr int CC = C / 8, NVL = 256 / CC;
+  __shared__ float red[256 * 32];
+  const int n = blockIdx.x;
+  const int cc = threadIdx.x % CC, vl = threadIdx.x / CC;
+  const __half* base = dy + (long long)n * G * G * G * C + cc * 8;
+  for (int bin = 0; bin < 125; bin++) {
+    const int cls[3] = {bin / 25, (bin / 5) % 5, bin % 5};
+    int lo[3], cnt[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      lo[a] = cls[a] == 0 ? 0 : (cls[a] == 1 ? 1 : (cls[a] == 2 ? 2 : (cls[a] == 3 ? G - 2 : G - 1)));
+      cnt[a] = cls[a] == 2 ? G - 4 : 1;
+    }
+    const int total = cnt[0] * cnt[1] * cnt[2];
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) acc[i] = 0.f;
+    for (int i = vl; i < total; i += NVL) {
+      const int z = lo[2] + i % cnt[2], y = lo[1] + (i / cnt[2]) % cnt[1], x = lo[0] + i / (cnt[2] * cnt[1]);
+      float f[8];
+      nm_unpack8(*reinterpret_cast<const half8*>(base + (((long long)x * G + y) * G + z) * C), f);
+      const float fx = (float)x, fy = (float)y, fz = (float)z;
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        acc[k] += f[k];
+        acc[8 + k] = fmaf(fx, f[k], acc[8 + k]);
+        acc[16 + k] = fmaf(fy, f[k], acc[16 + k]);
+        acc[24 + k] = fmaf(fz, f[k], acc[24 + k]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 32; i++) red[i * 256 + threadIdx.x] = acc[i];
+    __syncthreads();
+    // moment q (0..3), channel c: sum over the voxel lanes in order
+    for (int i = threadIdx.x; i < 4 * C; i += 256) {
+      const int q = i / C, c = i % C, c8 = c / 8, k = c % 8;
+      float t = 0.f;
+      for (int l = 0; l < NVL; l++) t += red[(q * 8 + k) * 256 + l * CC + c8];
+      bins[(((long long)n * 125 + bin) * 4 + q) * C + c] = t;
+    }
+  }
+}
+
+// occupancy channel: partial[n][125][C] = sum over occupied u of occ[u] * dY[u - (t - 2)]
+template <int C>
+__global__ void __launch_bounds__(256)
+first_wgrad_occ_kernel(const float* __restrict__ occ, const __half* __restrict__ dy, int G, float* __restrict__ partial) {
+  constexpr int CHUNK = 4096, CPL = C / 32;               // channels per lane
+  __shared__ int s_idx[CHUNK];
+  __shared__ float s_val[CHUNK];
+  __shared__ int s_cnt[9];
+  const int n = blockIdx.x, S = G * G * G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc[16][CPL];
+#pragma unroll
+  for (int i = 0; i < 16; i++)
+#pragma unroll
+    for (int j = 0; j < CPL; j++) acc[i][j] = 0.f;
+  const float* on = occ + (long long)n * S;
+  const __half* dyn = dy + (long long)n * S * C + lane * CPL;
+  for (int c0 = 0; c0 < S; c0 += CHUNK) {
+    // ordered compaction of the chunk's non-zero voxels (16 candidates per thread, contiguous)
+    __syncthreads();
+    float v[16];
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const int s = c0 + threadIdx.x * 16 + j;
+      v[j] = s < S ? on[s] : 0.f;
+      mine += v[j] != 0.f;
+    }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_cnt[warp + 1] = incl;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_cnt[0] = 0;
+      for (int k = 1; k <= 8; k++) s_cnt[k] += s_cnt[k - 1];
+    }
+    __syncthreads();
+    int pos = s_cnt[warp] + incl - mine;
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      if (v[j] != 0.f) { s_idx[pos] = c0 + threadIdx.x * 16 + j; s_val[pos] = v[j]; pos++; }
+    __syncthreads();
+    const int count = s_cnt[8];
+    for (int e = 0; e < count; e++) {
+      const int u = s_idx[e];
+      const float val = s_val[e];
+      const int uz = u % G, uy = (u / G) % G, ux = u / (G * G);
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const int t = warp + 8 * i;
+        if (t < 125) {
+          const int vx = ux - (t / 25 - 2), vy = uy - ((t / 5) % 5 - 2), vz = uz - (t % 5 - 2);
+          if ((unsigned)vx < (unsigned)G && (unsigned)vy < (unsigned)G && (unsigned)vz < (unsigned)G) {
+            const __half* p = dyn + (((long long)vx * G + vy) * G + vz) * C;
+            if (CPL == 1) {
+              acc[i][0] = fmaf(val, __half2float(*p), acc[i][0]);
+            } else {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(p));
+              acc[i][0] = fmaf(val, f.x, acc[i][0]);
+              acc[i][CPL - 1] = fmaf(val, f.y, acc[i][CPL - 1]);
+            }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int t = warp + 8 * i;
+    if (t < 125)
+#pragma unroll
+      for (int j = 0; j < CPL; j++) partial[((long long)n * 125 + t) * C + lane * CPL + j] = acc[i][j];
+  }
+}
+
+// dW (C, 4, 5, 5, 5) from the per-frame bins and occupancy partials (fixed order over the frames, fp64)
+__global__ void first_wgrad_finalize_kernel(const float* __restrict__ bins, const float* __restrict__ occp, int n, int C, int G,
+                                            const float* __restrict__ lin, float out_scale, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= C * 4 * 125) return;
+  const int t = i % 125, ch = (i / 125) % 4, co = i / 500;
+  double acc = 0.0;
+  if (ch == 0) {
+    for (int f = 0; f < n; f++) acc += (double)occp[((long long)f * 125 + t) * C + co];
+  } else {
+    const int a = ch - 1;
+    const int tap[3] = {t / 25, (t / 5) % 5, t % 5};
+    const double l0 = lin[0], delta = ((double)lin[G - 1] - (double)lin[0]) / (double)(G - 1);
+    double m0 = 0.0, ma = 0.0;
+    for (int f = 0; f < n; f++)
+      for (int bx = max(0, 2 - tap[0]); bx <= min(4, 6 - tap[0]); bx++)
+        for (int by = max(0, 2 - tap[1]); by <= min(4, 6 - tap[1]); by++)
+          for (int bz = max(0, 2 - tap[2]); bz <= min(4, 6 - tap[2]); bz++) {
+            const float* b = bins + (((long long)f * 125 + (bx * 25 + by * 5 + bz)) * 4) * C;
+            m0 += (double)b[co];
+            ma += (double)b[(1 + a) * C + co];
+          }
+    acc = (l0 + delta * (double)(tap[a] - 2)) * m0 + delta * ma;
+  }
+  dw[i] = (float)(acc * (double)out_scale);
+}
+
+// ------------------------------------------------------------------ Adam (torch.optim.Adam defaults: no amsgrad, no decay)
+__global__ void grad_nonfinite_kernel(const float* __restrict__ g, long long n, int* __restrict__ flag) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = g[i];
+    bad |= !(fabsf(v) <= 3.0e38f);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                            float grad_mul, const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_mul;
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n, int D, int H, int W, int C, void* stream) {
+  NM_CHECK_ARG(grad_out && grad_in, "nm_upsample2x_backward: null pointer");
+  NM_CHECK_ARG(C % 8 == 0 && n > 0 && D > 0 && H > 0 && W > 0, "nm_upsample2x_backward: bad shape");
+  const long long total8 = (long long)n * D * H * W * (C / 8);
+  const int blocks = (int)min((long long)nm_num_sms() * 16, (total8 + 255) / 256);
+  upsample2x_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(grad_out),
+                                                                  reinterpret_cast<__half*>(grad_in), D, H, W, C, total8);
+  NM_CHECK_LAUNCH("upsample2x_bwd_kernel");
+  return NM_OK;
+}
+
+extern "C" size_t nm_final_recon_backward_workspace_bytes(int n) { return ((size_t)n * kFrbBlocks * 33 + 64) * sizeof(float); }
+
+extern "C" int nm_final_recon_backward(const void* x, const float* a, const float* b, const float* w, float bias,
+                                       const float* first_frame, int frames_per_clip, float sharpness, float translation,
+                                       const float* recon, const float* target, const float* grad_bce, float grad_scale,
+                                       void* grad_act, float* dw, float* dbias, void* workspace, int n, int S, int C,
+                                       void* stream) {
+  NM_CHECK_ARG(x && a && b && w && recon && target && grad_bce && grad_act && dw && dbias && workspace,
+               "nm_final_recon_backward: null pointer");
+  NM_CHECK_ARG(C == 32, "nm_final_recon_backward: C=%d unsupported (decoder tail is 32 channels)", C);
+  if (n == 0) return NM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  final_recon_bwd_kernel<<<dim3(kFrbBlocks, n), 256, 0, st>>>(reinterpret_cast<const __half*>(x), a, b, w, bias, first_frame,
+                                                             frames_per_clip, sharpness, translation, recon, target, grad_bce,
+                                                             grad_scale, reinterpret_cast<__half*>(grad_act), partial, S);
+  NM_CHECK_LAUNCH("final_recon_bwd_kernel");
+  // columns 0..31 -> dw, column 32 -> dbias
+  reduce_cols_kernel<<<1, 32, 0, st>>>(partial, (long long)n * kFrbBlocks, 33, 32, 1.0f, dw);
+  NM_CHECK_LAUNCH("final_recon_bwd(reduce dw)");
+  reduce_cols_kernel<<<1, 32, 0, st>>>(partial + 32, (long long)n * kFrbBlocks, 33, 1, 1.0f, dbias);
+  NM_CHECK_LAUNCH("final_recon_bwd(reduce dbias)");
+  return NM_OK;
+}
+
+extern "C" size_t nm_heatmap_head_backward_workspace_bytes(int n, int C, int K) {
+  return ((size_t)n * K * C + (size_t)n * K + (size_t)n * 3) * sizeof(float);
+}
+
+extern "C" int nm_heatmap_head_backward(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K, int mode,
+                                        const float* prev, int frames_per_clip, float pw0, float pw1, float pb,
+                                        const float* linspace, const float* heat, const float* keypoints,
+                                        const float* heat_mean, const float* grad_keypoints, const float* grad_heat_mean,
+                                        const float* grad_heat, const float* dq_in, float grad_scale, void* grad_feature,
+                                        float* dq_out, float* dw1, float* db1, float* dprop, void* workspace, void* stream) {
+  NM_CHECK_ARG(feature && w1 && b1 && linspace && grad_feature && dw1 && db1 && workspace, "nm_heatmap_head_backward: null pointer");
+  NM_CHECK_ARG(K <= KMAX && (g == 8 || g == 16 || g == 32), "nm_heatmap_head_backward: K=%d g=%d unsupported", K, g);
+  NM_CHECK_ARG(mode == 0 || (prev && heat && keypoints && heat_mean && dq_out && dprop),
+               "nm_heatmap_head_backward: mode 1 needs prev, heat, keypoints, heat_mean, dq_out and dprop");
+  NM_CHECK_ARG(C == 128 || C == 256, "nm_heatmap_head_backward: C=%d unsupported", C);
+  if (n == 0) return NM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* pwp = reinterpret_cast<float*>(workspace);
+  float* pbp = pwp + (size_t)n * K * C;
+  float* ppp = pbp + (size_t)n * K;
+  const size_t smem = (size_t)(KMAX * C + 64 * (C + 1) + KMAX * 64 + KMAX * 4 + 256 * 3) * sizeof(float);
+  if (C == 128) {
+    NM_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_bwd_kernel<128><<<n, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
+                                               pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
+                                               grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
+  } else {
+    NM_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_bwd_kernel<256><<<n, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
+                                               pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
+                                               grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
+  }
+  NM_CHECK_LAUNCH("head_bwd_kernel");
+  reduce_cols_kernel<<<nm_cdiv(K * C, 128), 128, 0, st>>>(pwp, n, K * C, K * C, 1.0f, dw1);
+  NM_CHECK_LAUNCH("head_bwd(reduce dw1)");
+  reduce_cols_kernel<<<1, 32, 0, st>>>(pbp, n, K, K, 1.0f, db1);
+  NM_CHECK_LAUNCH("head_bwd(reduce db1)");
+  if (mode == 1) {
+    reduce_cols_kernel<<<1, 32, 0, st>>>(ppp, n, 3, 3, 1.0f, dprop);
+    NM_CHECK_LAUNCH("head_bwd(reduce dprop)");
+  }
+  return NM_OK;
+}
+
+constexpr int kAdjSplits = 8;
+extern "C" size_t nm_decoder_adjust_backward_workspace_bytes(int n_clips, int frames_per_clip) {
+  const size_t n = (size_t)n_clips * frames_per_clip;
+  return (n * kAdjC * KMAX + n * kAdjC + (size_t)n_clips * kAdjSplits * kAdjC * (kAdjC + KMAX + 3) +
+          (size_t)n_clips * kAdjSplits * KMAX * 4) * sizeof(float);
+}
+
+extern "C" int nm_decoder_adjust_backward(const void* grad_out, const void* out, const void* first_feature, const float* keypoints,
+                                          const float* weight, int n_clips, int frames_per_clip, int g, int K,
+                                          const float* linspace, float gauss_width, float grad_scale, void* grad_first_feature,
+                                          float* grad_keypoints, float* dweight, float* dbias, void* workspace, void* stream) {
+  NM_CHECK_ARG(grad_out && out && first_feature && keypoints && weight && linspace && grad_first_feature && grad_keypoints &&
+               dweight && dbias && workspace, "nm_decoder_adjust_backward: null pointer");
+  NM_CHECK_ARG(K <= KMAX && (g == 8 || g == 16 || g == 32), "nm_decoder_adjust_backward: K=%d g=%d unsupported", K, g);
+  if (n_clips == 0) return NM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = n_clips * frames_per_clip, S = g * g * g, ld = 2 * K + kAdjC + 3;
+  float* pwg = reinterpret_cast<float*>(workspace);
+  float* pbias = pwg + (size_t)n * kAdjC * KMAX;
+  float* pw = pbias + (size_t)n * kAdjC;
+  float* dkp0 = pw + (size_t)n_clips * kAdjSplits * kAdjC * (kAdjC + KMAX + 3);
+  const float inv_scale = 1.0f / grad_scale;
+  const size_t smem_f = (size_t)(kAdjC * KMAX + kAdjC * (kAdjTS + 1) + KMAX * kAdjTS + KMAX * 96 + KMAX * 4 + 256 * 24) * sizeof(float);
+  NM_CHECK_CUDA(cudaFuncSetAttribute(adjust_bwd_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
+  adjust_bwd_frame_kernel<<<n, 256, smem_f, st>>>(reinterpret_cast<const __half*>(grad_out), reinterpret_cast<const __half*>(out),
+                                                  keypoints, weight, ld, K, g, linspace, gauss_width, inv_scale, grad_keypoints, pwg, pbias);
+  NM_CHECK_LAUNCH("adjust_bwd_frame_kernel");
+  const size_t smem_c = smem_f + (size_t)(kAdjC * kAdjC + kAdjTS * kAdjC) * sizeof(float);
+  NM_CHECK_CUDA(cudaFuncSetAttribute(adjust_bwd_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+  adjust_bwd_clip_kernel<<<dim3(n_clips, kAdjSplits), 256, smem_c, st>>>(
+      reinterpret_cast<const __half*>(grad_out), reinterpret_cast<const __half*>(out), reinterpret_cast<const __half*>(first_feature),
+      keypoints, weight, ld, K, g, frames_per_clip, linspace, gauss_width, inv_scale, grad_scale,
+      reinterpret_cast<__half*>(grad_first_feature), dkp0, pw);
+  NM_CHECK_LAUNCH("adjust_bwd_clip_kernel");
+  const int total = kAdjC * ld + kAdjC + n_clips * K * 4;
+  adjust_bwd_finalize_kernel<<<nm_cdiv(total, 128), 128, 0, st>>>(pwg, pbias, pw, dkp0, n, n_clips * kAdjSplits, n_clips, kAdjSplits,
+                                                                 frames_per_clip, K, dweight, dbias, grad_keypoints);
+  NM_CHECK_LAUNCH("adjust_bwd_finalize_kernel");
+  return NM_OK;
+}
+
+extern "C" size_t nm_chamfer_vol_fit_backward_workspace_bytes(int n, int K) { return (size_t)n * kChbBlocks * (K * 3 + 1) * sizeof(float); }
+
+extern "C" int nm_chamfer_vol_fit_backward(const float* seq, const float* keypoints, const float* linspace, const float* grad_out,
+                                           int n, int K, int G, float* grad_keypoints, void* workspace, void* stream) {
+  NM_CHECK_ARG(seq && keypoints && linspace && grad_out && grad_keypoints && workspace, "nm_chamfer_vol_fit_backward: null pointer");
+  NM_CHECK_ARG(K <= KMAX, "nm_chamfer_vol_fit_backward: K=%d unsupported", K);
+  if (n == 0) return NM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)(KMAX * 3 + KMAX * 3 * 256) * sizeof(float);
+  NM_CHECK_CUDA(cudaFuncSetAttribute(chamfer_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  chamfer_bwd_kernel<<<dim3(kChbBlocks, n), 256, smem, st>>>(seq, keypoints, K, G, linspace, reinterpret_cast<float*>(workspace));
+  NM_CHECK_LAUNCH("chamfer_bwd_kernel");
+  chamfer_bwd_finalize_kernel<<<nm_cdiv((long long)n * K * 4, 128), 128, 0, st>>>(reinterpret_cast<const float*>(workspace), grad_out, n, K,
+                                                                                 kChbBlocks, grad_keypoints);
+  NM_CHECK_LAUNCH("chamfer_bwd_finalize_kernel");
+  return NM_OK;
+}
+
+extern "C" size_t nm_first_conv_wgrad_workspace_bytes(int n, int Cout) { return (size_t)(n + 1) * 125 * 5 * Cout * sizeof(float); }
+
+extern "C" int nm_first_conv_wgrad(const float* occ, const void* grad_out, const float* linspace, int n, int G, int Cout,
+                                   float out_scale, float* dw, void* workspace, void* stream) {
+  NM_CHECK_ARG(occ && grad_out && linspace && dw && workspace, "nm_first_conv_wgrad: null pointer");
+  NM_CHECK_ARG((Cout == 32 || Cout == 64) && G >= 8 && G % 16 == 0, "nm_first_conv_wgrad: Cout=%d G=%d unsupported", Cout, G);
+  if (n == 0) return NM_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  float* bins = reinterpret_cast<float*>(workspace);
+  float* occp = bins + (size_t)n * 125 * 4 * Cout;
+  const __half* dy = reinterpret_cast<const __half*>(grad_out);
+  if (Cout == 32) {
+    first_wgrad_moments_kernel<32><<<n, 256, 0, st>>>(dy, G, bins);
+    NM_CHECK_LAUNCH("first_wgrad_moments_kernel");
+    first_wgrad_occ_kernel<32><<<n, 256, 0, st>>>(occ, dy, G, occp);
+  } else {
+    first_wgrad_moments_kernel<64><<<n, 256, 0, st>>>(dy, G, bins);
+    NM_CHECK_LAUNCH("first_wgrad_moments_kernel");
+    first_wgrad_occ_kernel<64><<<n, 256, 0, st>>>(occ, dy, G, occp);
+  }
+  NM_CHECK_LAUNCH("first_wgrad_occ_kernel");
+  // sum over the frames first (fixed order), then assemble the (Cout, 4, 5, 5, 5) tensor
+  float* rbins = occp + (size_t)n * 125 * Cout;
+  float* roccp = rbins + (size_t)125 * 4 * Cout;
+  reduce_cols_kernel<<<nm_cdiv(500 * Cout, 128), 128, 0, st>>>(bins, n, 500 * Cout, 500 * Cout, 1.0f, rbins);
+  NM_CHECK_LAUNCH("first_wgrad(reduce bins)");
+  reduce_cols_kernel<<<nm_cdiv(125 * Cout, 128), 128, 0, st>>>(occp, n, 125 * Cout, 125 * Cout, 1.0f, roccp);
+  NM_CHECK_LAUNCH("first_wgrad(reduce occ)");
+  first_wgrad_finalize_kernel<<<nm_cdiv(Cout * 500, 128), 128, 0, st>>>(rbins, roccp, 1, Cout, G, linspace, out_scale, dw);
+  NM_CHECK_LAUNCH("first_wgrad_finalize_kernel");
+  return NM_OK;
+}
+
+extern "C" int nm_grad_nonfinite(const float* grad, long long count, int* flag, void* stream) {
+  NM_CHECK_ARG(grad && flag, "nm_grad_nonfinite: null pointer");
+  if (count <= 0) return NM_OK;
+  const int blocks = (int)min((long long)nm_num_sms() * 4, (count + 255) / 256);
+  grad_nonfinite_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, count, flag);
+  NM_CHECK_LAUNCH("grad_nonfinite_kernel");
+  return NM_OK;
+}
+
+extern "C" int nm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr,
+                            float beta1, float beta2, float eps, int step, float grad_mul, const int* skip_flag, void* stream) {
+  NM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "nm_adam_step: null pointer");
+  NM_CHECK_ARG(step >= 1, "nm_adam_step: step counts from 1");
+  if (count <= 0) return NM_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const int blocks = (int)min((long long)nm_num_sms() * 8, (count + 255) / 256);
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, (float)bc1,
+                                                        (float)sqrt(bc2), grad_mul, skip_flag);
+  NM_CHECK_LAUNCH("adam_kernel");
+  return NM_OK;
+}

@@ -145,7 +145,8 @@ conv_wgrad_k3_kernel(const __half* __restrict__ x, const __half* __restrict__ gy
 }
 
 // fixed-order sum over the chunks, written in the PyTorch layout (Cout, Cin, 3, 3, 3)
-__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int Cin, int Cout, float* __restrict__ dw) {
+__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partial, int chunks, int Cin, int Cout, float out_scale,
+                                         float* __restrict__ dw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * Cin * 27) return;
   const int tap = i % 27, ci = (i / 27) % Cin, co = i / (27 * Cin);
@@ -155,7 +156,7 @@ __global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partial, int 
   const long long stride = (long long)cib * cob * (27 * 1024);
   float s = 0.f;
   for (int c = 0; c < chunks; c++) s += partial[c * stride + off];
-  dw[i] = s;
+  dw[i] = s * out_scale;
 }
 
 int wgrad_chunks(int N, int D, int H, int Cin, int Cout) {
@@ -174,8 +175,8 @@ extern "C" size_t nm_conv3d_k3_wgrad_workspace_bytes(int N, int D, int H, int W,
   return (size_t)wgrad_chunks(N, D, H, Cin, Cout) * (Cin / 32) * (Cout / 32) * 27 * 1024 * sizeof(float);
 }
 
-extern "C" int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int N, int D, int H, int W, int Cin, int Cout, float* dw,
-                                  void* workspace, void* stream) {
+extern "C" int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int N, int D, int H, int W, int Cin, int Cout,
+                                  float out_scale, float* dw, void* workspace, void* stream) {
   NM_CHECK_ARG(x && grad_out && dw && workspace, "nm_conv3d_k3_wgrad: null pointer");
   NM_CHECK_ARG(N > 0 && D > 0 && H > 0, "nm_conv3d_k3_wgrad: empty input");
   NM_CHECK_ARG(W % 16 == 0 && W >= 16 && W <= kMaxW, "nm_conv3d_k3_wgrad: W must be 16, 32, 48 or 64 (got %d)", W);
@@ -184,15 +185,11 @@ extern "C" int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int N, in
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = wgrad_chunks(N, D, H, Cin, Cout);
   const size_t smem = (size_t)(kMaxW + 9 * (W + 2)) * kRowHalfs * sizeof(__half);
-  static bool attr = false;
-  static int use_async = 0;
-  if (!attr) {
-    NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_k3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_k3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    const char* e = getenv("NM_WGRAD_ASYNC");       // experiment switch, default = the verified synchronous staging
-    use_async = e && atoi(e) != 0;
-    attr = true;
-  }
+  // the attribute is per device: set it on every call (cheap) rather than once per process
+  NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_k3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_k3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  const char* e = getenv("NM_WGRAD_ASYNC");         // experiment switch, default = the synchronous staging
+  const int use_async = e && atoi(e) != 0;
   const dim3 grid(chunks, Cin / 32, Cout / 32);
   if (use_async)
     conv_wgrad_k3_kernel<true><<<grid, kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(grad_out),
@@ -202,7 +199,7 @@ extern "C" int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int N, in
                                                               N, D, H, W, Cin, Cout, reinterpret_cast<float*>(workspace));
   NM_CHECK_LAUNCH("conv_wgrad_k3_kernel");
   conv_wgrad_reduce_kernel<<<nm_cdiv((long long)Cout * Cin * 27, 256), 256, 0, st>>>(reinterpret_cast<const float*>(workspace),
-                                                                                     chunks, Cin, Cout, dw);
+                                                                                     chunks, Cin, Cout, out_scale, dw);
   NM_CHECK_LAUNCH("conv_wgrad_reduce_kernel");
   return NM_OK;
 }

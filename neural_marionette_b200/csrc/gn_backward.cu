@@ -80,17 +80,22 @@ gnb_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, c
 }
 
 // mean / rstd per (sample, group) from the pass-A partials (fp64, fixed order)
-__global__ void gnb_stats_finalize_kernel(const float* __restrict__ partial, GnbShape s, float eps, float* __restrict__ mean_rstd) {
+__global__ void gnb_stats_finalize_kernel(const float* __restrict__ partial, GnbShape s, float eps, float* __restrict__ mean_rstd,
+                                          float* __restrict__ xsum /* [n][C] */) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s.n * s.groups) return;
   const int n = i / s.groups, grp = i % s.groups;
   double s1 = 0.0, s2 = 0.0;
-  for (int ch = 0; ch < kGnbChunks; ch++)
-    for (int c = grp * s.cpg; c < (grp + 1) * s.cpg; c++) {
+  for (int c = grp * s.cpg; c < (grp + 1) * s.cpg; c++) {
+    double c1 = 0.0;
+    for (int ch = 0; ch < kGnbChunks; ch++) {
       const float* p = partial + (((long long)n * kGnbChunks + ch) * s.C + c) * 2;
-      s1 += p[0];
+      c1 += p[0];
       s2 += p[1];
     }
+    xsum[(long long)n * s.C + c] = (float)c1;
+    s1 += c1;
+  }
   const double M = (double)s.cpg * (double)s.S;
   const double mu = s1 / M;
   double var = s2 / M - mu * mu;                                        // biased variance, as nn.GroupNorm
@@ -101,8 +106,9 @@ __global__ void gnb_stats_finalize_kernel(const float* __restrict__ partial, Gnb
 
 // per (sample, channel) totals of pass B -> group means m1, m2 (per sample, group) and dgamma / dbeta contributions
 __global__ void gnb_grad_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                         const float* __restrict__ mean_rstd, GnbShape s, float* __restrict__ m12,
-                                         float* __restrict__ chan /* [n][C][2]: sum dy, sum dy*xhat */) {
+                                         const float* __restrict__ mean_rstd, const float* __restrict__ xsum, GnbShape s,
+                                         float* __restrict__ m12,
+                                         float* __restrict__ chan /* [n][C][3]: sum dy, sum dy*xhat, sum dx */) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= s.n * s.groups) return;
   const int n = i / s.groups, grp = i % s.groups;
@@ -116,26 +122,98 @@ __global__ void gnb_grad_finalize_kernel(const float* __restrict__ partial, cons
       p2 += p[1];
     }
     const double dyxhat = rs * (p2 - mu * p1);                          // sum dy * xhat
-    chan[((long long)n * s.C + c) * 2] = (float)p1;
-    chan[((long long)n * s.C + c) * 2 + 1] = (float)dyxhat;
+    chan[((long long)n * s.C + c) * 3] = (float)p1;
+    chan[((long long)n * s.C + c) * 3 + 1] = (float)dyxhat;
     a1 += (double)gamma[c] * p1;
     a2 += (double)gamma[c] * dyxhat;
   }
   const double M = (double)s.cpg * (double)s.S;
-  m12[i * 2] = (float)(a1 / M);
-  m12[i * 2 + 1] = (float)(a2 / M);
+  const double m1 = a1 / M, m2 = a2 / M;
+  m12[i * 2] = (float)m1;
+  m12[i * 2 + 1] = (float)m2;
+  // sum over the voxels of dx = rstd * (gamma * dy - m1 - xhat * m2), in closed form from the channel totals
+  for (int c = grp * s.cpg; c < (grp + 1) * s.cpg; c++) {
+    const double p1 = chan[((long long)n * s.C + c) * 3];
+    const double xhat_sum = rs * ((double)xsum[(long long)n * s.C + c] - (double)s.S * mu);
+    chan[((long long)n * s.C + c) * 3 + 2] = (float)(rs * ((double)gamma[c] * p1 - (double)s.S * m1 - xhat_sum * m2));
+  }
 }
 
-__global__ void gnb_param_grad_kernel(const float* __restrict__ chan, GnbShape s, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+__global__ void gnb_param_grad_kernel(const float* __restrict__ chan, int n_samples, int C, float out_scale,
+                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= s.C) return;
-  double db = 0.0, dg = 0.0;
-  for (int n = 0; n < s.n; n++) {                                        // fixed order over the samples
-    db += chan[((long long)n * s.C + c) * 2];
-    dg += chan[((long long)n * s.C + c) * 2 + 1];
+  if (c >= C) return;
+  double db = 0.0, dg = 0.0, dx = 0.0;
+  for (int n = 0; n < n_samples; n++) {                                  // fixed order over the samples
+    db += chan[((long long)n * C + c) * 3];
+    dg += chan[((long long)n * C + c) * 3 + 1];
+    dx += chan[((long long)n * C + c) * 3 + 2];
   }
-  if (dbeta) dbeta[c] = (float)db;
-  if (dgamma) dgamma[c] = (float)dg;
+  if (dbeta) dbeta[c] = (float)(db * (double)out_scale);
+  if (dgamma) dgamma[c] = (float)(dg * (double)out_scale);
+  if (dxsum) dxsum[c] = (float)(dx * (double)out_scale);
+}
+
+// Any (C, groups) on small tensors (hour-glass levels with 48 / 72 channels, 18 channels per group): one warp per
+// (sample, group), three sweeps over the group's S * cpg values, butterfly reductions (fixed order).
+__global__ void __launch_bounds__(32)
+gnb_small_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int C, int groups, long long S, float eps, int leaky,
+                 __half* __restrict__ dx, float* __restrict__ chan /* [n][C][3] */) {
+  const int n = blockIdx.y, grp = blockIdx.x, lane = threadIdx.x;
+  const int cpg = C / groups, c0 = grp * cpg;
+  const long long M = (long long)cpg * S;
+  const __half* xs = x + (long long)n * S * C;
+  const __half* ds = dz + (long long)n * S * C;
+  float s1 = 0.f, s2 = 0.f;
+  for (long long i = lane; i < M; i += 32) {
+    const float v = __half2float(xs[(i / cpg) * C + c0 + (int)(i % cpg)]);
+    s1 += v;
+    s2 = fmaf(v, v, s2);
+  }
+  s1 = nm_warp_sum(s1);
+  s2 = nm_warp_sum(s2);
+  const float mu = s1 / (float)M;
+  const float rs = rsqrtf(fmaxf(s2 / (float)M - mu * mu, 0.f) + eps);
+  float a1 = 0.f, a2 = 0.f;
+  for (int c = c0; c < c0 + cpg; c++) {
+    const float g = gamma[c], b = beta[c];
+    float p1 = 0.f, p2 = 0.f, xh = 0.f;
+    for (long long v = lane; v < S; v += 32) {
+      const float xhat = (__half2float(xs[v * C + c]) - mu) * rs;
+      const float y = fmaf(g, xhat, b);
+      const float d = __half2float(ds[v * C + c]);
+      const float dy = (leaky && !(y > 0.f)) ? 0.01f * d : d;
+      p1 += dy;
+      p2 = fmaf(dy, xhat, p2);
+      xh += xhat;
+    }
+    p1 = nm_warp_sum(p1);
+    p2 = nm_warp_sum(p2);
+    xh = nm_warp_sum(xh);
+    if (lane == 0) {
+      chan[((long long)n * C + c) * 3] = p1;
+      chan[((long long)n * C + c) * 3 + 1] = p2;
+      chan[((long long)n * C + c) * 3 + 2] = xh;             // completed below once m1, m2 are known
+    }
+    a1 = fmaf(g, p1, a1);
+    a2 = fmaf(g, p2, a2);
+  }
+  const float m1 = a1 / (float)M, m2 = a2 / (float)M;
+  __syncwarp();
+  for (int c = c0 + lane; c < c0 + cpg; c += 32) {
+    float* q = chan + ((long long)n * C + c) * 3;
+    q[2] = rs * (gamma[c] * q[0] - (float)S * m1 - q[2] * m2);
+  }
+  for (long long i = lane; i < M; i += 32) {
+    const long long off = (i / cpg) * C + c0 + (int)(i % cpg);
+    const int c = c0 + (int)(i % cpg);
+    const float xhat = (__half2float(xs[off]) - mu) * rs;
+    const float y = fmaf(gamma[c], xhat, beta[c]);
+    const float d = __half2float(ds[off]);
+    const float dy = (leaky && !(y > 0.f)) ? 0.01f * d : d;
+    dx[(long long)n * S * C + off] = __float2half_rn(rs * (gamma[c] * dy - m1 - xhat * m2));
+  }
 }
 
 // pass C: dx = rstd * (gamma * dy - m1 - xhat * m2)
@@ -172,46 +250,55 @@ bool gnb_shape(int n, long long S, int C, int groups, GnbShape* s) {
   return true;
 }
 
-size_t gnb_ws_floats(const GnbShape& s) {
-  return (size_t)s.n * kGnbChunks * s.C * 2 /* partial */ + (size_t)s.n * s.groups * 4 /* mean_rstd, m12 */ +
-         (size_t)s.n * s.C * 2 /* chan */;
+size_t gnb_ws_floats(int n, int C, int groups) {
+  return (size_t)n * kGnbChunks * C * 2 /* partial */ + (size_t)n * groups * 4 /* mean_rstd, m12 */ +
+         (size_t)n * C * 3 /* chan */ + (size_t)n * C /* xsum */;
 }
 
 }  // namespace
 
 extern "C" size_t nm_groupnorm_backward_workspace_bytes(int n, int C, int groups) {
-  GnbShape s;
-  if (!gnb_shape(n, 1, C, groups, &s)) return 0;
-  return gnb_ws_floats(s) * sizeof(float) + 64;
+  if (n <= 0 || C <= 0 || groups <= 0 || C % groups) return 0;
+  return gnb_ws_floats(n, C, groups) * sizeof(float) + 64;
 }
 
 extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const float* gamma, const float* beta, int n,
-                                     long long S, int C, int groups, float eps, int leaky, void* grad_in, float* dgamma,
-                                     float* dbeta, void* workspace, void* stream) {
+                                     long long S, int C, int groups, float eps, int leaky, float out_scale, void* grad_in,
+                                     float* dgamma, float* dbeta, float* dxsum, void* workspace, void* stream) {
   NM_CHECK_ARG(x && grad_out && gamma && beta && grad_in && workspace, "nm_groupnorm_backward: null pointer");
-  GnbShape s;
-  NM_CHECK_ARG(gnb_shape(n, S, C, groups, &s),
-               "nm_groupnorm_backward: need C in {8, 16, 32, 64, 128, 256} and channels per group a multiple of 8 (got C=%d, groups=%d)",
-               C, groups);
+  NM_CHECK_ARG(n > 0 && S > 0 && C > 0 && groups > 0 && C % groups == 0, "nm_groupnorm_backward: bad shape (C=%d, groups=%d)", C, groups);
   NM_CHECK_ARG(n <= 65535, "nm_groupnorm_backward: at most 65535 samples per call");
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
   float* mean_rstd = partial + (size_t)n * kGnbChunks * C * 2;
   float* m12 = mean_rstd + (size_t)n * groups * 2;
   float* chan = m12 + (size_t)n * groups * 2;
+  float* xsum = chan + (size_t)n * C * 3;
   const __half* xh = reinterpret_cast<const __half*>(x);
   const __half* dz = reinterpret_cast<const __half*>(grad_out);
+  GnbShape s;
+  if (!gnb_shape(n, S, C, groups, &s)) {
+    // shapes outside the streaming kernels (48 / 72 channels): the small-tensor kernel, one warp per (sample, group)
+    NM_CHECK_ARG(S * (C / groups) <= (1 << 16), "nm_groupnorm_backward: C=%d (groups=%d) is only supported on small tensors", C, groups);
+    gnb_small_kernel<<<dim3(groups, n), 32, 0, st>>>(xh, dz, gamma, beta, C, groups, S, eps, leaky, reinterpret_cast<__half*>(grad_in), chan);
+    NM_CHECK_LAUNCH("gnb_small_kernel");
+    if (dgamma || dbeta || dxsum) {
+      gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, n, C, out_scale, dgamma, dbeta, dxsum);
+      NM_CHECK_LAUNCH("gnb_param_grad_kernel");
+    }
+    return NM_OK;
+  }
   const dim3 rgrid(kGnbChunks, n);
   gnb_reduce_kernel<true><<<rgrid, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, s, leaky, partial);
   NM_CHECK_LAUNCH("gnb_reduce_kernel<stats>");
-  gnb_stats_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, s, eps, mean_rstd);
+  gnb_stats_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, s, eps, mean_rstd, xsum);
   NM_CHECK_LAUNCH("gnb_stats_finalize_kernel");
   gnb_reduce_kernel<false><<<rgrid, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, s, leaky, partial);
   NM_CHECK_LAUNCH("gnb_reduce_kernel<grad>");
-  gnb_grad_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, gamma, mean_rstd, s, m12, chan);
+  gnb_grad_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, gamma, mean_rstd, xsum, s, m12, chan);
   NM_CHECK_LAUNCH("gnb_grad_finalize_kernel");
-  if (dgamma || dbeta) {
-    gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, s, dgamma, dbeta);
+  if (dgamma || dbeta || dxsum) {
+    gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, n, C, out_scale, dgamma, dbeta, dxsum);
     NM_CHECK_LAUNCH("gnb_param_grad_kernel");
   }
   const long long total = (long long)n * S * s.ccs;

@@ -11,13 +11,17 @@ arithmetic runs through the nm_b200 CUDA kernels:
     the decoder's 179-channel concat is never built (its clip-constant part is hoisted), the final 1x1 conv,
     tanh/sigmoid and the BCE reduction are one kernel.
 
-Inference only for now: calling forward with autograd enabled in training mode raises (no silent fallback).
+Training (`net.train()` with autograd enabled, reference train.py:387-409): `KyptDetector.forward` runs the same
+kernels through the autograd Functions of `neural_marionette_b200/autograd.py`; `loss.backward()` then runs the backward
+kernels (data / weight gradients of the convs, GroupNorm, up-sampling, heads, render, losses) and leaves fp32 gradients
+in `param.grad` like the reference.  `VoxToKyptNet.forward` / `KyptToVoxNet.forward` on their own stay inference-only.
 """
 from __future__ import annotations
 
 import torch
 from torch import nn
 
+from .. import autograd as AG
 from .. import ops
 from ..modules.vox_modules import HG, Basic3DBlock, Pool3DBlock, Res3DBlock
 from ..utils.kypt_detector_utils import (get_graph_consistency_loss, get_graph_traj_loss,
@@ -40,11 +44,15 @@ ST_OVERLAP = __import__("os").environ.get("NM_ST_OVERLAP", "1") != "0"
 UP_DEC1 = __import__("os").environ.get("NM_UP_DEC1", "1") != "0"
 
 
+def _training(module) -> bool:
+    return module.training and torch.is_grad_enabled()
+
+
 def _no_training(module):
-    if module.training and torch.is_grad_enabled():
+    if _training(module):
         raise NotImplementedError(
-            "neural_marionette_b200: the backward kernels are not implemented yet; call .eval() / use "
-            "torch.no_grad() (inference), or train with the reference implementation")
+            "neural_marionette_b200: autograd is wired through KyptDetector.forward only; call this sub-module under "
+            "torch.no_grad() / .eval(), or train through KyptDetector / NeuralMarionette")
 
 
 def _heatmap_net(in_channels, out_channels, act):
@@ -72,6 +80,14 @@ def run_feature_net(net: nn.Sequential, occ: torch.Tensor) -> torch.Tensor:
     x = net[3].run(raw, in_affine=(a, b, False, x2, a2, b2))
     for block in list(net)[4:]:
         x = block.run(x)
+    return x
+
+
+def run_feature_net_train(net: nn.Sequential, occ: torch.Tensor) -> torch.Tensor:
+    """Training-mode feature net: every block through its autograd Function (activations kept for the backward)."""
+    x = net[0].run_coordconv_train(occ)
+    for block in list(net)[1:]:
+        x = block.run_train(x)
     return x
 
 
@@ -143,6 +159,30 @@ class VoxToKyptNet(nn.Module):
                         gaussians=gss.view(B, T, K, g, g, g) if want_gaussians else None,
                         first_feature=ops.act_to_ncdhw(ff_act), first_feature_act=ff_act,
                         heat_mean=hmean.view(B, T, K))
+
+    def detect_train(self, seq):
+        """Training-mode `detect` (autograd): same outputs, `gaussians` omitted (the decoder re-renders them from the
+        keypoints), `first_feature_act` / `keypoints` / `heat_mean` carry the graph."""
+        B, T = seq.shape[:2]
+        G, K, g = self.grid_size, self.nkeypoints, self.grid_size // 4
+        assert seq.shape[2] == 1 and tuple(seq.shape[3:]) == (G, G, G), "expected (B, T, 1, G, G, G) occupancy"
+        if B * T > frames_per_pass(G):
+            raise ValueError(f"training step: {B * T} frames exceed one pass ({frames_per_pass(G)}); lower the batch "
+                             "or raise NM_FRAME_CHUNK")
+        seq = seq.detach().float().contiguous()
+        sigma = float(self.sigmas[0])
+        link = {}
+        st = run_feature_net_train(self.extract_spatio_temporal_features, ops.mean_over_frames(seq))
+        st_head = self.extract_spatio_temporal_heatmaps_from_features[0]
+        prev = AG.HeadST.apply(st, st_head.weight, st_head.bias, st_head, K, link)
+        feat = run_feature_net_train(self.extract_features, seq.view(B * T, G, G, G))
+        head, prop = self.extract_heatmaps_from_features[0], self.propagate_heatmaps[0]
+        heat, kps, hmean = AG.Head.apply(feat, head.weight, head.bias, prev, prop.weight, prop.bias, head, prop, K, T,
+                                         sigma, link)
+        ff_act = feat.view(B, T, g, g, g, self.feat_dim)[:, 0].contiguous()
+        return dict(heatmaps=heat.view(B, T, K, g, g, g), keypoints=kps.view(B, T, K, 4), gaussians=None,
+                    first_feature=ops.act_to_ncdhw(ff_act.detach()), first_feature_act=ff_act,
+                    heat_mean=hmean.view(B, T, K))
 
     def forward(self, seq, Tcond=None):
         out = self.detect(seq)
@@ -227,6 +267,25 @@ class KyptToVoxNet(nn.Module):
                                 bce_out=bce[b0:b1].view(n) if target is not None else None)
             return (recon, bce) if target is not None else recon
 
+    def decode_train(self, first_feature_act, first_frame, keypoints, target, sigma=1.5, sharpness=10.0, translation=0.5):
+        """Training-mode `decode` (autograd): keypoints (B, T, K, 4) with graph -> (recon (B, T, 1, G, G, G), BCE (B, T))."""
+        B, T = keypoints.shape[:2]
+        G, g, K = self.grid_size, self.output_map_width, self.nkeypoints
+        dec = self.decode_voxel_from_combined_representation
+        adj = self.adjust_combined_representation[0]
+        n = B * T
+        first_frame = first_frame.detach().float().contiguous().view(B, G, G, G)
+        target = target.detach().float().contiguous().view(n, G, G, G)
+        x = AG.Adjust.apply(first_feature_act, keypoints.reshape(n, K, 4).contiguous(), adj.weight, adj.bias, adj, T, g, K,
+                            sigma)
+        x = AG.conv_gn_act(AG.Upsample2x.apply(x), dec[1], dec[2], True)
+        x = AG.conv_gn_act(x, dec[4], dec[5], True)
+        x = AG.conv_gn_act(AG.Upsample2x.apply(x), dec[8], dec[9], True)
+        recon, bce = AG.ConvGNFinalRecon.apply(x, dec[11].weight, dec[11].bias, dec[12].weight, dec[12].bias,
+                                               dec[14].weight, dec[14].bias, first_frame, target, dec[11], dec[12],
+                                               dec[14], T, sharpness, translation)
+        return recon.view(B, T, 1, G, G, G), bce.view(B, T)
+
     def forward(self, gaussians, first_feature, first_frame, sharpness=10.0, translation=0.5):
         """gaussians (B, T, K, g, g, g), first_feature (B, 128, g, g, g), first_frame (B, 1, G, G, G)."""
         return self.decode(ops.ncdhw_to_act(first_feature), first_frame, gaussians=gaussians, sharpness=sharpness,
@@ -296,7 +355,45 @@ class KyptDetector(nn.Module):
         lower = torch.cat([torch.tril(w, diagonal=-1), torch.zeros_like(w[..., :1])], dim=-1)
         return (upper + lower).unsqueeze(-1)
 
+    def forward_train(self, seq):
+        """`forward` with the autograd graph (reference kypt_detector.py:81-169 under `network.train()`): every loss
+        term is differentiable w.r.t. the detector parameters it depends on."""
+        B, T = seq.shape[:2]
+        dev = seq.device
+        G, K = self.grid_size, self.nkeypoints
+        det = self.vox_to_kypt.detect_train(seq)
+        keypoints, heatmaps = det["keypoints"], det["heatmaps"]
+        recon, bce = self.kypt_to_vox.decode_train(det["first_feature_act"], seq[:, 0], keypoints, seq,
+                                                   sigma=float(self.sigmas[0]))
+        zeros = torch.zeros(B, T, device=dev)
+        if self.vol_fit_type == "chamfer":
+            frames = seq.detach().float().contiguous().view(B * T, G, G, G)
+            vol_fit = AG.ChamferVolFit.apply(frames, keypoints.reshape(B * T, K, 4).contiguous()).view(B, T)
+        else:
+            vol_fit = get_volume_fitting_loss(seq, keypoints, self.vox_to_kypt.sigmas, self.vol_fit_type)
+        if self.keypoints_graph == "none" or not self.affinity_start:
+            affinity = None
+            local = timec = sparse = inten = traj = zeros
+        else:
+            affinity = self.get_affinity()
+            kp_graph = keypoints.detach() if self.keypoints_detach else keypoints
+            local, timec, sparse, inten = get_graph_consistency_loss(
+                kp_graph, affinity, local_const=self.using_local_const, time_const=self.using_time_const,
+                sparsity_const=self.using_sparsity_const, intensity_const=self.using_intensity_const,
+                ver=self.graph_loss_ver)
+            traj = get_graph_traj_loss(kp_graph, affinity, ver=self.graph_loss_ver) if self.using_graph_traj else zeros
+        return dict(
+            recon=recon, keypoints=keypoints, heatmaps=heatmaps, affinity=affinity,
+            recon_loss=bce.mean(), vol_fit_reg=vol_fit.mean(), kypt_const_loss=zeros.mean(),
+            separation_loss=get_temporal_separation_loss(keypoints, self.sep_sigma).mean(),
+            sparsity_loss=sparsity_loss_from_means(det["heat_mean"]).mean(),
+            local_const_loss=local.mean(), time_const_loss=timec.mean(), sparsity_const_loss=sparse.mean(),
+            intensity_const_loss=inten.mean(), graph_traj_loss=traj.mean(), graph_vol_loss=zeros.mean(),
+            first_feature=det["first_feature"])
+
     def forward(self, seq, Tcond=None):
+        if _training(self):
+            return self.forward_train(seq)
         B, T = seq.shape[:2]
         dev = seq.device
         det = self.vox_to_kypt.detect(seq, want_gaussians=False)

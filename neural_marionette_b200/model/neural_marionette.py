@@ -2,6 +2,8 @@
 dynamics module, routes `forward` (track) and `generate` (condition + roll-out + decode)."""
 from __future__ import annotations
 
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -38,7 +40,8 @@ class NeuralMarionette(nn.Module):
         """vox_seq (B, T, 1, G, G, G).  Detector (no grad if inactive) then `dyna_module.encode`."""
         log = {}
         if module_actives["detector"] or module_actives["learner"]:
-            ctx = torch.enable_grad() if module_actives["detector"] else torch.no_grad()
+            # the caller's grad mode is inherited when the detector is active (reference neural_marionette.py:40-44)
+            ctx = contextlib.nullcontext() if module_actives["detector"] else torch.no_grad()
             with ctx:
                 det = self.kypt_detector(vox_seq)
             log.update(det)

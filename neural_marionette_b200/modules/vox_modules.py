@@ -12,6 +12,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
+from .. import autograd as AG
 from .. import ops
 
 
@@ -20,7 +21,8 @@ def _norm(channels: int) -> nn.GroupNorm:
 
 
 class _ActModule(nn.Module):
-    """forward() = NCDHW fp32 in/out around run() (inference only: no autograd graph)."""
+    """forward() = NCDHW fp32 in/out around run() (no autograd graph: the training step goes through
+    KyptDetector.forward, which calls run_train())."""
 
     def forward(self, x):
         with torch.no_grad():
@@ -57,6 +59,12 @@ class Basic3DBlock(_ActModule):
     def run(self, x):
         return conv_gn_lrelu(x, self.block[0], self.block[1])
 
+    def run_train(self, x):
+        return AG.conv_gn_act(x, self.block[0], self.block[1], True)
+
+    def run_coordconv_train(self, occ):
+        return AG.first_conv_gn_act(occ, self.block[0], self.block[1])
+
     def run_coordconv(self, occ):
         """occ (n, G, G, G) fp32 occupancy; the 3 coordinate channels are synthesised in-kernel."""
         raw, a, b = self.run_coordconv_raw(occ)
@@ -86,6 +94,12 @@ class Res3DBlock(_ActModule):
         raw, a, b, x2, a2, b2 = self.run_raw(x)
         return ops.affine_act(raw, a, b, False, x2=x2, a2=a2, b2=b2)
 
+    def run_train(self, x):
+        """Training-mode forward (autograd Functions; activations are materialised for the backward)."""
+        h = AG.conv_gn_act(x, self.res_branch[0], self.res_branch[1], True)
+        skip = x if len(self.skip_con) == 0 else AG.conv_gn_act(x, self.skip_con[0], self.skip_con[1], False)
+        return AG.conv_gn_act(h, self.res_branch[3], self.res_branch[4], False, res=skip)
+
     def run_raw(self, x):
         """-> (raw, scale, shift, x2, scale2, shift2) with block output = raw*scale+shift + x2*scale2+shift2 (x2 as is
         when scale2 is None): a consumer that can apply this in its operand path avoids one pass over the tensor."""
@@ -113,6 +127,9 @@ class Pool3DBlock(_ActModule):
     def run(self, x, in_affine=None):
         return conv_gn_lrelu(x, self.stride_conv[0], self.stride_conv[1], in_affine)
 
+    def run_train(self, x):
+        return AG.conv_gn_act(x, self.stride_conv[0], self.stride_conv[1], True)
+
 
 class Upsample3DBlock(_ActModule):
     """ConvTranspose3d(k2, s2) -> GN -> LReLU (reference vox_modules.py:63-75)."""
@@ -128,6 +145,9 @@ class Upsample3DBlock(_ActModule):
     def run(self, x, skip=None):
         raw, a, b = ops.conv_transpose3d(x, self.block[0], self.block[1])
         return ops.affine_act(raw, a, b, True, x2=skip)
+
+    def run_train(self, x, skip=None):
+        return AG.conv_gn_act(x, self.block[0], self.block[1], True, res=skip)
 
 
 class HG(_ActModule):
@@ -164,3 +184,15 @@ class HG(_ActModule):
         x = self.decoder_res2.run(self.decoder_upsample3.run(x, skip=s3))
         x = self.decoder_res1.run(self.decoder_upsample2.run(x, skip=s2))
         return self.decoder_upsample1.run(x, skip=s1)
+
+    def run_train(self, x):
+        s1 = self.skip_res1.run_train(x)
+        x = self.encoder_res1.run_train(self.encoder_pool1.run_train(x))
+        s2 = self.skip_res2.run_train(x)
+        x = self.encoder_res2.run_train(self.encoder_pool2.run_train(x))
+        s3 = self.skip_res3.run_train(x)
+        x = self.encoder_res3.run_train(self.encoder_pool3.run_train(x))
+        x = self.decoder_res3.run_train(x)
+        x = self.decoder_res2.run_train(self.decoder_upsample3.run_train(x, skip=s3))
+        x = self.decoder_res1.run_train(self.decoder_upsample2.run_train(x, skip=s2))
+        return self.decoder_upsample1.run_train(x, skip=s1)

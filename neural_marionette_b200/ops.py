@@ -223,41 +223,106 @@ def can_conv_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d) -> bool:
         bool(L.query("nm_conv3d_up2x_supported", n, 2 * D, 2 * H, 2 * W, Cin, conv.out_channels))
 
 
+# ------------------------------------------------------------------ backward bricks (config #4 training step)
+# Activation gradients are fp16 tensors multiplied by a loss scale; every fp32 output (parameter / keypoint
+# gradients) is divided by it inside the kernels.  `ConvGNFinalRecon.backward` (autograd.py) picks the scale of a
+# backward pass from the incoming loss gradient; the other backward functions read it from here.
+_GRAD_SCALE = [4096.0]
+
+
+def grad_scale() -> float:
+    return _GRAD_SCALE[0]
+
+
+def set_grad_scale(value: float) -> None:
+    _GRAD_SCALE[0] = float(value)
+
+
+def _zero_bias_mirror(kind, cin, cout, k, stride, weight):
+    cls = torch.nn.ConvTranspose3d if kind == "convT" else torch.nn.Conv3d
+    pad = (k - 1) // 2 if stride == 1 else 0
+    m = cls(cin, cout, k, stride=stride, padding=pad, bias=True).to(weight.device).requires_grad_(False)
+    m.weight.copy_(weight)
+    m.bias.zero_()
+    return m
+
+
 def conv3d_input_grad(grad_out: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:
-    """dL/dx of a stride-1 "same" Conv3d (k = 1 or 3): the conv of dL/dy with the spatially flipped taps and the
-    in / out channels swapped - it runs on the forward tensor-core kernels (first brick of the config #4 backward;
-    DESIGN.md §7).  grad_out act (n, D, H, W, Cout) -> act (n, D, H, W, Cin)."""
-    k = conv.kernel_size[0]
-    if conv.stride[0] != 1 or k not in (1, 3) or conv.padding[0] != (k - 1) // 2 or conv.groups != 1:
-        raise NotImplementedError("conv3d_input_grad: stride-1 'same' convolutions with k in (1, 3) only")
+    """dL/dx of an nn.Conv3d of the detector.  Stride-1 "same" convs (k = 1 or 3): the conv of dL/dy with the
+    spatially flipped taps and the in / out channels swapped, on the forward tensor-core kernels.  k2/s2 "pool" convs:
+    the transposed convolution with the same weight tensor.  grad_out act (n, OD, OH, OW, Cout) -> act (n, D, H, W, Cin)."""
+    k, s = conv.kernel_size[0], conv.stride[0]
+    if conv.groups != 1:
+        raise NotImplementedError("conv3d_input_grad: groups != 1")
+    if s == 1 and k in (1, 3) and conv.padding[0] == (k - 1) // 2:
+        mirror = _cached(conv, "dgrad_mirror", [conv.weight], lambda: _zero_bias_mirror(
+            "conv", conv.out_channels, conv.in_channels, k, 1, conv.weight.detach().flip(2, 3, 4).transpose(0, 1)))
+        return conv3d(grad_out, mirror)
+    if s == 2 and k == 2 and conv.padding[0] == 0:
+        # weight (Cout, Cin, 2, 2, 2) read as the (in = Cout, out = Cin) weight of a ConvTranspose3d
+        mirror = _cached(conv, "dgrad_mirror", [conv.weight], lambda: _zero_bias_mirror(
+            "convT", conv.out_channels, conv.in_channels, 2, 2, conv.weight.detach()))
+        return conv_transpose3d(grad_out, mirror)
+    raise NotImplementedError("conv3d_input_grad: stride-1 'same' convolutions with k in (1, 3) or k2/s2 only")
 
-    def build():
-        mirror = torch.nn.Conv3d(conv.out_channels, conv.in_channels, k, stride=1, padding=(k - 1) // 2, bias=True)
-        mirror = mirror.to(conv.weight.device).requires_grad_(False)
-        mirror.weight.copy_(conv.weight.detach().flip(2, 3, 4).transpose(0, 1))
-        mirror.bias.zero_()
-        return mirror
-    return conv3d(grad_out, _cached(conv, "dgrad_mirror", [conv.weight], build))
+
+def conv_transpose3d_input_grad(grad_out: torch.Tensor, conv: torch.nn.ConvTranspose3d) -> torch.Tensor:
+    """dL/dx of nn.ConvTranspose3d(k2, s2): the k2/s2 convolution of dL/dy with the same weight tensor read as
+    (out = Cin, in = Cout, 2, 2, 2).  grad_out act (n, 2D, 2H, 2W, Cout) -> act (n, D, H, W, Cin)."""
+    mirror = _cached(conv, "dgrad_mirror", [conv.weight], lambda: _zero_bias_mirror(
+        "conv", conv.out_channels, conv.in_channels, 2, 2, conv.weight.detach()))
+    return conv3d(grad_out, mirror)
 
 
-def conv3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
-    """dL/dW of a stride-1 3x3x3 "same" Conv3d: x act (n, D, H, W, Cin), grad_out act (n, D, H, W, Cout) ->
-    (Cout, Cin, 3, 3, 3) fp32 (the nn.Conv3d weight layout).  First version (mma.sync, fixed-order split-K)."""
+def _slab_wgrad_ok(x, Cout) -> bool:
+    n, D, H, W, Cin = x.shape
+    return Cin % 32 == 0 and Cout % 32 == 0 and Cin <= 256 and Cout <= 256 and W in (16, 32, 48, 64)
+
+
+def conv3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor, k: int = 3, stride: int = 1,
+                       out_scale: float = 1.0, force_gather: bool = False) -> torch.Tensor:
+    """dL/dW of an nn.Conv3d ((k, stride) in {(1, 1), (3, 1), (2, 2)}): x act (n, D, H, W, Cin), grad_out act
+    (n, OD, OH, OW, Cout) -> (Cout, Cin, k, k, k) fp32, multiplied by out_scale."""
     _need_cuda(x, grad_out)
     n, D, H, W, Cin = x.shape
     Cout = grad_out.shape[-1]
-    assert grad_out.shape[:4] == x.shape[:4] and x.dtype == ACT_DTYPE and grad_out.dtype == ACT_DTYPE
-    assert x.is_contiguous() and grad_out.is_contiguous()
-    nbytes = L.query("nm_conv3d_k3_wgrad_workspace_bytes", n, D, H, W, Cin, Cout)
-    dw = torch.empty(Cout, Cin, 3, 3, 3, dtype=torch.float32, device=x.device)
+    assert x.dtype == ACT_DTYPE and grad_out.dtype == ACT_DTYPE and x.is_contiguous() and grad_out.is_contiguous()
+    assert tuple(grad_out.shape[1:4]) == (D // stride, H // stride, W // stride) and grad_out.shape[0] == n
+    dw = torch.empty(Cout, Cin, k, k, k, dtype=torch.float32, device=x.device)
+    if k == 3 and stride == 1 and _slab_wgrad_ok(x, Cout) and not force_gather:
+        nbytes = L.query("nm_conv3d_k3_wgrad_workspace_bytes", n, D, H, W, Cin, Cout)
+        ws = workspace(max(nbytes, 16), x.device, "wgrad")
+        L.call("nm_conv3d_k3_wgrad", L.ptr(x), L.ptr(grad_out), n, D, H, W, Cin, Cout, float(out_scale), L.ptr(dw),
+               L.ptr(ws), L.stream())
+        return dw
+    OD, OH, OW = grad_out.shape[1:4]
+    nbytes = L.query("nm_conv3d_wgrad_gather_workspace_bytes", n, OD, OH, OW, Cout, Cin, k, stride)
     ws = workspace(max(nbytes, 16), x.device, "wgrad")
-    L.call("nm_conv3d_k3_wgrad", L.ptr(x), L.ptr(grad_out), n, D, H, W, Cin, Cout, L.ptr(dw), L.ptr(ws), L.stream())
+    L.call("nm_conv3d_wgrad_gather", L.ptr(grad_out), L.ptr(x), n, OD, OH, OW, Cout, Cin, k, stride, float(out_scale),
+           L.ptr(dw), L.ptr(ws), L.stream())
     return dw
 
 
-def groupnorm_backward(x: torch.Tensor, grad_out: torch.Tensor, gn: torch.nn.GroupNorm, leaky: bool = True):
+def conv_transpose3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor, out_scale: float = 1.0) -> torch.Tensor:
+    """dL/dW of nn.ConvTranspose3d(k2, s2): x act (n, D, H, W, Cin), grad_out act (n, 2D, 2H, 2W, Cout) ->
+    (Cin, Cout, 2, 2, 2) fp32, multiplied by out_scale."""
+    _need_cuda(x, grad_out)
+    n, D, H, W, Cin = x.shape
+    Cout = grad_out.shape[-1]
+    assert tuple(grad_out.shape[:4]) == (n, 2 * D, 2 * H, 2 * W) and x.is_contiguous() and grad_out.is_contiguous()
+    dw = torch.empty(Cin, Cout, 2, 2, 2, dtype=torch.float32, device=x.device)
+    nbytes = L.query("nm_conv3d_wgrad_gather_workspace_bytes", n, D, H, W, Cin, Cout, 2, 2)
+    ws = workspace(max(nbytes, 16), x.device, "wgrad")
+    L.call("nm_conv3d_wgrad_gather", L.ptr(x), L.ptr(grad_out), n, D, H, W, Cin, Cout, 2, 2, float(out_scale), L.ptr(dw),
+           L.ptr(ws), L.stream())
+    return dw
+
+
+def groupnorm_backward(x: torch.Tensor, grad_out: torch.Tensor, gn: torch.nn.GroupNorm, leaky: bool = True,
+                       out_scale: float = 1.0):
     """Backward of LeakyReLU(GroupNorm(x)) (`leaky`) or GroupNorm(x): x, grad_out act (n, D, H, W, C) ->
-    (grad_in act, dgamma (C) fp32, dbeta (C) fp32)."""
+    (grad_in act, dgamma (C), dbeta (C), dxsum (C)) - the fp32 outputs multiplied by out_scale; dxsum = sum of grad_in
+    over samples and voxels = gradient of the bias of the conv that produced x."""
     _need_cuda(x, grad_out)
     assert x.shape == grad_out.shape and x.dtype == ACT_DTYPE and grad_out.dtype == ACT_DTYPE
     assert x.is_contiguous() and grad_out.is_contiguous()
@@ -266,10 +331,116 @@ def groupnorm_backward(x: torch.Tensor, grad_out: torch.Tensor, gn: torch.nn.Gro
     dx = torch.empty_like(x)
     dg = torch.empty(C, dtype=torch.float32, device=x.device)
     db = torch.empty(C, dtype=torch.float32, device=x.device)
+    dxs = torch.empty(C, dtype=torch.float32, device=x.device)
     ws = workspace(max(L.query("nm_groupnorm_backward_workspace_bytes", n, C, gn.num_groups), 16), x.device, "gnb")
     L.call("nm_groupnorm_backward", L.ptr(x), L.ptr(grad_out), L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), n, S, C,
-           gn.num_groups, float(gn.eps), int(leaky), L.ptr(dx), L.ptr(dg), L.ptr(db), L.ptr(ws), L.stream())
-    return dx, dg, db
+           gn.num_groups, float(gn.eps), int(leaky), float(out_scale), L.ptr(dx), L.ptr(dg), L.ptr(db), L.ptr(dxs),
+           L.ptr(ws), L.stream())
+    return dx, dg, db, dxs
+
+
+def upsample2x_backward(grad_out: torch.Tensor) -> torch.Tensor:
+    """Backward of upsample2x without prologue: act (n, 2D, 2H, 2W, C) -> act (n, D, H, W, C)."""
+    _need_cuda(grad_out)
+    n, D2, H2, W2, C = grad_out.shape
+    assert grad_out.dtype == ACT_DTYPE and grad_out.is_contiguous()
+    dx = torch.empty(n, D2 // 2, H2 // 2, W2 // 2, C, dtype=ACT_DTYPE, device=grad_out.device)
+    L.call("nm_upsample2x_backward", L.ptr(grad_out), L.ptr(dx), n, D2 // 2, H2 // 2, W2 // 2, C, L.stream())
+    return dx
+
+
+def first_conv_weight_grad(occ: torch.Tensor, grad_out: torch.Tensor, out_scale: float = 1.0) -> torch.Tensor:
+    """dL/dW of the CoordConv first layer: occ (n, G, G, G) fp32, grad_out act (n, G, G, G, Cout) -> (Cout, 4, 5, 5, 5)."""
+    _need_cuda(occ, grad_out)
+    n, G = occ.shape[0], occ.shape[1]
+    Cout = grad_out.shape[-1]
+    assert occ.dtype == torch.float32 and occ.is_contiguous() and grad_out.is_contiguous()
+    dw = torch.empty(Cout, 4, 5, 5, 5, dtype=torch.float32, device=occ.device)
+    ws = workspace(L.query("nm_first_conv_wgrad_workspace_bytes", n, Cout), occ.device, "wgrad")
+    L.call("nm_first_conv_wgrad", L.ptr(occ), L.ptr(grad_out), L.ptr(linspace(G, occ.device)), n, G, Cout,
+           float(out_scale), L.ptr(dw), L.ptr(ws), L.stream())
+    return dw
+
+
+def final_recon_backward(raw, a, b, conv: torch.nn.Conv3d, first_frame, frames_per_clip, sharpness, translation,
+                         recon, target, grad_bce, scale: float):
+    """-> (grad_act act (n, D, H, W, C) times `scale`, dw (1, C, 1, 1, 1), dbias (1))."""
+    n, D, H, W, C = raw.shape
+    S = D * H * W
+    w = f32(conv, "weight").reshape(-1)
+    bias = _cached(conv, "bias_host", [conv.bias], lambda: float(conv.bias.detach().float().item()))
+    dact = torch.empty_like(raw)
+    dw = torch.empty(1, C, 1, 1, 1, dtype=torch.float32, device=raw.device)
+    db = torch.empty(1, dtype=torch.float32, device=raw.device)
+    ws = workspace(L.query("nm_final_recon_backward_workspace_bytes", n), raw.device, "recon_bwd")
+    L.call("nm_final_recon_backward", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), bias, L.ptr(first_frame), frames_per_clip,
+           float(sharpness), float(translation), L.ptr(recon), L.ptr(target), L.ptr(grad_bce), float(scale), L.ptr(dact),
+           L.ptr(dw), L.ptr(db), L.ptr(ws), n, S, C, L.stream())
+    return dact, dw, db
+
+
+def heatmap_head_backward(feature, conv1: torch.nn.Conv3d, K: int, mode: int, scale: float, prev=None,
+                          frames_per_clip: int = 1, prop: Optional[torch.nn.Conv3d] = None, heat=None, keypoints=None,
+                          heat_mean=None, grad_keypoints=None, grad_heat_mean=None, grad_heat=None, dq_in=None):
+    """Backward of heatmap_head.  mode 1 -> (grad_feature act, dq (n, K, g, g, g), dw1, db1, dprop (3));
+    mode 0 -> (grad_feature act, None, dw1, db1, None)."""
+    n, g, C = feature.shape[0], feature.shape[1], feature.shape[-1]
+    dev = feature.device
+    w1 = f32(conv1, "weight").reshape(K, C)
+    b1 = f32(conv1, "bias")
+    dfeat = torch.empty_like(feature)
+    dw1 = torch.empty(K, C, 1, 1, 1, dtype=torch.float32, device=dev)
+    db1 = torch.empty(K, dtype=torch.float32, device=dev)
+    ws = workspace(L.query("nm_heatmap_head_backward_workspace_bytes", n, C, K), dev, "head_bwd")
+    if mode == 1:
+        pw = _prop_host(prop)
+        dq = torch.empty(n, K, g, g, g, dtype=torch.float32, device=dev)
+        dprop = torch.empty(3, dtype=torch.float32, device=dev)
+    else:
+        pw, dq, dprop = (0.0, 0.0, 0.0), None, None
+        if dq_in is not None:
+            pw = (0.0, _prop_host(prop)[1], 0.0)
+    L.call("nm_heatmap_head_backward", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, mode, L.ptr(prev),
+           frames_per_clip, pw[0], pw[1], pw[2], L.ptr(linspace(g, dev)), L.ptr(heat), L.ptr(keypoints), L.ptr(heat_mean),
+           L.ptr(grad_keypoints), L.ptr(grad_heat_mean), L.ptr(grad_heat), L.ptr(dq_in), float(scale), L.ptr(dfeat),
+           L.ptr(dq), L.ptr(dw1), L.ptr(db1), L.ptr(dprop), L.ptr(ws), L.stream())
+    return dfeat, dq, dw1, db1, dprop
+
+
+def decoder_adjust_backward(grad_out, out, ff_act, keypoints, conv: torch.nn.Conv3d, frames_per_clip: int, g: int, K: int,
+                            sigma: float, scale: float):
+    """-> (grad_first_feature act (B, g, g, g, 128) times scale, grad_keypoints (n, K, 4), dweight, dbias)."""
+    B = ff_act.shape[0]
+    n = B * frames_per_clip
+    dev = ff_act.device
+    dff = torch.empty_like(ff_act)
+    dkp = torch.empty(n, K, 4, dtype=torch.float32, device=dev)
+    dw = torch.empty(conv.out_channels, conv.in_channels, 1, 1, 1, dtype=torch.float32, device=dev)
+    db = torch.empty(conv.out_channels, dtype=torch.float32, device=dev)
+    ws = workspace(L.query("nm_decoder_adjust_backward_workspace_bytes", B, frames_per_clip), dev, "adjust_bwd")
+    w = f32(conv, "weight").reshape(conv.out_channels, -1)
+    L.call("nm_decoder_adjust_backward", L.ptr(grad_out), L.ptr(out), L.ptr(ff_act), L.ptr(keypoints), L.ptr(w), B,
+           frames_per_clip, g, K, L.ptr(linspace(g, dev)), gauss_width(sigma, g), float(scale), L.ptr(dff), L.ptr(dkp),
+           L.ptr(dw), L.ptr(db), L.ptr(ws), L.stream())
+    return dff, dkp, dw, db
+
+
+def chamfer_vol_fit_backward(seq_frames: torch.Tensor, keypoints: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """-> grad_keypoints (n, K, 4) fp32."""
+    n, G = seq_frames.shape[0], seq_frames.shape[-1]
+    K = keypoints.shape[1]
+    dkp = torch.empty(n, K, 4, dtype=torch.float32, device=seq_frames.device)
+    ws = workspace(L.query("nm_chamfer_vol_fit_backward_workspace_bytes", n, K), seq_frames.device, "chamfer_bwd")
+    L.call("nm_chamfer_vol_fit_backward", L.ptr(seq_frames), L.ptr(keypoints), L.ptr(linspace(G, seq_frames.device)),
+           L.ptr(grad_out), n, K, G, L.ptr(dkp), L.ptr(ws), L.stream())
+    return dkp
+
+
+def invalidate_caches(module: torch.nn.Module) -> None:
+    """Drop every derived (packed / transposed) weight cached on the sub-modules: call after editing parameters through
+    `.data` or raw pointers (the fused optimizer does), which does not bump `Tensor._version`."""
+    for m in module.modules():
+        m.__dict__.pop("_nm_cache", None)
 
 
 def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):
@@ -455,6 +626,13 @@ def chamfer_vol_fit(seq_frames: torch.Tensor, keypoints: torch.Tensor) -> torch.
 
 
 # ------------------------------------------------------------------ heads
+def _prop_host(prop: torch.nn.Conv3d):
+    """[w0, w1, bias] of the propagate conv (1, 2, 1, 1, 1) as host floats (kernel arguments)."""
+    return _cached(prop, "host", [prop.weight, prop.bias],
+                   lambda: [float(v) for v in prop.weight.detach().float().reshape(-1).tolist()] +
+                           [float(prop.bias.detach().float().item())])
+
+
 def heatmap_head(feature, conv1: torch.nn.Conv3d, K: int, mode: int, prev=None, frames_per_clip: int = 1,
                  prop: Optional[torch.nn.Conv3d] = None, sigma: float = 1.0, want_gaussians: bool = True,
                  out=None):
@@ -470,9 +648,7 @@ def heatmap_head(feature, conv1: torch.nn.Conv3d, K: int, mode: int, prev=None, 
         L.call("nm_heatmap_head", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, 0, None, 1, 0.0, 0.0, 0.0,
                L.ptr(linspace(g, dev)), 1.0, L.ptr(heat), None, None, None, L.stream())
         return heat
-    pw = _cached(prop, "host", [prop.weight, prop.bias],
-                 lambda: [float(v) for v in prop.weight.detach().float().reshape(-1).tolist()] +
-                         [float(prop.bias.detach().float().item())])
+    pw = _prop_host(prop)
     if out is not None:
         kp, gs, hm_mean = out[1], out[2], out[3]
     else:

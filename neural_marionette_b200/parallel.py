@@ -28,6 +28,9 @@ def world() -> Tuple[int, int]:
 
 
 def barrier() -> None:
+    """Drain this rank's device queue, meet the other ranks, and drain again (the barrier itself may enqueue work)."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
     if torch.cuda.is_available():
@@ -67,6 +70,13 @@ class GradientBuckets:
     launched asynchronously and overlaps the rest of the backward; `finish()` waits for all buckets and divides by the
     world size.  Stage 1 of the reference trains 8 557 044 detector values (34.2 MB): 4 buckets of ≈ 8.6 MB, each
     far above NCCL's latency floor over NVLink and small enough to overlap.  Backend: NCCL on GPUs, gloo in the CPU tests.
+
+    Aliasing contract: `zero()` (or `zero_grad(set_to_none=False)`) keeps `param.grad` inside the flat buffer.  If a
+    caller drops the alias (`optimizer.zero_grad()` with torch's default `set_to_none=True`, `p.grad = None`), the next
+    `ready(param)` / `finish()` notices that `param.grad` no longer points at its slot, copies the fresh gradient into
+    the flat buffer and re-attaches it - so the all-reduce never runs on a stale buffer.  A parameter whose gradient is
+    still `None` at `finish()` contributed nothing on this rank: its slot stays zero (as with an unused parameter).
+    `attach_hooks()` registers post-accumulate hooks so that a plain `loss.backward()` drives `ready()`.
     """
 
     def __init__(self, params, n_buckets: int = 4, device=None):
@@ -80,8 +90,10 @@ class GradientBuckets:
         self.bounds: List[Tuple[int, int]] = []            # [lo, hi) offsets of the buckets in `flat`
         self._bucket_of, self._pending = {}, []
         target, lo, off, b = total / max(1, n_buckets), 0, 0, 0
+        self._slot = {}
         for p, n in zip(self.params, sizes):
             p.grad = self.flat[off:off + n].view_as(p)
+            self._slot[id(p)] = (off, n)
             self._bucket_of[id(p)] = b
             off += n
             last = p is self.params[-1]
@@ -95,10 +107,29 @@ class GradientBuckets:
 
     def zero(self) -> None:
         self.flat.zero_()
+        for p in self.params:
+            self._attach(p, copy=False)
         self._left, self._work, self._launched = list(self._need), [None] * len(self.bounds), [False] * len(self.bounds)
+
+    def _attach(self, p, copy: bool = True) -> None:
+        """Make `p.grad` the view of its slot again (copying a detached gradient into the slot first)."""
+        off, n = self._slot[id(p)]
+        slot = self.flat[off:off + n]
+        if p.grad is not None and p.grad.data_ptr() == slot.data_ptr() and p.grad.numel() == n:
+            return
+        if p.grad is not None and copy:
+            slot.copy_(p.grad.reshape(-1))
+        p.grad = slot.view_as(p)
+
+    def attach_hooks(self):
+        """Drive `ready()` from autograd: one post-accumulate hook per parameter (returns the handles)."""
+        return [p.register_post_accumulate_grad_hook(lambda q: self.ready(q)) for p in self.params]
 
     def ready(self, param) -> None:
         """The gradient of `param` is complete on this rank."""
+        if id(param) not in self._bucket_of:
+            return
+        self._attach(param)
         b = self._bucket_of[id(param)]
         self._left[b] -= 1
         if self._left[b] == 0:
@@ -114,6 +145,11 @@ class GradientBuckets:
 
     def finish(self) -> None:
         """Launch whatever was not reported ready, wait for every bucket, average over the ranks."""
+        for b, launched in enumerate(self._launched):
+            if not launched:                                   # gradients nobody reported: make sure they are in the buffer
+                for p in self.params:
+                    if self._bucket_of[id(p)] == b and p.grad is not None:
+                        self._attach(p)
         for b in range(len(self.bounds)):
             self._launch(b)
         for w in self._work:

@@ -1,0 +1,356 @@
+"""GPU parity of the config #4 training step (reference train.py:387-409): every backward kernel against
+torch.autograd over the fp32 CPU restatement of its stage (oracle/nm_oracle.py, pinned to the reference), and the
+assembled `KyptDetector` backward against the reference's own `loss.backward()` (tests/golden/detector_grad_g32.npz,
+written by oracle/make_golden_grad.py from the unmodified reference).
+
+Tolerances: activations and activation gradients are fp16 (2^-11 relative rounding per tensor), accumulation fp32.
+Per-kernel checks use fp16-rounded inputs and bound the error relative to the largest entry of the reference
+gradient.  End to end the bound is 5e-2 of each gradient tensor's L2 norm (measured values are printed) - the same
+order as the forward's 1e-2 heat-map budget accumulated over the ~40 layers of the backward chain."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import nm_oracle as O
+from oracle import nm_oracle_grad as OG
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from neural_marionette_b200 import ops as _ops
+    return _ops
+
+
+def to_act(x):
+    return x.permute(0, 2, 3, 4, 1).contiguous().half().cuda()
+
+
+def from_act(y):
+    return y.float().cpu().permute(0, 4, 1, 2, 3).contiguous()
+
+
+def rel_err(got, ref):
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+
+
+def h(x):
+    return x.half().float()
+
+
+# ------------------------------------------------------------------------------------------------ weight gradients
+@pytest.mark.parametrize("n,grid,cin,cout,k,stride", [
+    (2, 16, 32, 64, 1, 1), (1, 16, 64, 128, 1, 1), (3, 8, 64, 32, 1, 1), (2, 4, 32, 48, 1, 1), (2, 2, 48, 72, 1, 1),
+    (2, 16, 32, 32, 2, 2), (1, 16, 64, 64, 2, 2), (3, 4, 48, 48, 2, 2), (1, 32, 32, 32, 2, 2),
+    (2, 8, 64, 32, 3, 1), (3, 4, 32, 48, 3, 1), (3, 4, 48, 48, 3, 1), (5, 2, 72, 72, 3, 1), (1, 16, 32, 32, 3, 1)])
+def test_conv_weight_grad_gather(ops, n, grid, cin, cout, k, stride):
+    """dL/dW of 1x1, pool (k2 s2) and small-grid / odd-channel k3 convs against torch.nn.grad.conv3d_weight."""
+    g = torch.Generator().manual_seed(grid + 3 * cin + 7 * cout + 11 * k)
+    og = grid // stride
+    x = h(torch.randn(n, cin, grid, grid, grid, generator=g))
+    gy = h(torch.randn(n, cout, og, og, og, generator=g) / og ** 1.5)
+    pad = (k - 1) // 2 if stride == 1 else 0
+    ref = torch.nn.grad.conv3d_weight(x, (cout, cin, k, k, k), gy, stride=stride, padding=pad)
+    got = ops.conv3d_weight_grad(to_act(x), to_act(gy), k=k, stride=stride, force_gather=True)
+    assert got.shape == ref.shape
+    assert rel_err(got.cpu(), ref) < 1e-3
+    again = ops.conv3d_weight_grad(to_act(x), to_act(gy), k=k, stride=stride, force_gather=True)
+    assert torch.equal(got, again)                                       # fixed-order split-K
+    half = ops.conv3d_weight_grad(to_act(x), to_act(gy), k=k, stride=stride, out_scale=0.5, force_gather=True)
+    assert torch.allclose(half, got * 0.5, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("n,grid,cin,cout", [(2, 2, 72, 48), (3, 4, 48, 32), (2, 8, 32, 64), (1, 8, 32, 128)])
+def test_conv_transpose_grads(ops, n, grid, cin, cout):
+    """dL/dW and dL/dx of ConvTranspose3d(k2, s2) (Upsample3DBlock) against torch.autograd."""
+    g = torch.Generator().manual_seed(grid + cin + 5 * cout)
+    conv = torch.nn.ConvTranspose3d(cin, cout, 2, 2)
+    with torch.no_grad():
+        conv.weight.copy_(h(torch.randn(conv.weight.shape, generator=g) / (8 * cin) ** 0.5))
+    x = h(torch.randn(n, cin, grid, grid, grid, generator=g)).requires_grad_(True)
+    gy = h(torch.randn(n, cout, 2 * grid, 2 * grid, 2 * grid, generator=g) / grid ** 1.5)
+    (conv(x) * gy).sum().backward()
+    dw = ops.conv_transpose3d_weight_grad(to_act(x.detach()), to_act(gy))
+    assert rel_err(dw.cpu(), conv.weight.grad) < 1e-3
+    dx = from_act(ops.conv_transpose3d_input_grad(to_act(gy), conv.cuda()))
+    assert rel_err(dx, x.grad) < 2e-3
+
+
+@pytest.mark.parametrize("n,grid,cin,cout", [(2, 16, 32, 32), (1, 16, 64, 64), (2, 8, 48, 48), (1, 32, 64, 64)])
+def test_pool_conv_input_grad(ops, n, grid, cin, cout):
+    """dL/dx of the k2/s2 pool convs = the transposed convolution with the same weights."""
+    g = torch.Generator().manual_seed(grid + cin + 3 * cout)
+    conv = torch.nn.Conv3d(cin, cout, 2, 2, 0)
+    with torch.no_grad():
+        conv.weight.copy_(h(torch.randn(conv.weight.shape, generator=g) / (8 * cin) ** 0.5))
+    x = torch.randn(n, cin, grid, grid, grid, generator=g).requires_grad_(True)
+    gy = h(torch.randn(n, cout, grid // 2, grid // 2, grid // 2, generator=g))
+    (conv(x) * gy).sum().backward()
+    dx = from_act(ops.conv3d_input_grad(to_act(gy), conv.cuda()))
+    assert rel_err(dx, x.grad) < 2e-3
+
+
+def test_upsample2x_backward(ops):
+    g = torch.Generator().manual_seed(5)
+    for n, grid, C in ((2, 4, 32), (1, 8, 64), (1, 16, 128)):
+        x = torch.randn(n, C, grid, grid, grid, generator=g).requires_grad_(True)
+        gy = h(torch.randn(n, C, 2 * grid, 2 * grid, 2 * grid, generator=g))
+        (F.interpolate(x, scale_factor=2.0, mode="trilinear", align_corners=False) * gy).sum().backward()
+        got = from_act(ops.upsample2x_backward(to_act(gy)))
+        assert rel_err(got, x.grad) < 2e-3
+
+
+@pytest.mark.parametrize("n,G,C", [(2, 16, 32), (1, 32, 64), (3, 16, 64)])
+def test_first_conv_weight_grad(ops, n, G, C):
+    """dL/dW of the CoordConv layer (analytic coordinate channels + occupancy gather) against autograd over
+    conv3d(add_coord_channels(occ)); `occ` holds fractional values as the spatio-temporal branch's frame mean does."""
+    g = torch.Generator().manual_seed(G + C)
+    occ = (torch.rand(n, 1, G, G, G, generator=g) < 0.05).float() * (torch.randint(1, 4, (n, 1, G, G, G), generator=g) / 3.0)
+    w = (torch.randn(C, 4, 5, 5, 5, generator=g) / 500 ** 0.5).requires_grad_(True)
+    gy = h(torch.randn(n, C, G, G, G, generator=g) / G ** 1.5)
+    (F.conv3d(O.add_coord_channels(occ), w, None, padding=2) * gy).sum().backward()
+    got = ops.first_conv_weight_grad(occ[:, 0].contiguous().cuda(), to_act(gy))
+    assert got.shape == w.grad.shape
+    for c in range(4):
+        assert rel_err(got[:, c].cpu(), w.grad[:, c]) < 1e-3, f"input channel {c}"
+    assert torch.equal(got, ops.first_conv_weight_grad(occ[:, 0].contiguous().cuda(), to_act(gy)))
+
+
+# ------------------------------------------------------------------------------------------------ decoder tail
+def test_final_recon_backward(ops):
+    g = torch.Generator().manual_seed(9)
+    n, G, C, T = 4, 16, 32, 2
+    raw = h(torch.randn(n, C, G, G, G, generator=g))
+    a = 1 + 0.2 * torch.randn(n, C, generator=g)
+    b = 0.2 * torch.randn(n, C, generator=g)
+    conv = torch.nn.Conv3d(C, 1, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(1, C, 1, 1, 1, generator=g) * 0.3)
+    ff = (torch.rand(n // T, 1, G, G, G, generator=g) < 0.3).float()
+    tgt = (torch.rand(n, 1, G, G, G, generator=g) < 0.3).float()
+    gb = torch.rand(n, generator=g) + 0.5
+    act = F.leaky_relu(raw * a[:, :, None, None, None] + b[:, :, None, None, None], 0.01).requires_grad_(True)
+    x14 = conv(act)
+    recon = torch.sigmoid(10.0 * (torch.tanh(x14) + ff.repeat_interleave(T, 0) - 0.5))
+    bce = F.binary_cross_entropy(recon, tgt, reduction="none").mean(dim=(1, 2, 3, 4))
+    (bce * gb).sum().backward()
+    conv_c = conv.cuda()
+    rec_c, bce_c = ops.final_recon(to_act(raw), a.cuda(), b.cuda(), conv_c, ff[:, 0].contiguous().cuda(), T, 10.0, 0.5,
+                                   target=tgt[:, 0].contiguous().cuda())
+    scale = 2.0 ** 12
+    dact, dw, db = ops.final_recon_backward(to_act(raw), a.cuda(), b.cuda(), conv_c, ff[:, 0].contiguous().cuda(), T, 10.0,
+                                            0.5, rec_c, tgt[:, 0].contiguous().cuda(), gb.cuda(), scale)
+    assert rel_err(from_act(dact) / scale, act.grad) < 3e-3
+    assert rel_err(dw.cpu(), conv.weight.grad) < 2e-3
+    assert rel_err(db.cpu(), conv.bias.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------ heads
+def _head_setup(seed, B, T, g, K=24):
+    gen = torch.Generator().manual_seed(seed)
+    n = B * T
+    feat = h(torch.randn(n, 128, g, g, g, generator=gen))
+    fst = h(torch.randn(B, 256, g, g, g, generator=gen))
+    head = torch.nn.Conv3d(128, K, 1)
+    hst = torch.nn.Conv3d(256, K, 1)
+    prop = torch.nn.Conv3d(2, 1, 1)
+    with torch.no_grad():
+        head.weight.copy_(torch.randn(head.weight.shape, generator=gen) / 128 ** 0.5)
+        hst.weight.copy_(torch.randn(hst.weight.shape, generator=gen) / 256 ** 0.5)
+        prop.weight.copy_(torch.tensor([0.9, 0.6]).view(1, 2, 1, 1, 1))
+        prop.bias.fill_(-0.3)
+    return gen, feat, fst, head, hst, prop
+
+
+def test_heatmap_head_backward(ops):
+    """Both heads, the propagate conv, Softplus, soft-argmax and the heat-map mean against autograd over the oracle's
+    formulation; the upstream gradients are random d keypoints (coordinates and intensity) and d heat_mean."""
+    from neural_marionette_b200 import autograd as AG
+    B, T, g, K = 2, 3, 8, 24
+    gen, feat, fst, head, hst, prop = _head_setup(21, B, T, g, K)
+    n = B * T
+    dkp = torch.randn(n, K, 4, generator=gen)
+    dhm = torch.randn(n, K, generator=gen)
+    # reference
+    feat_r, fst_r = feat.clone().requires_grad_(True), fst.clone().requires_grad_(True)
+    prev = F.leaky_relu(hst(fst_r), 0.01)                                                   # (B, K, g, g, g)
+    u = F.leaky_relu(head(feat_r), 0.01).view(n * K, 1, g, g, g)
+    pv = prev.repeat_interleave(T, 0).reshape(n * K, 1, g, g, g)
+    hm = F.softplus(prop(torch.cat([u, pv], 1))).view(n, K, g, g, g)
+    kp = O.keypoints_from_heatmap(hm)
+    ((kp * dkp).sum() + (hm.mean(dim=(2, 3, 4)) * dhm).sum()).backward()
+    # kernels through the autograd Functions
+    head_c, hst_c, prop_c = head.cuda(), hst.cuda(), prop.cuda()
+    ref_grads = {k: v.grad.clone() for k, v in dict(hw=head.weight, hb=head.bias, sw=hst.weight, sb=hst.bias,
+                                                    pw=prop.weight, pb=prop.bias).items()}
+    for p in list(head_c.parameters()) + list(hst_c.parameters()) + list(prop_c.parameters()):
+        p.grad = None
+    ops.set_grad_scale(256.0)
+    fa = to_act(feat).requires_grad_(True)
+    fs = to_act(fst).requires_grad_(True)
+    link = {}
+    prev_c = AG.HeadST.apply(fs, hst_c.weight, hst_c.bias, hst_c, K, link)
+    heat_c, kp_c, mean_c = AG.Head.apply(fa, head_c.weight, head_c.bias, prev_c, prop_c.weight, prop_c.bias, head_c, prop_c,
+                                         K, T, 1.5, link)
+    assert float((kp_c.cpu() - kp).abs().max()) < 1e-4
+    ((kp_c * dkp.cuda()).sum() + (mean_c * dhm.cuda()).sum()).backward()
+    assert rel_err(from_act(fa.grad) / 256.0, feat_r.grad) < 3e-3
+    assert rel_err(from_act(fs.grad) / 256.0, fst_r.grad) < 3e-3
+    got = dict(hw=head_c.weight.grad, hb=head_c.bias.grad, sw=hst_c.weight.grad, sb=hst_c.bias.grad, pw=prop_c.weight.grad,
+               pb=prop_c.bias.grad)
+    for k in ref_grads:
+        assert rel_err(got[k].cpu(), ref_grads[k]) < 2e-3, k
+
+
+def test_decoder_adjust_backward(ops):
+    """Gaussian render + adjust conv: d first_feature, d keypoints (through gauss_t and gauss_0), dW, db."""
+    from neural_marionette_b200 import autograd as AG
+    gen = torch.Generator().manual_seed(33)
+    B, T, g, K = 2, 3, 8, 24
+    n = B * T
+    ff = h(torch.randn(B, 128, g, g, g, generator=gen))
+    kp = torch.cat([torch.rand(n, K, 3, generator=gen) * 1.4 - 0.7, torch.rand(n, K, 1, generator=gen) * 0.8 + 0.2], -1)
+    conv = torch.nn.Conv3d(128 + 2 * K + 3, 128, 1)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=gen) / 179 ** 0.5)
+    gy = h(torch.randn(n, 128, g, g, g, generator=gen))
+    ff_r, kp_r = ff.clone().requires_grad_(True), kp.clone().requires_grad_(True)
+    gs = O.render_gaussians(kp_r, 1.5, g).view(B, T, K, g, g, g)
+    outs = []
+    for t in range(T):
+        comb = O.add_coord_channels(torch.cat([gs[:, t], ff_r, gs[:, 0]], 1))
+        outs.append(F.leaky_relu(conv(comb), 0.01))
+    y = torch.stack(outs, 1).reshape(n, 128, g, g, g)
+    (y * gy).sum().backward()
+    conv_c = conv.cuda()
+    ref_w, ref_b = conv.weight.grad.clone(), conv.bias.grad.clone()
+    conv_c.weight.grad = None
+    conv_c.bias.grad = None
+    ops.set_grad_scale(64.0)
+    ffa = to_act(ff).requires_grad_(True)
+    kpc = kp.cuda().requires_grad_(True)
+    yc = AG.Adjust.apply(ffa, kpc, conv_c.weight, conv_c.bias, conv_c, T, g, K, 1.5)
+    assert rel_err(from_act(yc), y.detach()) < 5e-3
+    yc.backward((to_act(gy).float() * 64.0).half())
+    assert rel_err(from_act(ffa.grad) / 64.0, ff_r.grad) < 3e-3
+    assert rel_err(kpc.grad.cpu(), kp_r.grad) < 3e-3
+    assert rel_err(conv_c.weight.grad.cpu(), ref_w) < 3e-3
+    assert rel_err(conv_c.bias.grad.cpu(), ref_b) < 3e-3
+
+
+def test_chamfer_backward(ops):
+    gen = torch.Generator().manual_seed(44)
+    B, T, G, K = 2, 2, 16, 24
+    seq = (torch.rand(B, T, 1, G, G, G, generator=gen) < 0.08).float()
+    kp = torch.cat([torch.rand(B, T, K, 3, generator=gen) * 1.6 - 0.8, torch.rand(B, T, K, 1, generator=gen)], -1)
+    kp_r = kp.clone().requires_grad_(True)
+    go = torch.rand(B, T, generator=gen) + 0.5
+    (O.chamfer_vol_fit(seq, kp_r) * go).sum().backward()
+    got = ops.chamfer_vol_fit_backward(seq.view(B * T, G, G, G).cuda(), kp.view(B * T, K, 4).cuda(), go.view(-1).cuda())
+    assert rel_err(got.cpu().view(B, T, K, 4), kp_r.grad) < 1e-4
+
+
+def test_fused_adam_matches_torch():
+    from neural_marionette_b200 import optim
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(17, 9), torch.nn.Linear(9, 5)).cuda()
+    ref = torch.nn.Sequential(torch.nn.Linear(17, 9), torch.nn.Linear(9, 5)).cuda()
+    ref.load_state_dict(net.state_dict())
+    opt = optim.FusedAdam(net.parameters(), lr=4e-4)
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=4e-4)
+    for step in range(4):
+        x = torch.randn(8, 17, device="cuda")
+        for m, o in ((net, opt), (ref, opt_ref)):
+            o.zero_grad()
+            m(x).pow(2).sum().backward()
+            o.step()
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert float((p - q).abs().max()) <= 2e-6
+    # a non-finite gradient skips the step
+    before = [p.detach().clone() for p in net.parameters()]
+    opt.zero_grad()
+    net(torch.randn(8, 17, device="cuda")).sum().backward()
+    next(net.parameters()).grad[0, 0] = float("inf")
+    assert opt.step() is False
+    for p, q in zip(net.parameters(), before):
+        assert torch.equal(p, q)
+
+
+# ------------------------------------------------------------------------------------------------ assembled backward
+def _golden_case(golden_dir):
+    z = np.load(os.path.join(golden_dir, "detector_grad_g32.npz"))
+    G, B, T, seed, vseed, N = (int(v) for v in z["meta"])
+    hp = O.default_hparams(grid_size=G, Tcond=3, Ttot=10)
+    sd = O.synthetic_state_dict(hp, seed=seed)
+    vox = torch.from_numpy(np.stack([O.voxelize_clip(O.episodic_normalization(O.synthetic_clip(vseed + b, T, N)), G)
+                                     for b in range(B)], 0)).float()
+    return z, hp, sd, vox
+
+
+@pytest.mark.parametrize("tag", ["recon", "full"])
+def test_detector_backward_vs_reference_golden(golden_dir, tag):
+    """`loss.backward()` through the CUDA training step against the gradients the REFERENCE produced for the same
+    weights and clips: 100 * recon_loss (314 tensors) and the full stage-1 weighted sum (315 tensors)."""
+    import neural_marionette_b200 as nm
+    z, hp, sd, vox = _golden_case(golden_dir)
+    net = nm.NeuralMarionette(hp)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().train()
+    net.anneal(1)
+    out = net.kypt_detector(vox.cuda())
+    loss = OG.detector_loss(out, recon_only=(tag == "recon"))
+    assert abs(float(loss) - float(z[f"{tag}_loss"])) <= 2e-2 * abs(float(z[f"{tag}_loss"]))
+    loss.backward()
+    grads = {"kypt_detector." + k: p.grad for k, p in net.kypt_detector.named_parameters() if p.grad is not None}
+    keys = [str(k) for k in z[f"{tag}_keys"]]
+    assert sorted(grads) == keys, sorted(set(keys) ^ set(grads))
+    pos = lambda m: torch.from_numpy((np.arange(8, dtype=np.int64) * 2654435761 % max(m, 1)).astype(np.int64))
+    worst_norm, worst_full, bad = 0.0, 0.0, []
+    for i, k in enumerate(keys):
+        g = grads[k].detach().float().cpu()
+        assert torch.isfinite(g).all(), k
+        ref_norm = float(z[f"{tag}_norm"][i])
+        e_norm = abs(float(g.double().norm()) - ref_norm) / max(ref_norm, 1e-12)
+        e_samp = float(np.abs(g.reshape(-1)[pos(g.numel())].numpy() - z[f"{tag}_samples"][i]).max()) / max(ref_norm, 1e-12)
+        worst_norm = max(worst_norm, e_norm)
+        if tag == "recon" and ("recon_grad::" + k) in z.files:
+            ref = torch.from_numpy(z["recon_grad::" + k])
+            e_full = float((g - ref).double().norm()) / max(ref_norm, 1e-12)
+            worst_full = max(worst_full, e_full)
+            if e_full > 5e-2:
+                bad.append((k, "full", e_full))
+        if e_norm > 5e-2 or e_samp > 5e-2:
+            bad.append((k, e_norm, e_samp))
+    print(f"[{tag}] loss {float(loss):.6f} (reference {float(z[f'{tag}_loss']):.6f}); worst relative norm error "
+          f"{worst_norm:.3e}; worst ||g - g_ref|| / ||g_ref|| over the fully stored tensors {worst_full:.3e}")
+    assert not bad, bad[:10]
+
+
+def test_training_step_decreases_loss_and_is_reproducible(golden_dir):
+    """Two Adam steps on the golden clips: identical losses run to run (fixed-order reductions everywhere) and the
+    reconstruction loss goes down."""
+    import neural_marionette_b200 as nm
+    from neural_marionette_b200 import optim
+    z, hp, sd, vox = _golden_case(golden_dir)
+    runs = []
+    for _ in range(2):
+        net = nm.NeuralMarionette(hp)
+        net.load_state_dict(sd, strict=True)
+        net = net.cuda().train()
+        net.anneal(1)
+        opt = optim.FusedAdam(net.kypt_detector.parameters(), lr=4e-4, owner=net)
+        losses = []
+        for step in range(3):
+            opt.zero_grad()
+            out = net.kypt_detector(vox.cuda())
+            loss = OG.detector_loss(out, recon_only=False)
+            loss.backward()
+            assert opt.step()
+            losses.append(float(out["recon_loss"]))
+        runs.append(losses)
+    assert runs[0] == runs[1], runs
+    assert runs[0][-1] < runs[0][0], runs[0]

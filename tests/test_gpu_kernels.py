@@ -533,12 +533,16 @@ def test_conv3d_weight_grad(ops, n, grid, cin, cout):
     assert got.shape == ref.shape
     assert rel_err(got, ref) < 1e-3
     assert torch.equal(got, ops.conv3d_weight_grad(to_act(x), to_act(gy)).cpu())      # fixed-order split-K
-    with pytest.raises(Exception):
-        ops.conv3d_weight_grad(to_act(x[:, :24]), to_act(gy))                          # Cin not a multiple of 32
+    # the gather kernel computes the same tensor (any channel count that is a multiple of 8)
+    alt = ops.conv3d_weight_grad(to_act(x), to_act(gy), force_gather=True).cpu()
+    assert rel_err(alt, ref) < 1e-3
+    got24 = ops.conv3d_weight_grad(to_act(x[:, :24]), to_act(gy)).cpu()                # Cin = 24 -> gather kernel
+    assert rel_err(got24, ref[:, :24]) < 1e-3
 
 
 @pytest.mark.parametrize("n,grid,C,groups,leaky", [(2, 16, 32, 2, True), (3, 8, 64, 4, True), (1, 32, 32, 2, False),
-                                                  (2, 8, 128, 8, True)])
+                                                  (2, 8, 128, 8, True), (3, 4, 48, 3, True), (2, 2, 72, 4, False),
+                                                  (2, 4, 48, 3, False), (5, 2, 72, 4, True)])
 def test_groupnorm_backward(ops, n, grid, C, groups, leaky):
     """dL/dx, dL/dgamma, dL/dbeta of LeakyReLU(GroupNorm(x)) against torch.autograd on the CPU (fp32 on the fp16-rounded
     tensors).  An element whose pre-activation sits within rounding of 0 may take the other LeakyReLU branch: the check
@@ -555,13 +559,19 @@ def test_groupnorm_backward(ops, n, grid, C, groups, leaky):
     (z * dz).sum().backward()
     gn_cuda = torch.nn.GroupNorm(groups, C).cuda()
     gn_cuda.load_state_dict(gn.state_dict())
-    dx, dg, db = ops.groupnorm_backward(to_act(x.detach()), to_act(dz), gn_cuda, leaky=leaky)
+    dx, dg, db, dxs = ops.groupnorm_backward(to_act(x.detach()), to_act(dz), gn_cuda, leaky=leaky)
     dx = from_act(dx)
+    # dxsum = gradient of a bias added to x (the producing conv's bias): per-channel sum of dL/dx
+    ref_bias = x.grad.sum(dim=(0, 2, 3, 4))
+    assert float((dxs.cpu() - ref_bias).abs().max()) <= 1e-3 * float(x.grad.abs().sum(dim=(0, 2, 3, 4)).max())
     scale = float(x.grad.abs().max())
     diff = (dx - x.grad).abs()
     assert float((diff > 3e-3 * scale).float().mean()) <= 1e-5
     assert float(diff.mean()) <= 3e-4 * scale
     assert float((dg.cpu() - gn.weight.grad).abs().max()) <= 2e-3 * float(gn.weight.grad.abs().max())
     assert float((db.cpu() - gn.bias.grad).abs().max()) <= 2e-3 * float(gn.bias.grad.abs().max())
-    dx2, dg2, db2 = ops.groupnorm_backward(to_act(x.detach()), to_act(dz), gn_cuda, leaky=leaky)
-    assert torch.equal(from_act(dx2), dx) and torch.equal(dg2, dg) and torch.equal(db2, db)
+    dx2, dg2, db2, dxs2 = ops.groupnorm_backward(to_act(x.detach()), to_act(dz), gn_cuda, leaky=leaky)
+    assert torch.equal(from_act(dx2), dx) and torch.equal(dg2, dg) and torch.equal(db2, db) and torch.equal(dxs2, dxs)
+    # out_scale multiplies the fp32 outputs only
+    _, dg3, db3, dxs3 = ops.groupnorm_backward(to_act(x.detach()), to_act(dz), gn_cuda, leaky=leaky, out_scale=0.25)
+    assert torch.allclose(dg3, dg * 0.25, rtol=1e-6, atol=0) and torch.allclose(db3, db * 0.25, rtol=1e-6, atol=0)

@@ -158,13 +158,21 @@ def test_state_dict_roundtrip_and_cache_invalidation():
         assert torch.equal(v.cpu(), sd[k]), k
 
 
-def test_training_mode_raises():
+def test_training_mode_submodules_raise_but_detector_trains():
+    """Autograd is wired through KyptDetector.forward; the sub-networks called on their own in training mode with
+    autograd enabled still refuse (no silent graph-less result)."""
     hp = O.default_hparams(grid_size=32)
     net, _ = build(hp, 53)
     net.train()
     vox = torch.zeros(1, 2, 1, 32, 32, 32, device="cuda")
+    vox[:, :, :, 8:20, 8:20, 8:20] = 1.0
     with pytest.raises(NotImplementedError):
-        net.kypt_detector(vox)
+        net.kypt_detector.vox_to_kypt(vox)
+    out = net.kypt_detector(vox)
+    assert out["recon_loss"].requires_grad and out["keypoints"].requires_grad
+    with torch.no_grad():                                   # the caller's no_grad is respected in training mode
+        out = net(vox, {"detector": True, "learner": False})
+    assert not out["recon_loss"].requires_grad
 
 
 def test_stress_resolution_g128_vs_oracle():
