@@ -17,10 +17,17 @@ has it divided out again, so `param.grad` holds true values as with the referenc
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
 from . import ops
+
+
+# log2 of the magnitude the largest entry gradient (dL/d pre-sigmoid map) is scaled to.  fp16 tops out at 2^16: the
+# default leaves 2^10 of head-room for gradients that grow on the way down and keeps the small gradients of the
+# spatio-temporal branch (1e-5 of the decoder's) out of the subnormal range.
+GRAD_HEADROOM_LOG2 = int(os.environ.get("NM_GRAD_HEADROOM_LOG2", "6"))
 
 
 def _c(t):
@@ -173,10 +180,10 @@ class ConvGNFinalRecon(torch.autograd.Function):
             return (None,) * 15
         dbce = _c(dbce.float())
         S = raw.shape[1] * raw.shape[2] * raw.shape[3]
-        # |dL/dx14| <= gmax * sharp / S; scale it to O(1) in fp16 (a power of two: exact scaling)
+        # |dL/dx14| <= gmax * sharp / S; scale it to 2^GRAD_HEADROOM_LOG2 in fp16 (a power of two: exact scaling)
         gmax = float(dbce.abs().max().item())
         if gmax > 0.0 and math.isfinite(gmax):
-            ops.set_grad_scale(2.0 ** max(0, min(24, round(math.log2(S / (gmax * sharp))))))
+            ops.set_grad_scale(2.0 ** max(0, min(30, round(math.log2(S / (gmax * sharp))) + GRAD_HEADROOM_LOG2)))
         scale = ops.grad_scale()
         dact, dw14, db14 = ops.final_recon_backward(raw, a, sh, conv14, first_frame, T, sharp, trans, recon, target, dbce, scale)
         draw, dg, db, dbias = ops.groupnorm_backward(raw, dact, gn, leaky=True, out_scale=1.0 / scale)
