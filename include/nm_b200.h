@@ -231,6 +231,14 @@ int nm_linear_blend_skinning(const float* points, int N, const float* joints, co
 size_t nm_conv3d_k3_wgrad_workspace_bytes(int n, int D, int H, int W, int Cin, int Cout);
 int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int n, int D, int H, int W, int Cin, int Cout,
                        float out_scale, float* dw, void* workspace, void* stream);
+/* The same weight gradient on the 5th-gen tensor cores: tcgen05.mma with MN-major operands straight from the TMA-loaded
+ * voxel-major tiles (K = voxels), kw shifts stacked along M and the three kh rows along N through the descriptor
+ * strides, fp32 accumulators in TMEM, fixed-order split-K (bit-reproducible).  Cin, Cout multiples of 32 (<= 256),
+ * W in {16, 32, 64, 128}, H a multiple of 256 / W: nm_conv3d_k3_wgrad_tc_supported. */
+int nm_conv3d_k3_wgrad_tc_supported(int n, int D, int H, int W, int Cin, int Cout);
+size_t nm_conv3d_k3_wgrad_tc_workspace_bytes(int n, int D, int H, int W, int Cin, int Cout);
+int nm_conv3d_k3_wgrad_tc(const void* x, const void* grad_out, int n, int D, int H, int W, int Cin, int Cout,
+                          float out_scale, float* dw, void* workspace, void* stream);
 /* Backward of z = LeakyReLU_0.01(GroupNorm(x)) (leaky != 0) or of GroupNorm alone (modules/vox_modules.py:8-75 under
  * autograd): x, grad_out (= dL/dz), grad_in (= dL/dx) act (n, S, C) fp16; gamma, beta (C) fp32.  Optional fp32 outputs,
  * summed over the n samples and multiplied by out_scale (= 1 / loss scale): dgamma, dbeta (C) and dxsum (C) = the sum of

@@ -88,6 +88,9 @@ PROTOTYPES = {
     "nm_linear_blend_skinning": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "nm_conv3d_k3_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "nm_conv3d_k3_wgrad": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
+    "nm_conv3d_k3_wgrad_tc_supported": (_i, [_i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_k3_wgrad_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "nm_conv3d_k3_wgrad_tc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nm_groupnorm_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "nm_groupnorm_backward": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nm_conv3d_wgrad_gather_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),

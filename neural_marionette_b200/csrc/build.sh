@@ -6,8 +6,8 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr ${NM_NVCC_EXTRA}"
 mkdir -p _obj
 pids=()
-for f in api voxelize pointwise conv_direct conv_pw conv_tc heatmap dynamics eval conv_wgrad gn_backward conv_wgrad_gather backward; do
-  if [ ! -f _obj/$f.o ] || [ $f.cu -nt _obj/$f.o ] || [ common.cuh -nt _obj/$f.o ] || [ ../../include/nm_b200.h -nt _obj/$f.o ]; then
+for f in api voxelize pointwise conv_direct conv_pw conv_tc heatmap dynamics eval conv_wgrad gn_backward conv_wgrad_gather conv_wgrad_tc backward; do
+  if [ ! -f _obj/$f.o ] || [ $f.cu -nt _obj/$f.o ] || [ common.cuh -nt _obj/$f.o ] || [ tc_ptx.cuh -nt _obj/$f.o ] || [ ../../include/nm_b200.h -nt _obj/$f.o ]; then
     $NVCC $FLAGS -c $f.cu -o _obj/$f.o &
     pids+=($!)
   fi

@@ -279,17 +279,30 @@ def _slab_wgrad_ok(x, Cout) -> bool:
     return Cin % 32 == 0 and Cout % 32 == 0 and Cin <= 256 and Cout <= 256 and W in (16, 32, 48, 64)
 
 
+WGRAD_TC = __import__("os").environ.get("NM_WGRAD_TC", "1") != "0"
+
+
 def conv3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor, k: int = 3, stride: int = 1,
-                       out_scale: float = 1.0, force_gather: bool = False) -> torch.Tensor:
+                       out_scale: float = 1.0, force_gather: bool = False, impl: Optional[str] = None) -> torch.Tensor:
     """dL/dW of an nn.Conv3d ((k, stride) in {(1, 1), (3, 1), (2, 2)}): x act (n, D, H, W, Cin), grad_out act
-    (n, OD, OH, OW, Cout) -> (Cout, Cin, k, k, k) fp32, multiplied by out_scale."""
+    (n, OD, OH, OW, Cout) -> (Cout, Cin, k, k, k) fp32, multiplied by out_scale.  The k3 layers go to the tcgen05
+    kernel where it covers the shape (`impl`: "tc" | "slab" | "gather" forces a kernel - tests)."""
     _need_cuda(x, grad_out)
     n, D, H, W, Cin = x.shape
     Cout = grad_out.shape[-1]
     assert x.dtype == ACT_DTYPE and grad_out.dtype == ACT_DTYPE and x.is_contiguous() and grad_out.is_contiguous()
     assert tuple(grad_out.shape[1:4]) == (D // stride, H // stride, W // stride) and grad_out.shape[0] == n
     dw = torch.empty(Cout, Cin, k, k, k, dtype=torch.float32, device=x.device)
-    if k == 3 and stride == 1 and _slab_wgrad_ok(x, Cout) and not force_gather:
+    if force_gather:
+        impl = "gather"
+    tc_ok = k == 3 and stride == 1 and bool(L.query("nm_conv3d_k3_wgrad_tc_supported", n, D, H, W, Cin, Cout))
+    if impl == "tc" or (impl is None and WGRAD_TC and tc_ok):
+        nbytes = L.query("nm_conv3d_k3_wgrad_tc_workspace_bytes", n, D, H, W, Cin, Cout)
+        ws = workspace(max(nbytes, 16), x.device, "wgrad")
+        L.call("nm_conv3d_k3_wgrad_tc", L.ptr(x), L.ptr(grad_out), n, D, H, W, Cin, Cout, float(out_scale), L.ptr(dw),
+               L.ptr(ws), L.stream())
+        return dw
+    if k == 3 and stride == 1 and _slab_wgrad_ok(x, Cout) and impl != "gather":
         nbytes = L.query("nm_conv3d_k3_wgrad_workspace_bytes", n, D, H, W, Cin, Cout)
         ws = workspace(max(nbytes, 16), x.device, "wgrad")
         L.call("nm_conv3d_k3_wgrad", L.ptr(x), L.ptr(grad_out), n, D, H, W, Cin, Cout, float(out_scale), L.ptr(dw),

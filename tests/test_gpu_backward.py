@@ -64,6 +64,25 @@ def test_conv_weight_grad_gather(ops, n, grid, cin, cout, k, stride):
     assert torch.allclose(half, got * 0.5, rtol=1e-6, atol=0)
 
 
+@pytest.mark.parametrize("n,grid,cin,cout", [(2, 16, 32, 32), (1, 32, 64, 32), (1, 16, 128, 64), (2, 16, 64, 64),
+                                            (1, 32, 32, 64), (1, 64, 32, 32), (1, 64, 64, 32), (1, 16, 256, 128),
+                                            (3, 32, 64, 64), (5, 16, 64, 128)])
+def test_conv_weight_grad_tcgen05(ops, n, grid, cin, cout):
+    """The tcgen05 weight-gradient kernel (MN-major operands, taps stacked through descriptor strides) against
+    torch.nn.grad.conv3d_weight on the CPU: fp16-rounded operands, fp32 accumulation over K = n * grid^3 voxels."""
+    g = torch.Generator().manual_seed(5 * grid + cin + 13 * cout)
+    x = h(torch.randn(n, cin, grid, grid, grid, generator=g))
+    gy = h(torch.randn(n, cout, grid, grid, grid, generator=g) / grid ** 1.5)
+    ref = torch.nn.grad.conv3d_weight(x, (cout, cin, 3, 3, 3), gy, padding=1)
+    got = ops.conv3d_weight_grad(to_act(x), to_act(gy), impl="tc")
+    assert got.shape == ref.shape
+    err = (got.cpu() - ref).abs().amax(dim=(0, 1)) / ref.abs().max()
+    assert float(err.max()) < 1e-3, f"per-tap error {err.reshape(-1).tolist()}"
+    assert torch.equal(got, ops.conv3d_weight_grad(to_act(x), to_act(gy), impl="tc"))   # fixed-order split-K
+    half = ops.conv3d_weight_grad(to_act(x), to_act(gy), impl="tc", out_scale=0.5)
+    assert torch.allclose(half, got * 0.5, rtol=1e-6, atol=0)
+
+
 @pytest.mark.parametrize("n,grid,cin,cout", [(2, 2, 72, 48), (3, 4, 48, 32), (2, 8, 32, 64), (1, 8, 32, 128)])
 def test_conv_transpose_grads(ops, n, grid, cin, cout):
     """dL/dW and dL/dx of ConvTranspose3d(k2, s2) (Upsample3DBlock) against torch.autograd."""
