@@ -104,12 +104,14 @@ class GradientBuckets:
         for p in self.params:
             self._need[self._bucket_of[id(p)]] += 1
         self._left, self._work, self._launched = list(self._need), [None] * len(self.bounds), [False] * len(self.bounds)
+        self._finished = False
 
     def zero(self) -> None:
         self.flat.zero_()
         for p in self.params:
             self._attach(p, copy=False)
         self._left, self._work, self._launched = list(self._need), [None] * len(self.bounds), [False] * len(self.bounds)
+        self._finished = False
 
     def _attach(self, p, copy: bool = True) -> None:
         """Make `p.grad` the view of its slot again (copying a detached gradient into the slot first)."""
@@ -144,7 +146,11 @@ class GradientBuckets:
             self._work[b] = dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
 
     def finish(self) -> None:
-        """Launch whatever was not reported ready, wait for every bucket, average over the ranks."""
+        """Launch whatever was not reported ready, wait for every bucket, average over the ranks.  Idempotent until the
+        next `zero()`."""
+        if self._finished:
+            return
+        self._finished = True
         for b, launched in enumerate(self._launched):
             if not launched:                                   # gradients nobody reported: make sure they are in the buffer
                 for p in self.params:
