@@ -24,10 +24,22 @@ import torch
 from . import ops
 
 
-# log2 of the magnitude the largest entry gradient (dL/d pre-sigmoid map) is scaled to.  fp16 tops out at 2^16: the
-# default leaves 2^10 of head-room for gradients that grow on the way down and keeps the small gradients of the
-# spatio-temporal branch (1e-5 of the decoder's) out of the subnormal range.
-GRAD_HEADROOM_LOG2 = int(os.environ.get("NM_GRAD_HEADROOM_LOG2", "6"))
+# log2 of the magnitude the largest entry gradient (dL/d pre-sigmoid map) is scaled to.  fp16 tops out at 2^16 and the
+# GroupNorm backward multiplies by 1/sigma of the normalised tensors, so gradients can grow by 2^10 and more on the way
+# down: the default scales the entry gradient to O(1).  The measured gradient error does not depend on the scale from
+# 2^8 to 2^19 (profiles/r02_training.md), i.e. underflow is not what limits the accuracy.  `FusedAdam.step` lowers the
+# head-room by 2^2 whenever a step overflowed (and skipped) and raises it again slowly - dynamic loss scaling.
+GRAD_HEADROOM_LOG2 = int(os.environ.get("NM_GRAD_HEADROOM_LOG2", "0"))
+_HEADROOM = [GRAD_HEADROOM_LOG2]
+
+
+def headroom_log2() -> int:
+    return _HEADROOM[0]
+
+
+def adjust_headroom(delta: int) -> int:
+    _HEADROOM[0] = max(-16, min(8, _HEADROOM[0] + int(delta)))
+    return _HEADROOM[0]
 
 
 def _c(t):
@@ -180,10 +192,10 @@ class ConvGNFinalRecon(torch.autograd.Function):
             return (None,) * 15
         dbce = _c(dbce.float())
         S = raw.shape[1] * raw.shape[2] * raw.shape[3]
-        # |dL/dx14| <= gmax * sharp / S; scale it to 2^GRAD_HEADROOM_LOG2 in fp16 (a power of two: exact scaling)
+        # |dL/dx14| <= gmax * sharp / S; scale it to 2^headroom in fp16 (a power of two: exact scaling)
         gmax = float(dbce.abs().max().item())
         if gmax > 0.0 and math.isfinite(gmax):
-            ops.set_grad_scale(2.0 ** max(0, min(30, round(math.log2(S / (gmax * sharp))) + GRAD_HEADROOM_LOG2)))
+            ops.set_grad_scale(2.0 ** max(0, min(30, round(math.log2(S / (gmax * sharp))) + _HEADROOM[0])))
         scale = ops.grad_scale()
         dact, dw14, db14 = ops.final_recon_backward(raw, a, sh, conv14, first_frame, T, sharp, trans, recon, target, dbce, scale)
         draw, dg, db, dbias = ops.groupnorm_backward(raw, dact, gn, leaky=True, out_scale=1.0 / scale)

@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 
 from . import _lib as L
+from . import autograd as AG
 from . import ops
 from .parallel import GradientBuckets
 
@@ -44,6 +45,7 @@ class FusedAdam:
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.steps = 0
         self.skipped = 0
+        self._good = 0
         self._hooks = self.buckets.attach_hooks() if overlap else []
         if owner is not None:
             ops.invalidate_caches(owner)
@@ -59,9 +61,15 @@ class FusedAdam:
         self.flag.zero_()
         L.call("nm_grad_nonfinite", L.ptr(g), g.numel(), L.ptr(self.flag), L.stream())
         if int(self.flag.item()) != 0:
+            # an fp16 activation gradient overflowed somewhere in the backward: skip, and scale the next pass 4x lower
             self.skipped += 1
+            self._good = 0
+            AG.adjust_headroom(-2)
             return False
         self.steps += 1
+        self._good += 1
+        if self._good % 500 == 0 and AG.headroom_log2() < AG.GRAD_HEADROOM_LOG2:
+            AG.adjust_headroom(+1)
         L.call("nm_adam_step", L.ptr(self.flat_param), L.ptr(g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), g.numel(),
                self.lr, self.betas[0], self.betas[1], self.eps, self.steps, 1.0, None, L.stream())
         if self.owner is not None:
