@@ -260,6 +260,12 @@ size_t nm_conv3d_wgrad_gather_workspace_bytes(int n, int Ds, int Hs, int Ws, int
 int nm_conv3d_wgrad_gather(const void* small_side, const void* large_side, int n, int Ds, int Hs, int Ws, int Ca, int Cb,
                            int k, int stride, float out_scale, float* dw, void* workspace, void* stream);
 
+/* Data gradient of the k2/s2 "pool" convs (modules/vox_modules.py:53 under autograd) on the tensor cores: the transposed
+ * conv is a 1x1 conv dL/dy -> (tap, ci) (nm_conv3d_tc with the weight read as [(tap, ci)][co]) followed by this scatter
+ * of the tap-major result y (n, D, H, W, ntaps, C) - taps tap0 .. tap0 + ntaps - 1, tap = kd*4 + kh*2 + kw - to
+ * out (n, 2D, 2H, 2W, C). */
+int nm_depth_to_space2(const void* y, void* out, int n, int D, int H, int W, int C, int tap0, int ntaps, void* stream);
+
 /* Backward of nm_upsample2x without the fused prologue (nn.Upsample(scale 2, trilinear, align_corners=False),
  * model/kypt_detector.py:427,441): grad_out act (n, 2D, 2H, 2W, C) -> grad_in act (n, D, H, W, C). */
 int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n, int D, int H, int W, int C, void* stream);

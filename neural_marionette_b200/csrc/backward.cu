@@ -59,6 +59,28 @@ upsample2x_bwd_kernel(const __half* __restrict__ g, __half* __restrict__ dx, int
   }
 }
 
+// ------------------------------------------------------------------ depth-to-space (k2/s2 transposed conv as a 1x1 conv)
+// The data gradient of a k2/s2 "pool" conv is a transposed conv: out[2v + t][ci] = sum_co W[co][ci][t] dy[v][co].  For
+// wide layers it runs as a 1x1 convolution dy -> (taps, ci) on the tensor cores (nm_conv3d_tc); this kernel scatters the
+// tap-major result y (n, D, H, W, ntaps, C) of taps tap0 .. tap0 + ntaps - 1 to their voxels of out (n, 2D, 2H, 2W, C).
+__global__ void __launch_bounds__(256)
+depth_to_space2_kernel(const __half* __restrict__ y, __half* __restrict__ out, int D, int H, int W, int C, int tap0, int ntaps,
+                       long long total8) {
+  const int c8n = C >> 3;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total8; i += (long long)gridDim.x * 256) {
+    const int c8 = (int)(i % c8n);
+    long long r = i / c8n;
+    const int tl = (int)(r % ntaps); r /= ntaps;
+    const int w = (int)(r % W); r /= W;
+    const int h = (int)(r % H); r /= H;
+    const int d = (int)(r % D);
+    const long long n = r / D;
+    const int t = tap0 + tl;
+    const long long o = (((n * (2 * D) + 2 * d + (t >> 2)) * (2 * H) + 2 * h + ((t >> 1) & 1)) * (2 * W) + 2 * w + (t & 1)) * C + c8 * 8;
+    *reinterpret_cast<uint4*>(out + o) = reinterpret_cast<const uint4*>(y)[i];
+  }
+}
+
 // ------------------------------------------------------------------ decoder tail backward
 // forward: act = lrelu(x*a + b); x14 = w . act + bias; p = sigmoid(sharp * (tanh(x14) + ff - trans)); bce = mean BCE(p, y)
 // backward (PyTorch's binary_cross_entropy_backward: (p - y) / max(p (1 - p), 1e-12)):
@@ -660,12 +682,14 @@ __global__ void chamfer_bwd_finalize_kernel(const float* __restrict__ partial, c
 // moments (sum dY, sum x dY, sum y dY, sum z dY).  Occupancy channel: a gather over the occupied voxels.
 template <int C>
 __global__ void __launch_bounds__(256)
-first_wgrad_moments_kernel(const __half* __restrict__ dy, int G, float* __restrict__ bins /* [n][125][4][C] */) {
+first_wgrad_moments_kernel(const __half* __restrict__ dy, int G, float* __restrict__ bins /* [n][parts][125][4][C] */) {
   constexpr int CC = C / 8, NVL = 256 / CC;
   __shared__ float red[256 * 32];
-  const int n = blockIdx.x;
+  const int n = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
+  const int xs = G * part / parts, xe = G * (part + 1) / parts;        // this CTA's x slab
   const int cc = threadIdx.x % CC, vl = threadIdx.x / CC;
   const __half* base = dy + (long long)n * G * G * G * C + cc * 8;
+  float* out = bins + ((long long)n * parts + part) * 125 * 4 * C;
   for (int bin = 0; bin < 125; bin++) {
     const int cls[3] = {bin / 25, (bin / 5) % 5, bin % 5};
     int lo[3], cnt[3];
@@ -674,7 +698,16 @@ first_wgrad_moments_kernel(const __half* __restrict__ dy, int G, float* __restri
       lo[a] = cls[a] == 0 ? 0 : (cls[a] == 1 ? 1 : (cls[a] == 2 ? 2 : (cls[a] == 3 ? G - 2 : G - 1)));
       cnt[a] = cls[a] == 2 ? G - 4 : 1;
     }
+    {
+      const int a0 = max(lo[0], xs), a1 = min(lo[0] + cnt[0], xe);
+      lo[0] = a0;
+      cnt[0] = max(0, a1 - a0);
+    }
     const int total = cnt[0] * cnt[1] * cnt[2];
+    if (total == 0) {                                                   // block-uniform: the bin lies outside the slab
+      for (int i = threadIdx.x; i < 4 * C; i += 256) out[(long long)bin * 4 * C + i] = 0.f;
+      continue;
+    }
     float acc[32];
 #pragma unroll
     for (int i = 0; i < 32; i++) acc[i] = 0.f;
@@ -700,12 +733,12 @@ first_wgrad_moments_kernel(const __half* __restrict__ dy, int G, float* __restri
       const int q = i / C, c = i % C, c8 = c / 8, k = c % 8;
       float t = 0.f;
       for (int l = 0; l < NVL; l++) t += red[(q * 8 + k) * 256 + l * CC + c8];
-      bins[(((long long)n * 125 + bin) * 4 + q) * C + c] = t;
+      out[((long long)bin * 4 + q) * C + c] = t;
     }
   }
 }
 
-// occupancy channel: partial[n][125][C] = sum over occupied u of occ[u] * dY[u - (t - 2)]
+// occupancy channel: partial[n][parts][125][C] = sum over this part's occupied u of occ[u] * dY[u - (t - 2)]
 template <int C>
 __global__ void __launch_bounds__(256)
 first_wgrad_occ_kernel(const float* __restrict__ occ, const __half* __restrict__ dy, int G, float* __restrict__ partial) {
@@ -713,7 +746,7 @@ first_wgrad_occ_kernel(const float* __restrict__ occ, const __half* __restrict__
   __shared__ int s_idx[CHUNK];
   __shared__ float s_val[CHUNK];
   __shared__ int s_cnt[9];
-  const int n = blockIdx.x, S = G * G * G;
+  const int n = blockIdx.x, part = blockIdx.y, parts = gridDim.y, S = G * G * G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float acc[16][CPL];
 #pragma unroll
@@ -722,7 +755,7 @@ first_wgrad_occ_kernel(const float* __restrict__ occ, const __half* __restrict__
     for (int j = 0; j < CPL; j++) acc[i][j] = 0.f;
   const float* on = occ + (long long)n * S;
   const __half* dyn = dy + (long long)n * S * C + lane * CPL;
-  for (int c0 = 0; c0 < S; c0 += CHUNK) {
+  for (int c0 = part * CHUNK; c0 < S; c0 += parts * CHUNK) {
     // ordered compaction of the chunk's non-zero voxels (16 candidates per thread, contiguous)
     __syncthreads();
     float v[16];
@@ -780,7 +813,7 @@ first_wgrad_occ_kernel(const float* __restrict__ occ, const __half* __restrict__
     const int t = warp + 8 * i;
     if (t < 125)
 #pragma unroll
-      for (int j = 0; j < CPL; j++) partial[((long long)n * 125 + t) * C + lane * CPL + j] = acc[i][j];
+      for (int j = 0; j < CPL; j++) partial[(((long long)n * parts + part) * 125 + t) * C + lane * CPL + j] = acc[i][j];
   }
 }
 
@@ -847,6 +880,18 @@ extern "C" int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n
   upsample2x_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(grad_out),
                                                                   reinterpret_cast<__half*>(grad_in), D, H, W, C, total8);
   NM_CHECK_LAUNCH("upsample2x_bwd_kernel");
+  return NM_OK;
+}
+
+extern "C" int nm_depth_to_space2(const void* y, void* out, int n, int D, int H, int W, int C, int tap0, int ntaps, void* stream) {
+  NM_CHECK_ARG(y && out, "nm_depth_to_space2: null pointer");
+  NM_CHECK_ARG(C % 8 == 0 && tap0 >= 0 && ntaps >= 1 && tap0 + ntaps <= 8 && n > 0 && D > 0 && H > 0 && W > 0,
+               "nm_depth_to_space2: bad shape");
+  const long long total8 = (long long)n * D * H * W * ntaps * (C / 8);
+  const int blocks = (int)min((long long)nm_num_sms() * 16, (total8 + 255) / 256);
+  depth_to_space2_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(y), reinterpret_cast<__half*>(out),
+                                                                   D, H, W, C, tap0, ntaps, total8);
+  NM_CHECK_LAUNCH("depth_to_space2_kernel");
   return NM_OK;
 }
 
@@ -978,7 +1023,15 @@ extern "C" int nm_chamfer_vol_fit_backward(const float* seq, const float* keypoi
   return NM_OK;
 }
 
-extern "C" size_t nm_first_conv_wgrad_workspace_bytes(int n, int Cout) { return (size_t)(n + 1) * 125 * 5 * Cout * sizeof(float); }
+// CTAs per frame: the once-per-clip branch has few (dense) frames, the per-frame encoder many sparse ones
+static int first_wgrad_parts(int n) {
+  int p = (2 * nm_num_sms() + n - 1) / n;
+  return p < 1 ? 1 : (p > 8 ? 8 : p);
+}
+
+extern "C" size_t nm_first_conv_wgrad_workspace_bytes(int n, int Cout) {
+  return ((size_t)n * first_wgrad_parts(n) + 1) * 125 * 5 * Cout * sizeof(float);
+}
 
 extern "C" int nm_first_conv_wgrad(const float* occ, const void* grad_out, const float* linspace, int n, int G, int Cout,
                                    float out_scale, float* dw, void* workspace, void* stream) {
@@ -986,25 +1039,28 @@ extern "C" int nm_first_conv_wgrad(const float* occ, const void* grad_out, const
   NM_CHECK_ARG((Cout == 32 || Cout == 64) && G >= 8 && G % 16 == 0, "nm_first_conv_wgrad: Cout=%d G=%d unsupported", Cout, G);
   if (n == 0) return NM_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const int parts = first_wgrad_parts(n);
+  const long long rows = (long long)n * parts;
   float* bins = reinterpret_cast<float*>(workspace);
-  float* occp = bins + (size_t)n * 125 * 4 * Cout;
+  float* occp = bins + (size_t)rows * 125 * 4 * Cout;
   const __half* dy = reinterpret_cast<const __half*>(grad_out);
+  const dim3 grid(n, parts);
   if (Cout == 32) {
-    first_wgrad_moments_kernel<32><<<n, 256, 0, st>>>(dy, G, bins);
+    first_wgrad_moments_kernel<32><<<grid, 256, 0, st>>>(dy, G, bins);
     NM_CHECK_LAUNCH("first_wgrad_moments_kernel");
-    first_wgrad_occ_kernel<32><<<n, 256, 0, st>>>(occ, dy, G, occp);
+    first_wgrad_occ_kernel<32><<<grid, 256, 0, st>>>(occ, dy, G, occp);
   } else {
-    first_wgrad_moments_kernel<64><<<n, 256, 0, st>>>(dy, G, bins);
+    first_wgrad_moments_kernel<64><<<grid, 256, 0, st>>>(dy, G, bins);
     NM_CHECK_LAUNCH("first_wgrad_moments_kernel");
-    first_wgrad_occ_kernel<64><<<n, 256, 0, st>>>(occ, dy, G, occp);
+    first_wgrad_occ_kernel<64><<<grid, 256, 0, st>>>(occ, dy, G, occp);
   }
   NM_CHECK_LAUNCH("first_wgrad_occ_kernel");
-  // sum over the frames first (fixed order), then assemble the (Cout, 4, 5, 5, 5) tensor
-  float* rbins = occp + (size_t)n * 125 * Cout;
+  // sum over the frames and parts first (fixed order), then assemble the (Cout, 4, 5, 5, 5) tensor
+  float* rbins = occp + (size_t)rows * 125 * Cout;
   float* roccp = rbins + (size_t)125 * 4 * Cout;
-  reduce_cols_kernel<<<nm_cdiv(500 * Cout, 128), 128, 0, st>>>(bins, n, 500 * Cout, 500 * Cout, 1.0f, rbins);
+  reduce_cols_kernel<<<nm_cdiv(500 * Cout, 128), 128, 0, st>>>(bins, rows, 500 * Cout, 500 * Cout, 1.0f, rbins);
   NM_CHECK_LAUNCH("first_wgrad(reduce bins)");
-  reduce_cols_kernel<<<nm_cdiv(125 * Cout, 128), 128, 0, st>>>(occp, n, 125 * Cout, 125 * Cout, 1.0f, roccp);
+  reduce_cols_kernel<<<nm_cdiv(125 * Cout, 128), 128, 0, st>>>(occp, rows, 125 * Cout, 125 * Cout, 1.0f, roccp);
   NM_CHECK_LAUNCH("first_wgrad(reduce occ)");
   first_wgrad_finalize_kernel<<<nm_cdiv(Cout * 500, 128), 128, 0, st>>>(rbins, roccp, 1, Cout, G, linspace, out_scale, dw);
   NM_CHECK_LAUNCH("first_wgrad_finalize_kernel");

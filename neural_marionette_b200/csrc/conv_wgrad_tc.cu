@@ -38,6 +38,11 @@ struct WgTcParams {
   float* partial;                // [split][group][mg][128][3 * co]
 };
 
+// CI / CO: channel block sizes (32 -> 64-byte rows, SW64; 64 -> 128-byte rows, SW128); KS = W / 16 K steps per w-row.
+// Everything the MMA-issuing lane needs per instruction is a compile-time offset from two per-stage base words: one
+// thread issues all MMAs, so every scalar instruction between two tcgen05.mma is exposed issue latency (the first,
+// runtime-indexed loop spent ~160 cycles per MMA on descriptor arithmetic; the tensor work is 50-100).
+template <int CI, int CO, int KS>
 __global__ void __launch_bounds__(192, 1)
 conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -53,11 +58,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
   const int group = blockIdx.y;
   const int kd = group % 3, cib = (group / 3) % p.ci_blocks, cob = group / (3 * p.ci_blocks);
   const int htiles = p.H / p.ht;
-  const long long units = (long long)p.N * p.D * htiles;
-  const long long u0 = units * blockIdx.x / gridDim.x, u1 = units * (blockIdx.x + 1) / gridDim.x;
-  const int slots = 128 / p.ci;                    // kw shifts stacked along M
-  const int gm = (3 + slots - 1) / slots;          // M groups: 1 (ci = 32) or 2 (ci = 64)
-  const int ncols = 3 * p.co;
+  const long long units = (long long)p.N * p.D * htiles;              // < 2^31 (checked by the host)
+  const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+  constexpr int slots = 128 / CI;                  // kw shifts stacked along M
+  constexpr int gm = (3 + slots - 1) / slots;      // M groups: 1 (CI = 32) or 2 (CI = 64)
+  constexpr int ncols = 3 * CO;
+  constexpr int HT = 16 / KS;                      // X rows per unit (HT * W = 256 voxels)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmap_x) : "memory");
@@ -80,10 +86,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (long long u = u0; u < u1; u++) {
-        const int ht = (int)(u % htiles);
-        const int d = (int)((u / htiles) % p.D);
-        const int n = (int)(u / ((long long)htiles * p.D));
+      for (int u = u0; u < u1; u++) {
+        const int ht = u % htiles;
+        const int d = (u / htiles) % p.D;
+        const int n = u / (htiles * p.D);
         const int dy = d - kd + 1;                                   // plane of dY paired with X plane d
         if ((unsigned)dy >= (unsigned)p.D) continue;                 // all-zero operand: nothing to add
         mbar_wait(&empty[stage], phase ^ 1, "nm_conv3d_k3_wgrad_tc(producer)");
@@ -97,36 +103,47 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // instruction descriptor: D = F32 (bit 4), A = B = F16, A and B MN-major (bits 15, 16), N >> 3 at [17,23), M >> 4 at [24,29)
-    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t row_a = p.ci * 2, row_b = p.co * 2;               // bytes per voxel row: 128 (SW128) or 64 (SW64)
-    const uint32_t lay_a = row_a == 128 ? 2u : 4u, lay_b = row_b == 128 ? 2u : 4u;
-    const uint32_t xrow = (uint32_t)(p.W + 3) * row_a, yrow = (uint32_t)p.W * row_b;
+    constexpr uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t row_a = CI * 2, row_b = CO * 2;               // bytes per voxel row: 128 (SW128) or 64 (SW64)
+    constexpr uint32_t lay_a = row_a == 128 ? 2u : 4u, lay_b = row_b == 128 ? 2u : 4u;
+    const uint32_t xrow16 = ((uint32_t)(p.W + 3) * row_a) >> 4, yrow16 = ((uint32_t)p.W * row_b) >> 4;
+    // descriptor words: hi = SBO (8 voxel rows) | version | layout, lo = start >> 4 | LBO << 16
+    constexpr uint32_t hi_a = ((8 * row_a) >> 4) | (1u << 14) | (lay_a << 29);
+    constexpr uint32_t hi_b = ((8 * row_b) >> 4) | (1u << 14) | (lay_b << 29);
+    const uint32_t lbo_a = (row_a >> 4) << 16;                      // next kw shift = next voxel row
+    const uint32_t lbo_b = yrow16 << 16;                            // next kh = next w-row of the dY tile
     int stage = 0;
-    uint32_t phase = 0, any = 0;
-    for (long long u = u0; u < u1; u++) {
-      const int d = (int)((u / htiles) % p.D);
+    uint32_t phase = 0, accum = 0;
+    for (int u = u0; u < u1; u++) {
+      const int d = (u / htiles) % p.D;
       if ((unsigned)(d - kd + 1) >= (unsigned)p.D) continue;
       mbar_wait(&full[stage], phase, "nm_conv3d_k3_wgrad_tc(mma)");
       tc_fence_after();
       __syncwarp();
       if (elect_one()) {
         const uint32_t sx = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sy = sx + p.x_bytes;
-        for (int r = 0; r < p.ht; r++) {
-          for (int ks = 0; ks < p.W / 16; ks++) {
+        uint32_t a_r = lbo_a | ((sx & 0x3FFFFu) >> 4);
+        uint32_t b_r = lbo_b | (((sx + (uint32_t)p.x_bytes) & 0x3FFFFu) >> 4);
+#pragma unroll
+        for (int r = 0; r < HT; r++) {
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) {
             // B: dY rows h-1, h, h+1 (the tile starts at row h0 - 1) of the 16 voxels w = 16 ks ...
-            const uint64_t db = smem_desc(sy + (uint32_t)r * yrow + (uint32_t)(16 * ks) * row_b, yrow, 8 * row_b, lay_b);
+            const uint64_t db = ((uint64_t)hi_b << 32) | (b_r + (uint32_t)(ks * ((16 * row_b) >> 4)));
+#pragma unroll
             for (int mg = 0; mg < gm; mg++) {
               // A: X rows (w + 1) = 16 ks + jw .. for the kw shifts jw = mg * slots + (0 .. slots - 1)
-              const uint64_t da = smem_desc(sx + (uint32_t)r * xrow + (uint32_t)(16 * ks + mg * slots) * row_a, row_a, 8 * row_a, lay_a);
-              umma_f16(tmem_base + (uint32_t)(mg * ncols), da, db, idesc, (any | (uint32_t)r | (uint32_t)ks) != 0 ? 1u : 0u);
+              const uint64_t da = ((uint64_t)hi_a << 32) | (a_r + (uint32_t)(((16 * ks + mg * slots) * row_a) >> 4));
+              umma_f16(tmem_base + (uint32_t)(mg * ncols), da, db, idesc, (r | ks) == 0 ? accum : 1u);
             }
           }
+          a_r += xrow16;
+          b_r += yrow16;
         }
         umma_commit(&empty[stage]);
       }
       __syncwarp();
-      any = 1;
+      accum = 1;
       if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
     if (elect_one()) umma_commit(tfull);
@@ -136,8 +153,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     bool any = false;
-    for (long long u = u0; u < u1 && !any; u++) {
-      const int d = (int)((u / htiles) % p.D);
+    for (int u = u0; u < u1 && !any; u++) {
+      const int d = (u / htiles) % p.D;
       any = (unsigned)(d - kd + 1) < (unsigned)p.D;
     }
     mbar_wait(tfull, 0, "nm_conv3d_k3_wgrad_tc(epilogue)");
@@ -216,6 +233,7 @@ bool wg_plan(int N, int D, int H, int W, int Cin, int Cout, WgPlan* q) {
   while (cols < q->gm * q->ncols) cols <<= 1;
   q->tmem_cols = cols;
   const long long units = (long long)N * D * (H / ht);
+  if (units >= (1LL << 31)) return false;
   long long splits = nm_num_sms() / q->groups;
   if (splits < 1) splits = 1;
   if (splits > units) splits = units;
@@ -276,8 +294,29 @@ extern "C" int nm_conv3d_k3_wgrad_tc(const void* x, const void* grad_out, int n,
     if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_k3_wgrad_tc: cuTensorMapEncodeTiled(grad_out) failed with %d", (int)r); return NM_ERR_DRIVER; }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smem));
-  conv_wgrad_tc_kernel<<<dim3(q.splits, q.groups), 192, q.smem, st>>>(p);
+  const dim3 grid(q.splits, q.groups);
+  int rc = NM_OK;
+#define NM_WG_LAUNCH(CI_, CO_, KS_)                                                                                              \
+  do {                                                                                                                           \
+    cudaError_t e_ = cudaFuncSetAttribute(conv_wgrad_tc_kernel<CI_, CO_, KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          (int)q.smem);                                                                          \
+    if (e_ != cudaSuccess) { nm_set_error("nm_conv3d_k3_wgrad_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e_)); rc = NM_ERR_CUDA; } \
+    else conv_wgrad_tc_kernel<CI_, CO_, KS_><<<grid, 192, q.smem, st>>>(p);                                                      \
+  } while (0)
+#define NM_WG_KS(CI_, CO_)                                          \
+  do {                                                              \
+    if (W == 16) NM_WG_LAUNCH(CI_, CO_, 1);                         \
+    else if (W == 32) NM_WG_LAUNCH(CI_, CO_, 2);                    \
+    else if (W == 64) NM_WG_LAUNCH(CI_, CO_, 4);                    \
+    else NM_WG_LAUNCH(CI_, CO_, 8);                                 \
+  } while (0)
+  if (q.ci == 32 && q.co == 32) NM_WG_KS(32, 32);
+  else if (q.ci == 32) NM_WG_KS(32, 64);
+  else if (q.co == 32) NM_WG_KS(64, 32);
+  else NM_WG_KS(64, 64);
+#undef NM_WG_KS
+#undef NM_WG_LAUNCH
+  if (rc != NM_OK) return rc;
   NM_CHECK_LAUNCH("conv_wgrad_tc_kernel");
   conv_wgrad_tc_reduce_kernel<<<nm_cdiv((long long)Cout * Cin * 27, 256), 256, 0, st>>>(
       reinterpret_cast<const float*>(workspace), q.splits, q.groups, q.ci, q.co, q.ci_blocks, Cin, Cout, out_scale, dw);

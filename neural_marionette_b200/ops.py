@@ -258,6 +258,23 @@ def conv3d_input_grad(grad_out: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Te
         mirror = _cached(conv, "dgrad_mirror", [conv.weight], lambda: _zero_bias_mirror(
             "conv", conv.out_channels, conv.in_channels, k, 1, conv.weight.detach().flip(2, 3, 4).transpose(0, 1)))
         return conv3d(grad_out, mirror)
+    if s == 2 and k == 2 and conv.padding[0] == 0 and conv.in_channels >= 64 and conv.in_channels % 8 == 0 and \
+            conv.out_channels >= 16 and conv.out_channels % 8 == 0:
+        # wide layers: the transposed conv as 1x1 convs dL/dy -> (tap, ci) on the tensor cores + a depth-to-space scatter
+        Co, Ci = conv.out_channels, conv.in_channels
+        tp = max(1, min(8, 256 // Ci))                                     # taps per 1x1 conv (N = tp * Ci <= 256)
+
+        def build():
+            w = conv.weight.detach().reshape(Co, Ci, 8).permute(2, 1, 0)   # [tap][ci][co]
+            return [_zero_bias_mirror("conv", Co, tp * Ci, 1, 1, w[t0:t0 + tp].reshape(tp * Ci, Co, 1, 1, 1))
+                    for t0 in range(0, 8, tp)]
+        mirrors = _cached(conv, "dgrad_mirror_1x1", [conv.weight], build)
+        n, D, H, W, _ = grad_out.shape
+        dx = torch.empty(n, 2 * D, 2 * H, 2 * W, Ci, dtype=ACT_DTYPE, device=grad_out.device)
+        for j, m in enumerate(mirrors):
+            y = conv3d(grad_out, m)
+            L.call("nm_depth_to_space2", L.ptr(y), L.ptr(dx), n, D, H, W, Ci, j * tp, tp, L.stream())
+        return dx
     if s == 2 and k == 2 and conv.padding[0] == 0:
         # weight (Cout, Cin, 2, 2, 2) read as the (in = Cout, out = Cin) weight of a ConvTranspose3d
         mirror = _cached(conv, "dgrad_mirror", [conv.weight], lambda: _zero_bias_mirror(

@@ -175,6 +175,43 @@ def test_training_mode_submodules_raise_but_detector_trains():
     assert not out["recon_loss"].requires_grad
 
 
+@pytest.mark.parametrize("scale", [64.0, 1.0 / 64.0])
+def test_fp16_range_scaled_prenorm_tensors(scale):
+    """fp16 range stress (the raw pre-GroupNorm conv outputs are stored as fp16): every conv that feeds a GroupNorm has
+    its weight and bias multiplied by 64 or 1/64, which scales those raw tensors by the same factor while the reference
+    (fp32) output only changes through GroupNorm's eps.  The CUDA path must stay finite and inside the north-star
+    tolerances against the oracle run on the SAME scaled checkpoint."""
+    import neural_marionette_b200 as nm
+    G, B, T = 32, 1, 4
+    hp = O.default_hparams(grid_size=G)
+    sd = O.synthetic_state_dict(hp, seed=77)
+    gn_fed = [k[:-len(".weight")] for k in sd if k.endswith(".weight") and sd[k].dim() == 5 and
+              any(tag in k for tag in (".block.0", ".stride_conv.0", ".res_branch.0", ".res_branch.3", ".skip_con.0",
+                                       "decode_voxel_from_combined_representation.1.",
+                                       "decode_voxel_from_combined_representation.4.",
+                                       "decode_voxel_from_combined_representation.8.",
+                                       "decode_voxel_from_combined_representation.11."))]
+    assert len(gn_fed) >= 70
+    for k in gn_fed:
+        sd[k + ".weight"] = sd[k + ".weight"] * scale
+        sd[k + ".bias"] = sd[k + ".bias"] * scale
+    net = nm.NeuralMarionette(hp)
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    net.anneal(1)
+    vox, ref_vox = clips(7700, B, T, 20000, G)
+    with torch.no_grad():
+        out = net.kypt_detector(vox)
+        ref = O.detector_forward(ref_vox, sd, hp)
+    for k in ("keypoints", "heatmaps", "recon"):
+        assert torch.isfinite(out[k]).all(), k
+    kp_err = float((out["keypoints"].cpu() - ref["keypoints"]).abs().max())
+    hm_err = float((out["heatmaps"].cpu() - ref["heatmaps"]).abs().max() / ref["heatmaps"].max())
+    rec_err = float((out["recon"].cpu() - ref["recon"]).abs().mean())
+    print(f"[scale {scale:g}] keypoint max err {kp_err:.3e}, heat-map rel err {hm_err:.3e}, recon mean abs err {rec_err:.3e}")
+    assert kp_err <= KP_TOL and hm_err <= HM_TOL and rec_err <= 5e-3
+
+
 def test_stress_resolution_g128_vs_oracle():
     """Config #5: 2x the grid per axis (128^3, heat-map grid 32^3) with 100k points per frame."""
     import neural_marionette_b200 as nm
