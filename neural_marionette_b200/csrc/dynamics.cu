@@ -13,6 +13,7 @@
 // discrete decision; keep it as close to the reference arithmetic as possible).
 #include "common.cuh"
 #include "../../include/nm_b200.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -299,6 +300,358 @@ size_t step_smem_bytes(int S) {
   return f * sizeof(float) + (2 * KP_MAX + NB + 8) * sizeof(int);
 }
 
+// ------------------------------------------------------------------ small batches: one thread-block cluster per element
+// With one CTA per batch element a single SM walks the 6.1 MB of weights alone (296 us per step at B <= 148: 21 GB/s).
+// Here a cluster of kCl = 8 CTAs shares one element: the output columns of the big mat-vecs (the four first layers that
+// read h, the GRU's hidden-state half - 3.4 MB - and its input half) are split over the cluster ranks, every thread owns
+// a quad of columns and a slice of the input (16-byte weight loads, 8 in flight per thread), the 512 hidden values and
+// the 512 distribution parameters are broadcast into every CTA's shared memory through DSMEM, and two cluster barriers
+// order the three phases.  The small tail (z-part of the decoders, second layers from a shared-memory copy that is
+// prefetched with cp.async during the first phases, rotations, forward kinematics, nearest-sample pick) runs redundantly
+// in every CTA; each rank then finishes its 64 hidden units of the GRU.
+constexpr int kCl = 8;
+constexpr int kGruSlice = H / kCl;             // 64 hidden units per rank
+
+__device__ __forceinline__ uint32_t cl_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cl_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store v at the same shared-memory offset in every CTA of the cluster
+__device__ __forceinline__ void cl_bcast(float* local_ptr, float v) {
+  const uint32_t la = (uint32_t)__cvta_generic_to_shared(local_ptr);
+#pragma unroll
+  for (int r = 0; r < kCl; r++) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(r));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(ra), "f"(v) : "memory");
+  }
+}
+__device__ __forceinline__ void cl_cp_async16(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+
+// acc[v][0..3] += sum_{i in [i0, i1)} WT[i][col .. col+3] * x[v][i]; 16-byte weight loads, 8 rows in flight
+template <int NV>
+__device__ __forceinline__ void quad_dot(const float* __restrict__ WT, int ldw, int col, int i0, int i1, const float* x,
+                                         int xstride, float (&acc)[NV][4]) {
+  const float* w = WT + (long long)i0 * ldw + col;
+  int i = i0;
+  for (; i + 8 <= i1; i += 8) {
+    float4 q[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) q[u] = __ldg(reinterpret_cast<const float4*>(w + (long long)u * ldw));
+    w += 8LL * ldw;
+#pragma unroll
+    for (int u = 0; u < 8; u++)
+#pragma unroll
+      for (int v = 0; v < NV; v++) {
+        const float xv = x[v * xstride + i + u];
+        acc[v][0] = fmaf(q[u].x, xv, acc[v][0]);
+        acc[v][1] = fmaf(q[u].y, xv, acc[v][1]);
+        acc[v][2] = fmaf(q[u].z, xv, acc[v][2]);
+        acc[v][3] = fmaf(q[u].w, xv, acc[v][3]);
+      }
+  }
+  for (; i < i1; i++) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(w));
+    w += ldw;
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const float xv = x[v * xstride + i];
+      acc[v][0] = fmaf(q.x, xv, acc[v][0]);
+      acc[v][1] = fmaf(q.y, xv, acc[v][1]);
+      acc[v][2] = fmaf(q.z, xv, acc[v][2]);
+      acc[v][3] = fmaf(q.w, xv, acc[v][3]);
+    }
+  }
+}
+
+struct ClSmem {   // offsets in floats
+  int in, hid, ah, gh, dist, part, z, h2, dec, flat, rl, rg, x, off, w2, tree, total;
+};
+__host__ __device__ inline ClSmem cl_layout(int SV) {
+  ClSmem m;
+  int o = 0;
+  m.in = o;   o += H + 96;
+  m.hid = o;  o += 2 * HID;                 // prior0 | post0 outputs
+  m.ah = o;   o += 2 * HID;                 // root0 | joint0 applied to h (+ bias)
+  m.gh = o;   o += 3 * kGruSlice;           // this rank's W_hh h (3 gates x 64 units)
+  m.dist = o; o += 4 * Z;                   // prior mean | std, posterior mean | std
+  m.part = o; o += 4 * SV * 256 > 1024 ? 4 * SV * 256 : 1024;
+  m.z = o;    o += SV * Z;
+  m.h2 = o;   o += SV * 2 * HID;
+  m.dec = o;  o += SV * 176;
+  m.flat = o; o += SV * 96;
+  m.rl = o;   o += SV * KP_MAX * 9;
+  m.rg = o;   o += SV * KP_MAX * 9;
+  m.x = o;    o += 224;
+  m.off = o;  o += KP_MAX * 3;
+  m.w2 = o;   o += HID * (3 + KP_MAX) + HID * 6 * KP_MAX;
+  m.tree = o; o += 2 * KP_MAX + 8;
+  m.total = o;
+  return m;
+}
+
+template <int SV>
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kThreads, 1)
+hsvrnn_step_cluster_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const ClSmem L = cl_layout(SV);
+  float* s_in = sm + L.in;
+  float* s_hid = sm + L.hid;
+  float* s_ah = sm + L.ah;
+  float* s_gh = sm + L.gh;
+  float* s_dist = sm + L.dist;
+  float* s_part = sm + L.part;
+  float* s_z = sm + L.z;
+  float* s_h2 = sm + L.h2;
+  float* s_dec = sm + L.dec;
+  float* s_flat = sm + L.flat;
+  float* s_rl = sm + L.rl;
+  float* s_rg = sm + L.rg;
+  float* s_x = sm + L.x;
+  float* s_off = sm + L.off;
+  float* s_w2r = sm + L.w2;                              // root2^T [HID][3 + K]
+  int* s_tree = reinterpret_cast<int*>(sm + L.tree);
+  const int K = a.K, S = a.S, K4 = 4 * a.K, R2 = 3 + a.K, J2 = 6 * a.K;
+  float* s_w2j = s_w2r + HID * R2;                       // joint2^T [HID][6 K]
+  const int b = blockIdx.x / kCl;
+  const int rank = (int)cl_rank();
+  const int tid = threadIdx.x;
+  const bool need_prior = a.prior_out != nullptr || !a.posterior;
+  const int IN = H + K4;
+
+  // ---- stage 0: inputs; the second-layer weights start streaming into shared memory (16-byte aligned segments)
+  {
+    const int nr = HID * R2, nj = HID * J2;
+    const int head = (int)(((16 - ((uintptr_t)a.w.root2_wt & 15)) & 15) >> 2);   // floats until 16-byte alignment (0 in practice)
+    for (int i = tid * 4; i + 4 <= nr - head; i += kThreads * 4) cl_cp_async16(s_w2r + head + i, a.w.root2_wt + head + i);
+    for (int i = tid; i < head; i += kThreads) s_w2r[i] = a.w.root2_wt[i];
+    for (int i = head + ((nr - head) & ~3) + tid; i < nr; i += kThreads) s_w2r[i] = a.w.root2_wt[i];
+    // joint2: HID * 6K floats; s_w2j may start off 16-byte alignment when HID * R2 is odd -> plain loads
+    if ((((uintptr_t)s_w2j | (uintptr_t)a.w.joint2_wt) & 15) == 0) {
+      for (int i = tid * 4; i + 4 <= nj; i += kThreads * 4) cl_cp_async16(s_w2j + i, a.w.joint2_wt + i);
+      for (int i = (nj & ~3) + tid; i < nj; i += kThreads) s_w2j[i] = a.w.joint2_wt[i];
+    } else {
+      for (int i = tid; i < nj; i += kThreads) s_w2j[i] = __ldg(a.w.joint2_wt + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int j = tid; j < H + 96; j += kThreads) {
+    float val = 0.f;
+    if (j < H) val = a.h_in[(long long)b * H + j];
+    else if (a.posterior && j - H < K4) val = a.kp[(long long)b * K4 + (j - H)];
+    s_in[j] = val;
+  }
+  for (int i = tid; i < K * 3; i += kThreads) s_off[i] = a.offset[(long long)b * K * 3 + i];
+  for (int i = tid; i < K; i += kThreads) {
+    s_tree[i] = a.order[i];
+    s_tree[KP_MAX + i] = a.parents[i];
+  }
+  __syncthreads();
+
+  // ---- phase A: everything that reads h (and kp).  256 columns per rank = 64 quads x 4 input slices.
+  //   quads 0-3 prior0, 4-7 post0, 8-11 root0[:H], 12-15 joint0[:H] (16 columns each), 16-63 GRU hidden half (3 x 64)
+  {
+    const int qd = tid & 63, ks = tid >> 6;
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    if (qd < 16) {
+      const int job = qd >> 2, col = rank * 16 + (qd & 3) * 4;
+      const float* WT = job == 0 ? a.w.prior0_wt : (job == 1 ? a.w.post0_wt : (job == 2 ? a.w.root0_wt : a.w.joint0_wt));
+      const int I = job == 1 ? IN : H;
+      const bool live = job == 0 ? need_prior : (job == 1 ? a.posterior != 0 : true);
+      if (live) {
+        const int per = (I + 3) / 4;
+        quad_dot<1>(WT, HID, col, min(I, ks * per), min(I, (ks + 1) * per), s_in, 0, acc);
+      }
+    } else {
+      const int g = (qd - 16) >> 4, col = g * H + rank * kGruSlice + ((qd - 16) & 15) * 4;
+      quad_dot<1>(a.w.gru_hh_wt, 3 * H, col, ks * (H / 4), (ks + 1) * (H / 4), s_in, 0, acc);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) s_part[ks * 256 + qd * 4 + e] = acc[0][e];
+  }
+  __syncthreads();
+  {
+    const int c = tid;                                      // local column 0..255
+    const float v = s_part[c] + s_part[256 + c] + s_part[512 + c] + s_part[768 + c];
+    if (c < 64) {
+      const int job = c >> 4, col = rank * 16 + (c & 15);
+      if (job == 0) { if (need_prior) cl_bcast(s_hid + col, nm_lrelu(v + a.w.prior0_b[col])); }
+      else if (job == 1) { if (a.posterior) cl_bcast(s_hid + HID + col, nm_lrelu(v + a.w.post0_b[col])); }
+      else if (job == 2) cl_bcast(s_ah + col, v + a.w.root0_b[col]);
+      else cl_bcast(s_ah + HID + col, v + a.w.joint0_b[col]);
+    } else {
+      s_gh[c - 64] = v;                                    // [gate][unit]
+    }
+  }
+  cl_sync();
+
+  // ---- phase B: second layers of the prior / posterior MLPs: 512 columns, 64 per rank = 16 quads x 16 input slices
+  {
+    const int qd = tid & 15, ks = tid >> 4;
+    const int job = qd >> 3, col = rank * 32 + (qd & 7) * 4;   // job 0: prior2, 1: post2; 32 columns of each per rank
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    const bool live = job == 0 ? need_prior : a.posterior != 0;
+    if (live) quad_dot<1>(job == 0 ? a.w.prior2_wt : a.w.post2_wt, 2 * Z, col, ks * 8, ks * 8 + 8, s_hid + job * HID, 0, acc);
+#pragma unroll
+    for (int e = 0; e < 4; e++) s_part[ks * 64 + qd * 4 + e] = acc[0][e];
+  }
+  __syncthreads();
+  if (tid < 64) {
+    float v = 0.f;
+    for (int ks = 0; ks < 16; ks++) v += s_part[ks * 64 + tid];
+    const int job = tid >> 5, col = rank * 32 + (tid & 31);
+    const bool live = job == 0 ? need_prior : a.posterior != 0;
+    if (live) {
+      v += job == 0 ? a.w.prior2_b[col] : a.w.post2_b[col];
+      if (col >= Z) v = softplus_d(v) + 1e-4f;
+      cl_bcast(s_dist + job * 2 * Z + col, v);
+      float* gout = job == 0 ? a.prior_out : a.post_out;
+      if (gout) gout[(long long)b * 2 * Z + col] = v;
+    }
+  }
+  cl_sync();
+
+  // ---- from here on every rank works on its own copy.  z = mean + std * eps
+  const float* dsel = s_dist + (a.posterior ? 2 * Z : 0);
+  for (int i = tid; i < SV * Z; i += kThreads) {
+    const int sidx = i / Z, j = i % Z;
+    s_z[i] = sidx < S ? dsel[j] + dsel[Z + j] * a.eps[((long long)sidx * a.B + b) * Z + j] : 0.f;
+  }
+  __syncthreads();
+  // decoders, first layer, z part: 256 columns (root | joint) = 64 quads x 4 input slices, all samples at once
+  {
+    const int qd = tid & 63, ks = tid >> 6;
+    float acc[SV][4];
+#pragma unroll
+    for (int v = 0; v < SV; v++) acc[v][0] = acc[v][1] = acc[v][2] = acc[v][3] = 0.f;
+    const bool joint = qd >= 32;
+    const int col = (qd & 31) * 4;
+    quad_dot<SV>((joint ? a.w.joint0_wt : a.w.root0_wt) + (long long)H * HID, HID, col, ks * (Z / 4), (ks + 1) * (Z / 4), s_z, Z, acc);
+#pragma unroll
+    for (int v = 0; v < SV; v++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) s_part[(ks * SV + v) * 256 + qd * 4 + e] = acc[v][e];
+  }
+  __syncthreads();
+  for (int i = tid; i < S * 256; i += kThreads) {
+    const int v = i >> 8, c = i & 255;
+    const float t = s_part[(0 * SV + v) * 256 + c] + s_part[(1 * SV + v) * 256 + c] + s_part[(2 * SV + v) * 256 + c] +
+                    s_part[(3 * SV + v) * 256 + c];
+    s_h2[v * 2 * HID + c] = nm_lrelu(t + s_ah[c]);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // second layers from shared memory: root / intensity (3 + K, tanh) at s_dec[0..], joint 6-D rotations at s_dec[32..]
+  for (int i = tid; i < S * (R2 + J2); i += kThreads) {
+    const int v = i / (R2 + J2), c = i % (R2 + J2);
+    float t;
+    if (c < R2) {
+      t = a.w.root2_b[c];
+      const float* hv = s_h2 + v * 2 * HID;
+      for (int k = 0; k < HID; k++) t = fmaf(s_w2r[k * R2 + c], hv[k], t);
+      s_dec[v * 176 + c] = tanhf(t);
+    } else {
+      const int cj = c - R2;
+      t = a.w.joint2_b[cj];
+      const float* hv = s_h2 + v * 2 * HID + HID;
+      for (int k = 0; k < HID; k++) t = fmaf(s_w2j[k * J2 + cj], hv[k], t);
+      s_dec[v * 176 + 32 + cj] = t;
+    }
+  }
+  __syncthreads();
+  // rotations in parallel over (sample, joint), then the kinematic chain per sample
+  for (int i = tid; i < S * K; i += kThreads) rot6d(s_dec + (i / K) * 176 + 32 + (i % K) * 6, s_rl + (i / K) * KP_MAX * 9 + (i % K) * 9);
+  __syncthreads();
+  if (tid < S) {
+    const int v = tid;
+    const float* raw = s_dec + v * 176;
+    float* Rg = s_rg + v * KP_MAX * 9;
+    float* flat = s_flat + v * 96;
+    const float* Rl0 = s_rl + v * KP_MAX * 9;
+    const int root = s_tree[0];
+    for (int e = 0; e < 9; e++) Rg[root * 9 + e] = Rl0[root * 9 + e];
+    flat[root * 4] = raw[0]; flat[root * 4 + 1] = raw[1]; flat[root * 4 + 2] = raw[2];
+    for (int j = 1; j < K; j++) {
+      const int i = s_tree[j], pa = s_tree[KP_MAX + i];
+      const float* Rl = Rl0 + i * 9;
+      const float* Rp = Rg + pa * 9;
+      float* Ri = Rg + i * 9;
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) Ri[r * 3 + c] = Rp[r * 3] * Rl[c] + Rp[r * 3 + 1] * Rl[3 + c] + Rp[r * 3 + 2] * Rl[6 + c];
+      const float* o = s_off + i * 3;
+#pragma unroll
+      for (int r = 0; r < 3; r++) flat[i * 4 + r] = Ri[r * 3] * o[0] + Ri[r * 3 + 1] * o[1] + Ri[r * 3 + 2] * o[2] + flat[pa * 4 + r];
+    }
+    for (int i = 0; i < K; i++) flat[i * 4 + 3] = (raw[3 + i] + 1.0f) * 0.5f;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int best = 0;
+    if (a.posterior) {
+      float bd = INFINITY;
+      for (int sidx = 0; sidx < S; sidx++) {
+        float d = 0.f;
+        for (int j = 0; j < K4; j++) {
+          const float t = s_in[H + j] - s_flat[sidx * 96 + j];
+          d += t * t;
+        }
+        if (d < bd) { bd = d; best = sidx; }
+      }
+    }
+    s_tree[2 * KP_MAX] = best;
+  }
+  __syncthreads();
+  const int best = s_tree[2 * KP_MAX];
+  for (int j = tid; j < 224; j += kThreads) {
+    float val = 0.f;
+    if (j < K4) val = s_flat[best * 96 + j];
+    else if (j < K4 + Z) val = s_z[best * Z + (j - K4)];
+    s_x[j] = val;
+    if (rank == 0) {
+      if (j < K4) a.kp_out[(long long)b * K4 + j] = val;
+      else if (j < K4 + Z && a.z_out) a.z_out[(long long)b * Z + (j - K4)] = val;
+    }
+  }
+  if (rank == 0 && a.R_out)
+    for (int j = tid; j < K * 9; j += kThreads) a.R_out[(long long)b * K * 9 + j] = s_rg[best * KP_MAX * 9 + j];
+  __syncthreads();
+  // ---- GRU: this rank's 64 hidden units; input half W_ih x: 192 columns = 48 quads x 4 input slices
+  {
+    const int XI = K4 + Z;
+    const int qd = tid & 63, ks = tid >> 6;
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    if (qd < 48) {
+      const int g = qd >> 4, col = g * H + rank * kGruSlice + (qd & 15) * 4;
+      const int per = (XI + 3) / 4;
+      quad_dot<1>(a.w.gru_ih_wt, 3 * H, col, min(XI, ks * per), min(XI, (ks + 1) * per), s_x, 0, acc);
+    }
+#pragma unroll
+    for (int e = 0; e < 4; e++) s_part[ks * 256 + qd * 4 + e] = acc[0][e];
+  }
+  __syncthreads();
+  if (tid < kGruSlice) {
+    const int j = rank * kGruSlice + tid;
+    float gi[3];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const int c = g * kGruSlice + tid;
+      gi[g] = s_part[c] + s_part[256 + c] + s_part[512 + c] + s_part[768 + c];
+    }
+    const float r = sigmoid_d(gi[0] + a.w.gru_ih_b[j] + s_gh[tid] + a.w.gru_hh_b[j]);
+    const float zg = sigmoid_d(gi[1] + a.w.gru_ih_b[H + j] + s_gh[kGruSlice + tid] + a.w.gru_hh_b[H + j]);
+    const float ng = tanhf(gi[2] + a.w.gru_ih_b[2 * H + j] + r * (s_gh[2 * kGruSlice + tid] + a.w.gru_hh_b[2 * H + j]));
+    a.h_out[(long long)b * H + j] = (1.0f - zg) * ng + zg * s_in[j];
+  }
+}
+
 // Pose decoding on its own (extract_kypt_from_latent_and_state, hsvrnn_bvh.py:255-286) for callers that
 // drive the sub-modules by hand (vis_generation.py:108-113).
 __global__ void __launch_bounds__(kThreads)
@@ -373,7 +726,22 @@ extern "C" int nm_hsvrnn_step(const nm_hsvrnn_weights* w, const float* h_in, con
   a.h_out = h_out; a.kp_out = kp_out; a.z_out = z_out; a.R_out = R_out; a.post_out = post_out; a.prior_out = prior_out;
   a.B = B; a.K = K; a.S = S; a.posterior = posterior;
   cudaStream_t st = (cudaStream_t)stream;
-  if (B >= 4 * nm_num_sms()) {
+  // small and medium batches: a cluster of 8 CTAs per element (weights split over the ranks, DSMEM broadcasts)
+  static const bool use_cluster = []() { const char* e = getenv("NM_HSVRNN_CLUSTER"); return !(e && atoi(e) == 0); }();
+  if (use_cluster && S <= 10 && B <= 4 * nm_num_sms()) {
+    const int SV = S == 1 ? 1 : 10;
+    const size_t smem = (size_t)cl_layout(SV).total * sizeof(float);
+    if (SV == 1) {
+      NM_CHECK_CUDA(cudaFuncSetAttribute(hsvrnn_step_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hsvrnn_step_cluster_kernel<1><<<B * kCl, kThreads, smem, st>>>(a);
+    } else {
+      NM_CHECK_CUDA(cudaFuncSetAttribute(hsvrnn_step_cluster_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hsvrnn_step_cluster_kernel<10><<<B * kCl, kThreads, smem, st>>>(a);
+    }
+    NM_CHECK_LAUNCH("hsvrnn_step(cluster)");
+    return NM_OK;
+  }
+  if (B >= 4 * nm_num_sms() && step_smem_bytes<4>(S) <= 227 * 1024) {
     const size_t smem = step_smem_bytes<4>(S);
     NM_CHECK_CUDA(cudaFuncSetAttribute(hsvrnn_step_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hsvrnn_step_kernel<4><<<nm_cdiv(B, 4), kThreads, smem, st>>>(a);
