@@ -121,10 +121,14 @@ int nm_first_conv_k5(const float* occ, const void* tables, const float* bias, co
  * nn.GroupNorm(C//16, C) statistics (modules/vox_modules.py:14,...) folded to per-(sample, channel)
  * scale/shift: y = x*scale + shift.  x: act (n, S, C). */
 size_t nm_gn_workspace_bytes(int n, int S, int C);
+/* mean_rstd (optional, (n, groups, 2)) and xsum (optional, (n, C) per-channel sums): the statistics the training path
+ * keeps for nm_groupnorm_backward. */
 int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int groups, const float* gamma, const float* beta,
-                             float eps, float* scale, float* shift, void* workspace, void* stream);
+                             float eps, float* scale, float* shift, void* workspace, float* mean_rstd, float* xsum,
+                             void* stream);
 int nm_groupnorm_finalize(const float* partial, int n, int S, int C, int groups, int chunks, const float* gamma,
-                          const float* beta, float eps, float* scale, float* shift, void* stream);
+                          const float* beta, float eps, float* scale, float* shift, float* mean_rstd, float* xsum,
+                          void* stream);
 /* out = act1(x1*a1+b1) + (x2*a2+b2 | x2 | nothing); act1: 0 none, 1 LeakyReLU(0.01).
  * Basic/Pool/Upsample blocks, Res3DBlock sums (vox_modules.py:44-47), HG skip adds (:111-118). */
 int nm_affine_act(const void* x1, const float* a1, const float* b1, int act1, const void* x2, const float* a2,
@@ -244,11 +248,13 @@ int nm_conv3d_k3_wgrad_tc(const void* x, const void* grad_out, int n, int D, int
  * summed over the n samples and multiplied by out_scale (= 1 / loss scale): dgamma, dbeta (C) and dxsum (C) = the sum of
  * grad_in over samples and voxels, i.e. the gradient of the bias of the convolution that produced x.  Streaming kernels
  * for C in {8, 16, 32, 64, 128, 256} with 8 | channels per group; any other (C, groups) (the hour-glass's 48 / 72
- * channels) on small tensors.  Statistics are recomputed from x; fixed-order reductions (bit-reproducible). */
+ * channels) on small tensors.  mean_rstd (n, groups, 2) + xsum (n, C) kept from the forward (nm_groupnorm_finalize)
+ * skip the statistics pass; when null they are recomputed from x.  Fixed-order reductions (bit-reproducible). */
 size_t nm_groupnorm_backward_workspace_bytes(int n, int C, int groups);
 int nm_groupnorm_backward(const void* x, const void* grad_out, const float* gamma, const float* beta, int n, long long S,
-                          int C, int groups, float eps, int leaky, float out_scale, void* grad_in, float* dgamma,
-                          float* dbeta, float* dxsum, void* workspace, void* stream);
+                          int C, int groups, float eps, int leaky, float out_scale, const float* mean_rstd,
+                          const float* xsum, void* grad_in, float* dgamma, float* dbeta, float* dxsum, void* workspace,
+                          void* stream);
 
 /* Weight gradient of the convolutions the slab kernel above does not cover - 1x1, k2/s2 "pool", ConvTranspose3d(k2, s2),
  * k3 on small grids or with 48 / 72 channels (modules/vox_modules.py:12-68 under autograd):

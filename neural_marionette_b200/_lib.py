@@ -53,7 +53,7 @@ PROTOTYPES = {
     "nm_pack_conv_pw_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "nm_conv3d_pw": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "nm_conv3d_tc_fused": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
-    "nm_groupnorm_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp]),
+    "nm_groupnorm_finalize": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp]),
     "nm_conv3d_direct": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_conv_transpose3d_k2s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "nm_first_conv_tables_bytes": (_sz, [_i]),
@@ -61,7 +61,7 @@ PROTOTYPES = {
     "nm_first_conv_stats_chunks": (_i, [_i]),
     "nm_first_conv_k5": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "nm_gn_workspace_bytes": (_sz, [_i, _i, _i]),
-    "nm_groupnorm_scale_shift": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp]),
+    "nm_groupnorm_scale_shift": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nm_affine_act": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "nm_upsample2x": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "nm_ndhwc_to_ncdhw_f32": (_i, [_vp, _vp, _i, _i, _i, _ll, _vp]),
@@ -92,7 +92,7 @@ PROTOTYPES = {
     "nm_conv3d_k3_wgrad_tc_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "nm_conv3d_k3_wgrad_tc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nm_groupnorm_backward_workspace_bytes": (_sz, [_i, _i, _i]),
-    "nm_groupnorm_backward": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "nm_groupnorm_backward": (_i, [_vp, _vp, _vp, _vp, _i, _ll, _i, _i, _f, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nm_conv3d_wgrad_gather_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_wgrad_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nm_depth_to_space2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -46,20 +46,47 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# The largest incoming loss gradient decides the loss scale.  Reading it is a device -> host round trip in the middle of
+# the step (the host would stall until the whole forward has run and then trail the GPU through the backward); in a
+# training loop it is the same number every step (loss weight / number of frames), so the value read asynchronously
+# during the PREVIOUS backward of the same shape is used and the fresh one is only checked when it has arrived.
+_GMAX = {}
+
+
+def _entry_gradient_max(dbce: torch.Tensor) -> float:
+    key = (dbce.device.index, dbce.numel())
+    slot = _GMAX.get(key)
+    if slot is None:
+        slot = _GMAX[key] = dict(pinned=torch.zeros(1, dtype=torch.float32).pin_memory(), event=torch.cuda.Event(), value=None)
+    if slot["value"] is not None and slot["event"].query():
+        slot["value"] = float(slot["pinned"][0])              # last step's read-back has landed
+    if slot["value"] is None:
+        slot["value"] = float(dbce.abs().max().item())         # first call: synchronous
+    slot["pinned"].copy_(dbce.abs().max().reshape(1), non_blocking=True)
+    slot["event"].record()
+    return slot["value"]
+
+
+def _stats(sink):
+    """(mean_rstd, xsum) of the single GroupNorm a Function's forward finalised, or () when the kernel did not emit them."""
+    return tuple(sink[0]) if len(sink) == 1 else ()
+
+
 class FirstConvGNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, occ, w, b, gamma, beta, conv, gn):
-        raw, a, sh = ops.first_conv(occ, conv, gn)
-        ctx.save_for_backward(occ, raw)
+        with ops.capture_gn_stats() as sink:
+            raw, a, sh = ops.first_conv(occ, conv, gn)
+        ctx.save_for_backward(occ, raw, *_stats(sink))
         ctx.mods = (conv, gn)
         return ops.affine_act(raw, a, sh, True)
 
     @staticmethod
     def backward(ctx, dy):
-        occ, raw = ctx.saved_tensors
+        occ, raw, *stats = ctx.saved_tensors
         conv, gn = ctx.mods
         inv = 1.0 / ops.grad_scale()
-        draw, dg, db, dbias = ops.groupnorm_backward(raw, _c(dy), gn, leaky=True, out_scale=inv)
+        draw, dg, db, dbias = ops.groupnorm_backward(raw, _c(dy), gn, leaky=True, out_scale=inv, stats=stats or None)
         dw = ops.first_conv_weight_grad(occ, draw, out_scale=inv)
         return None, dw, dbias, dg, db, None, None
 
@@ -71,18 +98,19 @@ class ConvGNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, gamma, beta, res, conv, gn, act):
         transposed = isinstance(conv, torch.nn.ConvTranspose3d)
-        raw, a, sh = (ops.conv_transpose3d if transposed else ops.conv3d)(x, conv, gn)
-        ctx.save_for_backward(x, raw)
+        with ops.capture_gn_stats() as sink:
+            raw, a, sh = (ops.conv_transpose3d if transposed else ops.conv3d)(x, conv, gn)
+        ctx.save_for_backward(x, raw, *_stats(sink))
         ctx.cfg = (conv, gn, bool(act), transposed, res is not None)
         return ops.affine_act(raw, a, sh, bool(act), x2=res)
 
     @staticmethod
     def backward(ctx, dy):
-        x, raw = ctx.saved_tensors
+        x, raw, *stats = ctx.saved_tensors
         conv, gn, act, transposed, has_res = ctx.cfg
         dy = _c(dy)
         inv = 1.0 / ops.grad_scale()
-        draw, dg, db, dbias = ops.groupnorm_backward(raw, dy, gn, leaky=act, out_scale=inv)
+        draw, dg, db, dbias = ops.groupnorm_backward(raw, dy, gn, leaky=act, out_scale=inv, stats=stats or None)
         if transposed:
             dw = ops.conv_transpose3d_weight_grad(x, draw, out_scale=inv)
             dx = ops.conv_transpose3d_input_grad(draw, conv) if ctx.needs_input_grad[0] else None
@@ -176,9 +204,10 @@ class ConvGNFinalRecon(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w11, b11, gamma, beta, w14, b14, first_frame, target, conv11, gn, conv14, T, sharp, trans):
-        raw, a, sh = ops.conv3d(x, conv11, gn)
+        with ops.capture_gn_stats() as sink:
+            raw, a, sh = ops.conv3d(x, conv11, gn)
         recon, bce = ops.final_recon(raw, a, sh, conv14, first_frame, T, sharp, trans, target=target)
-        ctx.save_for_backward(x, raw, a, sh, recon, first_frame, target)
+        ctx.save_for_backward(x, raw, a, sh, recon, first_frame, target, *_stats(sink))
         ctx.cfg = (conv11, gn, conv14, T, sharp, trans)
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(recon)
@@ -186,19 +215,19 @@ class ConvGNFinalRecon(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _drecon, dbce):
-        x, raw, a, sh, recon, first_frame, target = ctx.saved_tensors
+        x, raw, a, sh, recon, first_frame, target, *stats = ctx.saved_tensors
         conv11, gn, conv14, T, sharp, trans = ctx.cfg
         if dbce is None:
             return (None,) * 15
         dbce = _c(dbce.float())
         S = raw.shape[1] * raw.shape[2] * raw.shape[3]
         # |dL/dx14| <= gmax * sharp / S; scale it to 2^headroom in fp16 (a power of two: exact scaling)
-        gmax = float(dbce.abs().max().item())
+        gmax = _entry_gradient_max(dbce)
         if gmax > 0.0 and math.isfinite(gmax):
             ops.set_grad_scale(2.0 ** max(0, min(30, round(math.log2(S / (gmax * sharp))) + _HEADROOM[0])))
         scale = ops.grad_scale()
         dact, dw14, db14 = ops.final_recon_backward(raw, a, sh, conv14, first_frame, T, sharp, trans, recon, target, dbce, scale)
-        draw, dg, db, dbias = ops.groupnorm_backward(raw, dact, gn, leaky=True, out_scale=1.0 / scale)
+        draw, dg, db, dbias = ops.groupnorm_backward(raw, dact, gn, leaky=True, out_scale=1.0 / scale, stats=stats or None)
         dw11 = ops.conv3d_weight_grad(x, draw, k=3, stride=1, out_scale=1.0 / scale)
         dx = ops.conv3d_input_grad(draw, conv11) if ctx.needs_input_grad[0] else None
         return (dx, dw11, dbias, dg, db, dw14, db14) + (None,) * 8

@@ -263,8 +263,9 @@ extern "C" size_t nm_groupnorm_backward_workspace_bytes(int n, int C, int groups
 }
 
 extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const float* gamma, const float* beta, int n,
-                                     long long S, int C, int groups, float eps, int leaky, float out_scale, void* grad_in,
-                                     float* dgamma, float* dbeta, float* dxsum, void* workspace, void* stream) {
+                                     long long S, int C, int groups, float eps, int leaky, float out_scale,
+                                     const float* fwd_mean_rstd, const float* fwd_xsum, void* grad_in, float* dgamma,
+                                     float* dbeta, float* dxsum, void* workspace, void* stream) {
   NM_CHECK_ARG(x && grad_out && gamma && beta && grad_in && workspace, "nm_groupnorm_backward: null pointer");
   NM_CHECK_ARG(n > 0 && S > 0 && C > 0 && groups > 0 && C % groups == 0, "nm_groupnorm_backward: bad shape (C=%d, groups=%d)", C, groups);
   NM_CHECK_ARG(n <= 65535, "nm_groupnorm_backward: at most 65535 samples per call");
@@ -289,10 +290,15 @@ extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const 
     return NM_OK;
   }
   const dim3 rgrid(kGnbChunks, n);
-  gnb_reduce_kernel<true><<<rgrid, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, s, leaky, partial);
-  NM_CHECK_LAUNCH("gnb_reduce_kernel<stats>");
-  gnb_stats_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, s, eps, mean_rstd, xsum);
-  NM_CHECK_LAUNCH("gnb_stats_finalize_kernel");
+  if (fwd_mean_rstd && fwd_xsum) {                     // statistics kept from the forward: no pass over x for them
+    mean_rstd = const_cast<float*>(fwd_mean_rstd);
+    xsum = const_cast<float*>(fwd_xsum);
+  } else {
+    gnb_reduce_kernel<true><<<rgrid, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, s, leaky, partial);
+    NM_CHECK_LAUNCH("gnb_reduce_kernel<stats>");
+    gnb_stats_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, s, eps, mean_rstd, xsum);
+    NM_CHECK_LAUNCH("gnb_stats_finalize_kernel");
+  }
   gnb_reduce_kernel<false><<<rgrid, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, s, leaky, partial);
   NM_CHECK_LAUNCH("gnb_reduce_kernel<grad>");
   gnb_grad_finalize_kernel<<<nm_cdiv((long long)n * groups, 128), 128, 0, st>>>(partial, gamma, mean_rstd, xsum, s, m12, chan);

@@ -58,7 +58,8 @@ gn_stats_kernel(const act_t* __restrict__ x, int S, int C, int chunks, float* __
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const float* __restrict__ partial, int S, int C, int groups, int chunks,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   float* __restrict__ scale, float* __restrict__ shift) {
+                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_rstd /* optional (n, groups, 2) */,
+                   float* __restrict__ xsum /* optional (n, C): per-channel sums (GroupNorm backward) */) {
   // one block per (sample, group): 256 threads stride over the (chunk, channel-in-group) partials in a fixed
   // order, fp64 accumulation, shuffle tree + fixed-order fold of the 8 warps -> deterministic.  (The conv
   // epilogues emit up to 1024 chunks per sample; a single warp per group was latency-bound at ~20 us.)
@@ -90,6 +91,18 @@ gn_finalize_kernel(const float* __restrict__ partial, int S, int C, int groups, 
     const double var = fmax(q / cnt - mean * mean, 0.0);
     s_stat[0] = mean;
     s_stat[1] = 1.0 / sqrt(var + (double)eps);
+    if (mean_rstd) {
+      mean_rstd[((long long)n * groups + g) * 2] = (float)mean;
+      mean_rstd[((long long)n * groups + g) * 2 + 1] = (float)s_stat[1];
+    }
+  }
+  if (xsum) {
+    // per-channel totals in a fixed order (one thread per channel of the group)
+    for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += 256) {
+      double t = 0.0;
+      for (int k = 0; k < chunks; k++) t += (double)partial[(((long long)n * chunks + k) * C + c) * 2];
+      xsum[(long long)n * C + c] = (float)t;
+    }
   }
   __syncthreads();
   for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += 256) {
@@ -500,7 +513,7 @@ extern "C" size_t nm_gn_workspace_bytes(int n, int S, int C) {
 
 extern "C" int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int groups, const float* gamma,
                                         const float* beta, float eps, float* scale, float* shift,
-                                        void* workspace, void* stream) {
+                                        void* workspace, float* mean_rstd, float* xsum, void* stream) {
   NM_CHECK_ARG(x && gamma && beta && scale && shift && workspace, "nm_groupnorm_scale_shift: null pointer");
   NM_CHECK_ARG(C % 8 == 0 && kStatThreads % (C / 8) == 0 && groups > 0 && groups <= 32 && C % groups == 0,
                "nm_groupnorm_scale_shift: unsupported C=%d groups=%d", C, groups);
@@ -509,7 +522,8 @@ extern "C" int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int 
   const int chunks = nm_gn_stats_chunks(S);
   gn_stats_kernel<<<dim3(chunks, n), kStatThreads, 0, st>>>((const act_t*)x, S, C, chunks, (float*)workspace);
   NM_CHECK_LAUNCH("gn_stats");
-  gn_finalize_kernel<<<dim3(n, groups), 256, 0, st>>>((const float*)workspace, S, C, groups, chunks, gamma, beta, eps, scale, shift);
+  gn_finalize_kernel<<<dim3(n, groups), 256, 0, st>>>((const float*)workspace, S, C, groups, chunks, gamma, beta, eps, scale, shift,
+                                                      mean_rstd, xsum);
   NM_CHECK_LAUNCH("gn_finalize");
   return NM_OK;
 }
@@ -518,12 +532,13 @@ extern "C" int nm_groupnorm_scale_shift(const void* x, int n, int S, int C, int 
 // partial [n][chunks][C][2] = (sum, sum of squares) over disjoint pieces of each sample.
 extern "C" int nm_groupnorm_finalize(const float* partial, int n, int S, int C, int groups, int chunks,
                                      const float* gamma, const float* beta, float eps, float* scale, float* shift,
-                                     void* stream) {
+                                     float* mean_rstd, float* xsum, void* stream) {
   NM_CHECK_ARG(partial && gamma && beta && scale && shift, "nm_groupnorm_finalize: null pointer");
   NM_CHECK_ARG(groups > 0 && groups <= 32 && C % groups == 0 && chunks > 0, "nm_groupnorm_finalize: bad C=%d groups=%d chunks=%d",
                C, groups, chunks);
   if (n == 0) return NM_OK;
-  gn_finalize_kernel<<<dim3(n, groups), 256, 0, (cudaStream_t)stream>>>(partial, S, C, groups, chunks, gamma, beta, eps, scale, shift);
+  gn_finalize_kernel<<<dim3(n, groups), 256, 0, (cudaStream_t)stream>>>(partial, S, C, groups, chunks, gamma, beta, eps, scale, shift,
+                                                                        mean_rstd, xsum);
   NM_CHECK_LAUNCH("gn_finalize");
   return NM_OK;
 }

@@ -209,11 +209,7 @@ def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNo
         return out
     if chunks == 0:
         return (out,) + gn_scale_shift(out, gn)
-    a = torch.empty(n, Cout, dtype=torch.float32, device=x.device)
-    b = torch.empty_like(a)
-    S = out.numel() // (n * Cout)
-    L.call("nm_groupnorm_finalize", L.ptr(partial), n, S, Cout, gn.num_groups, chunks, L.ptr(f32(gn, "weight")),
-           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+    a, b = _gn_finalize(partial, n, out.numel() // (n * Cout), Cout, gn, chunks, x.device)
     return out, a, b
 
 
@@ -349,10 +345,11 @@ def conv_transpose3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor, out_sc
 
 
 def groupnorm_backward(x: torch.Tensor, grad_out: torch.Tensor, gn: torch.nn.GroupNorm, leaky: bool = True,
-                       out_scale: float = 1.0):
+                       out_scale: float = 1.0, stats=None):
     """Backward of LeakyReLU(GroupNorm(x)) (`leaky`) or GroupNorm(x): x, grad_out act (n, D, H, W, C) ->
     (grad_in act, dgamma (C), dbeta (C), dxsum (C)) - the fp32 outputs multiplied by out_scale; dxsum = sum of grad_in
-    over samples and voxels = gradient of the bias of the conv that produced x."""
+    over samples and voxels = gradient of the bias of the conv that produced x.  `stats` = (mean_rstd, xsum) kept from the
+    forward (`capture_gn_stats`) skips the statistics pass over x."""
     _need_cuda(x, grad_out)
     assert x.shape == grad_out.shape and x.dtype == ACT_DTYPE and grad_out.dtype == ACT_DTYPE
     assert x.is_contiguous() and grad_out.is_contiguous()
@@ -363,9 +360,10 @@ def groupnorm_backward(x: torch.Tensor, grad_out: torch.Tensor, gn: torch.nn.Gro
     db = torch.empty(C, dtype=torch.float32, device=x.device)
     dxs = torch.empty(C, dtype=torch.float32, device=x.device)
     ws = workspace(max(L.query("nm_groupnorm_backward_workspace_bytes", n, C, gn.num_groups), 16), x.device, "gnb")
+    mr, xs = stats if stats is not None else (None, None)
     L.call("nm_groupnorm_backward", L.ptr(x), L.ptr(grad_out), L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), n, S, C,
-           gn.num_groups, float(gn.eps), int(leaky), float(out_scale), L.ptr(dx), L.ptr(dg), L.ptr(db), L.ptr(dxs),
-           L.ptr(ws), L.stream())
+           gn.num_groups, float(gn.eps), int(leaky), float(out_scale), L.ptr(mr), L.ptr(xs), L.ptr(dx), L.ptr(dg),
+           L.ptr(db), L.ptr(dxs), L.ptr(ws), L.stream())
     return dx, dg, db, dxs
 
 
@@ -496,10 +494,7 @@ def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn
         PROFILE.setdefault((n, 2 * D, Cin, Cout, 3, 1, flops), []).append((e0, e1))
     if gn is None:
         return out
-    a = torch.empty(n, Cout, dtype=torch.float32, device=x_lo.device)
-    b = torch.empty_like(a)
-    L.call("nm_groupnorm_finalize", L.ptr(partial), n, 8 * D * H * W, Cout, gn.num_groups, chunks,
-           L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+    a, b = _gn_finalize(partial, n, 8 * D * H * W, Cout, gn, chunks, x_lo.device)
     return out, a, b
 
 
@@ -534,10 +529,7 @@ def conv_transpose3d(x: torch.Tensor, conv: torch.nn.ConvTranspose3d, gn: Option
                Cout, L.ptr(partial), L.stream())
         if gn is None:
             return out
-        a = torch.empty(n, Cout, dtype=torch.float32, device=x.device)
-        b = torch.empty_like(a)
-        L.call("nm_groupnorm_finalize", L.ptr(partial), n, 8 * D * H * W, Cout, gn.num_groups, chunks,
-               L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+        a, b = _gn_finalize(partial, n, 8 * D * H * W, Cout, gn, chunks, x.device)
         return out, a, b
     wt = _cached(conv, "tapmajor", [conv.weight],
                  lambda: conv.weight.detach().float().permute(2, 3, 4, 0, 1).reshape(8, Cin, Cout).contiguous())
@@ -566,22 +558,55 @@ def first_conv(occ: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.G
            n, G, Cout, L.ptr(out), L.ptr(partial), L.stream())
     if gn is None:
         return out
-    a = torch.empty(n, Cout, dtype=torch.float32, device=occ.device)
-    b = torch.empty_like(a)
-    L.call("nm_groupnorm_finalize", L.ptr(partial), n, G ** 3, Cout, gn.num_groups, chunks, L.ptr(f32(gn, "weight")),
-           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.stream())
+    a, b = _gn_finalize(partial, n, G ** 3, Cout, gn, chunks, occ.device)
     return out, a, b
 
 
 # ------------------------------------------------------------------ GroupNorm / pointwise
+# The training path keeps the forward's GroupNorm statistics for the backward (mean / rstd per (sample, group) and the
+# per-(sample, channel) sums), so that nm_groupnorm_backward skips its statistics pass: inside `capture_gn_stats()` every
+# GroupNorm finalize of this module appends (mean_rstd (n, groups, 2), xsum (n, C)) to the yielded list.
+_GN_SINK = [None]
+
+
+@__import__("contextlib").contextmanager
+def capture_gn_stats():
+    prev, sink = _GN_SINK[0], []
+    _GN_SINK[0] = sink
+    try:
+        yield sink
+    finally:
+        _GN_SINK[0] = prev
+
+
+def _gn_stat_outputs(n, C, groups, device):
+    if _GN_SINK[0] is None:
+        return None, None
+    mr = torch.empty(n, groups, 2, dtype=torch.float32, device=device)
+    xs = torch.empty(n, C, dtype=torch.float32, device=device)
+    _GN_SINK[0].append((mr, xs))
+    return mr, xs
+
+
+def _gn_finalize(partial, n, S, C, gn, chunks, device):
+    """scale / shift (n, C) of the GroupNorm from the partial statistics a conv epilogue produced."""
+    a = torch.empty(n, C, dtype=torch.float32, device=device)
+    b = torch.empty_like(a)
+    mr, xs = _gn_stat_outputs(n, C, gn.num_groups, device)
+    L.call("nm_groupnorm_finalize", L.ptr(partial), n, S, C, gn.num_groups, chunks, L.ptr(f32(gn, "weight")),
+           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.ptr(mr), L.ptr(xs), L.stream())
+    return a, b
+
+
 def gn_scale_shift(raw: torch.Tensor, gn: torch.nn.GroupNorm) -> Tuple[torch.Tensor, torch.Tensor]:
     n, C = raw.shape[0], raw.shape[-1]
     S = raw.numel() // (n * C)
     a = torch.empty(n, C, dtype=torch.float32, device=raw.device)
     b = torch.empty_like(a)
+    mr, xs = _gn_stat_outputs(n, C, gn.num_groups, raw.device)
     ws = workspace(L.query("nm_gn_workspace_bytes", n, S, C), raw.device, "gn")
     L.call("nm_groupnorm_scale_shift", L.ptr(raw), n, S, C, gn.num_groups, L.ptr(f32(gn, "weight")),
-           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.ptr(ws), L.stream())
+           L.ptr(f32(gn, "bias")), float(gn.eps), L.ptr(a), L.ptr(b), L.ptr(ws), L.ptr(mr), L.ptr(xs), L.stream())
     return a, b
 
 
