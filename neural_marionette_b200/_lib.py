@@ -169,5 +169,14 @@ def call(name: str, *args):
         raise NmError(f"{name} failed ({rc}): {handle.nm_last_error().decode()}")
 
 
+_QUERY_CACHE = {}
+
+
 def query(name: str, *args):
-    return getattr(lib(), name)(*args)
+    """Shape queries (`*_supported`, `*_chunks`, `*_bytes`): pure functions of their integer arguments, memoised - the
+    launch-bound hour-glass levels make several of them per layer and per step."""
+    key = (name, args)
+    hit = _QUERY_CACHE.get(key)
+    if hit is None:
+        hit = _QUERY_CACHE[key] = getattr(lib(), name)(*args)
+    return hit

@@ -234,13 +234,23 @@ def set_grad_scale(value: float) -> None:
     _GRAD_SCALE[0] = float(value)
 
 
+class _ConvSpec:
+    """What conv3d / conv_transpose3d read of an nn.Conv3d / nn.ConvTranspose3d, for the derived (mirrored) convolutions of
+    the backward: built on the device from the live weight - no host-side module construction, no host -> device copy
+    (the mirrors are rebuilt after every optimizer step)."""
+
+    def __init__(self, transposed, cin, cout, k, stride, weight):
+        pad = (k - 1) // 2 if stride == 1 else 0
+        self.transposed = transposed
+        self.in_channels, self.out_channels = cin, cout
+        self.kernel_size, self.stride, self.padding = (k, k, k), (stride, stride, stride), (pad, pad, pad)
+        self.output_padding, self.groups = (0, 0, 0), 1
+        self.weight = weight.detach().float().contiguous()
+        self.bias = torch.zeros(cout, dtype=torch.float32, device=weight.device)
+
+
 def _zero_bias_mirror(kind, cin, cout, k, stride, weight):
-    cls = torch.nn.ConvTranspose3d if kind == "convT" else torch.nn.Conv3d
-    pad = (k - 1) // 2 if stride == 1 else 0
-    m = cls(cin, cout, k, stride=stride, padding=pad, bias=True).to(weight.device).requires_grad_(False)
-    m.weight.copy_(weight)
-    m.bias.zero_()
-    return m
+    return _ConvSpec(kind == "convT", cin, cout, k, stride, weight)
 
 
 def conv3d_input_grad(grad_out: torch.Tensor, conv: torch.nn.Conv3d) -> torch.Tensor:

@@ -74,3 +74,25 @@ if "--profile" in sys.argv:
     print(f"device time of one step: {tot / 1e3:.1f} ms")
     for r in rows[:45]:
         print(f"{r.device_time_total / 1e3:9.2f} ms {100 * r.device_time_total / tot:5.1f}% x{r.count:4d}  {r.key[:110]}")
+if "--gaps" in sys.argv:
+    # where the GPU idles inside a step: gaps between consecutive kernels on the device timeline, by the kernel that follows
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step()
+        torch.cuda.synchronize()
+    ev = sorted([(e.time_range.start, e.time_range.end, e.name) for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA],
+                key=lambda t: t[0])
+    span = ev[-1][1] - ev[0][0]
+    busy = sum(e[1] - e[0] for e in ev)
+    gaps = {}
+    last_end = ev[0][1]
+    for st, en, name in ev[1:]:
+        if st > last_end:
+            key = name.split("(")[0].replace("void ", "").replace("(anonymous namespace)::", "")[:60]
+            g = gaps.setdefault(key, [0, 0.0])
+            g[0] += 1
+            g[1] += st - last_end
+        last_end = max(last_end, en)
+    print(f"device span {span / 1e3:.1f} ms, busy {busy / 1e3:.1f} ms, idle {(span - busy) / 1e3:.1f} ms over {len(ev)} launches")
+    for k, (c, t) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
+        print(f"  idle before {k:60s} x{c:4d} {t / 1e3:7.2f} ms ({t / max(c, 1):6.1f} us each)")
