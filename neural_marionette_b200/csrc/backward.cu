@@ -1028,9 +1028,14 @@ static int first_wgrad_parts(int n) {
   int p = (2 * nm_num_sms() + n - 1) / n;
   return p < 1 ? 1 : (p > 8 ? 8 : p);
 }
+// the occupancy gather is latency-bound (64-byte rows from L2): several resident CTAs per SM keep more loads in flight
+static int first_wgrad_occ_parts(int n) {
+  int p = (6 * nm_num_sms() + n - 1) / n;
+  return p < 1 ? 1 : (p > 16 ? 16 : p);
+}
 
 extern "C" size_t nm_first_conv_wgrad_workspace_bytes(int n, int Cout) {
-  return ((size_t)n * first_wgrad_parts(n) + 1) * 125 * 5 * Cout * sizeof(float);
+  return ((size_t)n * first_wgrad_parts(n) * 4 + (size_t)n * first_wgrad_occ_parts(n) + 5) * 125 * Cout * sizeof(float);
 }
 
 extern "C" int nm_first_conv_wgrad(const float* occ, const void* grad_out, const float* linspace, int n, int G, int Cout,
@@ -1039,28 +1044,28 @@ extern "C" int nm_first_conv_wgrad(const float* occ, const void* grad_out, const
   NM_CHECK_ARG((Cout == 32 || Cout == 64) && G >= 8 && G % 16 == 0, "nm_first_conv_wgrad: Cout=%d G=%d unsupported", Cout, G);
   if (n == 0) return NM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const int parts = first_wgrad_parts(n);
-  const long long rows = (long long)n * parts;
+  const int parts = first_wgrad_parts(n), oparts = first_wgrad_occ_parts(n);
+  const long long rows = (long long)n * parts, orows = (long long)n * oparts;
   float* bins = reinterpret_cast<float*>(workspace);
   float* occp = bins + (size_t)rows * 125 * 4 * Cout;
   const __half* dy = reinterpret_cast<const __half*>(grad_out);
-  const dim3 grid(n, parts);
+  const dim3 grid(n, parts), ogrid(n, oparts);
   if (Cout == 32) {
     first_wgrad_moments_kernel<32><<<grid, 256, 0, st>>>(dy, G, bins);
     NM_CHECK_LAUNCH("first_wgrad_moments_kernel");
-    first_wgrad_occ_kernel<32><<<grid, 256, 0, st>>>(occ, dy, G, occp);
+    first_wgrad_occ_kernel<32><<<ogrid, 256, 0, st>>>(occ, dy, G, occp);
   } else {
     first_wgrad_moments_kernel<64><<<grid, 256, 0, st>>>(dy, G, bins);
     NM_CHECK_LAUNCH("first_wgrad_moments_kernel");
-    first_wgrad_occ_kernel<64><<<grid, 256, 0, st>>>(occ, dy, G, occp);
+    first_wgrad_occ_kernel<64><<<ogrid, 256, 0, st>>>(occ, dy, G, occp);
   }
   NM_CHECK_LAUNCH("first_wgrad_occ_kernel");
   // sum over the frames and parts first (fixed order), then assemble the (Cout, 4, 5, 5, 5) tensor
-  float* rbins = occp + (size_t)rows * 125 * Cout;
+  float* rbins = occp + (size_t)orows * 125 * Cout;
   float* roccp = rbins + (size_t)125 * 4 * Cout;
   reduce_cols_kernel<<<nm_cdiv(500 * Cout, 128), 128, 0, st>>>(bins, rows, 500 * Cout, 500 * Cout, 1.0f, rbins);
   NM_CHECK_LAUNCH("first_wgrad(reduce bins)");
-  reduce_cols_kernel<<<nm_cdiv(125 * Cout, 128), 128, 0, st>>>(occp, rows, 125 * Cout, 125 * Cout, 1.0f, roccp);
+  reduce_cols_kernel<<<nm_cdiv(125 * Cout, 128), 128, 0, st>>>(occp, orows, 125 * Cout, 125 * Cout, 1.0f, roccp);
   NM_CHECK_LAUNCH("first_wgrad(reduce occ)");
   first_wgrad_finalize_kernel<<<nm_cdiv(Cout * 500, 128), 128, 0, st>>>(rbins, roccp, 1, Cout, G, linspace, out_scale, dw);
   NM_CHECK_LAUNCH("first_wgrad_finalize_kernel");
