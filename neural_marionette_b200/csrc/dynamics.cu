@@ -334,19 +334,21 @@ __device__ __forceinline__ void cl_cp_async16(void* dst_smem, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
 
-// acc[v][0..3] += sum_{i in [i0, i1)} WT[i][col .. col+3] * x[v][i]; 16-byte weight loads, 8 rows in flight
+// acc[v][0..3] += sum_{i in [i0, i1)} WT[i][col .. col+3] * x[v][i]; 16-byte weight loads, U rows in flight per thread
+// (the mat-vecs are L2-latency bound: 16 rows = 64 KB in flight per CTA for the single-vector phases)
 template <int NV>
 __device__ __forceinline__ void quad_dot(const float* __restrict__ WT, int ldw, int col, int i0, int i1, const float* x,
                                          int xstride, float (&acc)[NV][4]) {
+  constexpr int U = NV == 1 ? 16 : 8;
   const float* w = WT + (long long)i0 * ldw + col;
   int i = i0;
-  for (; i + 8 <= i1; i += 8) {
-    float4 q[8];
+  for (; i + U <= i1; i += U) {
+    float4 q[U];
 #pragma unroll
-    for (int u = 0; u < 8; u++) q[u] = __ldg(reinterpret_cast<const float4*>(w + (long long)u * ldw));
-    w += 8LL * ldw;
+    for (int u = 0; u < U; u++) q[u] = __ldg(reinterpret_cast<const float4*>(w + (long long)u * ldw));
+    w += (long long)U * ldw;
 #pragma unroll
-    for (int u = 0; u < 8; u++)
+    for (int u = 0; u < U; u++)
 #pragma unroll
       for (int v = 0; v < NV; v++) {
         const float xv = x[v * xstride + i + u];
