@@ -262,6 +262,7 @@ class Bench:
             dist.init_process_group("nccl", device_id=self.dev)
         _lib.call("nm_device_supported")
         self.G = args.grid
+        self.training_profile = False
 
     def model(self, Tcond=5):
         hp = self.O.default_hparams(grid_size=self.G, Tcond=Tcond)
@@ -384,6 +385,10 @@ class Bench:
         launches = self.lib.CALLS - calls0
         clocks = sampler.result()
         torch.cuda.synchronize()
+        # per-launch CUDA events of the tensor-core convs / weight gradients over two more steps (kept out of `ms`)
+        ops.PROFILE = {}
+        prof_ms = self.timed(lambda: step(raw_dev), 2)
+        prof, ops.PROFILE = ops.PROFILE, None
         exposed = float(np.mean([a.elapsed_time(b) for a, b in ev["finish"]]))
         ms_e2e = self.timed(lambda: float(step(raw_host)["recon_loss"].detach()), steps)
         # the all-reduce on its own (no overlap): the 4 buckets back to back on an idle GPU
@@ -405,7 +410,7 @@ class Bench:
                    h2d=int(raw_host.numel() * 4), d2h=4, launches=launches,
                    grad_bytes=int(opt.buckets.flat.numel() * 4), buckets=len(opt.buckets.bounds), exposed_ms=exposed,
                    allreduce_alone_ms=ar_ms, skipped=opt.skipped, peak_gib=torch.cuda.max_memory_allocated() / 2 ** 30,
-                   grad_scale=ops.grad_scale(), clocks=clocks)
+                   grad_scale=ops.grad_scale(), clocks=clocks, prof=prof, prof_ms=prof_ms)
         if G == 64:   # training ~ 3x the forward's conv FLOPs (fwd + dgrad + wgrad)
             res["model_tflops"] = 3 * self.world * B * (GF_ST_CLIP + T * (GF_ENC_FRAME + GF_DEC_FRAME)) / (ms / 1e3) / 1e3
         del net, opt
@@ -436,25 +441,28 @@ class Bench:
             return None
         tot_ms = sum(v[0] for v in by_shape.values())
         tot_flop = sum(k[-1] * v[1] for k, v in by_shape.items())
-        (tn, tD, tci, tco, tk, ts, tflop), (t_ms, cnt) = max(by_shape.items(), key=lambda kv: kv[1][0])
+        (kind, tn, tD, tci, tco, tk, ts, tflop), (t_ms, cnt) = max(by_shape.items(), key=lambda kv: kv[1][0])
         ach = tflop * cnt / (t_ms / 1e3) / 1e12
         slab3 = tk == 3 and ts == 1 and tD % 16 == 0 and tci in (32, 64, 128) and tco <= 128 and \
             tco % (32 if tci <= 64 else 16) == 0
-        kernel = "conv3d_slab3_kernel" if slab3 else "conv3d_tc_kernel"
+        kernel = "conv_wgrad_tc_kernel" if kind == "wgrad" else ("conv3d_slab3_kernel" if slab3 else "conv3d_tc_kernel")
         layer = f"grid={tD} Cin={tci} Cout={tco} k={tk} s={ts}"
         per_frame, src = profiled_traffic(kernel, layer)
-        return {"bound": "tensor", "kernel": kernel + " (nm_conv3d_tc, tcgen05 implicit GEMM)",
+        entry = "nm_conv3d_k3_wgrad_tc, tcgen05 weight gradient" if kind == "wgrad" else "nm_conv3d_tc, tcgen05 implicit GEMM"
+        return {"bound": "tensor", "kernel": f"{kernel} ({entry})",
                 "layer": f"n={tn} " + layer, "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                 "frac": ach / pk["tf_sust"],
                 "traffic": per_frame * tn if per_frame is not None else None, "traffic_source": src,
                 "note": "dec.8: conv3d_k3(upsample2x(LeakyReLU(GroupNorm(x)))) in one kernel; FLOPs counted are the "
-                        "conv's only" if (tD, tci, tco, tk) == (64, 64, 32, 3) else None,
+                        "conv's only" if (kind, tD, tci, tco, tk) == ("conv", 64, 64, 32, 3) and not self.training_profile else
+                        ("forward convs and data gradients (the same kernels on mirrored weights) share a shape key" if
+                         self.training_profile and kind == "conv" else None),
                 "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                 "launch_ms": t_ms / cnt, "share_of_step": t_ms / (ms * steps),
                 "all_tc_convs": {"achieved": tot_flop / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / (ms * steps)},
-                "by_layer": [{"layer": f"n={k[0]} grid={k[1]} {k[2]}->{k[3]} k{k[4]}s{k[5]}", "launches": v[1],
+                "by_layer": [{"layer": f"{k[0]} n={k[1]} grid={k[2]} {k[3]}->{k[4]} k{k[5]}s{k[6]}", "launches": v[1],
                               "ms_per_launch": round(v[0] / v[1], 4),
-                              "tflops": round(k[6] * v[1] / (v[0] / 1e3) / 1e12, 1),
+                              "tflops": round(k[7] * v[1] / (v[0] / 1e3) / 1e12, 1),
                               "share_of_step": round(v[0] / (ms * steps), 4)}
                              for k, v in sorted(by_shape.items(), key=lambda kv: -kv[1][0])[:30]]}
 
@@ -484,8 +492,10 @@ def main():
     if args.workload == "train":
         r = be.run_train(B, T, N, steps, warmup)
         rec = be.train_record(r, B, T)
+        be.training_profile = True
         line.update(value=r["value"], ms_per_step=r["ms"], e2e=rec["e2e"], gpu_launches=int(r["launches"]),
-                    model_tflops=r.get("model_tflops"), train=rec, roofline=None, clocks=r["clocks"])
+                    model_tflops=r.get("model_tflops"), train=rec, roofline=be.roofline(r["prof"], r["prof_ms"], 2),
+                    clocks=r["clocks"])
         line["e2e"]["note"] = "host points -> device every step; the step's loss read back"
     else:
         r = be.run_inference(args.workload, B, T, N, steps, warmup, want_roofline=True)

@@ -13,8 +13,8 @@ from . import _lib as L
 
 ACT_DTYPE = torch.float16
 _scratch = {}
-# bench.py sets this to a dict to bracket every tensor-core conv launch with CUDA events on the launching
-# stream: {(n, grid, Cin, Cout, k, stride, flops): [(start, end), ...]}
+# bench.py sets this to a dict to bracket every tensor-core conv / weight-gradient launch with CUDA events on the
+# launching stream: {(kind, n, grid, Cin, Cout, k, stride, flops): [(start, end), ...]}, kind = "conv" | "wgrad"
 PROFILE = None
 
 
@@ -204,7 +204,7 @@ def conv3d(x: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNo
     if PROFILE is not None:
         e1.record()
         flops = 2.0 * n * (D // s) * (H // s) * (W // s) * Cout * Cin * k ** 3
-        PROFILE.setdefault((n, D, Cin, Cout, k, s, flops), []).append((e0, e1))
+        PROFILE.setdefault(("conv", n, D, Cin, Cout, k, s, flops), []).append((e0, e1))
     if gn is None:
         return out
     if chunks == 0:
@@ -322,8 +322,14 @@ def conv3d_weight_grad(x: torch.Tensor, grad_out: torch.Tensor, k: int = 3, stri
     if impl == "tc" or (impl is None and WGRAD_TC and tc_ok):
         nbytes = L.query("nm_conv3d_k3_wgrad_tc_workspace_bytes", n, D, H, W, Cin, Cout)
         ws = workspace(max(nbytes, 16), x.device, "wgrad")
+        if PROFILE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         L.call("nm_conv3d_k3_wgrad_tc", L.ptr(x), L.ptr(grad_out), n, D, H, W, Cin, Cout, float(out_scale), L.ptr(dw),
                L.ptr(ws), L.stream())
+        if PROFILE is not None:
+            e1.record()
+            PROFILE.setdefault(("wgrad", n, D, Cin, Cout, 3, 1, 2.0 * n * D * H * W * Cout * Cin * 27), []).append((e0, e1))
         return dw
     if k == 3 and stride == 1 and _slab_wgrad_ok(x, Cout) and impl != "gather":
         nbytes = L.query("nm_conv3d_k3_wgrad_workspace_bytes", n, D, H, W, Cin, Cout)
@@ -501,7 +507,7 @@ def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn
     if PROFILE is not None:
         e1.record()
         flops = 2.0 * n * 8 * D * H * W * Cout * Cin * 27
-        PROFILE.setdefault((n, 2 * D, Cin, Cout, 3, 1, flops), []).append((e0, e1))
+        PROFILE.setdefault(("conv", n, 2 * D, Cin, Cout, 3, 1, flops), []).append((e0, e1))
     if gn is None:
         return out
     a, b = _gn_finalize(partial, n, 8 * D * H * W, Cout, gn, chunks, x_lo.device)
