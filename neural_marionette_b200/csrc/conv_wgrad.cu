@@ -1,5 +1,6 @@
-// Weight gradient of the stride-1 3x3x3 "same" convolutions (config #4 backward) - FIRST VERSION on
-// mma.sync (m16n8k16, fp16 operands, fp32 accumulate); the tcgen05 version with TMA-fed halo slabs is the plan of record.
+// Weight gradient of the stride-1 3x3x3 "same" convolutions (config #4 backward) - the round-1 version on
+// mma.sync (m16n8k16, fp16 operands, fp32 accumulate), 84 TFLOP/s.  Superseded by conv_wgrad_tc.cu (tcgen05, 800-1200
+// TFLOP/s) wherever that kernel covers the shape; kept as the fallback for W = 48 and as a cross-check in the tests.
 //
 //   dW[co][ci][kd][kh][kw] = sum over voxels v = (n, d, h, w) of  dY[v][co] * X[n, d+kd-1, h+kh-1, w+kw-1][ci]
 //
@@ -30,17 +31,6 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// 16-byte asynchronous global -> shared copy; src_bytes = 0 zero-fills the destination (conv padding)
-__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem),
-               "r"(src_bytes) : "memory");
-}
-
-// kAsync = false: the staging loops below as verified on B200 (tests/test_gpu_kernels.py::test_conv3d_weight_grad).
-// kAsync = true (NM_WGRAD_ASYNC=1, NOT YET VERIFIED ON HARDWARE): the same tiles staged with cp.async, so that all
-// 16-byte loads of a row are in flight at once instead of one L2 round trip per loop iteration (the synchronous loop
-// is what bounds the first version: ~6 us per row for 42 KB).
-template <bool kAsync>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_k3_kernel(const __half* __restrict__ x, const __half* __restrict__ gy, int N, int D, int H, int W, int Cin, int Cout,
                      float* __restrict__ partial) {
@@ -70,12 +60,8 @@ conv_wgrad_k3_kernel(const __half* __restrict__ x, const __half* __restrict__ gy
     for (int i = threadIdx.x; i < W * 4; i += kWgThreads) {
       const int w = i >> 2, c = i & 3;
       const __half* src = gy + ((long long)row * W + w) * Cout + co0 + c * 8;
-      if constexpr (kAsync) {
-        cp_async16(sY + w * kRowHalfs + c * 8, src, 16);
-      } else {
-        const uint4 v = *reinterpret_cast<const uint4*>(src);
-        *reinterpret_cast<uint4*>(sY + w * kRowHalfs + c * 8) = v;
-      }
+      const uint4 v = *reinterpret_cast<const uint4*>(src);
+      *reinterpret_cast<uint4*>(sY + w * kRowHalfs + c * 8) = v;
     }
     // ---- stage the 9 halo rows of X: (W + 2) voxels x 4 chunks each, zero outside the tensor
     for (int i = threadIdx.x; i < 9 * (W + 2) * 4; i += kWgThreads) {
@@ -83,16 +69,10 @@ conv_wgrad_k3_kernel(const __half* __restrict__ x, const __half* __restrict__ gy
       const int wj = t % (W + 2), r9 = t / (W + 2);
       const int dd = d + r9 / 3 - 1, hh = h + r9 % 3 - 1, ww = wj - 1;
       const bool inside = (unsigned)dd < (unsigned)D && (unsigned)hh < (unsigned)H && (unsigned)ww < (unsigned)W;
-      if constexpr (kAsync) {
-        const __half* src = inside ? x + ((((long long)n * D + dd) * H + hh) * W + ww) * Cin + ci0 + c * 8 : x;
-        cp_async16(sX + r9 * xrow + wj * kRowHalfs + c * 8, src, inside ? 16 : 0);
-      } else {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (inside) v = *reinterpret_cast<const uint4*>(x + ((((long long)n * D + dd) * H + hh) * W + ww) * Cin + ci0 + c * 8);
-        *reinterpret_cast<uint4*>(sX + r9 * xrow + wj * kRowHalfs + c * 8) = v;
-      }
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (inside) v = *reinterpret_cast<const uint4*>(x + ((((long long)n * D + dd) * H + hh) * W + ww) * Cin + ci0 + c * 8);
+      *reinterpret_cast<uint4*>(sX + r9 * xrow + wj * kRowHalfs + c * 8) = v;
     }
-    if constexpr (kAsync) asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
     // ---- MMAs: K = the W voxels of the row, 16 per step
     for (int k0 = 0; k0 < W; k0 += 16) {
@@ -186,17 +166,10 @@ extern "C" int nm_conv3d_k3_wgrad(const void* x, const void* grad_out, int N, in
   const int chunks = wgrad_chunks(N, D, H, Cin, Cout);
   const size_t smem = (size_t)(kMaxW + 9 * (W + 2)) * kRowHalfs * sizeof(__half);
   // the attribute is per device: set it on every call (cheap) rather than once per process
-  NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_k3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_k3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  const char* e = getenv("NM_WGRAD_ASYNC");         // experiment switch, default = the synchronous staging
-  const int use_async = e && atoi(e) != 0;
+  NM_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_k3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
   const dim3 grid(chunks, Cin / 32, Cout / 32);
-  if (use_async)
-    conv_wgrad_k3_kernel<true><<<grid, kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(grad_out),
-                                                             N, D, H, W, Cin, Cout, reinterpret_cast<float*>(workspace));
-  else
-    conv_wgrad_k3_kernel<false><<<grid, kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(grad_out),
-                                                              N, D, H, W, Cin, Cout, reinterpret_cast<float*>(workspace));
+  conv_wgrad_k3_kernel<<<grid, kWgThreads, smem, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(grad_out),
+                                                       N, D, H, W, Cin, Cout, reinterpret_cast<float*>(workspace));
   NM_CHECK_LAUNCH("conv_wgrad_k3_kernel");
   conv_wgrad_reduce_kernel<<<nm_cdiv((long long)Cout * Cin * 27, 256), 256, 0, st>>>(reinterpret_cast<const float*>(workspace),
                                                                                      chunks, Cin, Cout, out_scale, dw);

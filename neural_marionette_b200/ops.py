@@ -61,11 +61,19 @@ def gauss_width(sigma: float, g: int) -> float:
 
 
 # ------------------------------------------------------------------ weight caches
+# derived weights live OUTSIDE the modules (weak keys): `copy.deepcopy(model)` / `torch.save(model)` never see the packed
+# tensors or the ctypes structs, and a collected module drops its entries
+_CACHES = __import__("weakref").WeakKeyDictionary()
+
+
 def _cached(module, tag: str, params, build):
-    """Cache derived (packed) weights on the module; rebuilt when a source parameter changes
-    in place (load_state_dict / optimizer step bump ``_version``) or moves (``.cuda()``)."""
+    """Cache derived (packed) weights per module; rebuilt when a source parameter changes in place (load_state_dict /
+    optimizer step bump ``_version``) or moves (``.cuda()``).  Edits through ``p.data`` or raw pointers do not bump
+    ``_version``: call `invalidate_caches(model)` after those."""
     key = tuple((p._version, p.data_ptr(), str(p.device)) for p in params)
-    slot = module.__dict__.setdefault("_nm_cache", {})
+    slot = _CACHES.get(module)
+    if slot is None:
+        slot = _CACHES[module] = {}
     hit = slot.get(tag)
     if hit is None or hit[0] != key:
         with torch.no_grad():
@@ -484,7 +492,7 @@ def invalidate_caches(module: torch.nn.Module) -> None:
     """Drop every derived (packed / transposed) weight cached on the sub-modules: call after editing parameters through
     `.data` or raw pointers (the fused optimizer does), which does not bump `Tensor._version`."""
     for m in module.modules():
-        m.__dict__.pop("_nm_cache", None)
+        _CACHES.pop(m, None)
 
 
 def conv3d_up2x(x_lo: torch.Tensor, conv: torch.nn.Conv3d, gn: Optional[torch.nn.GroupNorm] = None, in_affine=None):

@@ -158,6 +158,25 @@ def test_state_dict_roundtrip_and_cache_invalidation():
         assert torch.equal(v.cpu(), sd[k]), k
 
 
+def test_deepcopy_and_pickle_after_a_forward():
+    """The derived-weight caches (packed fp16 weights, ctypes structs of the HSVRNN matrices) live outside the modules:
+    a model that has run can be deep-copied / pickled, and the copy computes the same result."""
+    import copy
+    import io
+    hp = O.default_hparams(grid_size=32)
+    net, _ = build(hp, 57)
+    vox, _ = clips(5700, 1, 3, 20000, 32)
+    act = {"detector": True, "learner": True}
+    with torch.no_grad():
+        net(vox, act)
+        ref = net.kypt_detector(vox)["keypoints"]
+        twin = copy.deepcopy(net)
+        buf = io.BytesIO()
+        torch.save(net, buf)
+        assert torch.equal(twin.kypt_detector(vox)["keypoints"], ref)
+        twin.dyna_module.encode(ref, net.kypt_detector.get_affinity())
+
+
 def test_training_mode_submodules_raise_but_detector_trains():
     """Autograd is wired through KyptDetector.forward; the sub-networks called on their own in training mode with
     autograd enabled still refuse (no silent graph-less result)."""
