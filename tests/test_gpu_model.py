@@ -133,11 +133,16 @@ def test_generate_vs_reference_golden(golden_dir):
                            eps_gen=torch.from_numpy(z["eps_gen"]).cuda())
     kp_ref = z["keypoints"]
     Tc = hp.Tcond
-    assert np.abs(out["keypoints"][:, :Tc].cpu().numpy() - kp_ref[:, :Tc]).max() <= KP_TOL
-    # generated frames go through a recurrent network fed by the detected keypoints: allow the detector's
-    # tolerance to be amplified a little
-    assert np.abs(out["keypoints"][:, Tc:].cpu().numpy() - kp_ref[:, Tc:]).max() <= 2e-2
-    assert np.abs(out["gen"][..., ::2, ::2, ::2].cpu().numpy() - z["gen_sub_f16"].astype(np.float32)).mean() <= 1e-2
+    cond_err = np.abs(out["keypoints"][:, :Tc].cpu().numpy() - kp_ref[:, :Tc]).max()
+    gen_err = np.abs(out["keypoints"][:, Tc:].cpu().numpy() - kp_ref[:, Tc:]).max()
+    vol_err = np.abs(out["gen"][..., ::2, ::2, ::2].cpu().numpy() - z["gen_sub_f16"].astype(np.float32)).mean()
+    print(f"[generate] detected keypoints max err {cond_err:.3e}, generated keypoints (15-step roll-out) max err "
+          f"{gen_err:.3e}, generated volumes mean abs err {vol_err:.3e}")
+    assert cond_err <= KP_TOL
+    # generated frames go through a recurrent network (GRU + best-of-10 sample pick) fed by the detected keypoints; they
+    # stay inside the same north-star keypoint budget (measured 4.0e-4; detected 9.6e-4; volumes 2.9e-5)
+    assert gen_err <= KP_TOL
+    assert vol_err <= 1e-3
     assert out["gen"].shape == (1, T, 1, 32, 32, 32) and out["A_hats"] is None
 
 
