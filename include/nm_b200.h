@@ -273,8 +273,11 @@ int nm_conv3d_wgrad_gather(const void* small_side, const void* large_side, int n
 int nm_depth_to_space2(const void* y, void* out, int n, int D, int H, int W, int C, int tap0, int ntaps, void* stream);
 
 /* Backward of nm_upsample2x without the fused prologue (nn.Upsample(scale 2, trilinear, align_corners=False),
- * model/kypt_detector.py:427,441): grad_out act (n, 2D, 2H, 2W, C) -> grad_in act (n, D, H, W, C). */
-int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n, int D, int H, int W, int C, void* stream);
+ * model/kypt_detector.py:427,441): grad_out act (n, 2D, 2H, 2W, C) -> grad_in act (n, D, H, W, C); three separable
+ * passes (w, h, d) through two fp16 intermediates in `workspace`. */
+size_t nm_upsample2x_backward_workspace_bytes(int n, int D, int H, int W, int C);
+int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n, int D, int H, int W, int C, void* workspace,
+                           void* stream);
 
 /* Backward of nm_final_recon with the BCE (model/kypt_detector.py:410,453-457,:91-92).  x, a, b, w, bias, first_frame,
  * recon (the saved forward output), target as in the forward; grad_bce (n) = dL/d(per-frame BCE mean).

@@ -96,7 +96,8 @@ PROTOTYPES = {
     "nm_conv3d_wgrad_gather_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
     "nm_conv3d_wgrad_gather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nm_depth_to_space2": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "nm_upsample2x_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "nm_upsample2x_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "nm_upsample2x_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "nm_final_recon_backward_workspace_bytes": (_sz, [_i]),
     "nm_final_recon_backward": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i,
                                      _i, _vp]),

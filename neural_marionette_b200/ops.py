@@ -397,7 +397,8 @@ def upsample2x_backward(grad_out: torch.Tensor) -> torch.Tensor:
     n, D2, H2, W2, C = grad_out.shape
     assert grad_out.dtype == ACT_DTYPE and grad_out.is_contiguous()
     dx = torch.empty(n, D2 // 2, H2 // 2, W2 // 2, C, dtype=ACT_DTYPE, device=grad_out.device)
-    L.call("nm_upsample2x_backward", L.ptr(grad_out), L.ptr(dx), n, D2 // 2, H2 // 2, W2 // 2, C, L.stream())
+    ws = workspace(L.query("nm_upsample2x_backward_workspace_bytes", n, D2 // 2, H2 // 2, W2 // 2, C), grad_out.device, "up_bwd")
+    L.call("nm_upsample2x_backward", L.ptr(grad_out), L.ptr(dx), n, D2 // 2, H2 // 2, W2 // 2, C, L.ptr(ws), L.stream())
     return dx
 
 
