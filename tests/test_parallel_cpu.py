@@ -96,6 +96,55 @@ def test_gloo_world2_gradient_buckets():
     assert res == [(0, True), (1, True)]
 
 
+def _autograd_worker(rank, world, port, out):
+    """A real backward drives the buckets through post-accumulate hooks; between the steps the caller drops the `.grad`
+    aliases the way torch's default `optimizer.zero_grad(set_to_none=True)` does."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    ref.load_state_dict(net.state_dict())
+    gb = P.GradientBuckets(net.parameters(), n_buckets=2)
+    gb.attach_hooks()
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    g = torch.Generator().manual_seed(1)
+    x_all = torch.randn(3, world * 4, 6, generator=g)        # the same data on every rank; rank r takes its 4 rows
+    ok = True
+    for step in range(3):
+        if step == 1:
+            opt.zero_grad()                                   # set_to_none=True: every alias is dropped
+            ok = ok and all(p.grad is None for p in net.parameters())
+        gb.zero()                                             # re-attaches (and zeroes) whatever the caller did
+        if step == 2:
+            for p in net.parameters():
+                p.grad = None                                 # dropped AFTER zero(): the hooks must re-home the fresh gradients
+        net(x_all[step, rank * 4:(rank + 1) * 4]).pow(2).sum().backward()
+        gb.finish()
+        ref.zero_grad()
+        (ref(x_all[step]).pow(2).sum() / world).backward()    # mean over the ranks of the per-rank sums
+        for p, q in zip(net.parameters(), ref.parameters()):
+            ok = ok and bool(torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6))
+            off, n = gb._slot[id(p)]
+            ok = ok and p.grad.data_ptr() == gb.flat[off:off + n].data_ptr()
+    out.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_buckets_survive_dropped_grad_aliases():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_autograd_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(out.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True), (1, True)]
+
+
 def test_gradient_buckets_single_process():
     net = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
     gb = P.GradientBuckets(net.parameters(), n_buckets=8)   # more buckets than tensors: one tensor per bucket at most
