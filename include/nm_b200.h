@@ -289,6 +289,18 @@ int nm_final_recon_backward(const void* x, const float* a, const float* b, const
                             const float* recon, const float* target, const float* grad_bce, float grad_scale,
                             void* grad_act, float* dw, float* dbias, void* workspace, int n, int S, int C, void* stream);
 
+/* The same backward fused with the GroupNorm + LeakyReLU that feeds the tail (decode_voxel_from_combined_representation
+ * .12 - .14): the tail's gradient w.r.t. the activated tensor is rank one per voxel (w[c] * dx14[v]) and is never
+ * written.  gamma / beta / groups: that GroupNorm; mean_rstd (n, groups, 2), xsum (n, C): its forward statistics
+ * (nm_groupnorm_finalize).  Outputs: grad_x act (n, S, C) = grad_scale * dL/d(raw conv output), dw (C), dbias (1) of the
+ * 1x1 conv, dgamma / dbeta (C) and dxsum (C) = the producing conv's bias gradient (fp32, true scale). */
+size_t nm_final_recon_backward_fused_workspace_bytes(int n, long long S, int C, int groups);
+int nm_final_recon_backward_fused(const void* x, const float* a, const float* b, const float* w, float bias, float sharpness,
+                                  const float* recon, const float* target, const float* grad_bce, float grad_scale,
+                                  const float* gamma, const float* beta, const float* mean_rstd, const float* xsum,
+                                  int groups, void* grad_x, float* dw, float* dbias, float* dgamma, float* dbeta,
+                                  float* dxsum, void* workspace, int n, long long S, int C, void* stream);
+
 /* Backward of nm_heatmap_head (model/kypt_detector.py:273-297,336-343; utils/kypt_detector_utils.py:28-55).
  * mode 1: inputs as the forward plus its saved outputs heat, keypoints, heat_mean; upstream gradients (each optional)
  *   grad_keypoints (n, K, 4), grad_heat_mean (n, K), grad_heat (n, K, g^3).  Outputs: grad_feature act (n, g^3, C) times

@@ -101,6 +101,9 @@ PROTOTYPES = {
     "nm_final_recon_backward_workspace_bytes": (_sz, [_i]),
     "nm_final_recon_backward": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i,
                                      _i, _vp]),
+    "nm_final_recon_backward_fused_workspace_bytes": (_sz, [_i, _ll, _i, _i]),
+    "nm_final_recon_backward_fused": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp,
+                                           _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
     "nm_heatmap_head_backward_workspace_bytes": (_sz, [_i, _i, _i]),
     "nm_heatmap_head_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

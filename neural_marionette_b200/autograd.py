@@ -226,8 +226,14 @@ class ConvGNFinalRecon(torch.autograd.Function):
         if gmax > 0.0 and math.isfinite(gmax):
             ops.set_grad_scale(2.0 ** max(0, min(30, round(math.log2(S / (gmax * sharp))) + _HEADROOM[0])))
         scale = ops.grad_scale()
-        dact, dw14, db14 = ops.final_recon_backward(raw, a, sh, conv14, first_frame, T, sharp, trans, recon, target, dbce, scale)
-        draw, dg, db, dbias = ops.groupnorm_backward(raw, dact, gn, leaky=True, out_scale=1.0 / scale, stats=stats or None)
+        if stats:
+            # the tail's rank-one gradient is never materialised: dx14 per voxel + the GroupNorm-backward sums in one pass
+            draw, dw14, db14, dg, db, dbias = ops.final_recon_backward_fused(raw, a, sh, conv14, gn, stats, sharp, recon, target,
+                                                                           dbce, scale)
+        else:
+            dact, dw14, db14 = ops.final_recon_backward(raw, a, sh, conv14, first_frame, T, sharp, trans, recon, target, dbce,
+                                                        scale)
+            draw, dg, db, dbias = ops.groupnorm_backward(raw, dact, gn, leaky=True, out_scale=1.0 / scale)
         dw11 = ops.conv3d_weight_grad(x, draw, k=3, stride=1, out_scale=1.0 / scale)
         dx = ops.conv3d_input_grad(draw, conv11) if ctx.needs_input_grad[0] else None
         return (dx, dw11, dbias, dg, db, dw14, db14) + (None,) * 8

@@ -268,6 +268,134 @@ gnb_dx_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, const
   }
 }
 
+// ------------------------------------------------------------------ decoder tail fused with the last GroupNorm backward
+// The tail's gradient w.r.t. the activated tensor is rank one per voxel: dz[v][c] = w[c] * dx14[v].  Instead of writing
+// it (16.8 MB / frame) and re-reading it twice, pass 1 recomputes the tail, stores the per-voxel scalar dx14 and already
+// accumulates the GroupNorm-backward sums (sum dy, sum dy * x with dy = dz * LeakyReLU'), pass 2 forms dz on the fly.
+//   forward: y = x*a + b (GroupNorm folded), act = lrelu(y), x14 = w . act + bias, p = sigmoid(sharp (tanh(x14) + ff - trans))
+//   dx14 = gbce[n] / S * (p - t) * [p(1-p) / max(p(1-p), 1e-12)] * sharp * (1 - tanh^2(x14))       (model/kypt_detector.py:410,91-92)
+//   dw[c] = sum_v act[c] dx14 = a[c] * sum(dx14 m x) + b[c] * sum(dx14 m),  m = LeakyReLU'(y)
+template <int C>
+__global__ void __launch_bounds__(256)
+tail_bwd_pass1_kernel(const __half* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
+                      const float* __restrict__ w, float bias, float sharp, const float* __restrict__ recon,
+                      const float* __restrict__ target, const float* __restrict__ gbce, float grad_scale, long long S,
+                      float* __restrict__ dx14_out /* (n, S), times grad_scale */,
+                      float* __restrict__ gn_partial /* [n][kGnbChunks][C][2] */, float* __restrict__ tail_partial /* [n][chunks][C + 1] */) {
+  static_assert(C == 32, "decoder tail has 32 channels");
+  const int n = blockIdx.y;
+  __shared__ float sa[C], sb[C], sw[C];
+  __shared__ float red[8][2 * C + 1];
+  if (threadIdx.x < C) {
+    sa[threadIdx.x] = a[(long long)n * C + threadIdx.x];
+    sb[threadIdx.x] = b[(long long)n * C + threadIdx.x];
+    sw[threadIdx.x] = w[threadIdx.x];
+  }
+  __syncthreads();
+  const float gn = gbce[n] / (float)S;
+  float A[C], B[C], db = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; c++) A[c] = B[c] = 0.f;
+  const half8* base = reinterpret_cast<const half8*>(x + (long long)n * S * C);
+  for (long long s = (long long)blockIdx.x * 256 + threadIdx.x; s < S; s += (long long)gridDim.x * 256) {
+    half8 raw[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) raw[j] = base[s * 4 + j];
+    float x14 = bias;
+    uint32_t pos = 0;                                  // bit c: y_c > 0
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float f[8];
+      nm_unpack8(raw[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = j * 8 + k;
+        const float y = fmaf(f[k], sa[c], sb[c]);
+        pos |= (y > 0.f ? 1u : 0u) << c;
+        x14 = fmaf(y > 0.f ? y : 0.01f * y, sw[c], x14);
+      }
+    }
+    const float t = tanhf(x14);
+    const float p = recon[(long long)n * S + s], tg = target[(long long)n * S + s];
+    const float pq = p * (1.f - p);
+    const float dx14 = gn * (p - tg) * (pq / fmaxf(pq, 1e-12f)) * sharp * (1.f - t * t);
+    db += dx14;
+    dx14_out[(long long)n * S + s] = dx14 * grad_scale;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float f[8];
+      nm_unpack8(raw[j], f);
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int c = j * 8 + k;
+        const float dm = ((pos >> c) & 1u) ? dx14 : 0.01f * dx14;
+        A[c] += dm;
+        B[c] = fmaf(dm, f[k], B[c]);
+      }
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    const float va = nm_warp_sum(A[c]), vb = nm_warp_sum(B[c]);
+    if (lane == 0) { red[warp][c] = va; red[warp][C + c] = vb; }
+  }
+  db = nm_warp_sum(db);
+  if (lane == 0) red[warp][2 * C] = db;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    float ta = 0.f, tb = 0.f;
+    for (int k = 0; k < 8; k++) { ta += red[k][c]; tb += red[k][C + c]; }
+    // GroupNorm-backward partial sums of dy = grad_scale * w[c] * dx14 * m and dy * x
+    float* gp = gn_partial + (((long long)n * gridDim.x + blockIdx.x) * C + c) * 2;
+    gp[0] = grad_scale * sw[c] * ta;
+    gp[1] = grad_scale * sw[c] * tb;
+    tail_partial[((long long)n * gridDim.x + blockIdx.x) * (C + 1) + c] = sa[c] * tb + sb[c] * ta;    // dw[c]
+  } else if (threadIdx.x == C) {
+    float t = 0.f;
+    for (int k = 0; k < 8; k++) t += red[k][2 * C];
+    tail_partial[((long long)n * gridDim.x + blockIdx.x) * (C + 1) + C] = t;                            // dbias
+  }
+}
+
+// pass 2: dx = rstd * (gamma * dy - m1 - xhat * m2) with dy = w[c] * dx14[v] * LeakyReLU'(gamma * xhat + beta)
+__global__ void __launch_bounds__(kGnbThreads)
+gnb_dx_rank1_kernel(const __half* __restrict__ x, const float* __restrict__ dx14, const float* __restrict__ w,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean_rstd,
+                    const float* __restrict__ m12, GnbShape s, __half* __restrict__ dx) {
+  const long long total = (long long)s.n * s.S * s.ccs;
+  for (long long i = (long long)blockIdx.x * kGnbThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kGnbThreads) {
+    const int cc = (int)(i % s.ccs);
+    const long long v = i / s.ccs;                                        // n * S + voxel
+    const int n = (int)(v / s.S);
+    const int grp = (cc * 8) / s.cpg;
+    const float mu = mean_rstd[(n * s.groups + grp) * 2], rs = mean_rstd[(n * s.groups + grp) * 2 + 1];
+    const float m1 = m12[(n * s.groups + grp) * 2], m2 = m12[(n * s.groups + grp) * 2 + 1];
+    const float d14 = dx14[v];
+    float xf[8], o[8];
+    nm_unpack8(*reinterpret_cast<const half8*>(x + i * 8), xf);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const float gk = gamma[cc * 8 + k];
+      const float xhat = (xf[k] - mu) * rs;
+      const float y = fmaf(gk, xhat, beta[cc * 8 + k]);
+      const float dy = w[cc * 8 + k] * (y > 0.f ? d14 : 0.01f * d14);
+      o[k] = rs * (gk * dy - m1 - xhat * m2);
+    }
+    *reinterpret_cast<half8*>(dx + i * 8) = nm_pack8(o);
+  }
+}
+
+__global__ void tail_reduce_kernel(const float* __restrict__ partial, long long rows, int C, float* __restrict__ dw, float* __restrict__ dbias) {
+  const int j = threadIdx.x;
+  if (j > C) return;
+  double acc = 0.0;
+  for (long long r = 0; r < rows; r++) acc += (double)partial[r * (C + 1) + j];
+  if (j < C) dw[j] = (float)acc;
+  else dbias[0] = (float)acc;
+}
+
 bool gnb_shape(int n, long long S, int C, int groups, GnbShape* s) {
   if (n <= 0 || S <= 0 || C <= 0 || groups <= 0 || C % groups) return false;
   const int cpg = C / groups, ccs = C / 8;
@@ -337,5 +465,48 @@ extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const 
   const int blocks = (int)min((long long)nm_num_sms() * 8, (total + kGnbThreads - 1) / kGnbThreads);
   gnb_dx_kernel<<<blocks, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, m12, s, leaky, reinterpret_cast<__half*>(grad_in));
   NM_CHECK_LAUNCH("gnb_dx_kernel");
+  return NM_OK;
+}
+
+extern "C" size_t nm_final_recon_backward_fused_workspace_bytes(int n, long long S, int C, int groups) {
+  if (n <= 0 || C <= 0 || groups <= 0 || C % groups) return 0;
+  return (gnb_ws_floats(n, C, groups) + (size_t)n * S /* dx14 */ + (size_t)n * kGnbChunks * (C + 1) /* tail partials */) * sizeof(float) + 64;
+}
+
+extern "C" int nm_final_recon_backward_fused(const void* x, const float* a, const float* b, const float* w, float bias,
+                                             float sharpness, const float* recon, const float* target, const float* grad_bce,
+                                             float grad_scale, const float* gamma, const float* beta, const float* mean_rstd,
+                                             const float* xsum, int groups, void* grad_x, float* dw, float* dbias, float* dgamma,
+                                             float* dbeta, float* dxsum, void* workspace, int n, long long S, int C, void* stream) {
+  NM_CHECK_ARG(x && a && b && w && recon && target && grad_bce && gamma && beta && mean_rstd && xsum && grad_x && dw && dbias &&
+               workspace, "nm_final_recon_backward_fused: null pointer");
+  NM_CHECK_ARG(C == 32, "nm_final_recon_backward_fused: C=%d unsupported (decoder tail is 32 channels)", C);
+  GnbShape s;
+  NM_CHECK_ARG(gnb_shape(n, S, C, groups, &s) && n <= 65535, "nm_final_recon_backward_fused: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* mr_unused = partial + (size_t)n * kGnbChunks * C * 2;
+  float* m12 = mr_unused + (size_t)n * groups * 2;
+  float* chan = m12 + (size_t)n * groups * 2;
+  float* xs_unused = chan + (size_t)n * C * 3;
+  float* dx14 = xs_unused + (size_t)n * C;
+  float* tailp = dx14 + (size_t)n * S;
+  const __half* xh = reinterpret_cast<const __half*>(x);
+  const float inv = 1.0f / grad_scale;
+  tail_bwd_pass1_kernel<32><<<dim3(kGnbChunks, n), 256, 0, st>>>(xh, a, b, w, bias, sharpness, recon, target, grad_bce, grad_scale, S, dx14,
+                                                                partial, tailp);
+  NM_CHECK_LAUNCH("tail_bwd_pass1_kernel");
+  tail_reduce_kernel<<<1, 64, 0, st>>>(tailp, (long long)n * kGnbChunks, C, dw, dbias);
+  NM_CHECK_LAUNCH("tail_reduce_kernel");
+  gnb_grad_finalize_kernel<<<nm_cdiv((long long)n * groups, 4), 128, 0, st>>>(partial, gamma, mean_rstd, xsum, s, m12, chan);
+  NM_CHECK_LAUNCH("gnb_grad_finalize_kernel");
+  if (dgamma || dbeta || dxsum) {
+    gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, n, C, inv, dgamma, dbeta, dxsum);
+    NM_CHECK_LAUNCH("gnb_param_grad_kernel");
+  }
+  const long long total = (long long)n * S * s.ccs;
+  const int blocks = (int)min((long long)nm_num_sms() * 8, (total + kGnbThreads - 1) / kGnbThreads);
+  gnb_dx_rank1_kernel<<<blocks, kGnbThreads, 0, st>>>(xh, dx14, w, gamma, beta, mean_rstd, m12, s, reinterpret_cast<__half*>(grad_x));
+  NM_CHECK_LAUNCH("gnb_dx_rank1_kernel");
   return NM_OK;
 }

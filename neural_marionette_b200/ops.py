@@ -432,6 +432,27 @@ def final_recon_backward(raw, a, b, conv: torch.nn.Conv3d, first_frame, frames_p
     return dact, dw, db
 
 
+def final_recon_backward_fused(raw, a, b, conv: torch.nn.Conv3d, gn: torch.nn.GroupNorm, stats, sharpness, recon, target,
+                               grad_bce, scale: float):
+    """Decoder tail backward fused with the GroupNorm + LeakyReLU in front of it: -> (grad_raw act times `scale`,
+    dw14 (1, C, 1, 1, 1), db14 (1), dgamma (C), dbeta (C), dxsum (C) = bias gradient of the conv that produced `raw`)."""
+    n, D, H, W, C = raw.shape
+    S = D * H * W
+    dev = raw.device
+    w = f32(conv, "weight").reshape(-1)
+    bias = _cached(conv, "bias_host", [conv.bias], lambda: float(conv.bias.detach().float().item()))
+    draw = torch.empty_like(raw)
+    dw = torch.empty(1, C, 1, 1, 1, dtype=torch.float32, device=dev)
+    db = torch.empty(1, dtype=torch.float32, device=dev)
+    dg, dbeta, dxs = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(3))
+    ws = workspace(L.query("nm_final_recon_backward_fused_workspace_bytes", n, S, C, gn.num_groups), dev, "recon_bwd")
+    mr, xs = stats
+    L.call("nm_final_recon_backward_fused", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), bias, float(sharpness), L.ptr(recon),
+           L.ptr(target), L.ptr(grad_bce), float(scale), L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), L.ptr(mr), L.ptr(xs),
+           gn.num_groups, L.ptr(draw), L.ptr(dw), L.ptr(db), L.ptr(dg), L.ptr(dbeta), L.ptr(dxs), L.ptr(ws), n, S, C, L.stream())
+    return draw, dw, db, dg, dbeta, dxs
+
+
 def heatmap_head_backward(feature, conv1: torch.nn.Conv3d, K: int, mode: int, scale: float, prev=None,
                           frames_per_clip: int = 1, prop: Optional[torch.nn.Conv3d] = None, heat=None, keypoints=None,
                           heat_mean=None, grad_keypoints=None, grad_heat_mean=None, grad_heat=None, dq_in=None):

@@ -169,6 +169,46 @@ def test_final_recon_backward(ops):
     assert rel_err(db.cpu(), conv.bias.grad.cpu()) < 2e-3
 
 
+def test_final_recon_backward_fused(ops):
+    """The decoder tail fused with the GroupNorm + LeakyReLU in front of it (the rank-one gradient w.r.t. the activated
+    tensor is never written) against autograd over GN -> LeakyReLU -> 1x1 conv -> tanh / sigmoid -> BCE."""
+    import copy
+    g = torch.Generator().manual_seed(19)
+    n, G, C, T = 4, 16, 32, 2
+    raw = (h(torch.randn(n, C, G, G, G, generator=g)) * 1.3 + 0.2).requires_grad_(True)
+    gn = torch.nn.GroupNorm(2, C)
+    conv = torch.nn.Conv3d(C, 1, 1)
+    with torch.no_grad():
+        gn.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        gn.bias.copy_(0.3 * torch.randn(C, generator=g))
+        conv.weight.copy_(torch.randn(1, C, 1, 1, 1, generator=g) * 0.3)
+    ff = (torch.rand(n // T, 1, G, G, G, generator=g) < 0.3).float()
+    tgt = (torch.rand(n, 1, G, G, G, generator=g) < 0.3).float()
+    gb = torch.rand(n, generator=g) + 0.5
+    x14 = conv(F.leaky_relu(gn(raw), 0.01))
+    recon = torch.sigmoid(10.0 * (torch.tanh(x14) + ff.repeat_interleave(T, 0) - 0.5))
+    (F.binary_cross_entropy(recon, tgt, reduction="none").mean(dim=(1, 2, 3, 4)) * gb).sum().backward()
+    gn_c, conv_c = copy.deepcopy(gn).cuda(), copy.deepcopy(conv).cuda()
+    for p in list(gn_c.parameters()) + list(conv_c.parameters()):
+        p.grad = None
+    raw_c = to_act(raw.detach())
+    with ops.capture_gn_stats() as sink:
+        a, b = ops.gn_scale_shift(raw_c, gn_c)
+    rec_c, _ = ops.final_recon(raw_c, a, b, conv_c, ff[:, 0].contiguous().cuda(), T, 10.0, 0.5, target=tgt[:, 0].contiguous().cuda())
+    scale = 2.0 ** 10
+    draw, dw, db, dg, dbeta, dxs = ops.final_recon_backward_fused(raw_c, a, b, conv_c, gn_c, sink[0], 10.0, rec_c,
+                                                                 tgt[:, 0].contiguous().cuda(), gb.cuda(), scale)
+    diff = (from_act(draw) / scale - raw.grad).abs()
+    top = float(raw.grad.abs().max())
+    # elements whose pre-activation sits within fp32 rounding of zero may take the other LeakyReLU branch (their gradient
+    # then differs by O(1)): a handful of the 524 288 (measured 10); everything else agrees to fp16 output rounding
+    assert float((diff > 3e-3 * top).float().mean()) <= 1e-4 and float(diff.mean()) <= 3e-4 * top
+    assert rel_err(dw.cpu(), conv.weight.grad) < 2e-3 and rel_err(db.cpu(), conv.bias.grad) < 2e-3
+    assert rel_err(dg.cpu(), gn.weight.grad) < 2e-3 and rel_err(dbeta.cpu(), gn.bias.grad) < 2e-3
+    ref_bias = raw.grad.sum(dim=(0, 2, 3, 4))
+    assert float((dxs.cpu() - ref_bias).abs().max()) <= 1e-3 * float(raw.grad.abs().sum(dim=(0, 2, 3, 4)).max())
+
+
 # ------------------------------------------------------------------------------------------------ heads
 def _head_setup(seed, B, T, g, K=24):
     gen = torch.Generator().manual_seed(seed)
