@@ -47,8 +47,7 @@ __global__ void __launch_bounds__(kGwThreads, 1)
 wgrad_gather_kernel(const __half* __restrict__ Sx, const __half* __restrict__ Lx, GwShape g, float* __restrict__ partial) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int taps = g.k * g.k * g.k;
-  __half* sS = reinterpret_cast<__half*>(smem);                          // [KT][kGwRow]
-  __half* sL = sS + KT * kGwRow;                                         // [taps][KT][kGwRow]
+  __half* sS = reinterpret_cast<__half*>(smem);                          // per buffer: S tile [KT][kGwRow], L tiles [taps][KT][kGwRow]
   const int a0 = blockIdx.y * 32, b0 = blockIdx.z * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dl = g.Ds * g.stride, Hl = g.Hs * g.stride, Wl = g.Ws * g.stride;
@@ -65,42 +64,65 @@ wgrad_gather_kernel(const __half* __restrict__ Sx, const __half* __restrict__ Lx
 
   const int lj = lane >> 3, li = lane & 7;
   const long long tiles = (g.U + KT - 1) / KT;
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    __syncthreads();                                                     // the previous tile's fragments are consumed
+  // Few-tap layers (1x1, pool, transposed convs) are pure streaming: their tiles are double-buffered - the gather of tile
+  // i + 1 is in flight while tile i feeds the MMAs.  The 27-tap tile (143 KB) has no room for a second buffer.
+  constexpr bool kDouble = SLOTS == 1;
+  const int buf_halfs = (1 + taps) * KT * kGwRow;
+  auto stage = [&](long long tile, int buf) {
+    __half* bS = sS + (size_t)buf * buf_halfs;
+    __half* bL = bS + KT * kGwRow;
     for (int i = threadIdx.x; i < KT * 4; i += kGwThreads) {
       const int j = i >> 2, c = i & 3;
       const long long u = tile * KT + j;
       const bool uin = u < g.U;
-      const long long uu = uin ? u : 0;
-      const int w = (int)(uu % g.Ws), h = (int)((uu / g.Ws) % g.Hs), d = (int)((uu / ((long long)g.Ws * g.Hs)) % g.Ds);
-      const long long n = uu / ((long long)g.Ws * g.Hs * g.Ds);
+      const int uu = uin ? (int)u : 0;                                   // U < 2^31 (checked by the host): 32-bit index math
+      const int w = uu % g.Ws, q1 = uu / g.Ws, h = q1 % g.Hs, q2 = q1 / g.Hs, d = q2 % g.Ds;
+      const long long n = q2 / g.Ds;
       const bool aok = uin && (a0 + c * 8 < g.Ca);
-      gw_cp_async16(sS + j * kGwRow + c * 8, aok ? Sx + uu * g.Ca + a0 + c * 8 : Sx, aok ? 16 : 0);
+      gw_cp_async16(bS + j * kGwRow + c * 8, aok ? Sx + (long long)uu * g.Ca + a0 + c * 8 : Sx, aok ? 16 : 0);
       const bool bok = uin && (b0 + c * 8 < g.Cb);
       for (int t = 0; t < taps; t++) {
         const int kw = t % g.k, kh = (t / g.k) % g.k, kd = t / (g.k * g.k);
         const int dd = d * g.stride + kd - g.pad, hh = h * g.stride + kh - g.pad, ww = w * g.stride + kw - g.pad;
         const bool ok = bok && (unsigned)dd < (unsigned)Dl && (unsigned)hh < (unsigned)Hl && (unsigned)ww < (unsigned)Wl;
         const __half* src = ok ? Lx + ((((long long)n * Dl + dd) * Hl + hh) * Wl + ww) * g.Cb + b0 + c * 8 : Lx;
-        gw_cp_async16(sL + ((long long)t * KT + j) * kGwRow + c * 8, src, ok ? 16 : 0);
+        gw_cp_async16(bL + ((long long)t * KT + j) * kGwRow + c * 8, src, ok ? 16 : 0);
       }
     }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if (kDouble && (long long)blockIdx.x < tiles) stage(blockIdx.x, 0);
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    if (kDouble) {
+      if (tile + gridDim.x < tiles) {
+        stage(tile + gridDim.x, buf ^ 1);                                // next tile in flight
+        asm volatile("cp.async.wait_group 1;" ::: "memory");             // this tile has landed
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+    } else {
+      __syncthreads();                                                   // the previous tile's fragments are consumed
+      stage(tile, 0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     __syncthreads();
+    const __half* cS = sS + (size_t)buf * buf_halfs;
+    const __half* cL = cS + KT * kGwRow;
 #pragma unroll 1
     for (int k0 = 0; k0 < KT; k0 += 16) {
       if (taps == 1 && (k0 >> 4) != warp) continue;                      // k1: one K step per warp
       uint32_t a[2][4];
 #pragma unroll
       for (int m = 0; m < 2; m++) {
-        const __half* p = sS + (k0 + (lj >> 1) * 8 + li) * kGwRow + m * 16 + (lj & 1) * 8;
+        const __half* p = cS + (k0 + (lj >> 1) * 8 + li) * kGwRow + m * 16 + (lj & 1) * 8;
         gw_ldmatrix_x4_trans((uint32_t)__cvta_generic_to_shared(p), a[m][0], a[m][1], a[m][2], a[m][3]);
       }
 #pragma unroll
       for (int s = 0; s < SLOTS; s++) {
         const int tap = taps == 1 ? 0 : warp + 8 * s;
         if (tap < taps) {
-          const __half* base = sL + ((long long)tap * KT + k0) * kGwRow;
+          const __half* base = cL + ((long long)tap * KT + k0) * kGwRow;
 #pragma unroll
           for (int np = 0; np < 2; np++) {
             const __half* p = base + ((lj & 1) * 8 + li) * kGwRow + np * 16 + (lj >> 1) * 8;
@@ -114,6 +136,10 @@ wgrad_gather_kernel(const __half* __restrict__ Sx, const __half* __restrict__ Lx
           }
         }
       }
+    }
+    if (kDouble) {
+      __syncthreads();                                                   // this buffer may be overwritten two tiles on
+      buf ^= 1;
     }
   }
   // partial[part][a block][b block][tap][32][32]; part = chunk (k2 / k3) or chunk * 8 + warp (k1)
@@ -162,6 +188,7 @@ int gw_chunks(const GwShape& g) {
 bool gw_shape(int N, int Ds, int Hs, int Ws, int Ca, int Cb, int k, int stride, GwShape* g) {
   if (N <= 0 || Ds <= 0 || Hs <= 0 || Ws <= 0 || Ca <= 0 || Cb <= 0 || Ca % 8 || Cb % 8 || Ca > 256 || Cb > 256) return false;
   if (!((stride == 1 && (k == 1 || k == 3)) || (stride == 2 && k == 2))) return false;
+  if ((long long)N * Ds * Hs * Ws >= (1LL << 31)) return false;
   *g = GwShape{N, Ds, Hs, Ws, Ca, Cb, k, stride, stride == 1 ? (k - 1) / 2 : 0, (long long)N * Ds * Hs * Ws};
   return true;
 }
@@ -185,8 +212,9 @@ extern "C" int nm_conv3d_wgrad_gather(const void* small_side, const void* large_
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = gw_chunks(g), taps = k * k * k, KT = gw_tile(k);
   const int ab = (Ca + 31) / 32, bb = (Cb + 31) / 32;
-  const size_t smem = (size_t)(1 + taps) * KT * kGwRow * sizeof(__half);
+  const size_t smem = (size_t)(1 + taps) * KT * kGwRow * sizeof(__half) * (k == 3 ? 1 : 2);   // few-tap tiles are double-buffered
   NM_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gather_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  NM_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gather_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   const dim3 grid(chunks, ab, bb);
   const __half* S = reinterpret_cast<const __half*>(small_side);
   const __half* L = reinterpret_cast<const __half*>(large_side);
