@@ -8,6 +8,7 @@
 The profile and the build must come from the same source (the instruction counts are checked)."""
 import collections
 import csv
+import os
 import re
 import sys
 
@@ -17,7 +18,7 @@ line, ins = None, []
 for l in open(sass):
     m = re.search(r'//## File "(.*)", line (\d+)', l)
     if m:
-        line = int(m.group(2)) if m.group(1).endswith(cu.split("/")[-1]) else -1
+        line = int(m.group(2)) if m.group(1).endswith(cu.split("/")[-1]) else m.group(1).split("/")[-1] + ":" + m.group(2)
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
@@ -39,5 +40,10 @@ text = open(cu).read().split("\n")
 print("| line | samples | warp instructions | top stall reasons | source |\n|---|---|---|---|---|")
 for l, v in sorted(by.items(), key=lambda kv: -kv[1][0])[:top]:
     reasons = ", ".join(f"{k} {100 * c / max(v[0], 1):.0f}%" for k, c in v[2].most_common(3))
-    code = text[l - 1].strip()[:100].replace("|", "\\|") if l and l > 0 else "(inlined from another file / no line info)"
+    if isinstance(l, int):
+        code = text[l - 1].strip()[:100].replace("|", "\\|")
+    elif l and os.path.exists(os.path.join(os.path.dirname(cu), l.split(":")[0])):
+        code = open(os.path.join(os.path.dirname(cu), l.split(":")[0])).read().split("\n")[int(l.split(":")[1]) - 1].strip()[:100].replace("|", "\\|")
+    else:
+        code = "(inlined from another file / no line info)"
     print(f"| {l} | {100 * v[0] / tot:.1f}% | {v[1]} | {reasons} | `{code}` |")
