@@ -149,14 +149,23 @@ final_recon_bwd_kernel(const __half* __restrict__ x, const float* __restrict__ a
   }
 }
 
-// out[j] = scale * sum_r partial[r * ld + j], j < cols (fixed order, fp64)
-__global__ void reduce_cols_kernel(const float* __restrict__ partial, long long rows, int ld, int cols, float scale,
-                                   float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
+// out[j] = scale * sum_r partial[r * ld + j], j < cols: fp64, fixed order (8 interleaved row groups per column, combined
+// in order).  Launch with blockDim (32, 8).
+__global__ void __launch_bounds__(256)
+reduce_cols_kernel(const float* __restrict__ partial, long long rows, int ld, int cols, float scale, float* __restrict__ out) {
+  __shared__ double red[8][32];
+  const int j = blockIdx.x * 32 + threadIdx.x;
   double acc = 0.0;
-  for (long long r = 0; r < rows; r++) acc += (double)partial[r * ld + j];
-  out[j] = (float)(acc * (double)scale);
+  if (j < cols)
+    for (long long r = threadIdx.y; r < rows; r += 8) acc += (double)partial[r * ld + j];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < cols) {
+    double t = 0.0;
+#pragma unroll
+    for (int y = 0; y < 8; y++) t += red[y][threadIdx.x];
+    out[j] = (float)(t * (double)scale);
+  }
 }
 
 // ------------------------------------------------------------------ heat-map head backward
@@ -167,6 +176,12 @@ __global__ void reduce_cols_kernel(const float* __restrict__ partial, long long 
 //   dq = dhm * (1 - exp(-hm));  du = pw0 dq lrelu'(u)
 // mode 0 (spatio-temporal head): h = lrelu(u) is the output; dh[k][s] = pw1 * sum_t dq[clip*T + t][k][s]
 // outputs: dfeat = grad_scale * W1^T du (fp16), dq (mode 1), per-frame partials of dW1, db1, (dpw0, dpw1, dpb).
+// Work split: grid (frame, voxel split); a CTA walks its share of the S / 64 voxel tiles.  All three contractions are
+// register-tiled over shared memory (the first version did one FMA per two shared loads and was bound by the LDS pipe:
+// 2.05 ms for 240 frames, 2.7 ms for the 24 clips of the 256-channel head on 24 CTAs):
+//   u  [k][s] = w1 f      thread = (voxel, 6 keypoints): per 4 channels 1 LDS.128 of f + 6 broadcast LDS.128 of w1, 24 FMA
+//   dfeat[s][c] = W1^T du thread = (4 voxels, 8 channels): per keypoint 1 + 2 LDS.128, 32 FMA
+//   dW1[k][c] += du f^T   thread = (channel, 12 or 24 keypoints): per voxel 1 LDS + 3 or 6 broadcast LDS.128, 12 or 24 FMA
 template <int C>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const __half* __restrict__ feature, const float* __restrict__ w1, const float* __restrict__ b1, int K, int g,
@@ -174,18 +189,22 @@ head_bwd_kernel(const __half* __restrict__ feature, const float* __restrict__ w1
                 const float* __restrict__ lin, const float* __restrict__ heat, const float* __restrict__ kp,
                 const float* __restrict__ heat_mean, const float* __restrict__ dkp, const float* __restrict__ dmean_up,
                 const float* __restrict__ dheat, const float* __restrict__ dq_in, float grad_scale,
-                __half* __restrict__ dfeat, float* __restrict__ dq_out, float* __restrict__ pw_partial /* [n][K][C] */,
-                float* __restrict__ pb_partial /* [n][K] */, float* __restrict__ pp_partial /* [n][3] */) {
+                __half* __restrict__ dfeat, float* __restrict__ dq_out, float* __restrict__ pw_partial /* [n*splits][K][C] */,
+                float* __restrict__ pb_partial /* [n*splits][K] */, float* __restrict__ pp_partial /* [n*splits][3] */) {
   constexpr int TS = 64;                                   // voxels per tile
-  constexpr int FS = C + 1;                                // fp32 feature row stride (odd: conflict-free column reads)
-  constexpr int KPT = KMAX * C / 256;                      // dW1 accumulators per thread
+  constexpr int FS = C + 4;                                // fp32 feature row stride: 16-byte aligned rows, conflict-free LDS.128
+  constexpr int KPT = KMAX * C / 256;                      // dW1 accumulators per thread (12 or 24)
+  constexpr int NC8 = C / 8, VPT = TS / (256 / NC8);       // dfeat: voxels per thread (4 or 8, in rounds of 4)
   extern __shared__ __align__(16) float smem[];
   float* s_w = smem;                                       // [KMAX][C]
   float* s_f = s_w + KMAX * C;                             // [TS][FS]
   float* s_du = s_f + TS * FS;                             // [KMAX][TS]
-  float* s_co = s_du + KMAX * TS;                          // [KMAX][4]: A, Bx, By, Bz
+  float* s_duT = s_du + KMAX * TS;                         // [TS][KMAX]
+  float* s_co = s_duT + TS * KMAX;                         // [KMAX][4]: A, Bx, By, Bz
   float* s_red = s_co + KMAX * 4;                          // [256][3]
   const int n = blockIdx.x, S = g * g * g;
+  const int tiles = (S / TS) / gridDim.y, tile0 = blockIdx.y * tiles;
+  const long long part = (long long)n * gridDim.y + blockIdx.y;
   const int clip = n / frames_per_clip;
   for (int i = threadIdx.x; i < KMAX * C; i += 256) s_w[i] = (i / C) < K ? w1[i] : 0.f;
   if (mode == 1 && threadIdx.x < KMAX) {
@@ -224,35 +243,46 @@ head_bwd_kernel(const __half* __restrict__ feature, const float* __restrict__ w1
   float accb = 0.f, sp0 = 0.f, sp1 = 0.f, sp2 = 0.f;
   const int wc = threadIdx.x % C, wk0 = (threadIdx.x / C) * KPT;      // dW1 ownership: channel wc, keypoints wk0..
   const __half* fbase = feature + (long long)n * S * C;
-  for (int s0 = 0; s0 < S; s0 += TS) {
-    // feature tile -> fp32 shared
-    for (int i = threadIdx.x; i < TS * (C / 8); i += 256) {
-      const int sl = i / (C / 8), c8 = i % (C / 8);
-      float f[8];
-      nm_unpack8(*reinterpret_cast<const half8*>(fbase + (long long)(s0 + sl) * C + c8 * 8), f);
-#pragma unroll
-      for (int k = 0; k < 8; k++) s_f[sl * FS + c8 * 8 + k] = f[k];
+  for (int tile = tile0; tile < tile0 + tiles; tile++) {
+    const int s0 = tile * TS;
+    // feature tile -> fp32 shared (4 channels per thread: conflict-free 16-byte stores)
+    for (int i = threadIdx.x; i < TS * (C / 4); i += 256) {
+      const int sl = i / (C / 4), c4 = i % (C / 4);
+      const uint2 raw = *reinterpret_cast<const uint2*>(fbase + (long long)(s0 + sl) * C + c4 * 4);
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+      *reinterpret_cast<float4*>(s_f + sl * FS + c4 * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
     }
     __syncthreads();
     {
       // u, dq, du for 6 keypoints of one voxel
+      constexpr int KG = KMAX / 4;
       const int sl = threadIdx.x % TS, kg = threadIdx.x / TS, s = s0 + sl;
+      float u[KG];
+#pragma unroll
+      for (int j = 0; j < KG; j++) u[j] = kg * KG + j < K ? b1[kg * KG + j] : 0.f;
+      const float* fr = s_f + sl * FS;
+      const float* wr = s_w + kg * KG * C;
+#pragma unroll 2
+      for (int c = 0; c < C; c += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(fr + c);
+#pragma unroll
+        for (int j = 0; j < KG; j++) {
+          const float4 w = *reinterpret_cast<const float4*>(wr + j * C + c);
+          u[j] = fmaf(w.x, f.x, fmaf(w.y, f.y, fmaf(w.z, f.z, fmaf(w.w, f.w, u[j]))));
+        }
+      }
       const int x = s / (g * g), y = (s / g) % g, z = s % g;
       const float lx = lin[x], ly = lin[y], lz = lin[z];
 #pragma unroll
-      for (int kk = 0; kk < KMAX / 4; kk++) {
-        const int k = kg * (KMAX / 4) + kk;
+      for (int j = 0; j < KG; j++) {
+        const int k = kg * KG + j;
         float du = 0.f;
         if (k < K) {
-          float u = b1[k];
-          const float* fr = s_f + sl * FS;
-          const float* wr = s_w + k * C;
-#pragma unroll 8
-          for (int c = 0; c < C; c++) u = fmaf(wr[c], fr[c], u);
-          const float slope = u > 0.f ? 1.f : 0.01f;
+          const float slope = u[j] > 0.f ? 1.f : 0.01f;
           float dh;
           if (mode == 1) {
-            const float h = u > 0.f ? u : 0.01f * u;
+            const float h = u[j] > 0.f ? u[j] : 0.01f * u[j];
             const float pv = prev[((long long)clip * K + k) * S + s];
             const float hm = heat[((long long)n * K + k) * S + s];
             float dhm = s_co[k * 4] + s_co[k * 4 + 1] * lx + s_co[k * 4 + 2] * ly + s_co[k * 4 + 3] * lz;
@@ -274,51 +304,80 @@ head_bwd_kernel(const __half* __restrict__ feature, const float* __restrict__ w1
           du = dh * slope;
         }
         s_du[k * TS + sl] = du;
+        s_duT[sl * KMAX + k] = du;
       }
     }
     __syncthreads();
-    // dfeat[s][c] = grad_scale * sum_k du[k][s] w1[k][c]
-    for (int i = threadIdx.x; i < TS * (C / 8); i += 256) {
-      const int sl = i / (C / 8), c8 = i % (C / 8);
-      float o[8];
+    // dfeat[s][c] = grad_scale * sum_k du[k][s] w1[k][c]: thread = (4 voxels, channels c8*4 .. +3 and C/2 + c8*4 .. +3)
+    {
+      const int c8 = threadIdx.x % NC8, slg = threadIdx.x / NC8;
+#pragma unroll 1
+      for (int v0 = 0; v0 < VPT; v0 += 4) {
+        const int slb = slg * VPT + v0;
+        float o[4][8];
 #pragma unroll
-      for (int e = 0; e < 8; e++) o[e] = 0.f;
-      for (int k = 0; k < K; k++) {
-        const float d = s_du[k * TS + sl];
-        const float* wr = s_w + k * C + c8 * 8;
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = fmaf(d, wr[e], o[e]);
+          for (int e = 0; e < 8; e++) o[i][e] = 0.f;
+        for (int k = 0; k < K; k++) {
+          const float4 d = *reinterpret_cast<const float4*>(s_du + k * TS + slb);
+          const float4 w0 = *reinterpret_cast<const float4*>(s_w + k * C + c8 * 4);
+          const float4 w1v = *reinterpret_cast<const float4*>(s_w + k * C + C / 2 + c8 * 4);
+          const float dv[4] = {d.x, d.y, d.z, d.w};
+          const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1v.x, w1v.y, w1v.z, w1v.w};
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) o[i][e] = fmaf(dv[i], wv[e], o[i][e]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          __half2 h[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) h[e] = __floats2half2_rn(o[i][2 * e] * grad_scale, o[i][2 * e + 1] * grad_scale);
+          __half* dst = dfeat + ((long long)n * S + s0 + slb + i) * C + c8 * 4;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]));
+          *reinterpret_cast<uint2*>(dst + C / 2) = make_uint2(*reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+        }
       }
-#pragma unroll
-      for (int e = 0; e < 8; e++) o[e] *= grad_scale;
-      *reinterpret_cast<half8*>(dfeat + ((long long)n * S + s0 + sl) * C + c8 * 8) = nm_pack8(o);
     }
     // dW1[k][c] += sum_s du[k][s] f[s][c];  db1[k] += sum_s du[k][s]
+#pragma unroll 2
+    for (int sl = 0; sl < TS; sl++) {
+      const float f = s_f[sl * FS + wc];
+      const float4* dr = reinterpret_cast<const float4*>(s_duT + sl * KMAX + wk0);
 #pragma unroll
-    for (int i = 0; i < KPT; i++) {
-      const float* dr = s_du + (wk0 + i) * TS;
-      float t = 0.f;
-      for (int sl = 0; sl < TS; sl++) t = fmaf(dr[sl], s_f[sl * FS + wc], t);
-      accw[i] += t;
+      for (int q = 0; q < KPT / 4; q++) {
+        const float4 d = dr[q];
+        accw[q * 4] = fmaf(d.x, f, accw[q * 4]);
+        accw[q * 4 + 1] = fmaf(d.y, f, accw[q * 4 + 1]);
+        accw[q * 4 + 2] = fmaf(d.z, f, accw[q * 4 + 2]);
+        accw[q * 4 + 3] = fmaf(d.w, f, accw[q * 4 + 3]);
+      }
     }
     if (threadIdx.x < KMAX) {
+      const float4* dr = reinterpret_cast<const float4*>(s_du + threadIdx.x * TS);
       float t = 0.f;
-      for (int sl = 0; sl < TS; sl++) t += s_du[threadIdx.x * TS + sl];
+#pragma unroll 4
+      for (int q = 0; q < TS / 4; q++) {
+        const float4 d = dr[q];
+        t += (d.x + d.y) + (d.z + d.w);
+      }
       accb += t;
     }
     __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < KPT; i++)
-    if (wk0 + i < K) pw_partial[((long long)n * K + wk0 + i) * C + wc] = accw[i];
-  if (threadIdx.x < K) pb_partial[(long long)n * K + threadIdx.x] = accb;
+    if (wk0 + i < K) pw_partial[(part * K + wk0 + i) * C + wc] = accw[i];
+  if (threadIdx.x < K) pb_partial[part * K + threadIdx.x] = accb;
   if (mode == 1) {
     s_red[threadIdx.x * 3] = sp0; s_red[threadIdx.x * 3 + 1] = sp1; s_red[threadIdx.x * 3 + 2] = sp2;
     __syncthreads();
     if (threadIdx.x < 3) {
       float t = 0.f;
       for (int i = 0; i < 256; i++) t += s_red[i * 3 + threadIdx.x];
-      pp_partial[(long long)n * 3 + threadIdx.x] = t;
+      pp_partial[part * 3 + threadIdx.x] = t;
     }
   }
 }
@@ -327,8 +386,12 @@ head_bwd_kernel(const __half* __restrict__ feature, const float* __restrict__ w1
 // forward: y = lrelu(W cat[G_t (K), ff (128), G_0 (K), coords (3)] + b), G[k][s] = ex[x] ey[y] ez[z] I_k
 // dz = dy / grad_scale * lrelu'(y).  Per frame: dG_t = W[:, :K]^T dz -> d keypoints (render backward), dW[:, :K], db.
 // Per clip (on sum_t dz): d first_feature, d keypoints of frame 0 (through G_0), dW[:, K:].
+// All contractions are register-tiled over shared memory (the first version issued two shared loads per FMA and was
+// bound by the LDS pipe: 1.4 + 1.3 ms per step); dz lives in shared memory in both orientations.
 constexpr int kAdjC = 128;
 constexpr int kAdjTS = 64;
+constexpr int kAdjDS = kAdjTS + 4;     // s_dz  [co][68]: 16-byte aligned rows (broadcast LDS.128 over voxels)
+constexpr int kAdjDT = kAdjC + 4;      // s_dzT [sl][132]: conflict-free 16-byte stores with lanes over voxels
 
 __device__ __forceinline__ void adj_stage_exps(const float* kp, int K, int g, const float* lin, float width, float* s_e, float* s_kp) {
   for (int i = threadIdx.x; i < K * 3 * g; i += 256) {
@@ -339,31 +402,38 @@ __device__ __forceinline__ void adj_stage_exps(const float* kp, int K, int g, co
   for (int i = threadIdx.x; i < K * 4; i += 256) s_kp[i] = kp[i];
 }
 
-// dz tile -> shared, transposed [co][TS + 1]; frames = 1 (per-frame kernel) or T (sum over the clip's frames)
+// dz tile -> shared as s_dz [co][kAdjDS] and s_dzT [sl][kAdjDT]; frames = 1 (per-frame kernel) or T (sum over the clip's
+// frames).  Lanes run over voxels: both shared stores are conflict-free, the 8-byte global loads of a lane walk its
+// voxel's 256-byte channel row (sectors are reused from L1 by the next channel groups).
 __device__ __forceinline__ void adj_load_dz(const __half* dy, const __half* y, long long frame0, int frames, int S, int s0,
-                                            float inv_scale, float* s_dz) {
-  for (int i = threadIdx.x; i < kAdjTS * (kAdjC / 8); i += 256) {
-    const int sl = i / (kAdjC / 8), c8 = i % (kAdjC / 8);
-    float acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; e++) acc[e] = 0.f;
+                                            float inv_scale, float* s_dz, float* s_dzT) {
+  for (int i = threadIdx.x; i < kAdjTS * (kAdjC / 4); i += 256) {
+    const int sl = i % kAdjTS, c4 = i / kAdjTS;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int t = 0; t < frames; t++) {
-      const long long off = ((frame0 + t) * S + s0 + sl) * kAdjC + c8 * 8;
-      float d[8], o[8];
-      nm_unpack8(*reinterpret_cast<const half8*>(dy + off), d);
-      nm_unpack8(*reinterpret_cast<const half8*>(y + off), o);
-#pragma unroll
-      for (int e = 0; e < 8; e++) acc[e] += o[e] > 0.f ? d[e] : 0.01f * d[e];
+      const long long off = ((frame0 + t) * S + s0 + sl) * kAdjC + c4 * 4;
+      const uint2 rd = *reinterpret_cast<const uint2*>(dy + off), ro = *reinterpret_cast<const uint2*>(y + off);
+      const float2 d0 = __half22float2(*reinterpret_cast<const __half2*>(&rd.x)), d1 = __half22float2(*reinterpret_cast<const __half2*>(&rd.y));
+      const float2 o0 = __half22float2(*reinterpret_cast<const __half2*>(&ro.x)), o1 = __half22float2(*reinterpret_cast<const __half2*>(&ro.y));
+      acc[0] += o0.x > 0.f ? d0.x : 0.01f * d0.x;
+      acc[1] += o0.y > 0.f ? d0.y : 0.01f * d0.y;
+      acc[2] += o1.x > 0.f ? d1.x : 0.01f * d1.x;
+      acc[3] += o1.y > 0.f ? d1.y : 0.01f * d1.y;
     }
 #pragma unroll
-    for (int e = 0; e < 8; e++) s_dz[(c8 * 8 + e) * (kAdjTS + 1) + sl] = acc[e] * inv_scale;
+    for (int e = 0; e < 4; e++) {
+      acc[e] *= inv_scale;
+      s_dz[(c4 * 4 + e) * kAdjDS + sl] = acc[e];
+    }
+    *reinterpret_cast<float4*>(s_dzT + sl * kAdjDT + c4 * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
   }
 }
 
 // render backward accumulation for the keypoints owned by this thread (6 of them, one voxel)
 struct RenderAcc { float v[KMAX / 4][4]; };
 
-__device__ __forceinline__ void adj_gauss_tile(const float* s_e, const float* s_kp, int K, int g, int s0, float* s_G) {
+// Gaussians of the tile, voxel-major: s_GT[sl][KMAX]
+__device__ __forceinline__ void adj_gauss_tile(const float* s_e, const float* s_kp, int K, int g, int s0, float* s_GT) {
   for (int i = threadIdx.x; i < KMAX * kAdjTS; i += 256) {
     const int k = i / kAdjTS, sl = i % kAdjTS, s = s0 + sl;
     float v = 0.f;
@@ -371,30 +441,64 @@ __device__ __forceinline__ void adj_gauss_tile(const float* s_e, const float* s_
       const int x = s / (g * g), yy = (s / g) % g, z = s % g;
       v = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + yy]) * s_e[(k * 3 + 2) * 32 + z] * s_kp[k * 4 + 3];
     }
-    s_G[i] = v;
+    s_GT[sl * KMAX + k] = v;
   }
 }
 
-// dG[k][s] = sum_co W[co][col0 + k] dz[co][s] for this thread's 6 keypoints, accumulated into the render gradient
+// dG[k][s] = sum_co W[co][col0 + k] dz[co][s] for this thread's 6 keypoints (per co: one LDS of dz, three broadcast
+// LDS.64 of the weights, 6 FMA), accumulated into the render gradient
 __device__ __forceinline__ void adj_render_bwd(const float* s_wg /* [128][KMAX] */, const float* s_dz, const float* s_e,
                                                const float* s_kp, const float* lin, int K, int g, int s0, float width,
                                                RenderAcc& r) {
+  constexpr int KG = KMAX / 4;
   const int sl = threadIdx.x % kAdjTS, kg = threadIdx.x / kAdjTS, s = s0 + sl;
   const int x = s / (g * g), yy = (s / g) % g, z = s % g;
   const float lx = lin[x], ly = lin[yy], lz = lin[z];
+  float dG[KG];
 #pragma unroll
-  for (int kk = 0; kk < KMAX / 4; kk++) {
-    const int k = kg * (KMAX / 4) + kk;
+  for (int j = 0; j < KG; j++) dG[j] = 0.f;
+  const float* wr = s_wg + kg * KG;
+#pragma unroll 4
+  for (int co = 0; co < kAdjC; co++) {
+    const float d = s_dz[co * kAdjDS + sl];
+    const float2* w2 = reinterpret_cast<const float2*>(wr + co * KMAX);
+#pragma unroll
+    for (int j = 0; j < KG / 2; j++) {
+      const float2 w = w2[j];
+      dG[2 * j] = fmaf(w.x, d, dG[2 * j]);
+      dG[2 * j + 1] = fmaf(w.y, d, dG[2 * j + 1]);
+    }
+  }
+#pragma unroll
+  for (int kk = 0; kk < KG; kk++) {
+    const int k = kg * KG + kk;
     if (k < K) {
-      float dG = 0.f;
-      for (int co = 0; co < kAdjC; co++) dG = fmaf(s_wg[co * KMAX + k], s_dz[co * (kAdjTS + 1) + sl], dG);
       const float E = ((1.0f * s_e[(k * 3) * 32 + x]) * s_e[(k * 3 + 1) * 32 + yy]) * s_e[(k * 3 + 2) * 32 + z];
-      const float gG = dG * E * s_kp[k * 4 + 3] * (2.f / width);
+      const float gG = dG[kk] * E * s_kp[k * 4 + 3] * (2.f / width);
       r.v[kk][0] = fmaf(gG, lx - s_kp[k * 4], r.v[kk][0]);
       r.v[kk][1] = fmaf(gG, ly - s_kp[k * 4 + 1], r.v[kk][1]);
       r.v[kk][2] = fmaf(gG, lz - s_kp[k * 4 + 2], r.v[kk][2]);
-      r.v[kk][3] = fmaf(dG, E, r.v[kk][3]);
+      r.v[kk][3] = fmaf(dG[kk], E, r.v[kk][3]);
     }
+  }
+}
+
+// dWg[co][k0 .. k0+11] += sum_s dz[co][s] G[k][s] (thread = output channel co, 12 keypoints; per voxel one LDS of dz and
+// three broadcast LDS.128 of the Gaussians); returns sum_s dz[co][s] through `dsum`
+__device__ __forceinline__ void adj_wg_accumulate(const float* s_dzT, const float* s_GT, int co, int k0, float (&acc)[12], float& dsum) {
+#pragma unroll 2
+  for (int sl = 0; sl < kAdjTS; sl++) {
+    const float d = s_dzT[sl * kAdjDT + co];
+    const float4* gr = reinterpret_cast<const float4*>(s_GT + sl * KMAX + k0);
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const float4 gv = gr[q];
+      acc[q * 4] = fmaf(d, gv.x, acc[q * 4]);
+      acc[q * 4 + 1] = fmaf(d, gv.y, acc[q * 4 + 1]);
+      acc[q * 4 + 2] = fmaf(d, gv.z, acc[q * 4 + 2]);
+      acc[q * 4 + 3] = fmaf(d, gv.w, acc[q * 4 + 3]);
+    }
+    dsum += d;
   }
 }
 
@@ -414,6 +518,11 @@ __device__ __forceinline__ void adj_render_store(const RenderAcc& r, float* s_tm
   __syncthreads();
 }
 
+// shared-memory floats: frame kernel / extra of the clip kernel (s_tmp of adj_render_store aliases s_dz .. s_dzT)
+constexpr int kAdjFrameFloats = kAdjC * KMAX + kAdjC * kAdjDS + kAdjTS * kAdjDT + kAdjTS * KMAX + KMAX * 96 + KMAX * 4;
+constexpr int kAdjClipFloats = kAdjFrameFloats + kAdjC * kAdjC + kAdjTS * kAdjC + kAdjTS * 4;
+static_assert(256 * 24 <= kAdjC * kAdjDS + kAdjTS * kAdjDT, "s_tmp must fit in the dz buffers");
+
 __global__ void __launch_bounds__(256)
 adjust_bwd_frame_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const float* __restrict__ kp,
                         const float* __restrict__ W, int ld, int K, int g, const float* __restrict__ lin, float width,
@@ -421,11 +530,12 @@ adjust_bwd_frame_kernel(const __half* __restrict__ dy, const __half* __restrict_
                         float* __restrict__ pbias /* [n][128] */) {
   extern __shared__ __align__(16) float smem[];
   float* s_wg = smem;                                     // [128][KMAX]
-  float* s_dz = s_wg + kAdjC * KMAX;                      // [128][TS + 1]
-  float* s_G = s_dz + kAdjC * (kAdjTS + 1);               // [KMAX][TS]
-  float* s_e = s_G + KMAX * kAdjTS;                       // [KMAX][3][32]
+  float* s_dz = s_wg + kAdjC * KMAX;                      // [128][kAdjDS]
+  float* s_dzT = s_dz + kAdjC * kAdjDS;                   // [TS][kAdjDT]
+  float* s_GT = s_dzT + kAdjTS * kAdjDT;                  // [TS][KMAX]
+  float* s_e = s_GT + kAdjTS * KMAX;                      // [KMAX][3][32]
   float* s_kp = s_e + KMAX * 96;                          // [KMAX][4]
-  float* s_tmp = s_kp + KMAX * 4;                         // [256][24]
+  float* s_tmp = s_dz;                                    // [256][24], after the tile loop
   const int n = blockIdx.x, S = g * g * g;
   for (int i = threadIdx.x; i < kAdjC * KMAX; i += 256) {
     const int co = i / KMAX, k = i % KMAX;
@@ -443,24 +553,12 @@ adjust_bwd_frame_kernel(const __half* __restrict__ dy, const __half* __restrict_
   for (int i = 0; i < 12; i++) accw[i] = 0.f;
   const int wco = threadIdx.x % kAdjC, wk0 = (threadIdx.x / kAdjC) * 12;
   for (int s0 = 0; s0 < S; s0 += kAdjTS) {
-    adj_load_dz(dy, y, n, 1, S, s0, inv_scale, s_dz);
-    adj_gauss_tile(s_e, s_kp, K, g, s0, s_G);
+    adj_load_dz(dy, y, n, 1, S, s0, inv_scale, s_dz, s_dzT);
+    adj_gauss_tile(s_e, s_kp, K, g, s0, s_GT);
     __syncthreads();
     adj_render_bwd(s_wg, s_dz, s_e, s_kp, lin, K, g, s0, width, r);
     // dW[co][k] += sum_s dz[co][s] G[k][s];  db[co] += sum_s dz[co][s]
-    const float* dr = s_dz + wco * (kAdjTS + 1);
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-      const float* gr = s_G + (wk0 + i) * kAdjTS;
-      float t = 0.f;
-      for (int sl = 0; sl < kAdjTS; sl++) t = fmaf(dr[sl], gr[sl], t);
-      accw[i] += t;
-    }
-    if (threadIdx.x < kAdjC) {
-      float t = 0.f;
-      for (int sl = 0; sl < kAdjTS; sl++) t += dr[sl];
-      accb += t;
-    }
+    adj_wg_accumulate(s_dzT, s_GT, wco, wk0, accw, accb);
     __syncthreads();
   }
   adj_render_store(r, s_tmp, K, dkp + (long long)n * K * 4);
@@ -477,14 +575,16 @@ adjust_bwd_clip_kernel(const __half* __restrict__ dy, const __half* __restrict__
                        __half* __restrict__ dff /* [clips][S][128] */, float* __restrict__ dkp0 /* [clips][splits][K][4] */,
                        float* __restrict__ pw /* [clips][splits][128][128 + KMAX + 3] */) {
   extern __shared__ __align__(16) float smem[];
-  float* s_wff = smem;                                    // [128 co][128 c]
-  float* s_wg = s_wff + kAdjC * kAdjC;                    // [128][KMAX]  (gauss_0 columns)
-  float* s_dz = s_wg + kAdjC * KMAX;                      // [128][TS + 1]
-  float* s_ff = s_dz + kAdjC * (kAdjTS + 1);              // [TS][128]
-  float* s_G = s_ff + kAdjTS * kAdjC;                     // [KMAX][TS]
-  float* s_e = s_G + KMAX * kAdjTS;                       // [KMAX][3][32]
+  float* s_wg = smem;                                     // [128][KMAX]  (gauss_0 columns)
+  float* s_dz = s_wg + kAdjC * KMAX;                      // [128][kAdjDS]
+  float* s_dzT = s_dz + kAdjC * kAdjDS;                   // [TS][kAdjDT]
+  float* s_GT = s_dzT + kAdjTS * kAdjDT;                  // [TS][KMAX]
+  float* s_e = s_GT + kAdjTS * KMAX;                      // [KMAX][3][32]
   float* s_kp = s_e + KMAX * 96;                          // [KMAX][4]
-  float* s_tmp = s_kp + KMAX * 4;                         // [256][24]
+  float* s_wff = s_kp + KMAX * 4;                         // [128 co][128 c]
+  float* s_ff = s_wff + kAdjC * kAdjC;                    // [TS][128]
+  float* s_xyz = s_ff + kAdjTS * kAdjC;                   // [TS][4]: lin[x], lin[y], lin[z] of the tile's voxels
+  float* s_tmp = s_dz;                                    // [256][24], after the tile loop
   const int clip = blockIdx.x, split = blockIdx.y, splits = gridDim.y, S = g * g * g;
   const int per = S / splits;                             // multiple of TS (checked by the host)
   for (int i = threadIdx.x; i < kAdjC * kAdjC; i += 256) s_wff[i] = W[(long long)(i / kAdjC) * ld + K + i % kAdjC];
@@ -499,56 +599,90 @@ adjust_bwd_clip_kernel(const __half* __restrict__ dy, const __half* __restrict__
   for (int kk = 0; kk < KMAX / 4; kk++)
 #pragma unroll
     for (int q = 0; q < 4; q++) r.v[kk][q] = 0.f;
-  float accf[64], accg[12], accx[3] = {0.f, 0.f, 0.f};
+  // dW[:, K:K+128]: thread = (4 feature channels fc4*4.., 16 output channels cog*16..)
+  float accf[16][4], accg[12], accx[3] = {0.f, 0.f, 0.f}, dsum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 64; i++) accf[i] = 0.f;
+  for (int i = 0; i < 16; i++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) accf[i][e] = 0.f;
 #pragma unroll
   for (int i = 0; i < 12; i++) accg[i] = 0.f;
   const int wc = threadIdx.x % kAdjC, half_id = threadIdx.x / kAdjC;   // half_id: 0 / 1
+  const int fc4 = threadIdx.x % 32, cog = threadIdx.x / 32;            // cog doubles as the voxel group of d first_feature
   for (int s0 = split * per; s0 < (split + 1) * per; s0 += kAdjTS) {
-    adj_load_dz(dy, y, (long long)clip * frames_per_clip, frames_per_clip, S, s0, inv_scale, s_dz);
-    adj_gauss_tile(s_e, s_kp, K, g, s0, s_G);
-    for (int i = threadIdx.x; i < kAdjTS * (kAdjC / 8); i += 256) {
-      const int sl = i / (kAdjC / 8), c8 = i % (kAdjC / 8);
-      float f[8];
-      nm_unpack8(*reinterpret_cast<const half8*>(ff + ((long long)clip * S + s0 + sl) * kAdjC + c8 * 8), f);
-#pragma unroll
-      for (int e = 0; e < 8; e++) s_ff[sl * kAdjC + c8 * 8 + e] = f[e];
+    adj_load_dz(dy, y, (long long)clip * frames_per_clip, frames_per_clip, S, s0, inv_scale, s_dz, s_dzT);
+    adj_gauss_tile(s_e, s_kp, K, g, s0, s_GT);
+    for (int i = threadIdx.x; i < kAdjTS * (kAdjC / 4); i += 256) {
+      const int sl = i / (kAdjC / 4), c4 = i % (kAdjC / 4);
+      const uint2 raw = *reinterpret_cast<const uint2*>(ff + ((long long)clip * S + s0 + sl) * kAdjC + c4 * 4);
+      const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+      const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+      *reinterpret_cast<float4*>(s_ff + sl * kAdjC + c4 * 4) = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+    if (threadIdx.x < kAdjTS) {
+      const int s = s0 + threadIdx.x;
+      *reinterpret_cast<float4*>(s_xyz + threadIdx.x * 4) = make_float4(lin[s / (g * g)], lin[(s / g) % g], lin[s % g], 0.f);
     }
     __syncthreads();
     adj_render_bwd(s_wg, s_dz, s_e, s_kp, lin, K, g, s0, width, r);
-    // d first_feature[s][c] = grad_scale * sum_co W[co][K + c] dzs[co][s]: thread (c = wc, 32 voxels)
-    for (int sl = half_id * 32; sl < half_id * 32 + 32; sl++) {
-      float t = 0.f;
-#pragma unroll 8
-      for (int co = 0; co < kAdjC; co++) t = fmaf(s_wff[co * kAdjC + wc], s_dz[co * (kAdjTS + 1) + sl], t);
-      dff[((long long)clip * S + s0 + sl) * kAdjC + wc] = __float2half_rn(t * grad_scale);
-    }
-    // dW[co][K + c] += sum_s dzs[co][s] ff[s][c]: thread (c = wc, co = half_id * 64 ...)
-#pragma unroll 4
-    for (int sl = 0; sl < kAdjTS; sl++) {
-      const float f = s_ff[sl * kAdjC + wc];
+    // d first_feature[s][c] = grad_scale * sum_co W[co][K + c] dzs[co][s]: thread = (channels fc4*4.., voxels cog*8..);
+    // per co one LDS.128 of the weights and two broadcast LDS.128 of dzs for 32 FMA
+    {
+      float o[8][4];
 #pragma unroll
-      for (int i = 0; i < 64; i++) accf[i] = fmaf(s_dz[(half_id * 64 + i) * (kAdjTS + 1) + sl], f, accf[i]);
+      for (int v = 0; v < 8; v++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) o[v][e] = 0.f;
+#pragma unroll 2
+      for (int co = 0; co < kAdjC; co++) {
+        const float4 w = *reinterpret_cast<const float4*>(s_wff + co * kAdjC + fc4 * 4);
+        const float4 d0 = *reinterpret_cast<const float4*>(s_dz + co * kAdjDS + cog * 8);
+        const float4 d1 = *reinterpret_cast<const float4*>(s_dz + co * kAdjDS + cog * 8 + 4);
+        const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+          o[v][0] = fmaf(w.x, dv[v], o[v][0]);
+          o[v][1] = fmaf(w.y, dv[v], o[v][1]);
+          o[v][2] = fmaf(w.z, dv[v], o[v][2]);
+          o[v][3] = fmaf(w.w, dv[v], o[v][3]);
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < 8; v++) {
+        __half2 h0 = __floats2half2_rn(o[v][0] * grad_scale, o[v][1] * grad_scale);
+        __half2 h1 = __floats2half2_rn(o[v][2] * grad_scale, o[v][3] * grad_scale);
+        *reinterpret_cast<uint2*>(dff + ((long long)clip * S + s0 + cog * 8 + v) * kAdjC + fc4 * 4) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+    }
+    // dW[co][K + c] += sum_s dzs[co][s] ff[s][c]: per voxel one LDS.128 of ff and four broadcast LDS.128 of dzs for 64 FMA
+#pragma unroll 2
+    for (int sl = 0; sl < kAdjTS; sl++) {
+      const float4 f = *reinterpret_cast<const float4*>(s_ff + sl * kAdjC + fc4 * 4);
+      const float4* dr = reinterpret_cast<const float4*>(s_dzT + sl * kAdjDT + cog * 16);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4 d = dr[q];
+        const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          accf[q * 4 + e][0] = fmaf(dv[e], f.x, accf[q * 4 + e][0]);
+          accf[q * 4 + e][1] = fmaf(dv[e], f.y, accf[q * 4 + e][1]);
+          accf[q * 4 + e][2] = fmaf(dv[e], f.z, accf[q * 4 + e][2]);
+          accf[q * 4 + e][3] = fmaf(dv[e], f.w, accf[q * 4 + e][3]);
+        }
+      }
     }
     // dW[co][K + 128 + k] += sum_s dzs[co][s] G0[k][s]  (co = wc, 12 keypoints);  coords: thread co = wc of half 0
-    {
-      const float* dr = s_dz + wc * (kAdjTS + 1);
-#pragma unroll
-      for (int i = 0; i < 12; i++) {
-        const float* gr = s_G + (half_id * 12 + i) * kAdjTS;
-        float t = 0.f;
-        for (int sl = 0; sl < kAdjTS; sl++) t = fmaf(dr[sl], gr[sl], t);
-        accg[i] += t;
-      }
-      if (half_id == 0) {
-        for (int sl = 0; sl < kAdjTS; sl++) {
-          const int s = s0 + sl;
-          const float d = dr[sl];
-          accx[0] = fmaf(d, lin[s / (g * g)], accx[0]);
-          accx[1] = fmaf(d, lin[(s / g) % g], accx[1]);
-          accx[2] = fmaf(d, lin[s % g], accx[2]);
-        }
+    adj_wg_accumulate(s_dzT, s_GT, wc, half_id * 12, accg, dsum);
+    if (half_id == 0) {
+#pragma unroll 4
+      for (int sl = 0; sl < kAdjTS; sl++) {
+        const float d = s_dzT[sl * kAdjDT + wc];
+        const float4 c = *reinterpret_cast<const float4*>(s_xyz + sl * 4);
+        accx[0] = fmaf(d, c.x, accx[0]);
+        accx[1] = fmaf(d, c.y, accx[1]);
+        accx[2] = fmaf(d, c.z, accx[2]);
       }
     }
     __syncthreads();
@@ -558,7 +692,9 @@ adjust_bwd_clip_kernel(const __half* __restrict__ dy, const __half* __restrict__
   constexpr int LDP = kAdjC + KMAX + 3;
   float* o = pw + part * kAdjC * LDP;
 #pragma unroll
-  for (int i = 0; i < 64; i++) o[(long long)(half_id * 64 + i) * LDP + wc] = accf[i];
+  for (int i = 0; i < 16; i++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) o[(long long)(cog * 16 + i) * LDP + fc4 * 4 + e] = accf[i][e];
 #pragma unroll
   for (int i = 0; i < 12; i++) o[(long long)wc * LDP + kAdjC + half_id * 12 + i] = accg[i];
   if (half_id == 0)
@@ -933,15 +1069,23 @@ extern "C" int nm_final_recon_backward(const void* x, const float* a, const floa
                                                              grad_scale, reinterpret_cast<__half*>(grad_act), partial, S);
   NM_CHECK_LAUNCH("final_recon_bwd_kernel");
   // columns 0..31 -> dw, column 32 -> dbias
-  reduce_cols_kernel<<<1, 32, 0, st>>>(partial, (long long)n * kFrbBlocks, 33, 32, 1.0f, dw);
+  reduce_cols_kernel<<<1, dim3(32, 8), 0, st>>>(partial, (long long)n * kFrbBlocks, 33, 32, 1.0f, dw);
   NM_CHECK_LAUNCH("final_recon_bwd(reduce dw)");
-  reduce_cols_kernel<<<1, 32, 0, st>>>(partial + 32, (long long)n * kFrbBlocks, 33, 1, 1.0f, dbias);
+  reduce_cols_kernel<<<1, dim3(32, 8), 0, st>>>(partial + 32, (long long)n * kFrbBlocks, 33, 1, 1.0f, dbias);
   NM_CHECK_LAUNCH("final_recon_bwd(reduce dbias)");
   return NM_OK;
 }
 
+// voxel splits per frame: enough CTAs for ~4 per SM, at most 8 (a 8^3 heat-map has 8 tiles of 64 voxels)
+static int head_bwd_splits(int n) {
+  int splits = 1;
+  while (splits < 8 && (long long)n * splits < 592) splits *= 2;
+  return splits;
+}
+
 extern "C" size_t nm_heatmap_head_backward_workspace_bytes(int n, int C, int K) {
-  return ((size_t)n * K * C + (size_t)n * K + (size_t)n * 3) * sizeof(float);
+  const size_t rows = (size_t)n * head_bwd_splits(n);
+  return (rows * K * C + rows * K + rows * 3) * sizeof(float);
 }
 
 extern "C" int nm_heatmap_head_backward(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K, int mode,
@@ -957,28 +1101,31 @@ extern "C" int nm_heatmap_head_backward(const void* feature, const float* w1, co
   NM_CHECK_ARG(C == 128 || C == 256, "nm_heatmap_head_backward: C=%d unsupported", C);
   if (n == 0) return NM_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  const int splits = head_bwd_splits(n);
+  const long long rows = (long long)n * splits;
   float* pwp = reinterpret_cast<float*>(workspace);
-  float* pbp = pwp + (size_t)n * K * C;
-  float* ppp = pbp + (size_t)n * K;
-  const size_t smem = (size_t)(KMAX * C + 64 * (C + 1) + KMAX * 64 + KMAX * 4 + 256 * 3) * sizeof(float);
+  float* pbp = pwp + (size_t)rows * K * C;
+  float* ppp = pbp + (size_t)rows * K;
+  const size_t smem = (size_t)(KMAX * C + 64 * (C + 4) + 2 * KMAX * 64 + KMAX * 4 + 256 * 3) * sizeof(float);
+  const dim3 grid(n, splits);
   if (C == 128) {
     NM_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_bwd_kernel<128><<<n, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
-                                               pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
-                                               grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
+    head_bwd_kernel<128><<<grid, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
+                                                  pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
+                                                  grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
   } else {
     NM_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    head_bwd_kernel<256><<<n, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
-                                               pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
-                                               grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
+    head_bwd_kernel<256><<<grid, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
+                                                  pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
+                                                  grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
   }
   NM_CHECK_LAUNCH("head_bwd_kernel");
-  reduce_cols_kernel<<<nm_cdiv(K * C, 128), 128, 0, st>>>(pwp, n, K * C, K * C, 1.0f, dw1);
+  reduce_cols_kernel<<<nm_cdiv(K * C, 32), dim3(32, 8), 0, st>>>(pwp, rows, K * C, K * C, 1.0f, dw1);
   NM_CHECK_LAUNCH("head_bwd(reduce dw1)");
-  reduce_cols_kernel<<<1, 32, 0, st>>>(pbp, n, K, K, 1.0f, db1);
+  reduce_cols_kernel<<<1, dim3(32, 8), 0, st>>>(pbp, rows, K, K, 1.0f, db1);
   NM_CHECK_LAUNCH("head_bwd(reduce db1)");
   if (mode == 1) {
-    reduce_cols_kernel<<<1, 32, 0, st>>>(ppp, n, 3, 3, 1.0f, dprop);
+    reduce_cols_kernel<<<1, dim3(32, 8), 0, st>>>(ppp, rows, 3, 3, 1.0f, dprop);
     NM_CHECK_LAUNCH("head_bwd(reduce dprop)");
   }
   return NM_OK;
@@ -1006,12 +1153,12 @@ extern "C" int nm_decoder_adjust_backward(const void* grad_out, const void* out,
   float* pw = pbias + (size_t)n * kAdjC;
   float* dkp0 = pw + (size_t)n_clips * kAdjSplits * kAdjC * (kAdjC + KMAX + 3);
   const float inv_scale = 1.0f / grad_scale;
-  const size_t smem_f = (size_t)(kAdjC * KMAX + kAdjC * (kAdjTS + 1) + KMAX * kAdjTS + KMAX * 96 + KMAX * 4 + 256 * 24) * sizeof(float);
+  const size_t smem_f = (size_t)kAdjFrameFloats * sizeof(float);
   NM_CHECK_CUDA(cudaFuncSetAttribute(adjust_bwd_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_f));
   adjust_bwd_frame_kernel<<<n, 256, smem_f, st>>>(reinterpret_cast<const __half*>(grad_out), reinterpret_cast<const __half*>(out),
                                                   keypoints, weight, ld, K, g, linspace, gauss_width, inv_scale, grad_keypoints, pwg, pbias);
   NM_CHECK_LAUNCH("adjust_bwd_frame_kernel");
-  const size_t smem_c = smem_f + (size_t)(kAdjC * kAdjC + kAdjTS * kAdjC) * sizeof(float);
+  const size_t smem_c = (size_t)kAdjClipFloats * sizeof(float);
   NM_CHECK_CUDA(cudaFuncSetAttribute(adjust_bwd_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
   adjust_bwd_clip_kernel<<<dim3(n_clips, kAdjSplits), 256, smem_c, st>>>(
       reinterpret_cast<const __half*>(grad_out), reinterpret_cast<const __half*>(out), reinterpret_cast<const __half*>(first_feature),
@@ -1086,9 +1233,9 @@ extern "C" int nm_first_conv_wgrad(const float* occ, const void* grad_out, const
   // sum over the frames and parts first (fixed order), then assemble the (Cout, 4, 5, 5, 5) tensor
   float* rbins = occp + (size_t)orows * 125 * Cout;
   float* roccp = rbins + (size_t)125 * 4 * Cout;
-  reduce_cols_kernel<<<nm_cdiv(500 * Cout, 128), 128, 0, st>>>(bins, rows, 500 * Cout, 500 * Cout, 1.0f, rbins);
+  reduce_cols_kernel<<<nm_cdiv(500 * Cout, 32), dim3(32, 8), 0, st>>>(bins, rows, 500 * Cout, 500 * Cout, 1.0f, rbins);
   NM_CHECK_LAUNCH("first_wgrad(reduce bins)");
-  reduce_cols_kernel<<<nm_cdiv(125 * Cout, 128), 128, 0, st>>>(occp, orows, 125 * Cout, 125 * Cout, 1.0f, roccp);
+  reduce_cols_kernel<<<nm_cdiv(125 * Cout, 32), dim3(32, 8), 0, st>>>(occp, orows, 125 * Cout, 125 * Cout, 1.0f, roccp);
   NM_CHECK_LAUNCH("first_wgrad(reduce occ)");
   first_wgrad_finalize_kernel<<<nm_cdiv(Cout * 500, 128), 128, 0, st>>>(rbins, roccp, 1, Cout, G, linspace, out_scale, dw);
   NM_CHECK_LAUNCH("first_wgrad_finalize_kernel");

@@ -165,19 +165,31 @@ gnb_grad_finalize_kernel(const float* __restrict__ partial, const float* __restr
   }
 }
 
-__global__ void gnb_param_grad_kernel(const float* __restrict__ chan, int n_samples, int C, float out_scale,
-                                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// One warp per channel: lane l sums samples l, l + 32, ... in order, then a butterfly (fixed order, fp64).  The
+// one-thread-per-channel version walked the samples serially: 23 us per launch, 76 launches per training step.
+__global__ void __launch_bounds__(128)
+gnb_param_grad_kernel(const float* __restrict__ chan, int n_samples, int C, float out_scale,
+                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dxsum) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;                                                     // warp-uniform
   double db = 0.0, dg = 0.0, dx = 0.0;
-  for (int n = 0; n < n_samples; n++) {                                  // fixed order over the samples
-    db += chan[((long long)n * C + c) * 3];
-    dg += chan[((long long)n * C + c) * 3 + 1];
-    dx += chan[((long long)n * C + c) * 3 + 2];
+  for (int n = lane; n < n_samples; n += 32) {
+    const float* p = chan + ((long long)n * C + c) * 3;
+    db += p[0];
+    dg += p[1];
+    dx += p[2];
   }
-  if (dbeta) dbeta[c] = (float)(db * (double)out_scale);
-  if (dgamma) dgamma[c] = (float)(dg * (double)out_scale);
-  if (dxsum) dxsum[c] = (float)(dx * (double)out_scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    db += gnb_shfl_xor(db, o);
+    dg += gnb_shfl_xor(dg, o);
+    dx += gnb_shfl_xor(dx, o);
+  }
+  if (lane == 0) {
+    if (dbeta) dbeta[c] = (float)(db * (double)out_scale);
+    if (dgamma) dgamma[c] = (float)(dg * (double)out_scale);
+    if (dxsum) dxsum[c] = (float)(dx * (double)out_scale);
+  }
 }
 
 // Any (C, groups) on small tensors (hour-glass levels with 48 / 72 channels, 18 channels per group): one warp per
@@ -438,7 +450,7 @@ extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const 
     gnb_small_kernel<<<dim3(groups, n), 32, 0, st>>>(xh, dz, gamma, beta, C, groups, S, eps, leaky, reinterpret_cast<__half*>(grad_in), chan);
     NM_CHECK_LAUNCH("gnb_small_kernel");
     if (dgamma || dbeta || dxsum) {
-      gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, n, C, out_scale, dgamma, dbeta, dxsum);
+      gnb_param_grad_kernel<<<nm_cdiv(C, 4), 128, 0, st>>>(chan, n, C, out_scale, dgamma, dbeta, dxsum);
       NM_CHECK_LAUNCH("gnb_param_grad_kernel");
     }
     return NM_OK;
@@ -458,7 +470,7 @@ extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const 
   gnb_grad_finalize_kernel<<<nm_cdiv((long long)n * groups, 4), 128, 0, st>>>(partial, gamma, mean_rstd, xsum, s, m12, chan);
   NM_CHECK_LAUNCH("gnb_grad_finalize_kernel");
   if (dgamma || dbeta || dxsum) {
-    gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, n, C, out_scale, dgamma, dbeta, dxsum);
+    gnb_param_grad_kernel<<<nm_cdiv(C, 4), 128, 0, st>>>(chan, n, C, out_scale, dgamma, dbeta, dxsum);
     NM_CHECK_LAUNCH("gnb_param_grad_kernel");
   }
   const long long total = (long long)n * S * s.ccs;
@@ -501,7 +513,7 @@ extern "C" int nm_final_recon_backward_fused(const void* x, const float* a, cons
   gnb_grad_finalize_kernel<<<nm_cdiv((long long)n * groups, 4), 128, 0, st>>>(partial, gamma, mean_rstd, xsum, s, m12, chan);
   NM_CHECK_LAUNCH("gnb_grad_finalize_kernel");
   if (dgamma || dbeta || dxsum) {
-    gnb_param_grad_kernel<<<nm_cdiv(C, 128), 128, 0, st>>>(chan, n, C, inv, dgamma, dbeta, dxsum);
+    gnb_param_grad_kernel<<<nm_cdiv(C, 4), 128, 0, st>>>(chan, n, C, inv, dgamma, dbeta, dxsum);
     NM_CHECK_LAUNCH("gnb_param_grad_kernel");
   }
   const long long total = (long long)n * S * s.ccs;
