@@ -1,5 +1,6 @@
 // Shared helpers for the nm_b200 kernels (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -70,3 +71,17 @@ __device__ __forceinline__ half8 nm_pack8(const float* f) {
   for (int i = 0; i < 4; i++) v.h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
   return v;
 }
+
+// Runs `body` on the first call per (call site, device) - kernel attributes such as the dynamic shared-memory limit are
+// per device.  Two threads racing on the first call both run the (idempotent) body before either sets the bit.
+#define NM_PER_DEVICE_ONCE(...)                                                       \
+  do {                                                                                \
+    static std::atomic<unsigned long long> nm_once_mask{0};                           \
+    int nm_once_dev = 0;                                                              \
+    cudaGetDevice(&nm_once_dev);                                                      \
+    const unsigned long long nm_once_bit = 1ull << (nm_once_dev & 63);                \
+    if (!(nm_once_mask.load(std::memory_order_acquire) & nm_once_bit)) {              \
+      __VA_ARGS__;                                                                    \
+      nm_once_mask.fetch_or(nm_once_bit, std::memory_order_release);                  \
+    }                                                                                 \
+  } while (0)

@@ -433,11 +433,9 @@ PwPlan plan_pw(int n, int D, int H, int W, int Cin, int Cout, int k, int stride)
 template <int CIN, int COUT, int TAPS, bool DUAL = false>
 int launch_pw(const PwParams& p, int chunks, int n, cudaStream_t st) {
   const size_t smem = (size_t)TAPS * (CIN / 16) * (COUT / 8) * 32 * sizeof(uint2);
-  static bool attr = false;
-  if (!attr && smem > 48 * 1024) {
+  if (smem > 48 * 1024) NM_PER_DEVICE_ONCE({
     NM_CHECK_CUDA(cudaFuncSetAttribute(conv_pw_kernel<CIN, COUT, TAPS, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  });
   conv_pw_kernel<CIN, COUT, TAPS, DUAL><<<dim3(chunks, n), 256, smem, st>>>(p);
   NM_CHECK_LAUNCH("conv3d_pw");
   return NM_OK;

@@ -1465,27 +1465,23 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { nm_set_error("nm_conv3d_tc(slab3): cuTensorMapEncodeTiled(out) failed with %d", (int)r); return NM_ERR_DRIVER; }
       }
-      static bool slab_attr = false;
-      if (!slab_attr) {
+      NM_PER_DEVICE_ONCE({
         NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        slab_attr = true;
-      }
+      });
       const int cols = n * q.nh * q.nw;
       int grid = cols < nm_num_sms() ? cols : nm_num_sms();
       if (use3) {
         const int parts = ntile / pn;
         grid = cols * parts < nm_num_sms() ? cols * parts : (nm_num_sms() / parts) * parts;
-        static bool slab3_attr = false;
-        if (!slab3_attr) {
+        NM_PER_DEVICE_ONCE({
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<32, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_slab3_kernel<64, 32, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          slab3_attr = true;
-        }
+        });
         static int xw_env = -1;
         if (xw_env < 0) { const char* e = getenv("NM_XFORM_WARPS"); xw_env = e ? atoi(e) : 6; if (xw_env != 4) xw_env = 6; }
         // the up-sampling producer runs on 4 warps (3 working): with 6 (5 working, 144 finer items) dec.8 got slower
@@ -1588,11 +1584,9 @@ int conv3d_tc_impl(const void* x, const void* packed_w, const float* bias, void*
   if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 2 * 8192 + 1024 /*align*/ + (2 * stages + 4) * 8 + 16 + 256 * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  NM_PER_DEVICE_ONCE({
     NM_CHECK_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  });
   const int total_tiles = p.nw * p.nh * p.nd * p.nn;
   const int grid = total_tiles < nm_num_sms() ? total_tiles : nm_num_sms();
   conv3d_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(p);

@@ -489,11 +489,9 @@ extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float
   NM_CHECK_LAUNCH("heatmap_head(heat)");
   if (mode == 0) return NM_OK;
   const size_t smem2 = (size_t)(3 * KMAX * 32 + KMAX * 4 + KMAX * 3 * 32 + 32 * 32 + 256 + 256 * 33) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  NM_PER_DEVICE_ONCE({
     cudaFuncSetAttribute(head_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    attr = true;
-  }
+  });
   head_reduce_kernel<<<n, 256, smem2, st>>>(K, g, linspace, gauss_width, heat, keypoints, gaussians, heat_mean);
   NM_CHECK_LAUNCH("heatmap_head(reduce)");
   return NM_OK;
@@ -532,11 +530,9 @@ extern "C" int nm_decoder_adjust(const void* first_feature, const float* keypoin
   adjust_pack_kernel<<<8, 256, 0, st>>>(weight, bias, K, 2 * K + kAdjFD + 3, frags, xyzb);
   NM_CHECK_LAUNCH("decoder_adjust(pack)");
   const size_t smem = (size_t)(kAdjFragG + kAdjFragFF) * sizeof(uint2);
-  static bool attr = false;
-  if (!attr) {
+  NM_PER_DEVICE_ONCE({
     NM_CHECK_CUDA(cudaFuncSetAttribute(adjust_base_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
+  });
   const int n = n_clips * frames_per_clip;
   const float* kp = gaussians ? nullptr : keypoints;
   adjust_base_kernel<<<dim3(S / 128, n_clips), 256, smem, st>>>((const act_t*)first_feature, kp, gaussians,
