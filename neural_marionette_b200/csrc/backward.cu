@@ -802,61 +802,133 @@ __global__ void chamfer_bwd_finalize_kernel(const float* __restrict__ partial, c
 // Coordinate channels: in_a[v + t - 2] = lin[v_a + t_a - 2] inside the volume -> affine in the voxel index, so the sums
 // over the tap's in-bounds box follow from 125 bins (5 position classes per axis: 0, 1, interior, G-2, G-1) of the
 // moments (sum dY, sum x dY, sum y dY, sum z dY).  Occupancy channel: a gather over the occupied voxels.
+// One pass over the CTA's x slab in memory order.  Rows (x, y) are grouped by their (x class, y class); inside a row
+// lane = (z lane, 16-byte channel chunk) and only the lanes that meet z = 0, 1, G-2, G-1 (in the first / last load of the
+// row) keep a second accumulator set, so a group's five z bins come out of one sweep.  A group ends with a butterfly over
+// the z lanes and a fixed-order fold of the 8 warps.  (The first version swept the slab once per bin: 125 block-wide
+// reductions per CTA, 1.9 TB/s.)
 template <int C>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 first_wgrad_moments_kernel(const __half* __restrict__ dy, int G, float* __restrict__ bins /* [n][parts][125][4][C] */) {
-  constexpr int CC = C / 8, NVL = 256 / CC;
-  __shared__ float red[256 * 32];
+  constexpr int CC = C / 8, ZL = 32 / CC;                    // channel chunks per voxel, lanes along z
+  __shared__ float red[8][5][4][C];
   const int n = blockIdx.x, part = blockIdx.y, parts = gridDim.y;
   const int xs = G * part / parts, xe = G * (part + 1) / parts;        // this CTA's x slab
-  const int cc = threadIdx.x % CC, vl = threadIdx.x / CC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cc = lane % CC, zl = lane / CC;
+  const int nj = G / ZL;                                     // loads per row and lane
   const __half* base = dy + (long long)n * G * G * G * C + cc * 8;
   float* out = bins + ((long long)n * parts + part) * 125 * 4 * C;
-  for (int bin = 0; bin < 125; bin++) {
-    const int cls[3] = {bin / 25, (bin / 5) % 5, bin % 5};
-    int lo[3], cnt[3];
+  // z class of this lane's boundary slot (first load: zl = 0, 1; last load: zl = ZL-2, ZL-1), -1: interior lanes only
+  const int bcls = zl == 0 ? 0 : (zl == 1 ? 1 : (zl == ZL - 2 ? 3 : (zl == ZL - 1 ? 4 : -1)));
+  const float bz = bcls == 0 ? 0.f : (bcls == 1 ? 1.f : (bcls == 3 ? (float)(G - 2) : (float)(G - 1)));
+  for (int grp = 0; grp < 25; grp++) {
+    const int cxc = grp / 5, cyc = grp % 5;
+    int lo[2], cnt[2];
+    const int cl2[2] = {cxc, cyc};
 #pragma unroll
-    for (int a = 0; a < 3; a++) {
-      lo[a] = cls[a] == 0 ? 0 : (cls[a] == 1 ? 1 : (cls[a] == 2 ? 2 : (cls[a] == 3 ? G - 2 : G - 1)));
-      cnt[a] = cls[a] == 2 ? G - 4 : 1;
+    for (int a = 0; a < 2; a++) {
+      lo[a] = cl2[a] == 0 ? 0 : (cl2[a] == 1 ? 1 : (cl2[a] == 2 ? 2 : (cl2[a] == 3 ? G - 2 : G - 1)));
+      cnt[a] = cl2[a] == 2 ? G - 4 : 1;
     }
     {
       const int a0 = max(lo[0], xs), a1 = min(lo[0] + cnt[0], xe);
       lo[0] = a0;
       cnt[0] = max(0, a1 - a0);
     }
-    const int total = cnt[0] * cnt[1] * cnt[2];
-    if (total == 0) {                                                   // block-uniform: the bin lies outside the slab
-      for (int i = threadIdx.x; i < 4 * C; i += 256) out[(long long)bin * 4 * C + i] = 0.f;
+    const int rows = cnt[0] * cnt[1];
+    float* og = out + (long long)grp * 5 * 4 * C;            // bins (cxc, cyc, 0..4)
+    if (rows == 0) {                                         // block-uniform: the group lies outside the slab
+      for (int i = threadIdx.x; i < 5 * 4 * C; i += 256) og[i] = 0.f;
       continue;
     }
-    float acc[32];
+    float s0[8], sx[8], sy[8], sz[8], b0[8], bx[8], by[8];
 #pragma unroll
-    for (int i = 0; i < 32; i++) acc[i] = 0.f;
-    for (int i = vl; i < total; i += NVL) {
-      const int z = lo[2] + i % cnt[2], y = lo[1] + (i / cnt[2]) % cnt[1], x = lo[0] + i / (cnt[2] * cnt[1]);
-      float f[8];
-      nm_unpack8(*reinterpret_cast<const half8*>(base + (((long long)x * G + y) * G + z) * C), f);
-      const float fx = (float)x, fy = (float)y, fz = (float)z;
+    for (int k = 0; k < 8; k++) s0[k] = sx[k] = sy[k] = sz[k] = b0[k] = bx[k] = by[k] = 0.f;
+    for (int r = warp; r < rows; r += 8) {
+      const int x = lo[0] + r / cnt[1], y = lo[1] + r % cnt[1];
+      const float fx = (float)x, fy = (float)y;
+      const __half* row = base + (((long long)x * G + y) * G + zl) * C;
+      // x and y are constant along a row: the row's plain sum r0 gives three of the four moments with 24 FMAs per row
+      float r0[8], rz[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) r0[k] = rz[k] = 0.f;
+      // loads are issued in batches of 8 ahead of the (divergent) accumulation so that they overlap
+#pragma unroll 1
+      for (int j0 = 0; j0 < nj; j0 += 8) {
+        half8 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+          if (j0 + u < nj) v[u] = *reinterpret_cast<const half8*>(row + (long long)(j0 + u) * ZL * C);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int j = j0 + u;
+          if (j >= nj) break;
+          float f[8];
+          nm_unpack8(v[u], f);
+          const bool bnd = (j == 0 && zl < 2) || (j == nj - 1 && zl >= ZL - 2);
+          if (bnd) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              b0[k] += f[k];
+              bx[k] = fmaf(fx, f[k], bx[k]);
+              by[k] = fmaf(fy, f[k], by[k]);
+            }
+          } else {
+            const float fz = (float)(zl + j * ZL);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              r0[k] += f[k];
+              rz[k] = fmaf(fz, f[k], rz[k]);
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        acc[k] += f[k];
-        acc[8 + k] = fmaf(fx, f[k], acc[8 + k]);
-        acc[16 + k] = fmaf(fy, f[k], acc[16 + k]);
-        acc[24 + k] = fmaf(fz, f[k], acc[24 + k]);
+        s0[k] += r0[k];
+        sx[k] = fmaf(fx, r0[k], sx[k]);
+        sy[k] = fmaf(fy, r0[k], sy[k]);
+        sz[k] += rz[k];
+      }
+    }
+    // interior z bin: butterfly over the z lanes (fixed order); boundary z bins: one lane each
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+#pragma unroll
+      for (int o = CC; o < 32; o <<= 1) {
+        s0[k] += __shfl_xor_sync(0xffffffffu, s0[k], o);
+        sx[k] += __shfl_xor_sync(0xffffffffu, sx[k], o);
+        sy[k] += __shfl_xor_sync(0xffffffffu, sy[k], o);
+        sz[k] += __shfl_xor_sync(0xffffffffu, sz[k], o);
+      }
+    }
+    if (zl == 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        red[warp][2][0][cc * 8 + k] = s0[k];
+        red[warp][2][1][cc * 8 + k] = sx[k];
+        red[warp][2][2][cc * 8 + k] = sy[k];
+        red[warp][2][3][cc * 8 + k] = sz[k];
+      }
+    }
+    if (bcls >= 0) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        red[warp][bcls][0][cc * 8 + k] = b0[k];
+        red[warp][bcls][1][cc * 8 + k] = bx[k];
+        red[warp][bcls][2][cc * 8 + k] = by[k];
+        red[warp][bcls][3][cc * 8 + k] = bz * b0[k];
       }
     }
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 32; i++) red[i * 256 + threadIdx.x] = acc[i];
-    __syncthreads();
-    // moment q (0..3), channel c: sum over the voxel lanes in order
-    for (int i = threadIdx.x; i < 4 * C; i += 256) {
-      const int q = i / C, c = i % C, c8 = c / 8, k = c % 8;
+    for (int i = threadIdx.x; i < 5 * 4 * C; i += 256) {
       float t = 0.f;
-      for (int l = 0; l < NVL; l++) t += red[(q * 8 + k) * 256 + l * CC + c8];
-      out[((long long)bin * 4 + q) * C + c] = t;
+#pragma unroll
+      for (int w = 0; w < 8; w++) t += (&red[w][0][0][0])[i];
+      og[i] = t;
     }
+    __syncthreads();
   }
 }
 
@@ -1192,7 +1264,7 @@ extern "C" int nm_chamfer_vol_fit_backward(const float* seq, const float* keypoi
 
 // CTAs per frame: the once-per-clip branch has few (dense) frames, the per-frame encoder many sparse ones
 static int first_wgrad_parts(int n) {
-  int p = (2 * nm_num_sms() + n - 1) / n;
+  int p = (12 * nm_num_sms() + n - 1) / n;                 // >= 6 waves of 2 CTAs per SM: the x slabs are uneven work
   return p < 1 ? 1 : (p > 8 ? 8 : p);
 }
 // the occupancy gather is latency-bound (64-byte rows from L2): several resident CTAs per SM keep more loads in flight
