@@ -18,6 +18,7 @@
 namespace {
 
 constexpr int kGwThreads = 256;
+constexpr int kGwStages = 2;                // ring depth of the streaming (few-tap) variants
 constexpr int kGwRow = 40;                    // halfs per staged row: 32 channels + 8 pad (80 bytes, conflict-free ldmatrix)
 
 __device__ __forceinline__ void gw_ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
@@ -39,14 +40,17 @@ struct GwShape {
   int Ca, Cb;                   // channels of S / L
   int k, stride, pad;           // taps per axis; L extent = Ds * stride etc.
   long long U;                  // N * Ds * Hs * Ws
+  int pow2, lw, lh, ld;         // Ds, Hs, Ws all powers of two: their log2 (voxel decomposition by shifts)
 };
 
-// SLOTS = taps per warp (k3: 4, k2: 1, k1: 1); KT = voxels per K tile
-template <int SLOTS, int KT>
+// SLOTS = taps per warp (k3: 4, k2: 1, k1: 1); KT = voxels per K tile; KK = taps per axis (compile time: the gather's
+// address arithmetic - tap decomposition, voxel decomposition on power-of-two grids - was 5 600 warp instructions per
+// 37 KB tile with run-time divisions, which bound the streaming layers at 3 TB/s)
+template <int SLOTS, int KT, int KK>
 __global__ void __launch_bounds__(kGwThreads, 1)
 wgrad_gather_kernel(const __half* __restrict__ Sx, const __half* __restrict__ Lx, GwShape g, float* __restrict__ partial) {
   extern __shared__ __align__(16) uint8_t smem[];
-  const int taps = g.k * g.k * g.k;
+  constexpr int taps = KK * KK * KK;
   __half* sS = reinterpret_cast<__half*>(smem);                          // per buffer: S tile [KT][kGwRow], L tiles [taps][KT][kGwRow]
   const int a0 = blockIdx.y * 32, b0 = blockIdx.z * 32;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -64,9 +68,11 @@ wgrad_gather_kernel(const __half* __restrict__ Sx, const __half* __restrict__ Lx
 
   const int lj = lane >> 3, li = lane & 7;
   const long long tiles = (g.U + KT - 1) / KT;
-  // Few-tap layers (1x1, pool, transposed convs) are pure streaming: their tiles are double-buffered - the gather of tile
-  // i + 1 is in flight while tile i feeds the MMAs.  The 27-tap tile (143 KB) has no room for a second buffer.
+  // Few-tap layers (1x1, pool, transposed convs) are pure streaming: their tiles go through a ring of kStages buffers -
+  // the gathers of the next kStages - 1 tiles are in flight while a tile feeds the MMAs (one tile ahead left the kernel
+  // latency-bound at 3 TB/s).  The 27-tap tile (143 KB) has no room for a second buffer.
   constexpr bool kDouble = SLOTS == 1;
+  constexpr int kStages = kDouble ? kGwStages : 1;
   const int buf_halfs = (1 + taps) * KT * kGwRow;
   auto stage = [&](long long tile, int buf) {
     __half* bS = sS + (size_t)buf * buf_halfs;
@@ -76,34 +82,50 @@ wgrad_gather_kernel(const __half* __restrict__ Sx, const __half* __restrict__ Lx
       const long long u = tile * KT + j;
       const bool uin = u < g.U;
       const int uu = uin ? (int)u : 0;                                   // U < 2^31 (checked by the host): 32-bit index math
-      const int w = uu % g.Ws, q1 = uu / g.Ws, h = q1 % g.Hs, q2 = q1 / g.Hs, d = q2 % g.Ds;
-      const long long n = q2 / g.Ds;
+      int w, h, d, n;
+      if (g.pow2) {
+        w = uu & (g.Ws - 1);
+        h = (uu >> g.lw) & (g.Hs - 1);
+        d = (uu >> (g.lw + g.lh)) & (g.Ds - 1);
+        n = uu >> (g.lw + g.lh + g.ld);
+      } else {
+        const int q1 = uu / g.Ws, q2 = q1 / g.Hs;
+        w = uu % g.Ws; h = q1 % g.Hs; d = q2 % g.Ds; n = q2 / g.Ds;
+      }
       const bool aok = uin && (a0 + c * 8 < g.Ca);
       gw_cp_async16(bS + j * kGwRow + c * 8, aok ? Sx + (long long)uu * g.Ca + a0 + c * 8 : Sx, aok ? 16 : 0);
       const bool bok = uin && (b0 + c * 8 < g.Cb);
+#pragma unroll
       for (int t = 0; t < taps; t++) {
-        const int kw = t % g.k, kh = (t / g.k) % g.k, kd = t / (g.k * g.k);
+        constexpr int kk2 = KK * KK;
+        const int kw = t % KK, kh = (t / KK) % KK, kd = t / kk2;
         const int dd = d * g.stride + kd - g.pad, hh = h * g.stride + kh - g.pad, ww = w * g.stride + kw - g.pad;
         const bool ok = bok && (unsigned)dd < (unsigned)Dl && (unsigned)hh < (unsigned)Hl && (unsigned)ww < (unsigned)Wl;
         const __half* src = ok ? Lx + ((((long long)n * Dl + dd) * Hl + hh) * Wl + ww) * g.Cb + b0 + c * 8 : Lx;
         gw_cp_async16(bL + ((long long)t * KT + j) * kGwRow + c * 8, src, ok ? 16 : 0);
       }
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int buf = 0;
-  if (kDouble && (long long)blockIdx.x < tiles) stage(blockIdx.x, 0);
+  if (kDouble) {
+    // prologue: tiles 0 .. kStages - 2 of this CTA (one commit group per ring slot, empty past the end)
+#pragma unroll
+    for (int s = 0; s < kStages - 1; s++) {
+      const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
+      if (t < tiles) stage(t, s);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  }
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     if (kDouble) {
-      if (tile + gridDim.x < tiles) {
-        stage(tile + gridDim.x, buf ^ 1);                                // next tile in flight
-        asm volatile("cp.async.wait_group 1;" ::: "memory");             // this tile has landed
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
+      const long long ahead = tile + (long long)(kStages - 1) * gridDim.x;
+      if (ahead < tiles) stage(ahead, (buf + kStages - 1) % kStages);    // the slot consumed in the previous iteration
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 1) : "memory");   // this tile has landed
     } else {
       __syncthreads();                                                   // the previous tile's fragments are consumed
       stage(tile, 0);
+      asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
@@ -138,8 +160,8 @@ wgrad_gather_kernel(const __half* __restrict__ Sx, const __half* __restrict__ Lx
       }
     }
     if (kDouble) {
-      __syncthreads();                                                   // this buffer may be overwritten two tiles on
-      buf ^= 1;
+      __syncthreads();                                                   // this slot is refilled in the next iteration
+      buf = (buf + 1) % kStages;
     }
   }
   // partial[part][a block][b block][tap][32][32]; part = chunk (k2 / k3) or chunk * 8 + warp (k1)
@@ -180,7 +202,8 @@ int gw_tile(int k) { return k == 1 ? 128 : 64; }
 int gw_chunks(const GwShape& g) {
   const int blocks = ((g.Ca + 31) / 32) * ((g.Cb + 31) / 32);
   const long long tiles = (g.U + gw_tile(g.k) - 1) / gw_tile(g.k);
-  long long c = (2LL * nm_num_sms() + blocks - 1) / blocks;
+  const long long per_sm = 2;                                          // resident CTAs per SM
+  long long c = (per_sm * nm_num_sms() + blocks - 1) / blocks;
   if (c > tiles) c = tiles;
   return (int)(c < 1 ? 1 : c);
 }
@@ -189,7 +212,9 @@ bool gw_shape(int N, int Ds, int Hs, int Ws, int Ca, int Cb, int k, int stride, 
   if (N <= 0 || Ds <= 0 || Hs <= 0 || Ws <= 0 || Ca <= 0 || Cb <= 0 || Ca % 8 || Cb % 8 || Ca > 256 || Cb > 256) return false;
   if (!((stride == 1 && (k == 1 || k == 3)) || (stride == 2 && k == 2))) return false;
   if ((long long)N * Ds * Hs * Ws >= (1LL << 31)) return false;
-  *g = GwShape{N, Ds, Hs, Ws, Ca, Cb, k, stride, stride == 1 ? (k - 1) / 2 : 0, (long long)N * Ds * Hs * Ws};
+  *g = GwShape{N, Ds, Hs, Ws, Ca, Cb, k, stride, stride == 1 ? (k - 1) / 2 : 0, (long long)N * Ds * Hs * Ws, 0, 0, 0, 0};
+  auto lg = [](int v) { int l = 0; while ((1 << l) < v) l++; return l; };
+  if (!(Ds & (Ds - 1)) && !(Hs & (Hs - 1)) && !(Ws & (Ws - 1))) { g->pow2 = 1; g->lw = lg(Ws); g->lh = lg(Hs); g->ld = lg(Ds); }
   return true;
 }
 
@@ -212,16 +237,17 @@ extern "C" int nm_conv3d_wgrad_gather(const void* small_side, const void* large_
   cudaStream_t st = (cudaStream_t)stream;
   const int chunks = gw_chunks(g), taps = k * k * k, KT = gw_tile(k);
   const int ab = (Ca + 31) / 32, bb = (Cb + 31) / 32;
-  const size_t smem = (size_t)(1 + taps) * KT * kGwRow * sizeof(__half) * (k == 3 ? 1 : 2);   // few-tap tiles are double-buffered
-  NM_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gather_kernel<4, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  NM_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gather_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  const size_t smem = (size_t)(1 + taps) * KT * kGwRow * sizeof(__half) * (k == 3 ? 1 : kGwStages);   // few-tap tiles: ring
+  NM_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gather_kernel<4, 64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  NM_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gather_kernel<1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  NM_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gather_kernel<1, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   const dim3 grid(chunks, ab, bb);
   const __half* S = reinterpret_cast<const __half*>(small_side);
   const __half* L = reinterpret_cast<const __half*>(large_side);
   float* ws = reinterpret_cast<float*>(workspace);
-  if (k == 3) wgrad_gather_kernel<4, 64><<<grid, kGwThreads, smem, st>>>(S, L, g, ws);
-  else if (k == 2) wgrad_gather_kernel<1, 64><<<grid, kGwThreads, smem, st>>>(S, L, g, ws);
-  else wgrad_gather_kernel<1, 128><<<grid, kGwThreads, smem, st>>>(S, L, g, ws);
+  if (k == 3) wgrad_gather_kernel<4, 64, 3><<<grid, kGwThreads, smem, st>>>(S, L, g, ws);
+  else if (k == 2) wgrad_gather_kernel<1, 64, 2><<<grid, kGwThreads, smem, st>>>(S, L, g, ws);
+  else wgrad_gather_kernel<1, 128, 1><<<grid, kGwThreads, smem, st>>>(S, L, g, ws);
   NM_CHECK_LAUNCH("wgrad_gather_kernel");
   const int parts = chunks * (k == 1 ? 8 : 1);
   wgrad_gather_reduce_kernel<<<nm_cdiv((long long)Ca * Cb * taps, 256), 256, 0, st>>>(ws, parts, ab, bb, taps, Ca, Cb, out_scale, dw);
