@@ -258,25 +258,33 @@ gnb_small_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, co
 __global__ void __launch_bounds__(kGnbThreads)
 gnb_dx_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, const float* __restrict__ gamma, const float* __restrict__ beta,
               const float* __restrict__ mean_rstd, const float* __restrict__ m12, GnbShape s, int leaky, __half* __restrict__ dx) {
-  const long long total = (long long)s.n * s.S * s.ccs;                  // 16-byte channel chunks
-  for (long long i = (long long)blockIdx.x * kGnbThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kGnbThreads) {
-    const int cc = (int)(i % s.ccs);
-    const int n = (int)(i / (s.S * s.ccs));
-    const int grp = (cc * 8) / s.cpg;
-    const float mu = mean_rstd[(n * s.groups + grp) * 2], rs = mean_rstd[(n * s.groups + grp) * 2 + 1];
-    const float m1 = m12[(n * s.groups + grp) * 2], m2 = m12[(n * s.groups + grp) * 2 + 1];
+  // grid (chunks, n); thread = (voxel lane, 16-byte channel chunk): the chunk's parameters live in registers and the voxel
+  // loop has no index arithmetic beyond one add (the flat-index version spent two 64-bit divisions per 16 bytes and was
+  // instruction-bound at 4.2 TB/s)
+  const int n = blockIdx.y;
+  const int cc = threadIdx.x % s.ccs, vl = threadIdx.x / s.ccs;
+  const int grp = (cc * 8) / s.cpg;
+  const float mu = mean_rstd[(n * s.groups + grp) * 2], rs = mean_rstd[(n * s.groups + grp) * 2 + 1];
+  const float m1 = m12[(n * s.groups + grp) * 2], m2 = m12[(n * s.groups + grp) * 2 + 1];
+  float g[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { g[k] = gamma[cc * 8 + k]; b[k] = beta[cc * 8 + k]; }
+  const long long base = (long long)n * s.S * s.C + cc * 8;
+  const long long step = (long long)gridDim.x * s.nvl;
+#pragma unroll 2
+  for (long long v = (long long)blockIdx.x * s.nvl + vl; v < s.S; v += step) {
+    const long long off = base + v * s.C;
     float xf[8], df[8], o[8];
-    nm_unpack8(*reinterpret_cast<const half8*>(x + i * 8), xf);
-    nm_unpack8(*reinterpret_cast<const half8*>(dz + i * 8), df);
+    nm_unpack8(*reinterpret_cast<const half8*>(x + off), xf);
+    nm_unpack8(*reinterpret_cast<const half8*>(dz + off), df);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float gk = gamma[cc * 8 + k];
       const float xhat = (xf[k] - mu) * rs;
-      const float y = fmaf(gk, xhat, beta[cc * 8 + k]);
+      const float y = fmaf(g[k], xhat, b[k]);
       const float dy = (leaky && !(y > 0.f)) ? 0.01f * df[k] : df[k];
-      o[k] = rs * (gk * dy - m1 - xhat * m2);
+      o[k] = rs * (g[k] * dy - m1 - xhat * m2);
     }
-    *reinterpret_cast<half8*>(dx + i * 8) = nm_pack8(o);
+    *reinterpret_cast<half8*>(dx + off) = nm_pack8(o);
   }
 }
 
@@ -376,26 +384,31 @@ __global__ void __launch_bounds__(kGnbThreads)
 gnb_dx_rank1_kernel(const __half* __restrict__ x, const float* __restrict__ dx14, const float* __restrict__ w,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ mean_rstd,
                     const float* __restrict__ m12, GnbShape s, __half* __restrict__ dx) {
-  const long long total = (long long)s.n * s.S * s.ccs;
-  for (long long i = (long long)blockIdx.x * kGnbThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kGnbThreads) {
-    const int cc = (int)(i % s.ccs);
-    const long long v = i / s.ccs;                                        // n * S + voxel
-    const int n = (int)(v / s.S);
-    const int grp = (cc * 8) / s.cpg;
-    const float mu = mean_rstd[(n * s.groups + grp) * 2], rs = mean_rstd[(n * s.groups + grp) * 2 + 1];
-    const float m1 = m12[(n * s.groups + grp) * 2], m2 = m12[(n * s.groups + grp) * 2 + 1];
-    const float d14 = dx14[v];
+  // grid (chunks, n), thread = (voxel lane, channel chunk) as gnb_dx_kernel
+  const int n = blockIdx.y;
+  const int cc = threadIdx.x % s.ccs, vl = threadIdx.x / s.ccs;
+  const int grp = (cc * 8) / s.cpg;
+  const float mu = mean_rstd[(n * s.groups + grp) * 2], rs = mean_rstd[(n * s.groups + grp) * 2 + 1];
+  const float m1 = m12[(n * s.groups + grp) * 2], m2 = m12[(n * s.groups + grp) * 2 + 1];
+  float g[8], b[8], wk[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { g[k] = gamma[cc * 8 + k]; b[k] = beta[cc * 8 + k]; wk[k] = w[cc * 8 + k]; }
+  const long long base = (long long)n * s.S * s.C + cc * 8;
+  const long long step = (long long)gridDim.x * s.nvl;
+#pragma unroll 2
+  for (long long v = (long long)blockIdx.x * s.nvl + vl; v < s.S; v += step) {
+    const long long off = base + v * s.C;
+    const float d14 = dx14[(long long)n * s.S + v];
     float xf[8], o[8];
-    nm_unpack8(*reinterpret_cast<const half8*>(x + i * 8), xf);
+    nm_unpack8(*reinterpret_cast<const half8*>(x + off), xf);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const float gk = gamma[cc * 8 + k];
       const float xhat = (xf[k] - mu) * rs;
-      const float y = fmaf(gk, xhat, beta[cc * 8 + k]);
-      const float dy = w[cc * 8 + k] * (y > 0.f ? d14 : 0.01f * d14);
-      o[k] = rs * (gk * dy - m1 - xhat * m2);
+      const float y = fmaf(g[k], xhat, b[k]);
+      const float dy = wk[k] * (y > 0.f ? d14 : 0.01f * d14);
+      o[k] = rs * (g[k] * dy - m1 - xhat * m2);
     }
-    *reinterpret_cast<half8*>(dx + i * 8) = nm_pack8(o);
+    *reinterpret_cast<half8*>(dx + off) = nm_pack8(o);
   }
 }
 
@@ -414,6 +427,15 @@ bool gnb_shape(int n, long long S, int C, int groups, GnbShape* s) {
   if (C % 8 || cpg % 8 || ccs > 32 || (kGnbThreads % ccs) != 0) return false;   // C in {8, 16, 32, 64, 128, 256}
   *s = GnbShape{n, C, groups, cpg, ccs, kGnbThreads / ccs, S};
   return true;
+}
+
+// grid (voxel chunks, samples) of the dx passes: about 16 CTAs per SM in total, at least one voxel-lane round per CTA
+dim3 gnb_dx_grid(const GnbShape& s) {
+  const long long rounds = (s.S + s.nvl - 1) / s.nvl;
+  long long chunks = (16LL * nm_num_sms() + s.n - 1) / s.n;
+  if (chunks > rounds) chunks = rounds;
+  if (chunks < 1) chunks = 1;
+  return dim3((unsigned)chunks, (unsigned)s.n);
 }
 
 size_t gnb_ws_floats(int n, int C, int groups) {
@@ -473,9 +495,7 @@ extern "C" int nm_groupnorm_backward(const void* x, const void* grad_out, const 
     gnb_param_grad_kernel<<<nm_cdiv(C, 4), 128, 0, st>>>(chan, n, C, out_scale, dgamma, dbeta, dxsum);
     NM_CHECK_LAUNCH("gnb_param_grad_kernel");
   }
-  const long long total = (long long)n * S * s.ccs;
-  const int blocks = (int)min((long long)nm_num_sms() * 8, (total + kGnbThreads - 1) / kGnbThreads);
-  gnb_dx_kernel<<<blocks, kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, m12, s, leaky, reinterpret_cast<__half*>(grad_in));
+  gnb_dx_kernel<<<gnb_dx_grid(s), kGnbThreads, 0, st>>>(xh, dz, gamma, beta, mean_rstd, m12, s, leaky, reinterpret_cast<__half*>(grad_in));
   NM_CHECK_LAUNCH("gnb_dx_kernel");
   return NM_OK;
 }
@@ -516,9 +536,7 @@ extern "C" int nm_final_recon_backward_fused(const void* x, const float* a, cons
     gnb_param_grad_kernel<<<nm_cdiv(C, 4), 128, 0, st>>>(chan, n, C, inv, dgamma, dbeta, dxsum);
     NM_CHECK_LAUNCH("gnb_param_grad_kernel");
   }
-  const long long total = (long long)n * S * s.ccs;
-  const int blocks = (int)min((long long)nm_num_sms() * 8, (total + kGnbThreads - 1) / kGnbThreads);
-  gnb_dx_rank1_kernel<<<blocks, kGnbThreads, 0, st>>>(xh, dx14, w, gamma, beta, mean_rstd, m12, s, reinterpret_cast<__half*>(grad_x));
+  gnb_dx_rank1_kernel<<<gnb_dx_grid(s), kGnbThreads, 0, st>>>(xh, dx14, w, gamma, beta, mean_rstd, m12, s, reinterpret_cast<__half*>(grad_x));
   NM_CHECK_LAUNCH("gnb_dx_rank1_kernel");
   return NM_OK;
 }
