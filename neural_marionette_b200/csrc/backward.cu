@@ -24,14 +24,27 @@ constexpr int KMAX = 24;
 // (w, then h, then d), each halving one axis with 4 taps per output: [outer][2L][inner] -> [outer][L][inner] in 16-byte
 // units of 8 channels.  A one-pass version reads every gradient value 8 x (64 GB through L2 for the decoder's 64^3 layer,
 // 9.6 ms); the passes move 8 + 4 + 4 + 2 + 2 + 1 = 21 GB.  fp32 arithmetic inside a pass, fp16 between passes.
+// POW2: L and inner8 are powers of two (every shape of the model): the index decomposition is two shifts and two masks
+// instead of four 64-bit divisions per 16-byte output (which held the passes at 4.9 TB/s).
+template <bool POW2>
 __global__ void __launch_bounds__(256)
 upsample2x_bwd_axis_kernel(const __half* __restrict__ g, __half* __restrict__ out, long long outer, int L, long long inner8,
-                           long long total8) {
+                           long long total8, int log_inner8, int log_L) {
+#pragma unroll 2
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total8; i += (long long)gridDim.x * 256) {
-    const long long in8 = i % inner8;
-    const long long r = i / inner8;
-    const int l = (int)(r % L);
-    const long long o = r / L;
+    long long in8, o;
+    int l;
+    if (POW2) {
+      in8 = i & (inner8 - 1);
+      const long long r = i >> log_inner8;
+      l = (int)(r & (L - 1));
+      o = r >> log_L;
+    } else {
+      in8 = i % inner8;
+      const long long r = i / inner8;
+      l = (int)(r % L);
+      o = r / L;
+    }
     const half8* base = reinterpret_cast<const half8*>(g) + (o * (2LL * L)) * inner8 + in8;
     const int j0 = max(2 * l - 1, 0), j3 = min(2 * l + 2, 2 * L - 1);
     float f0[8], f1[8], f2[8], f3[8], acc[8];
@@ -1105,7 +1118,12 @@ extern "C" int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n
   for (const Pass& p : passes) {
     const long long total8 = p.outer * p.L * p.inner8;
     const int blocks = (int)min((long long)nm_num_sms() * 16, (total8 + 255) / 256);
-    upsample2x_bwd_axis_kernel<<<blocks, 256, 0, st>>>(p.in, p.out, p.outer, p.L, p.inner8, total8);
+    auto lg = [](long long v) { int l = 0; while ((1LL << l) < v) l++; return l; };
+    const bool pow2 = !(p.L & (p.L - 1)) && !(p.inner8 & (p.inner8 - 1));
+    if (pow2)
+      upsample2x_bwd_axis_kernel<true><<<blocks, 256, 0, st>>>(p.in, p.out, p.outer, p.L, p.inner8, total8, lg(p.inner8), lg(p.L));
+    else
+      upsample2x_bwd_axis_kernel<false><<<blocks, 256, 0, st>>>(p.in, p.out, p.outer, p.L, p.inner8, total8, 0, 0);
     NM_CHECK_LAUNCH("upsample2x_bwd_axis_kernel");
   }
   return NM_OK;

@@ -57,6 +57,7 @@ gnb_reduce_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, c
 #pragma unroll
     for (int i = 0; i < 8; i++) { g[i] = gamma[cc * 8 + i]; b[i] = beta[cc * 8 + i]; }
   }
+#pragma unroll 2
   for (long long v = v0 + vl; v < v1; v += s.nvl) {
     const long long off = ((long long)n * s.S + v) * s.C + cc * 8;
     float xf[8];

@@ -151,6 +151,42 @@ affine_act_kernel(const act_t* __restrict__ x1, const float* __restrict__ a1, co
   }
 }
 
+// Same operation for C in {8, 16, 32, 64, 128, 256}: grid (voxel chunks, samples), thread = (voxel lane, 16-byte channel
+// chunk).  The chunk's scale / shift live in registers and the voxel loop has no index arithmetic beyond one add - the
+// flat-index kernel above spends two 64-bit divisions and up to 36 parameter loads per 16 bytes (instruction-bound).
+template <bool HAS2, bool AFF2>
+__global__ void __launch_bounds__(256)
+affine_act_rows_kernel(const act_t* __restrict__ x1, const float* __restrict__ a1, const float* __restrict__ b1,
+                       int act1, const act_t* __restrict__ x2, const float* __restrict__ a2,
+                       const float* __restrict__ b2, act_t* __restrict__ out, int S, int C) {
+  const int c8n = C >> 3, nvl = 256 / c8n;
+  const int n = blockIdx.y, c8 = threadIdx.x % c8n, vl = threadIdx.x / c8n;
+  float av[8], bv[8], a2v[8], b2v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    av[k] = a1[(long long)n * C + c8 * 8 + k];
+    bv[k] = b1[(long long)n * C + c8 * 8 + k];
+    a2v[k] = AFF2 ? a2[(long long)n * C + c8 * 8 + k] : 1.f;
+    b2v[k] = AFF2 ? b2[(long long)n * C + c8 * 8 + k] : 0.f;
+  }
+  const long long base = (long long)n * S * C + c8 * 8;
+  const int step = gridDim.x * nvl;
+#pragma unroll 2
+  for (int v = blockIdx.x * nvl + vl; v < S; v += step) {
+    const long long off = base + (long long)v * C;
+    float f[8], g[8];
+    nm_unpack8(*reinterpret_cast<const half8*>(x1 + off), f);
+    if (HAS2) nm_unpack8(*reinterpret_cast<const half8*>(x2 + off), g);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      float v1 = fmaf(f[k], av[k], bv[k]);
+      f[k] = act1 ? nm_lrelu(v1) : v1;
+      if (HAS2) f[k] += AFF2 ? fmaf(g[k], a2v[k], b2v[k]) : g[k];
+    }
+    *reinterpret_cast<half8*>(out + off) = nm_pack8(f);
+  }
+}
+
 // ------------------------------------------------------------------ trilinear x2 (align_corners=False)
 // Reference: nn.Upsample(scale_factor=2, mode='trilinear') at model/kypt_detector.py:427,441.
 // Optional fused prologue: v = lrelu(x*a + b) of the producing GroupNorm.
@@ -165,12 +201,23 @@ upsample2x_kernel(const act_t* __restrict__ x, const float* __restrict__ a, cons
   const int c8n = C >> 3;
   const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
   if (i >= total8) return;
-  const int c8 = (int)(i % c8n);
-  long long r = i / c8n;
-  const int w = (int)(r % W); r /= W;
-  const int h = (int)(r % H); r /= H;
-  const int d = (int)(r % D);
-  const long long n = r / D;
+  int c8, w, h, d;
+  long long n;
+  if (total8 <= 0x7fffffffLL) {                   // 32-bit index arithmetic (a 64-bit division costs ~4x as much)
+    unsigned r = (unsigned)i;
+    c8 = (int)(r % (unsigned)c8n); r /= (unsigned)c8n;
+    w = (int)(r % (unsigned)W); r /= (unsigned)W;
+    h = (int)(r % (unsigned)H); r /= (unsigned)H;
+    d = (int)(r % (unsigned)D);
+    n = r / (unsigned)D;
+  } else {
+    c8 = (int)(i % c8n);
+    long long r = i / c8n;
+    w = (int)(r % W); r /= W;
+    h = (int)(r % H); r /= H;
+    d = (int)(r % D);
+    n = r / D;
+  }
   float av[8], bv[8];
   if (AFFINE) {
     const float4* pa = reinterpret_cast<const float4*>(a + n * C + c8 * 8);
@@ -256,12 +303,23 @@ upsample2x_h2_kernel(const act_t* __restrict__ x, act_t* __restrict__ out, int D
   const int c8n = C >> 3;
   const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
   if (i >= total8) return;
-  const int c8 = (int)(i % c8n);
-  long long r = i / c8n;
-  const int w = (int)(r % W); r /= W;
-  const int h = (int)(r % H); r /= H;
-  const int d = (int)(r % D);
-  const long long n = r / D;
+  int c8, w, h, d;
+  long long n;
+  if (total8 <= 0x7fffffffLL) {                   // 32-bit index arithmetic (a 64-bit division costs ~4x as much)
+    unsigned r = (unsigned)i;
+    c8 = (int)(r % (unsigned)c8n); r /= (unsigned)c8n;
+    w = (int)(r % (unsigned)W); r /= (unsigned)W;
+    h = (int)(r % (unsigned)H); r /= (unsigned)H;
+    d = (int)(r % (unsigned)D);
+    n = r / (unsigned)D;
+  } else {
+    c8 = (int)(i % c8n);
+    long long r = i / c8n;
+    w = (int)(r % W); r /= W;
+    h = (int)(r % H); r /= H;
+    d = (int)(r % D);
+    n = r / D;
+  }
   const uint4* base = reinterpret_cast<const uint4*>(x) + n * (long long)D * H * W * c8n;
   const int wi[3] = {max(w - 1, 0), w, min(w + 1, W - 1)};
   const int hi[3] = {max(h - 1, 0), h, min(h + 1, H - 1)};
@@ -549,6 +607,24 @@ extern "C" int nm_affine_act(const void* x1, const float* a1, const float* b1, i
   NM_CHECK_ARG(C % 8 == 0, "nm_affine_act: C=%d not a multiple of 8", C);
   const long long total8 = (long long)n * S * (C / 8);
   if (total8 == 0) return NM_OK;
+  const int c8n = C / 8;
+  if (256 % c8n == 0 && n <= 65535) {
+    const int nvl = 256 / c8n;
+    long long chunks = (16LL * nm_num_sms() + n - 1) / n;
+    const long long rounds = ((long long)S + nvl - 1) / nvl;
+    if (chunks > rounds) chunks = rounds;
+    if (chunks < 1) chunks = 1;
+    const dim3 grid((unsigned)chunks, (unsigned)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!x2)
+      affine_act_rows_kernel<false, false><<<grid, 256, 0, st>>>((const act_t*)x1, a1, b1, act1, nullptr, nullptr, nullptr, (act_t*)out, S, C);
+    else if (a2)
+      affine_act_rows_kernel<true, true><<<grid, 256, 0, st>>>((const act_t*)x1, a1, b1, act1, (const act_t*)x2, a2, b2, (act_t*)out, S, C);
+    else
+      affine_act_rows_kernel<true, false><<<grid, 256, 0, st>>>((const act_t*)x1, a1, b1, act1, (const act_t*)x2, nullptr, nullptr, (act_t*)out, S, C);
+    NM_CHECK_LAUNCH("affine_act(rows)");
+    return NM_OK;
+  }
   const int blocks = (int)min((long long)nm_num_sms() * 16, (total8 + 255) / 256);
   affine_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const act_t*)x1, a1, b1, act1, (const act_t*)x2, a2,
                                                               b2, (act_t*)out, S, C, total8);
