@@ -318,10 +318,29 @@ tail_bwd_pass1_kernel(const __half* __restrict__ x, const float* __restrict__ a,
 #pragma unroll
   for (int c = 0; c < C; c++) A[c] = B[c] = 0.f;
   const half8* base = reinterpret_cast<const half8*>(x + (long long)n * S * C);
-  for (long long s = (long long)blockIdx.x * 256 + threadIdx.x; s < S; s += (long long)gridDim.x * 256) {
+  // software pipeline: the next voxel's 64 bytes (and its recon / target) are requested before this voxel's ~250
+  // instructions of arithmetic (16 warps per SM cannot hide the load latency otherwise: 2.2 TB/s)
+  const long long sstep = (long long)gridDim.x * 256;
+  long long s = (long long)blockIdx.x * 256 + threadIdx.x;
+  half8 nraw[4];
+  float np = 0.f, ntg = 0.f;
+  if (s < S) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) nraw[j] = base[s * 4 + j];
+    np = recon[(long long)n * S + s];
+    ntg = target[(long long)n * S + s];
+  }
+  for (; s < S; s += sstep) {
     half8 raw[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) raw[j] = base[s * 4 + j];
+    for (int j = 0; j < 4; j++) raw[j] = nraw[j];
+    const float p = np, tg = ntg;
+    if (s + sstep < S) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) nraw[j] = base[(s + sstep) * 4 + j];
+      np = recon[(long long)n * S + s + sstep];
+      ntg = target[(long long)n * S + s + sstep];
+    }
     float x14 = bias;
     uint32_t pos = 0;                                  // bit c: y_c > 0
 #pragma unroll
@@ -337,7 +356,6 @@ tail_bwd_pass1_kernel(const __half* __restrict__ x, const float* __restrict__ a,
       }
     }
     const float t = tanhf(x14);
-    const float p = recon[(long long)n * S + s], tg = target[(long long)n * S + s];
     const float pq = p * (1.f - p);
     const float dx14 = gn * (p - tg) * (pq / fmaxf(pq, 1e-12f)) * sharp * (1.f - t * t);
     db += dx14;
