@@ -971,18 +971,30 @@ first_wgrad_occ_kernel(const float* __restrict__ occ, const __half* __restrict__
     for (int i = 0; i < 16; i++) acc[hh][i] = 0.f;
   const float* on = occ + (long long)n * S;
   const __half* dyn = dy + (long long)n * S * C;
+  // this warp's taps t = warp + 8 i as offsets inside the staged region (in halfs): the gather's address is one subtraction
+  int toff[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const int t = warp + 8 * i;
+    toff[i] = (((t / 25) * kFoReg + (t / 5) % 5) * kFoReg + t % 5) * 32;
+  }
+  // the core's two occupancy values of this thread (2 consecutive z): read one core ahead of their use
+  auto occ_pair = [&](int core) -> float2 {
+    const int cx = (core / (cpa * cpa)) * kFoCore, cy = ((core / cpa) % cpa) * kFoCore, cz = (core % cpa) * kFoCore;
+    const int l = threadIdx.x * 2;
+    return *reinterpret_cast<const float2*>(on + ((long long)(cx + (l >> 6)) * G + cy + ((l >> 3) & 7)) * G + cz + (l & 7));
+  };
+  float2 nextv = make_float2(0.f, 0.f);
+  if (part < cores) nextv = occ_pair(part);
   for (int core = part; core < cores; core += parts) {
     const int cx = (core / (cpa * cpa)) * kFoCore, cy = ((core / cpa) % cpa) * kFoCore, cz = (core % cpa) * kFoCore;
     // ordered compaction of the core's non-zero voxels (2 consecutive z per thread)
     __syncthreads();                                                        // previous core's list / tile are consumed
-    float v[2];
+    const float v[2] = {nextv.x, nextv.y};
+    if (core + parts < cores) nextv = occ_pair(core + parts);
     int mine = 0;
 #pragma unroll
-    for (int j = 0; j < 2; j++) {
-      const int l = threadIdx.x * 2 + j;
-      v[j] = on[((long long)(cx + (l >> 6)) * G + cy + ((l >> 3) & 7)) * G + cz + (l & 7)];
-      mine += v[j] != 0.f;
-    }
+    for (int j = 0; j < 2; j++) mine += v[j] != 0.f;
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -1022,14 +1034,10 @@ first_wgrad_occ_kernel(const float* __restrict__ occ, const __half* __restrict__
         const float val = s_val[e];
         // region coordinates of dY[u - (t - 2)]: (l + 4 - t) per axis, always inside the staged region
         const int bx = (l >> 6) + 4, by = ((l >> 3) & 7) + 4, bz = (l & 7) + 4;
+        const __half* pe = s_dy + ((bx * kFoReg + by) * kFoReg + bz) * 32 + lane;
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const int t = warp + 8 * i;
-          if (t < 125) {
-            const int r = ((bx - t / 25) * kFoReg + (by - (t / 5) % 5)) * kFoReg + (bz - t % 5);
-            acc[hh][i] = fmaf(val, __half2float(s_dy[r * 32 + lane]), acc[hh][i]);
-          }
-        }
+        for (int i = 0; i < 16; i++)
+          if (warp + 8 * i < 125) acc[hh][i] = fmaf(val, __half2float(pe[-toff[i]]), acc[hh][i]);
       }
     }
   }
