@@ -775,7 +775,7 @@ conv3d_slab3_kernel(const __grid_constant__ ConvSlabParams p) {
         const bool split = nxw >= 6;
         const int n_items = split ? (kHaloH / 2) * 16 : (kHaloH / 2) * 8;
         const int n_workers = split ? 160 : 96;
-        for (int item = wtid >= 0 ? wtid : 99999; item < n_items; item += n_workers) {
+        for (int item = (wtid >= 0 && !(p.debug & 512)) ? wtid : 99999; item < n_items; item += n_workers) {   // 512: ablation, no interpolation
           const int j = split ? item >> 4 : item >> 3, c = split ? (item >> 1) & 7 : item & 7;
           const int half = split ? item & 1 : 2;                     // 0: columns 0..4, 1: 5..9, 2: all ten
           const int h0 = ih * 16 - 1 + 2 * j;                        // first row of the pair (may be -1)

@@ -11,7 +11,8 @@ import neural_marionette_b200 as nm          # noqa: E402
 from neural_marionette_b200 import ops       # noqa: E402
 from oracle import nm_oracle as O            # synthetic weights / clips only  # noqa: E402
 
-B, T, G = int(sys.argv[1]) if len(sys.argv) > 1 else 64, 20, 64
+_args = [a for a in sys.argv[1:] if not a.startswith("--")]
+B, T, G = int(_args[0]) if _args else 64, 20, 64
 hp = O.default_hparams(grid_size=G)
 net = nm.NeuralMarionette(hp)
 net.load_state_dict(O.synthetic_state_dict(hp, 0))
@@ -52,3 +53,15 @@ span = ev[-1][1] - ev[0][0]
 print(f"{B} clips: device span {span / 1e3:.1f} ms, busy (union over streams) {busy / 1e3:.1f} ms, idle {(span - busy) / 1e3:.1f} ms over {len(ev)} launches")
 for k, (c, t) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:12]:
     print(f"  idle before {k:60s} x{c:4d} {t / 1e3:7.2f} ms ({t / max(c, 1):6.1f} us each)")
+if "--kernels" in sys.argv:
+    # device time by kernel (torch.profiler durations; in-step, warm caches - the ncu launch lists are cold and serialised)
+    tot = {}
+    for st, en, name in ev:
+        key = name.replace("void ", "").replace("(anonymous namespace)::", "")[:110]
+        t = tot.setdefault(key, [0, 0.0])
+        t[0] += 1
+        t[1] += en - st
+    total = sum(v[1] for v in tot.values())
+    print(f"kernel time (sum over both streams) {total / 1e3:.1f} ms")
+    for k, (c, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:36]:
+        print(f"  {t / 1e3:8.2f} ms {100 * t / total:5.1f}% x{c:4d}  {k}")
