@@ -67,13 +67,25 @@ depth_to_space2_kernel(const __half* __restrict__ y, __half* __restrict__ out, i
                        long long total8) {
   const int c8n = C >> 3;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total8; i += (long long)gridDim.x * 256) {
-    const int c8 = (int)(i % c8n);
-    long long r = i / c8n;
-    const int tl = (int)(r % ntaps); r /= ntaps;
-    const int w = (int)(r % W); r /= W;
-    const int h = (int)(r % H); r /= H;
-    const int d = (int)(r % D);
-    const long long n = r / D;
+    int c8, tl, w, h, d;
+    long long n;
+    if (total8 <= 0x7fffffffLL) {                 // 32-bit index arithmetic (a 64-bit division costs ~4x as much)
+      unsigned r = (unsigned)i;
+      c8 = (int)(r % (unsigned)c8n); r /= (unsigned)c8n;
+      tl = (int)(r % (unsigned)ntaps); r /= (unsigned)ntaps;
+      w = (int)(r % (unsigned)W); r /= (unsigned)W;
+      h = (int)(r % (unsigned)H); r /= (unsigned)H;
+      d = (int)(r % (unsigned)D);
+      n = r / (unsigned)D;
+    } else {
+      c8 = (int)(i % c8n);
+      long long r = i / c8n;
+      tl = (int)(r % ntaps); r /= ntaps;
+      w = (int)(r % W); r /= W;
+      h = (int)(r % H); r /= H;
+      d = (int)(r % D);
+      n = r / D;
+    }
     const int t = tap0 + tl;
     const long long o = (((n * (2 * D) + 2 * d + (t >> 2)) * (2 * H) + 2 * h + ((t >> 1) & 1)) * (2 * W) + 2 * w + (t & 1)) * C + c8 * 8;
     *reinterpret_cast<uint4*>(out + o) = reinterpret_cast<const uint4*>(y)[i];
