@@ -141,9 +141,12 @@ int nm_ncdhw_f32_to_ndhwc(const float* x, void* out, int n, int S, int C, void* 
 /* seq.mean(dim=1) (kypt_detector.py:312): (n_clips, T, S) fp32 -> (n_clips, S) */
 int nm_mean_over_frames(const float* seq, float* out, int n_clips, int T, long long S, void* stream);
 /* decoder tail: GN-apply + LeakyReLU + Conv3d(32,1,k1) + sigmoid(sharp*(tanh(x)+first_frame-trans))
- * (kypt_detector.py:453-457,:410) and, when `target` is given, the per-frame mean BCE (:91-92). */
+ * (kypt_detector.py:453-457,:410) and, when `target` is given, the per-frame mean BCE (:91-92).
+ * bias_dev (optional, here and in the two backward entry points): device pointer to the 1x1 conv's bias - overrides
+ * `bias`, so that a training loop never reads the updated parameter back to the host. */
 size_t nm_final_recon_workspace_bytes(int n);
-int nm_final_recon(const void* x, const float* a, const float* b, const float* w, float bias, const float* first_frame,
+int nm_final_recon(const void* x, const float* a, const float* b, const float* w, float bias, const float* bias_dev,
+                   const float* first_frame,
                    int frames_per_clip, float sharpness, float translation, float* recon, const float* target,
                    float* bce_mean, void* workspace, int n, int S, int C, void* stream);
 /* get_volume_fitting_loss('chamfer') (utils/kypt_detector_utils.py:141-157): per-frame value, (n) fp32 */
@@ -158,10 +161,11 @@ int nm_chamfer_vol_fit(const float* seq, const float* keypoints, const float* li
  *         gaussians = extract_gaussian_map_from_keypoints(...)       (:57-90), optional
  * feature: act (n, g^3, C); w1 (K, C); prev (n/frames_per_clip, K, g^3); heat/gaussians (n, K, g^3); keypoints (n,K,4).
  * heat_mean (optional, (n,K)): per-keypoint heat-map mean = input of get_keypoint_sparsity_loss (:92-103).
- * gauss_width = 2*(sigma/g)^2 computed by the caller in double. */
+ * gauss_width = 2*(sigma/g)^2 computed by the caller in double.
+ * prop_dev (optional, also in nm_heatmap_head_backward): device pointer to (pw0, pw1, pb) - overrides the by-value copies. */
 int nm_heatmap_head(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K, int mode,
-                    const float* prev, int frames_per_clip, float pw0, float pw1, float pb, const float* linspace,
-                    float gauss_width, float* heat, float* keypoints, float* gaussians, float* heat_mean,
+                    const float* prev, int frames_per_clip, float pw0, float pw1, float pb, const float* prop_dev,
+                    const float* linspace, float gauss_width, float* heat, float* keypoints, float* gaussians, float* heat_mean,
                     void* stream);
 int nm_gaussian_render(const float* keypoints, int n, int K, int g, const float* linspace, float gauss_width,
                        float* gaussians, void* stream);
@@ -284,7 +288,7 @@ int nm_upsample2x_backward(const void* grad_out, void* grad_in, int n, int D, in
  * grad_act act (n, S, C) = grad_scale * dL/d(LeakyReLU(x*a+b)) (feed it to nm_groupnorm_backward with x);
  * dw (C), dbias (1) fp32 = gradient of the 1x1 conv (not scaled). */
 size_t nm_final_recon_backward_workspace_bytes(int n);
-int nm_final_recon_backward(const void* x, const float* a, const float* b, const float* w, float bias,
+int nm_final_recon_backward(const void* x, const float* a, const float* b, const float* w, float bias, const float* bias_dev,
                             const float* first_frame, int frames_per_clip, float sharpness, float translation,
                             const float* recon, const float* target, const float* grad_bce, float grad_scale,
                             void* grad_act, float* dw, float* dbias, void* workspace, int n, int S, int C, void* stream);
@@ -295,7 +299,8 @@ int nm_final_recon_backward(const void* x, const float* a, const float* b, const
  * (nm_groupnorm_finalize).  Outputs: grad_x act (n, S, C) = grad_scale * dL/d(raw conv output), dw (C), dbias (1) of the
  * 1x1 conv, dgamma / dbeta (C) and dxsum (C) = the producing conv's bias gradient (fp32, true scale). */
 size_t nm_final_recon_backward_fused_workspace_bytes(int n, long long S, int C, int groups);
-int nm_final_recon_backward_fused(const void* x, const float* a, const float* b, const float* w, float bias, float sharpness,
+int nm_final_recon_backward_fused(const void* x, const float* a, const float* b, const float* w, float bias,
+                                  const float* bias_dev, float sharpness,
                                   const float* recon, const float* target, const float* grad_bce, float grad_scale,
                                   const float* gamma, const float* beta, const float* mean_rstd, const float* xsum,
                                   int groups, void* grad_x, float* dw, float* dbias, float* dgamma, float* dbeta,
@@ -310,8 +315,8 @@ int nm_final_recon_backward_fused(const void* x, const float* a, const float* b,
  *   g^3)) [+ grad_heat]; outputs grad_feature, dw1, db1. */
 size_t nm_heatmap_head_backward_workspace_bytes(int n, int C, int K);
 int nm_heatmap_head_backward(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K, int mode,
-                             const float* prev, int frames_per_clip, float pw0, float pw1, float pb, const float* linspace,
-                             const float* heat, const float* keypoints, const float* heat_mean,
+                             const float* prev, int frames_per_clip, float pw0, float pw1, float pb, const float* prop_dev,
+                             const float* linspace, const float* heat, const float* keypoints, const float* heat_mean,
                              const float* grad_keypoints, const float* grad_heat_mean, const float* grad_heat,
                              const float* dq_in, float grad_scale, void* grad_feature, float* dq_out, float* dw1,
                              float* db1, float* dprop, void* workspace, void* stream);

@@ -68,10 +68,10 @@ PROTOTYPES = {
     "nm_ncdhw_f32_to_ndhwc": (_i, [_vp, _vp, _i, _i, _i, _vp]),
     "nm_mean_over_frames": (_i, [_vp, _vp, _i, _i, _ll, _vp]),
     "nm_final_recon_workspace_bytes": (_sz, [_i]),
-    "nm_final_recon": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "nm_final_recon": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "nm_chamfer_workspace_bytes": (_sz, [_i]),
     "nm_chamfer_vol_fit": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
-    "nm_heatmap_head": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _f, _vp, _vp, _vp, _vp,
+    "nm_heatmap_head": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _vp, _f, _vp, _vp, _vp, _vp,
                              _vp]),
     "nm_gaussian_render": (_i, [_vp, _i, _i, _i, _vp, _f, _vp, _vp]),
     "nm_decoder_adjust_workspace_bytes": (_sz, [_i, _i]),
@@ -99,13 +99,13 @@ PROTOTYPES = {
     "nm_upsample2x_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "nm_upsample2x_backward": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "nm_final_recon_backward_workspace_bytes": (_sz, [_i]),
-    "nm_final_recon_backward": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i,
+    "nm_final_recon_backward": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i,
                                      _i, _vp]),
     "nm_final_recon_backward_fused_workspace_bytes": (_sz, [_i, _ll, _i, _i]),
-    "nm_final_recon_backward_fused": (_i, [_vp, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp,
+    "nm_final_recon_backward_fused": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _f, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _vp, _vp,
                                            _vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp]),
     "nm_heatmap_head_backward_workspace_bytes": (_sz, [_i, _i, _i]),
-    "nm_heatmap_head_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+    "nm_heatmap_head_backward": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "nm_decoder_adjust_backward_workspace_bytes": (_sz, [_i, _i]),
     "nm_decoder_adjust_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -100,11 +100,13 @@ depth_to_space2_kernel(const __half* __restrict__ y, __half* __restrict__ out, i
 constexpr int kFrbBlocks = 64;
 __global__ void __launch_bounds__(256)
 final_recon_bwd_kernel(const __half* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
-                       const float* __restrict__ w, float bias, const float* __restrict__ first_frame, int frames_per_clip,
+                       const float* __restrict__ w, float bias, const float* __restrict__ bias_dev,
+                       const float* __restrict__ first_frame, int frames_per_clip,
                        float sharp, float trans, const float* __restrict__ recon, const float* __restrict__ target,
                        const float* __restrict__ gbce, float grad_scale, __half* __restrict__ dact,
                        float* __restrict__ partial /* [n][blocks][33] */, int S) {
   constexpr int C = 32;
+  if (bias_dev) bias = __ldg(bias_dev);
   const int n = blockIdx.y;
   __shared__ float sa[C], sb[C], sw[C];
   __shared__ float red[8][C + 1];
@@ -211,11 +213,13 @@ template <int C>
 __global__ void __launch_bounds__(256)
 head_bwd_kernel(const __half* __restrict__ feature, const float* __restrict__ w1, const float* __restrict__ b1, int K, int g,
                 int mode, const float* __restrict__ prev, int frames_per_clip, float pw0, float pw1, float pb,
+                const float* __restrict__ prop_dev,
                 const float* __restrict__ lin, const float* __restrict__ heat, const float* __restrict__ kp,
                 const float* __restrict__ heat_mean, const float* __restrict__ dkp, const float* __restrict__ dmean_up,
                 const float* __restrict__ dheat, const float* __restrict__ dq_in, float grad_scale,
                 __half* __restrict__ dfeat, float* __restrict__ dq_out, float* __restrict__ pw_partial /* [n*splits][K][C] */,
                 float* __restrict__ pb_partial /* [n*splits][K] */, float* __restrict__ pp_partial /* [n*splits][3] */) {
+  if (prop_dev) { pw0 = __ldg(prop_dev); pw1 = __ldg(prop_dev + 1); pb = __ldg(prop_dev + 2); }   // live parameters
   constexpr int TS = 64;                                   // voxels per tile
   constexpr int FS = C + 4;                                // fp32 feature row stride: 16-byte aligned rows, conflict-free LDS.128
   constexpr int KPT = KMAX * C / 256;                      // dW1 accumulators per thread (12 or 24)
@@ -1164,6 +1168,7 @@ extern "C" int nm_depth_to_space2(const void* y, void* out, int n, int D, int H,
 extern "C" size_t nm_final_recon_backward_workspace_bytes(int n) { return ((size_t)n * kFrbBlocks * 33 + 64) * sizeof(float); }
 
 extern "C" int nm_final_recon_backward(const void* x, const float* a, const float* b, const float* w, float bias,
+                                       const float* bias_dev,
                                        const float* first_frame, int frames_per_clip, float sharpness, float translation,
                                        const float* recon, const float* target, const float* grad_bce, float grad_scale,
                                        void* grad_act, float* dw, float* dbias, void* workspace, int n, int S, int C,
@@ -1174,7 +1179,7 @@ extern "C" int nm_final_recon_backward(const void* x, const float* a, const floa
   if (n == 0) return NM_OK;
   cudaStream_t st = (cudaStream_t)stream;
   float* partial = reinterpret_cast<float*>(workspace);
-  final_recon_bwd_kernel<<<dim3(kFrbBlocks, n), 256, 0, st>>>(reinterpret_cast<const __half*>(x), a, b, w, bias, first_frame,
+  final_recon_bwd_kernel<<<dim3(kFrbBlocks, n), 256, 0, st>>>(reinterpret_cast<const __half*>(x), a, b, w, bias, bias_dev, first_frame,
                                                              frames_per_clip, sharpness, translation, recon, target, grad_bce,
                                                              grad_scale, reinterpret_cast<__half*>(grad_act), partial, S);
   NM_CHECK_LAUNCH("final_recon_bwd_kernel");
@@ -1200,6 +1205,7 @@ extern "C" size_t nm_heatmap_head_backward_workspace_bytes(int n, int C, int K) 
 
 extern "C" int nm_heatmap_head_backward(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K, int mode,
                                         const float* prev, int frames_per_clip, float pw0, float pw1, float pb,
+                                        const float* prop_dev,
                                         const float* linspace, const float* heat, const float* keypoints,
                                         const float* heat_mean, const float* grad_keypoints, const float* grad_heat_mean,
                                         const float* grad_heat, const float* dq_in, float grad_scale, void* grad_feature,
@@ -1221,12 +1227,12 @@ extern "C" int nm_heatmap_head_backward(const void* feature, const float* w1, co
   if (C == 128) {
     NM_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     head_bwd_kernel<128><<<grid, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
-                                                  pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
+                                                  pw0, pw1, pb, prop_dev, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
                                                   grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
   } else {
     NM_CHECK_CUDA(cudaFuncSetAttribute(head_bwd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     head_bwd_kernel<256><<<grid, 256, smem, st>>>(reinterpret_cast<const __half*>(feature), w1, b1, K, g, mode, prev, frames_per_clip,
-                                                  pw0, pw1, pb, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
+                                                  pw0, pw1, pb, prop_dev, linspace, heat, keypoints, heat_mean, grad_keypoints, grad_heat_mean,
                                                   grad_heat, dq_in, grad_scale, reinterpret_cast<__half*>(grad_feature), dq_out, pwp, pbp, ppp);
   }
   NM_CHECK_LAUNCH("head_bwd_kernel");

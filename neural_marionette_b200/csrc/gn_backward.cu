@@ -299,11 +299,13 @@ gnb_dx_kernel(const __half* __restrict__ x, const __half* __restrict__ dz, const
 template <int C>
 __global__ void __launch_bounds__(256)
 tail_bwd_pass1_kernel(const __half* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
-                      const float* __restrict__ w, float bias, float sharp, const float* __restrict__ recon,
+                      const float* __restrict__ w, float bias, const float* __restrict__ bias_dev, float sharp,
+                      const float* __restrict__ recon,
                       const float* __restrict__ target, const float* __restrict__ gbce, float grad_scale, long long S,
                       float* __restrict__ dx14_out /* (n, S), times grad_scale */,
                       float* __restrict__ gn_partial /* [n][kGnbChunks][C][2] */, float* __restrict__ tail_partial /* [n][chunks][C + 1] */) {
   static_assert(C == 32, "decoder tail has 32 channels");
+  if (bias_dev) bias = __ldg(bias_dev);
   const int n = blockIdx.y;
   __shared__ float sa[C], sb[C], sw[C];
   __shared__ float red[8][2 * C + 1];
@@ -525,6 +527,7 @@ extern "C" size_t nm_final_recon_backward_fused_workspace_bytes(int n, long long
 }
 
 extern "C" int nm_final_recon_backward_fused(const void* x, const float* a, const float* b, const float* w, float bias,
+                                             const float* bias_dev,
                                              float sharpness, const float* recon, const float* target, const float* grad_bce,
                                              float grad_scale, const float* gamma, const float* beta, const float* mean_rstd,
                                              const float* xsum, int groups, void* grad_x, float* dw, float* dbias, float* dgamma,
@@ -544,7 +547,7 @@ extern "C" int nm_final_recon_backward_fused(const void* x, const float* a, cons
   float* tailp = dx14 + (size_t)n * S;
   const __half* xh = reinterpret_cast<const __half*>(x);
   const float inv = 1.0f / grad_scale;
-  tail_bwd_pass1_kernel<32><<<dim3(kGnbChunks, n), 256, 0, st>>>(xh, a, b, w, bias, sharpness, recon, target, grad_bce, grad_scale, S, dx14,
+  tail_bwd_pass1_kernel<32><<<dim3(kGnbChunks, n), 256, 0, st>>>(xh, a, b, w, bias, bias_dev, sharpness, recon, target, grad_bce, grad_scale, S, dx14,
                                                                 partial, tailp);
   NM_CHECK_LAUNCH("tail_bwd_pass1_kernel");
   tail_reduce_kernel<<<1, 64, 0, st>>>(tailp, (long long)n * kGnbChunks, C, dw, dbias);

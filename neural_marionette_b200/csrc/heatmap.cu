@@ -37,7 +37,8 @@ template <int C>
 __global__ void __launch_bounds__(256)
 head_heat_kernel(const act_t* __restrict__ feature, const float* __restrict__ w1, const float* __restrict__ b1,
                  int K, int S, int mode, const float* __restrict__ prev, int frames_per_clip, float pw0, float pw1,
-                 float pb, float* __restrict__ heat) {
+                 float pb, const float* __restrict__ prop_dev, float* __restrict__ heat) {
+  if (prop_dev) { pw0 = __ldg(prop_dev); pw1 = __ldg(prop_dev + 1); pb = __ldg(prop_dev + 2); }   // live parameters
   constexpr int KS = C / 16, NB = KMAX / 8;
   // the fp32 weights are split into fp16 hi + lo parts (two MMAs per k-step): the heat-maps keep fp32-weight accuracy
   __shared__ __align__(16) uint2 s_frag[KS * NB * 32];
@@ -467,7 +468,7 @@ adjust_frame_kernel(const float* __restrict__ base, const float* __restrict__ kp
 }  // namespace
 
 extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float* b1, int n, int g, int C, int K,
-                               int mode, const float* prev, int frames_per_clip, float pw0, float pw1, float pb,
+                               int mode, const float* prev, int frames_per_clip, float pw0, float pw1, float pb, const float* prop_dev,
                                const float* linspace, float gauss_width, float* heat, float* keypoints,
                                float* gaussians, float* heat_mean, void* stream) {
   NM_CHECK_ARG(feature && w1 && b1 && heat && linspace, "nm_heatmap_head: null pointer");
@@ -479,10 +480,10 @@ extern "C" int nm_heatmap_head(const void* feature, const float* w1, const float
   dim3 grid1(nm_cdiv(S, 512), n);
   if (C == 128) {
     head_heat_kernel<128><<<grid1, 256, 0, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
-                                                     pw0, pw1, pb, heat);
+                                                     pw0, pw1, pb, prop_dev, heat);
   } else if (C == 256) {
     head_heat_kernel<256><<<grid1, 256, 0, st>>>((const act_t*)feature, w1, b1, K, S, mode, prev, frames_per_clip,
-                                                     pw0, pw1, pb, heat);
+                                                     pw0, pw1, pb, prop_dev, heat);
   } else {
     NM_CHECK_ARG(false, "nm_heatmap_head: C=%d unsupported", C);
   }

@@ -419,9 +419,11 @@ mean_over_t_kernel(const float* __restrict__ seq, float* __restrict__ out, int T
 template <int C>
 __global__ void __launch_bounds__(256)
 final_recon_kernel(const act_t* __restrict__ x, const float* __restrict__ a, const float* __restrict__ b,
-                   const float* __restrict__ w, float bias, const float* __restrict__ first_frame,
+                   const float* __restrict__ w, float bias, const float* __restrict__ bias_dev,
+                   const float* __restrict__ first_frame,
                    int frames_per_clip, float sharp, float trans, float* __restrict__ recon,
                    const float* __restrict__ target, float* __restrict__ bce_partial, int S) {
+  if (bias_dev) bias = __ldg(bias_dev);            // the live parameter: no host copy (and no host sync) per training step
   // C/8 lanes per voxel: each loads one 16-byte channel chunk (consecutive lanes -> consecutive addresses),
   // partial dot product, shuffle-reduce inside the lane group
   constexpr int LPV = C / 8;                       // lanes per voxel (4 for C = 32)
@@ -681,7 +683,7 @@ extern "C" int nm_mean_over_frames(const float* seq, float* out, int n_clips, in
 constexpr int kReconBlocks = 64;
 extern "C" size_t nm_final_recon_workspace_bytes(int n) { return (size_t)n * kReconBlocks * sizeof(float); }
 
-extern "C" int nm_final_recon(const void* x, const float* a, const float* b, const float* w, float bias,
+extern "C" int nm_final_recon(const void* x, const float* a, const float* b, const float* w, float bias, const float* bias_dev,
                               const float* first_frame, int frames_per_clip, float sharpness, float translation,
                               float* recon, const float* target, float* bce_mean, void* workspace, int n, int S,
                               int C, void* stream) {
@@ -690,7 +692,7 @@ extern "C" int nm_final_recon(const void* x, const float* a, const float* b, con
   NM_CHECK_ARG(!target || (bce_mean && workspace), "nm_final_recon: BCE needs bce_mean and workspace");
   if (n == 0) return NM_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  final_recon_kernel<32><<<dim3(kReconBlocks, n), 256, 0, st>>>((const act_t*)x, a, b, w, bias, first_frame,
+  final_recon_kernel<32><<<dim3(kReconBlocks, n), 256, 0, st>>>((const act_t*)x, a, b, w, bias, bias_dev, first_frame,
                                                                frames_per_clip, sharpness, translation, recon,
                                                                target, target ? (float*)workspace : nullptr, S);
   NM_CHECK_LAUNCH("final_recon");

@@ -421,12 +421,12 @@ def final_recon_backward(raw, a, b, conv: torch.nn.Conv3d, first_frame, frames_p
     n, D, H, W, C = raw.shape
     S = D * H * W
     w = f32(conv, "weight").reshape(-1)
-    bias = _cached(conv, "bias_host", [conv.bias], lambda: float(conv.bias.detach().float().item()))
+    bias_dev = f32(conv, "bias")                       # the live parameter, read on the device (no host sync per step)
     dact = torch.empty_like(raw)
     dw = torch.empty(1, C, 1, 1, 1, dtype=torch.float32, device=raw.device)
     db = torch.empty(1, dtype=torch.float32, device=raw.device)
     ws = workspace(L.query("nm_final_recon_backward_workspace_bytes", n), raw.device, "recon_bwd")
-    L.call("nm_final_recon_backward", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), bias, L.ptr(first_frame), frames_per_clip,
+    L.call("nm_final_recon_backward", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), 0.0, L.ptr(bias_dev), L.ptr(first_frame), frames_per_clip,
            float(sharpness), float(translation), L.ptr(recon), L.ptr(target), L.ptr(grad_bce), float(scale), L.ptr(dact),
            L.ptr(dw), L.ptr(db), L.ptr(ws), n, S, C, L.stream())
     return dact, dw, db
@@ -440,14 +440,14 @@ def final_recon_backward_fused(raw, a, b, conv: torch.nn.Conv3d, gn: torch.nn.Gr
     S = D * H * W
     dev = raw.device
     w = f32(conv, "weight").reshape(-1)
-    bias = _cached(conv, "bias_host", [conv.bias], lambda: float(conv.bias.detach().float().item()))
+    bias_dev = f32(conv, "bias")
     draw = torch.empty_like(raw)
     dw = torch.empty(1, C, 1, 1, 1, dtype=torch.float32, device=dev)
     db = torch.empty(1, dtype=torch.float32, device=dev)
     dg, dbeta, dxs = (torch.empty(C, dtype=torch.float32, device=dev) for _ in range(3))
     ws = workspace(L.query("nm_final_recon_backward_fused_workspace_bytes", n, S, C, gn.num_groups), dev, "recon_bwd")
     mr, xs = stats
-    L.call("nm_final_recon_backward_fused", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), bias, float(sharpness), L.ptr(recon),
+    L.call("nm_final_recon_backward_fused", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), 0.0, L.ptr(bias_dev), float(sharpness), L.ptr(recon),
            L.ptr(target), L.ptr(grad_bce), float(scale), L.ptr(f32(gn, "weight")), L.ptr(f32(gn, "bias")), L.ptr(mr), L.ptr(xs),
            gn.num_groups, L.ptr(draw), L.ptr(dw), L.ptr(db), L.ptr(dg), L.ptr(dbeta), L.ptr(dxs), L.ptr(ws), n, S, C, L.stream())
     return draw, dw, db, dg, dbeta, dxs
@@ -466,16 +466,17 @@ def heatmap_head_backward(feature, conv1: torch.nn.Conv3d, K: int, mode: int, sc
     dw1 = torch.empty(K, C, 1, 1, 1, dtype=torch.float32, device=dev)
     db1 = torch.empty(K, dtype=torch.float32, device=dev)
     ws = workspace(L.query("nm_heatmap_head_backward_workspace_bytes", n, C, K), dev, "head_bwd")
+    prop_dev = None                                     # (pw0, pw1, pb) are read on the device
     if mode == 1:
-        pw = _prop_host(prop)
+        prop_dev = _prop_dev(prop)
         dq = torch.empty(n, K, g, g, g, dtype=torch.float32, device=dev)
         dprop = torch.empty(3, dtype=torch.float32, device=dev)
     else:
-        pw, dq, dprop = (0.0, 0.0, 0.0), None, None
+        dq, dprop = None, None
         if dq_in is not None:
-            pw = (0.0, _prop_host(prop)[1], 0.0)
+            prop_dev = _prop_dev(prop)                  # mode 0 only uses pw1
     L.call("nm_heatmap_head_backward", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, mode, L.ptr(prev),
-           frames_per_clip, pw[0], pw[1], pw[2], L.ptr(linspace(g, dev)), L.ptr(heat), L.ptr(keypoints), L.ptr(heat_mean),
+           frames_per_clip, 0.0, 0.0, 0.0, L.ptr(prop_dev), L.ptr(linspace(g, dev)), L.ptr(heat), L.ptr(keypoints), L.ptr(heat_mean),
            L.ptr(grad_keypoints), L.ptr(grad_heat_mean), L.ptr(grad_heat), L.ptr(dq_in), float(scale), L.ptr(dfeat),
            L.ptr(dq), L.ptr(dw1), L.ptr(db1), L.ptr(dprop), L.ptr(ws), L.stream())
     return dfeat, dq, dw1, db1, dprop
@@ -704,12 +705,12 @@ def final_recon(raw, a, b, conv: torch.nn.Conv3d, first_frame, frames_per_clip, 
     S = D * H * W
     recon = out if out is not None else torch.empty(n, D, H, W, dtype=torch.float32, device=raw.device)
     w = f32(conv, "weight").reshape(-1)
-    bias = _cached(conv, "bias_host", [conv.bias], lambda: float(conv.bias.detach().float().item()))
+    bias_dev = f32(conv, "bias")                       # the live parameter, read on the device (no host sync per step)
     bce = None
     if target is not None:
         bce = bce_out if bce_out is not None else torch.empty(n, dtype=torch.float32, device=raw.device)
     ws = workspace(L.query("nm_final_recon_workspace_bytes", n), raw.device, "recon") if target is not None else None
-    L.call("nm_final_recon", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), bias, L.ptr(first_frame), frames_per_clip,
+    L.call("nm_final_recon", L.ptr(raw), L.ptr(a), L.ptr(b), L.ptr(w), 0.0, L.ptr(bias_dev), L.ptr(first_frame), frames_per_clip,
            float(sharpness), float(translation), L.ptr(recon), L.ptr(target), L.ptr(bce), L.ptr(ws), n, S, C,
            L.stream())
     return recon, bce
@@ -727,11 +728,11 @@ def chamfer_vol_fit(seq_frames: torch.Tensor, keypoints: torch.Tensor) -> torch.
 
 
 # ------------------------------------------------------------------ heads
-def _prop_host(prop: torch.nn.Conv3d):
-    """[w0, w1, bias] of the propagate conv (1, 2, 1, 1, 1) as host floats (kernel arguments)."""
-    return _cached(prop, "host", [prop.weight, prop.bias],
-                   lambda: [float(v) for v in prop.weight.detach().float().reshape(-1).tolist()] +
-                           [float(prop.bias.detach().float().item())])
+def _prop_dev(prop: torch.nn.Conv3d) -> torch.Tensor:
+    """(w0, w1, bias) of the propagate conv (1, 2, 1, 1, 1) packed on the device: the kernels read it there, so a training
+    loop never reads the updated parameters back to the host (that was two synchronisations in the middle of every step)."""
+    return _cached(prop, "dev3", [prop.weight, prop.bias],
+                   lambda: torch.cat([prop.weight.detach().float().reshape(-1), prop.bias.detach().float().reshape(-1)]).contiguous())
 
 
 def heatmap_head(feature, conv1: torch.nn.Conv3d, K: int, mode: int, prev=None, frames_per_clip: int = 1,
@@ -746,10 +747,10 @@ def heatmap_head(feature, conv1: torch.nn.Conv3d, K: int, mode: int, prev=None, 
     w1 = f32(conv1, "weight").reshape(K, C)
     b1 = f32(conv1, "bias")
     if mode == 0:
-        L.call("nm_heatmap_head", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, 0, None, 1, 0.0, 0.0, 0.0,
+        L.call("nm_heatmap_head", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, 0, None, 1, 0.0, 0.0, 0.0, None,
                L.ptr(linspace(g, dev)), 1.0, L.ptr(heat), None, None, None, L.stream())
         return heat
-    pw = _prop_host(prop)
+    prop_dev = _prop_dev(prop)
     if out is not None:
         kp, gs, hm_mean = out[1], out[2], out[3]
     else:
@@ -757,7 +758,7 @@ def heatmap_head(feature, conv1: torch.nn.Conv3d, K: int, mode: int, prev=None, 
         gs = torch.empty(n, K, g, g, g, dtype=torch.float32, device=dev) if want_gaussians else None
         hm_mean = torch.empty(n, K, dtype=torch.float32, device=dev)
     L.call("nm_heatmap_head", L.ptr(feature), L.ptr(w1), L.ptr(b1), n, g, C, K, 1, L.ptr(prev), frames_per_clip,
-           pw[0], pw[1], pw[2], L.ptr(linspace(g, dev)), gauss_width(sigma, g), L.ptr(heat), L.ptr(kp), L.ptr(gs),
+           0.0, 0.0, 0.0, L.ptr(prop_dev), L.ptr(linspace(g, dev)), gauss_width(sigma, g), L.ptr(heat), L.ptr(kp), L.ptr(gs),
            L.ptr(hm_mean), L.stream())
     return heat, kp, gs, hm_mean
 
