@@ -41,7 +41,7 @@ gaps = {}
 for st, en, name in ev[1:]:
     if st > cur_e:
         busy += cur_e - cur_s
-        key = name.split("(")[0].replace("void ", "").replace("(anonymous namespace)::", "")[:60]
+        key = name.replace("void ", "").replace("(anonymous namespace)::", "").split("(")[0][:60]
         g = gaps.setdefault(key, [0, 0.0])
         g[0] += 1
         g[1] += st - cur_e

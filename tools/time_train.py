@@ -88,7 +88,7 @@ if "--gaps" in sys.argv:
     last_end = ev[0][1]
     for st, en, name in ev[1:]:
         if st > last_end:
-            key = name.split("(")[0].replace("void ", "").replace("(anonymous namespace)::", "")[:60]
+            key = name.replace("void ", "").replace("(anonymous namespace)::", "").split("(")[0][:60]
             g = gaps.setdefault(key, [0, 0.0])
             g[0] += 1
             g[1] += st - last_end
