@@ -403,6 +403,44 @@ def test_final_recon_and_bce(ops):
     assert (bce.cpu() - ref_bce).abs().max() < 2e-3 * float(ref_bce.max())
 
 
+def test_scalar_parameters_by_value_and_by_device_pointer_agree(ops):
+    """`bias` / (`pw0`, `pw1`, `pb`) can be passed by value or read from device memory (`bias_dev` / `prop_dev`, what the
+    host wrappers use so that a training loop never synchronises on a parameter): the two routes are bit-identical."""
+    from neural_marionette_b200 import _lib as L
+    gen = torch.Generator().manual_seed(16)
+    n, T, G, C, K, g = 4, 2, 16, 32, 24, 8
+    x = to_act(torch.randn(n, C, G, G, G, generator=gen))
+    a = (0.5 + torch.rand(n, C, generator=gen)).cuda()
+    b = torch.randn(n, C, generator=gen).cuda()
+    w = torch.randn(C, generator=gen).cuda()
+    bias = torch.tensor([0.37], device="cuda")
+    first = (torch.rand(n // T, G, G, G, generator=gen) < 0.1).float().cuda()
+    outs = []
+    for by_pointer in (False, True):
+        recon = torch.empty(n, G, G, G, device="cuda")
+        L.call("nm_final_recon", L.ptr(x), L.ptr(a), L.ptr(b), L.ptr(w), 0.0 if by_pointer else float(bias.item()),
+               L.ptr(bias) if by_pointer else None, L.ptr(first), T, 10.0, 0.5, L.ptr(recon), None, None, None, n, G ** 3, C,
+               L.stream())
+        outs.append(recon)
+    assert torch.equal(outs[0], outs[1])
+    feat = to_act(torch.randn(n, 128, g, g, g, generator=gen))
+    w1 = (torch.randn(K, 128, generator=gen) * 0.1).cuda()
+    b1 = torch.randn(K, generator=gen).cuda()
+    prev = torch.rand(n // T, K, g, g, g, generator=gen).cuda()
+    prop = torch.tensor([0.8, 0.3, -0.1], device="cuda")
+    lin = ops.linspace(g, feat.device)
+    outs = []
+    for by_pointer in (False, True):
+        heat = torch.empty(n, K, g, g, g, device="cuda")
+        kp = torch.empty(n, K, 4, device="cuda")
+        pw = (0.0, 0.0, 0.0) if by_pointer else tuple(float(v) for v in prop.tolist())
+        L.call("nm_heatmap_head", L.ptr(feat), L.ptr(w1), L.ptr(b1), n, g, 128, K, 1, L.ptr(prev), T, pw[0], pw[1], pw[2],
+               L.ptr(prop) if by_pointer else None, L.ptr(lin), ops.gauss_width(1.5, g), L.ptr(heat), L.ptr(kp), None, None,
+               L.stream())
+        outs.append((heat, kp))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_chamfer(ops):
     gen = torch.Generator().manual_seed(8)
     seq = (torch.rand(2, 3, 1, 16, 16, 16, generator=gen) < 0.05).float()
