@@ -28,6 +28,43 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().nm_version() == 100
 
 
+def test_header_prototypes_match_the_ctypes_bindings():
+    """Every declaration of include/nm_b200.h against its ctypes prototype: same number of parameters, and the same kind
+    (pointer / int / long long / size_t / float) in every position - an ABI drift between header, library and binding would
+    otherwise only show up as garbage arguments on the GPU."""
+    from neural_marionette_b200 import _lib
+    header = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "nm_b200.h")).read(), flags=re.S)
+    header = re.sub(r"//[^\n]*", " ", header)
+    decls = re.findall(r"\b(?:int|size_t|const char\s*\*)\s+(nm_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(decls) >= 80, len(decls)
+
+    def kind_of_c(param: str) -> str:
+        param = " ".join(param.split())
+        if "*" in param:
+            return "ptr"
+        base = param.rsplit(" ", 1)[0] if " " in param else param
+        return {"int": "int", "long long": "ll", "size_t": "size", "float": "float", "double": "double",
+                "unsigned long long": "ull"}.get(base.replace("const ", ""), base)
+
+    def kind_of_ctypes(t) -> str:
+        if isinstance(t, type) and issubclass(t, ctypes._Pointer):
+            return "ptr"
+        return {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "int", ctypes.c_longlong: "ll",
+                ctypes.c_size_t: "size", ctypes.c_float: "float", ctypes.c_double: "double",
+                ctypes.c_ulonglong: "ull"}.get(t, str(t))
+
+    seen = set()
+    for name, params in decls:
+        plist = [] if params.strip() in ("", "void") else [q for q in params.split(",")]
+        assert name in _lib.PROTOTYPES, name
+        _, argtypes = _lib.PROTOTYPES[name]
+        assert len(plist) == len(argtypes), f"{name}: header has {len(plist)} parameters, the binding {len(argtypes)}"
+        for i, (c, t) in enumerate(zip(plist, argtypes)):
+            assert kind_of_c(c) == kind_of_ctypes(t), f"{name}: parameter {i} is `{c.strip()}` in the header, {t} in the binding"
+        seen.add(name)
+    assert seen == set(_lib.PROTOTYPES), seen ^ set(_lib.PROTOTYPES)
+
+
 def test_state_dict_layout_matches_reference_contract():
     import neural_marionette_b200 as nm
     hp = O.default_hparams()
