@@ -8,6 +8,7 @@
 //  * ConvTranspose3d(k2, s2) of the hour-glass (modules/vox_modules.py:68) - tiny layers.
 //  * a generic direct convolution used as the on-device cross-check of the tcgen05 kernel.
 #include "common.cuh"
+#include "../../include/nm_b200.h"   // the definitions below must match the public declarations
 #include <type_traits>
 
 namespace {

@@ -14,6 +14,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2-5 = epilogue.
 // Persistent: grid = #SMs, static round-robin over output tiles.
 #include "common.cuh"
+#include "../../include/nm_b200.h"   // the definitions below must match the public declarations
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>

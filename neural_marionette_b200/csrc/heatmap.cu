@@ -11,6 +11,7 @@
 // One CTA per frame.  Shared-memory staging of the head weights, warp-shuffle reductions for
 // the marginals; the feature map is read once (HBM-bound: g^3*C fp16 per frame).
 #include "common.cuh"
+#include "../../include/nm_b200.h"   // the definitions below must match the public declarations
 
 namespace {
 

@@ -4,6 +4,7 @@
 // All activations are fp16 channels-last (N, S, C) with S = D*H*W; every kernel
 // moves 16-byte vectors (8 channels) per thread.
 #include "common.cuh"
+#include "../../include/nm_b200.h"   // the definitions below must match the public declarations
 
 namespace {
 

@@ -6,6 +6,7 @@
 // atomics; a warp-level __match_any_sync on the linear cell index lets one lane
 // per distinct cell issue the store (config #5: up to ~200 points per cell).
 #include "common.cuh"
+#include "../../include/nm_b200.h"   // the definitions below must match the public declarations
 
 namespace {
 
