@@ -441,7 +441,24 @@ class Bench:
             torch.cuda.synchronize()
             ar_ms = a.elapsed_time(b) / 5
         frames_total = self.world * B * T
-        res = dict(ms=ms, ms_e2e=ms_e2e, value=frames_total / (ms / 1e3), e2e=frames_total / (ms_e2e / 1e3),
+        # the same step captured in ONE CUDA graph and replayed (single rank: the NCCL exchange is driven from Python hooks);
+        # same launches, bit-identical results (tests/test_gpu_backward.py::test_captured_training_step_matches_eager)
+        graph_rec = None
+        if self.world == 1 and os.environ.get("NM_BENCH_TRAIN_GRAPH", "1") != "0":
+            from neural_marionette_b200 import graph as nm_graph
+            try:
+                cap = nm_graph.CapturedTrainStep(det, opt, lambda out: OG.detector_loss(out, recon_only=False), raw_dev, G, warmup=2)
+                g_ms = self.timed(lambda: cap(raw_dev), steps)
+                g_e2e = self.timed(lambda: float(cap(feed.next())), steps)
+                opt.sync_counters()
+                graph_rec = {"value": frames_total / (g_ms / 1e3), "unit": "frames/s", "ms_per_step": g_ms,
+                             "e2e": {"value": frames_total / (g_e2e / 1e3), "unit": "frames/s", "ms_per_step": g_e2e},
+                             "note": "graph.CapturedTrainStep: normalise + voxelize, forward, backward and the device-side Adam "
+                                     "step replayed as one CUDA graph; e2e adds the H2D copy of the points and the D2H read of "
+                                     "the loss every step"}
+            except Exception as e:      # report, do not hide: the eager numbers above stand on their own
+                graph_rec = {"error": f"{type(e).__name__}: {e}"[:300]}
+        res = dict(ms=ms, ms_e2e=ms_e2e, value=frames_total / (ms / 1e3), e2e=frames_total / (ms_e2e / 1e3), graph=graph_rec,
                    h2d=int(raw_host.numel() * 4), d2h=4, launches=launches,
                    grad_bytes=int(opt.buckets.flat.numel() * 4), buckets=len(opt.buckets.bounds), exposed_ms=exposed,
                    allreduce_alone_ms=ar_ms, skipped=opt.skipped, peak_gib=torch.cuda.max_memory_allocated() / 2 ** 30,
@@ -464,6 +481,8 @@ class Bench:
                              "note": "buckets are all-reduced asynchronously from post-accumulate hooks while the rest of the "
                                      "backward runs; exposed = device time spent waiting for them after the backward"},
                "skipped_steps": r["skipped"], "peak_memory_gib": r["peak_gib"], "loss_scale": r["grad_scale"]}
+        if r.get("graph") is not None:
+            rec["cuda_graph"] = r["graph"]
         return rec
 
     def roofline(self, prof, ms, steps):

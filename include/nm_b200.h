@@ -351,6 +351,12 @@ int nm_first_conv_wgrad(const float* occ, const void* grad_out, const float* lin
 int nm_grad_nonfinite(const float* grad, long long count, int* flag, void* stream);
 int nm_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
                  float beta2, float eps, int step, float grad_mul, const int* skip_flag, void* stream);
+/* The same step with the step count on the device: counters[0] = steps applied so far (the bias corrections use
+ * counters[0] + 1), counters[1] = steps skipped; both are advanced by the call.  No argument depends on host-side training
+ * state, so a CUDA graph that captured a whole training step (forward, backward, nm_grad_nonfinite, this call) can be
+ * replayed. */
+int nm_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr, float beta1,
+                     float beta2, float eps, int* counters, float grad_mul, const int* skip_flag, void* stream);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "nm_first_conv_wgrad": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp]),
     "nm_grad_nonfinite": (_i, [_vp, _ll, _vp, _vp]),
     "nm_adam_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _i, _f, _vp, _vp]),
+    "nm_adam_step_dev": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _vp, _f, _vp, _vp]),
 }
 
 _lib = None

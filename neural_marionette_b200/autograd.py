@@ -58,6 +58,8 @@ def _entry_gradient_max(dbce: torch.Tensor) -> float:
     slot = _GMAX.get(key)
     if slot is None:
         slot = _GMAX[key] = dict(pinned=torch.zeros(1, dtype=torch.float32).pin_memory(), event=torch.cuda.Event(), value=None)
+    if slot["value"] is not None and torch.cuda.is_current_stream_capturing():
+        return slot["value"]                                   # graph capture: the loss scale is frozen into the graph
     if slot["value"] is not None and slot["event"].query():
         slot["value"] = float(slot["pinned"][0])              # last step's read-back has landed
     if slot["value"] is None:

@@ -1118,6 +1118,31 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// The same step with the step count kept on the device (*step_dev = number of steps applied so far): nothing about the
+// launch depends on host state, so a captured CUDA graph of a whole training step can be replayed.  The bias corrections
+// are evaluated per thread in double, exactly as the host does for adam_kernel.
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                long long n, float lr, float beta1, float beta2, float eps, const int* __restrict__ step_dev,
+                                float grad_mul, const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag) return;
+  const double step = (double)(*step_dev + 1);
+  const float bc1 = (float)(1.0 - pow((double)beta1, step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * grad_mul;
+    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+// counters[0] += 1 when the step was applied, counters[1] += 1 when it was skipped (runs after adam_dev_kernel)
+__global__ void adam_advance_kernel(int* __restrict__ counters, const int* __restrict__ skip_flag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) counters[(skip_flag && *skip_flag) ? 1 : 0] += 1;
+}
+
 }  // namespace
 
 // =================================================================== C ABI
@@ -1364,6 +1389,20 @@ extern "C" int nm_grad_nonfinite(const float* grad, long long count, int* flag, 
   const int blocks = (int)min((long long)nm_num_sms() * 4, (count + 255) / 256);
   grad_nonfinite_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(grad, count, flag);
   NM_CHECK_LAUNCH("grad_nonfinite_kernel");
+  return NM_OK;
+}
+
+extern "C" int nm_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long count, float lr,
+                                float beta1, float beta2, float eps, int* counters, float grad_mul, const int* skip_flag,
+                                void* stream) {
+  NM_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && counters, "nm_adam_step_dev: null pointer");
+  if (count <= 0) return NM_OK;
+  const int blocks = (int)min((long long)nm_num_sms() * 8, (count + 255) / 256);
+  adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1, beta2, eps, counters,
+                                                            grad_mul, skip_flag);
+  NM_CHECK_LAUNCH("adam_dev_kernel");
+  adam_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(counters, skip_flag);
+  NM_CHECK_LAUNCH("adam_advance_kernel");
   return NM_OK;
 }
 

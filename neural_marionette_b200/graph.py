@@ -66,3 +66,48 @@ def capture_detector_from_points(detector, example_points: torch.Tensor, grid_si
         out["voxel"] = vox
         return out
     return CapturedCall(fn, example_points, warmup)
+
+
+class CapturedTrainStep:
+    """One training step - fused normalise + voxelize, `zero_grad`, forward, `loss_fn`, backward, `FusedAdam.step_device` -
+    captured into a CUDA graph and replayed: the ~1 800 launches of the step are enqueued without Python or driver work
+    between them (eager: 7 ms of the 132 ms step are GPU idle time).  The captured launches are the eager ones with the same
+    arguments, so a replayed step is bit-identical to an eager `step_device()` step.  `warmup` REAL training steps run
+    first (they build the scratch buffers the graph then refers to).  Frozen into the graph: the input shape, the loss
+    scale and the learning rate; overflowed steps are skipped on the device and counted (`optimizer.sync_counters()`).
+    Single-GPU only (the NCCL gradient exchange is driven from Python hooks)."""
+
+    def __init__(self, detector, optimizer, loss_fn: Callable, example_points: torch.Tensor, grid_size: int, warmup: int = 2):
+        if not example_points.is_cuda:
+            raise ops.L.NmError("CapturedTrainStep needs CUDA tensors (there is no CPU fallback)")
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
+            raise ops.L.NmError("CapturedTrainStep: single-process training only")
+        self.optimizer = optimizer
+        self.static_in = example_points.clone()
+        dev = example_points.device
+
+        def one() -> torch.Tensor:
+            vox = ops.normalize_voxelize(self.static_in, grid_size, check=False)
+            optimizer.zero_grad()
+            loss = loss_fn(detector(vox))
+            loss.backward()
+            optimizer.step_device()
+            return loss.detach()
+
+        self.stream = torch.cuda.Stream(device=dev)
+        self.stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.stream):
+            for _ in range(max(1, warmup)):
+                one()
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self.loss = one()
+
+    def __call__(self, points: torch.Tensor) -> torch.Tensor:
+        """Copy `points` (B, T, N, 3) into the static input, replay the step, return the (static) loss tensor."""
+        if points.shape != self.static_in.shape:
+            raise ValueError(f"captured for input shape {tuple(self.static_in.shape)}, got {tuple(points.shape)}")
+        self.static_in.copy_(points, non_blocking=True)
+        self.graph.replay()
+        return self.loss

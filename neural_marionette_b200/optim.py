@@ -43,6 +43,8 @@ class FusedAdam:
         self.exp_avg = torch.zeros_like(self.flat_param)
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.counters = torch.zeros(2, dtype=torch.int32, device=dev)   # step_device(): steps applied / skipped, on the device
+        self._device_mode = False
         self.steps = 0
         self.skipped = 0
         self._good = 0
@@ -54,8 +56,33 @@ class FusedAdam:
         """Zero the flat gradient buffer; the `.grad` views stay attached whatever `set_to_none` says."""
         self.buckets.zero()
 
+    def step_device(self) -> None:
+        """`step()` without any host synchronisation: the inf / NaN check, the skip decision and the step count (for the
+        bias corrections) stay on the device (`nm_adam_step_dev`), so the call can be captured in a CUDA graph together
+        with the forward and the backward (`graph.CapturedTrainStep`).  The loss scale is not adapted in this mode;
+        `sync_counters()` brings `steps` / `skipped` back to the host."""
+        if not self._device_mode:
+            self.counters.copy_(torch.tensor([self.steps, self.skipped], dtype=torch.int32), non_blocking=False)
+            self._device_mode = True
+        self.buckets.finish()
+        g = self.buckets.flat
+        self.flag.zero_()
+        L.call("nm_grad_nonfinite", L.ptr(g), g.numel(), L.ptr(self.flag), L.stream())
+        L.call("nm_adam_step_dev", L.ptr(self.flat_param), L.ptr(g), L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), g.numel(),
+               self.lr, self.betas[0], self.betas[1], self.eps, L.ptr(self.counters), 1.0, L.ptr(self.flag), L.stream())
+        if self.owner is not None:
+            ops.invalidate_caches(self.owner)
+
+    def sync_counters(self) -> None:
+        """After `step_device()` calls: read the device-side step / skip counts back (one synchronisation)."""
+        if self._device_mode:
+            c = self.counters.tolist()
+            self.steps, self.skipped = int(c[0]), int(c[1])
+            self._device_mode = False
+
     def step(self) -> bool:
         """-> False when a gradient was inf / NaN and the update was skipped."""
+        self.sync_counters()
         self.buckets.finish()
         g = self.buckets.flat
         self.flag.zero_()
@@ -77,6 +104,7 @@ class FusedAdam:
         return True
 
     def state_dict(self) -> dict:
+        self.sync_counters()
         return dict(steps=self.steps, lr=self.lr, betas=self.betas, eps=self.eps, exp_avg=self.exp_avg.clone(),
                     exp_avg_sq=self.exp_avg_sq.clone())
 

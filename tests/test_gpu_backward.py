@@ -442,6 +442,54 @@ def test_training_step_decreases_loss_and_is_reproducible(golden_dir):
     assert runs[0][-1] < runs[0][0], runs[0]
 
 
+def test_captured_training_step_matches_eager():
+    """`graph.CapturedTrainStep` (normalise + voxelize, forward, backward, device-side Adam in ONE CUDA graph) against the
+    same steps run eagerly with `FusedAdam.step_device()`: the replayed launches are the eager ones - identical losses
+    and parameters, step counters advanced on the device - and `step()` / `step_device()` agree with each other."""
+    import neural_marionette_b200 as nm
+    from neural_marionette_b200 import graph, ops, optim
+    G, B, T, N = 32, 2, 3, 4000
+    hp = O.default_hparams(grid_size=G, Tcond=3, Ttot=10)
+    sd = O.synthetic_state_dict(hp, seed=5)
+    raw = torch.from_numpy(np.stack([O.synthetic_clip(300 + b, T, N) for b in range(B)], 0)).cuda()
+    loss_fn = lambda out: OG.detector_loss(out, recon_only=False)
+
+    def fresh():
+        net = nm.NeuralMarionette(hp)
+        net.load_state_dict(sd, strict=True)
+        net = net.cuda().train()
+        net.anneal(1)
+        return net, optim.FusedAdam(net.kypt_detector.parameters(), lr=4e-4, owner=net)
+
+    steps = 4
+    results = {}
+    for mode in ("host", "device", "graph"):
+        net, opt = fresh()
+        losses = []
+        if mode == "graph":
+            step = graph.CapturedTrainStep(net.kypt_detector, opt, loss_fn, raw, G, warmup=2)   # 2 real steps + 1 captured... (capture does not execute)
+            for _ in range(steps - 2):
+                losses.append(float(step(raw)))
+        else:
+            for _ in range(steps):
+                vox = ops.normalize_voxelize(raw, G, check=False)
+                opt.zero_grad()
+                loss = loss_fn(net.kypt_detector(vox))
+                loss.backward()
+                if mode == "host":
+                    assert opt.step()
+                else:
+                    opt.step_device()
+                losses.append(float(loss.detach()))
+        opt.sync_counters()
+        assert (opt.steps, opt.skipped) == (steps, 0), (mode, opt.steps, opt.skipped)
+        results[mode] = (losses, torch.cat([p.detach().reshape(-1) for p in net.kypt_detector.parameters()]).clone())
+    assert results["host"][0] == results["device"][0]
+    assert torch.equal(results["host"][1], results["device"][1])
+    assert results["graph"][0] == results["device"][0][2:], (results["graph"][0], results["device"][0])
+    assert torch.equal(results["graph"][1], results["device"][1])
+
+
 def test_training_with_torch_adam_and_dropped_grads(golden_dir):
     """The gradients are ordinary fp32 `param.grad` tensors: the reference's own loop - `torch.optim.Adam`,
     `zero_grad()` with torch's default `set_to_none=True` - trains the CUDA model, and follows the fused optimizer."""

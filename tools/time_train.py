@@ -96,3 +96,21 @@ if "--gaps" in sys.argv:
     print(f"device span {span / 1e3:.1f} ms, busy {busy / 1e3:.1f} ms, idle {(span - busy) / 1e3:.1f} ms over {len(ev)} launches")
     for k, (c, t) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:25]:
         print(f"  idle before {k:60s} x{c:4d} {t / 1e3:7.2f} ms ({t / max(c, 1):6.1f} us each)")
+if "--graph" in sys.argv:
+    # the same step captured in a CUDA graph (graph.CapturedTrainStep: device-side Adam step counter / skip flag)
+    from neural_marionette_b200 import graph
+    cap = graph.CapturedTrainStep(net.kypt_detector, opt, lambda out: OG.detector_loss(out, recon_only=False), raw_dev, G, warmup=2)
+    for _ in range(2):
+        cap(raw_dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        loss = cap(raw_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    opt.sync_counters()
+    print(f"CUDA-graph replay: {ms:.1f} ms per step = {B * T / ms * 1e3:.0f} frames/s; loss {float(loss):.4f}; "
+          f"steps applied {opt.steps}, skipped {opt.skipped}")
