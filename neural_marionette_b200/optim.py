@@ -45,6 +45,7 @@ class FusedAdam:
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(2, dtype=torch.int32, device=dev)   # step_device(): steps applied / skipped, on the device
         self._device_mode = False
+        self._counters_live = False      # a captured graph may refer to `counters`: host-side steps keep them current
         self.steps = 0
         self.skipped = 0
         self._good = 0
@@ -62,8 +63,9 @@ class FusedAdam:
         with the forward and the backward (`graph.CapturedTrainStep`).  The loss scale is not adapted in this mode;
         `sync_counters()` brings `steps` / `skipped` back to the host."""
         if not self._device_mode:
-            self.counters.copy_(torch.tensor([self.steps, self.skipped], dtype=torch.int32), non_blocking=False)
+            self._upload_counters()
             self._device_mode = True
+            self._counters_live = True
         self.buckets.finish()
         g = self.buckets.flat
         self.flag.zero_()
@@ -72,6 +74,9 @@ class FusedAdam:
                self.lr, self.betas[0], self.betas[1], self.eps, L.ptr(self.counters), 1.0, L.ptr(self.flag), L.stream())
         if self.owner is not None:
             ops.invalidate_caches(self.owner)
+
+    def _upload_counters(self) -> None:
+        self.counters.copy_(torch.tensor([self.steps, self.skipped], dtype=torch.int32), non_blocking=False)
 
     def sync_counters(self) -> None:
         """After `step_device()` calls: read the device-side step / skip counts back (one synchronisation)."""
@@ -92,6 +97,8 @@ class FusedAdam:
             self.skipped += 1
             self._good = 0
             AG.adjust_headroom(-2)
+            if self._counters_live:
+                self._upload_counters()
             return False
         self.steps += 1
         self._good += 1
@@ -101,6 +108,8 @@ class FusedAdam:
                self.lr, self.betas[0], self.betas[1], self.eps, self.steps, 1.0, None, L.stream())
         if self.owner is not None:
             ops.invalidate_caches(self.owner)
+        if self._counters_live:
+            self._upload_counters()
         return True
 
     def state_dict(self) -> dict:
