@@ -44,8 +44,8 @@ class FusedAdam:
         self.exp_avg_sq = torch.zeros_like(self.flat_param)
         self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self.counters = torch.zeros(2, dtype=torch.int32, device=dev)   # step_device(): steps applied / skipped, on the device
-        self._device_mode = False
-        self._counters_live = False      # a captured graph may refer to `counters`: host-side steps keep them current
+        self._counters_live = False      # set by the first step_device(): the device counters are authoritative from then on
+                                         # (a captured graph advances them without Python); host-side steps mirror into them
         self.steps = 0
         self.skipped = 0
         self._good = 0
@@ -62,9 +62,8 @@ class FusedAdam:
         bias corrections) stay on the device (`nm_adam_step_dev`), so the call can be captured in a CUDA graph together
         with the forward and the backward (`graph.CapturedTrainStep`).  The loss scale is not adapted in this mode;
         `sync_counters()` brings `steps` / `skipped` back to the host."""
-        if not self._device_mode:
+        if not self._counters_live:
             self._upload_counters()
-            self._device_mode = True
             self._counters_live = True
         self.buckets.finish()
         g = self.buckets.flat
@@ -79,11 +78,10 @@ class FusedAdam:
         self.counters.copy_(torch.tensor([self.steps, self.skipped], dtype=torch.int32), non_blocking=False)
 
     def sync_counters(self) -> None:
-        """After `step_device()` calls: read the device-side step / skip counts back (one synchronisation)."""
-        if self._device_mode:
+        """After `step_device()` calls or graph replays: read the device-side step / skip counts back (one synchronisation)."""
+        if self._counters_live:
             c = self.counters.tolist()
             self.steps, self.skipped = int(c[0]), int(c[1])
-            self._device_mode = False
 
     def step(self) -> bool:
         """-> False when a gradient was inf / NaN and the update was skipped."""
@@ -121,3 +119,5 @@ class FusedAdam:
         self.steps, self.lr, self.betas, self.eps = int(state["steps"]), float(state["lr"]), tuple(state["betas"]), float(state["eps"])
         self.exp_avg.copy_(state["exp_avg"])
         self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        if self._counters_live:
+            self._upload_counters()

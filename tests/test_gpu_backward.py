@@ -483,6 +483,22 @@ def test_captured_training_step_matches_eager():
                 losses.append(float(loss.detach()))
         opt.sync_counters()
         assert (opt.steps, opt.skipped) == (steps, 0), (mode, opt.steps, opt.skipped)
+        # one host-side step() in between, then one more step: a graph replayed after it sees the advanced step count
+        for extra in range(2):
+            if mode == "graph" and extra == 1:
+                losses.append(float(step(raw)))
+                continue
+            vox = ops.normalize_voxelize(raw, G, check=False)
+            opt.zero_grad()
+            loss = loss_fn(net.kypt_detector(vox))
+            loss.backward()
+            if mode == "device" and extra == 1:
+                opt.step_device()
+            else:
+                assert opt.step()
+            losses.append(float(loss.detach()))
+        opt.sync_counters()
+        assert (opt.steps, opt.skipped) == (steps + 2, 0), (mode, opt.steps, opt.skipped)
         results[mode] = (losses, torch.cat([p.detach().reshape(-1) for p in net.kypt_detector.parameters()]).clone())
     assert results["host"][0] == results["device"][0]
     assert torch.equal(results["host"][1], results["device"][1])
