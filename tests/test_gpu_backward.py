@@ -342,6 +342,27 @@ def test_fused_adam_matches_torch():
     assert opt.step() is False
     for p, q in zip(net.parameters(), before):
         assert torch.equal(p, q)
+    # the device-side variant (what a captured CUDA graph replays): follows torch.optim.Adam step for step, and skips an
+    # overflowed step on the device without advancing the step count of the bias corrections
+    for step in range(3):
+        x = torch.randn(8, 17, device="cuda")
+        for m, o in ((net, opt), (ref, opt_ref)):
+            o.zero_grad()
+            m(x).pow(2).sum().backward()
+        if step == 1:
+            next(net.parameters()).grad[0, 0] = float("nan")
+            before = [p.detach().clone() for p in net.parameters()]
+            opt.step_device()
+            for p, q in zip(net.parameters(), before):
+                assert torch.equal(p, q)
+            opt.zero_grad()
+            net(x).pow(2).sum().backward()
+        opt.step_device()
+        opt_ref.step()
+    opt.sync_counters()
+    assert (opt.steps, opt.skipped) == (7, 2), (opt.steps, opt.skipped)
+    for p, q in zip(net.parameters(), ref.parameters()):
+        assert float((p - q).abs().max()) <= 2e-6
 
 
 # ------------------------------------------------------------------------------------------------ assembled backward
